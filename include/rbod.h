@@ -1,0 +1,170 @@
+/*
+ * rbod.h -- C ABI of the B200-native retrieval hot path ("rbod" = retrieval based object
+ * detection).  One shared library, librbod.so, exports exactly these symbols; the Python
+ * package `qdrant_client` in this repo (the drop-in for the third-party client the reference
+ * scripts import) binds them with ctypes.  No torch / C++ types cross this boundary: plain
+ * pointers, sizes and an opaque handle.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference repo):
+ *
+ *   rbod_create / rbod_destroy / rbod_count / rbod_truncate
+ *       client.recreate_collection(name, VectorParams(size, distance))
+ *           util/qdrant_manager.py:82-85 (defaults :56, :74), 02_qdrant_environment_setting.txt:12-14
+ *       client.get_collection(n).points_count      util/qdrant_manager.py:46-47, 112-113
+ *       client.count(n, exact=True).count          32_create_delegate_vector.py:67
+ *       client.delete_collection(n)                util/qdrant_manager.py:121, 138
+ *   rbod_upsert                                    (kernel K1 l2norm_pack)
+ *       client.upsert(collection, points=[PointStruct(id, vector, payload)])
+ *           31_clip_embedding_and_save_vector.py:178-179, 32_create_delegate_vector.py:41-42
+ *       plus the L2 normalisation a COSINE collection applies to every stored vector
+ *       (third-party Qdrant behaviour, see oracle/oracle_np.py header).
+ *   rbod_get_rows
+ *       client.scroll(..., with_vectors=True) -> Record.vector
+ *           32_create_delegate_vector.py:123-131,137; 33_run_all_experiments.py:96-110,139-149
+ *   rbod_segment_mean                              (kernel K2 segmented_mean_renorm)
+ *       compute_average  32_create_delegate_vector.py:9-10  (+ renormalise on upsert :41-42)
+ *   rbod_search                                    (kernel K3 cosine_topk + exact rescoring)
+ *       cosine_similarity(a, b)  33_run_all_experiments.py:76-77, used at :151, generalised
+ *       from one pair to Q x N with top-k selection (client.search / query_points semantics).
+ *   rbod_merge_topk                                (kernel K4 topk_merge)
+ *       no reference call site; merges per-GPU top-k lists after the NCCL all-gather.
+ *
+ * Conventions
+ *   - Every function returns 0 (RBOD_OK) or a negative errno-style code; rbod_last_error()
+ *     returns a thread-local, human-readable message for the last failure.  Nothing aborts.
+ *   - Pointers marked "host or device" are classified with cudaPointerGetAttributes; host
+ *     buffers are staged through pinned memory inside the call.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls that
+ *     write host outputs synchronise the stream before returning; rbod_search always does
+ *     (it reports certification statistics).
+ *   - A handle is used from one thread at a time.  One handle lives on one GPU; multi-GPU
+ *     search runs one process per GPU and merges with rbod_merge_topk.
+ */
+#ifndef RBOD_H_
+#define RBOD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBOD_ABI_VERSION 1
+
+/* return codes */
+#define RBOD_OK 0
+#define RBOD_E_IO (-5)           /* CUDA runtime / driver failure */
+#define RBOD_E_NOMEM (-12)       /* allocation failed */
+#define RBOD_E_INVAL (-22)       /* bad argument */
+#define RBOD_E_RANGE (-34)       /* row index / slot out of range */
+#define RBOD_E_OVERFLOW (-75)    /* tie cluster larger than the exact-fallback buffer */
+#define RBOD_E_UNSUPPORTED (-95) /* valid request this build does not implement */
+
+/* storage dtype of the gallery (the arithmetic is always fp32-accumulate + fp64 rescoring) */
+#define RBOD_F32 0
+#define RBOD_BF16 1
+#define RBOD_F16 2
+
+/* distance of the collection (Distance enum, util/qdrant_manager.py:61-66) */
+#define RBOD_COSINE 0
+#define RBOD_DOT 1
+
+/* rbod_upsert flags */
+#define RBOD_UPSERT_RAW 1 /* rows are already in stored form: do not normalise (used on reload) */
+
+typedef struct rbod_gallery rbod_gallery;
+
+typedef struct rbod_gallery_info {
+  int32_t dim;            /* logical vector size                                   */
+  int32_t dim_padded;     /* row stride (elements) of the 16-bit search operand    */
+  int32_t dtype;          /* RBOD_F32 / RBOD_BF16 / RBOD_F16                       */
+  int32_t metric;         /* RBOD_COSINE / RBOD_DOT                                */
+  int32_t device;         /* CUDA device ordinal                                   */
+  int32_t reserved;
+  int64_t rows;           /* number of row slots in use (max slot + 1)             */
+  int64_t capacity;       /* allocated row slots                                   */
+  int64_t bytes_device;   /* device bytes held by the handle (gallery + workspace) */
+  float max_row_norm;     /* max ||stored 16-bit row||                             */
+  float max_row_dev;      /* max ||stored 16-bit row - unit(master row)||          */
+} rbod_gallery_info;
+
+typedef struct rbod_search_stats {
+  int64_t queries;          /* Q                                                         */
+  int64_t fallback_queries; /* queries whose top-k was not certified by the tensor-core  */
+                            /* pass and went through the exact fp64 sweep                */
+  int64_t k3_launches;      /* kernel launches of the tcgen05 pass                       */
+  int64_t total_launches;   /* all kernel launches issued by this call                   */
+  int32_t candidates;       /* candidates kept per query before rescoring (k + slack)    */
+  int32_t slices;           /* gallery slices the tcgen05 pass was split into            */
+  float max_eps;            /* largest certification margin used                         */
+  float k3_ms;              /* device time of the tcgen05 pass (CUDA events), 0 if off   */
+} rbod_search_stats;
+
+const char* rbod_last_error(void);
+int rbod_abi_version(void);
+
+/* --- collection lifetime -------------------------------------------------------------- */
+int rbod_create(int32_t dim, int32_t dtype, int32_t metric, int64_t capacity_hint, int32_t device,
+                rbod_gallery** out);
+int rbod_destroy(rbod_gallery* g);
+int64_t rbod_count(const rbod_gallery* g);
+int rbod_info(const rbod_gallery* g, rbod_gallery_info* out);
+/* Shrinks the number of used row slots (rows beyond `rows` are forgotten). */
+int rbod_truncate(rbod_gallery* g, int64_t rows);
+/* Tunables: "k3_variant" (0 = A operand resident in TMEM, 1 = A streamed through smem),
+ * "slack" (extra candidates kept per query), "time_k3" (1 = fill stats.k3_ms). */
+int rbod_set_option(rbod_gallery* g, const char* key, int64_t value);
+
+/* --- K1: normalise + pack on upsert ----------------------------------------------------
+ * rows:      [n, dim] fp32, host or device.
+ * row_slots: [n] int64 destination slots (host or device), or NULL to append.
+ *            A slot equal to the current count appends; smaller overwrites (upsert-by-id
+ *            is resolved to a slot by the caller).
+ * out_norms: optional [n] fp32 L2 norms of the incoming rows (host or device), or NULL.   */
+int rbod_upsert(rbod_gallery* g, const float* rows, int64_t n, const int64_t* row_slots, float* out_norms,
+                int32_t flags, void* stream);
+
+/* Stored rows widened to fp32: out[i, :] = gallery[rows[i], :].  rows/out host or device. */
+int rbod_get_rows(rbod_gallery* g, const int64_t* rows, int64_t n, float* out, void* stream);
+
+/* Same kernel on caller-owned buffers (no handle): in [n, dim] fp32 device -> out [n, out_ld]
+ * of out_dtype, plus optional norms.  Device pointers only.                               */
+int rbod_l2norm_pack(const float* in, int64_t n, int32_t dim, int32_t out_dtype, void* out, int64_t out_ld,
+                     float* out_norms, void* stream);
+
+/* --- K2: delegate ("average") vectors ---------------------------------------------------
+ * Class c owns gallery rows row_idx[offsets[c] .. offsets[c+1]) (row_idx == NULL: the rows
+ * themselves are label-sorted, i.e. row_idx[i] = i).  out_centroids[c, :] is the fp32
+ * L2-normalised mean of those stored rows; an empty class or a zero mean gives zeros.
+ * row_idx / offsets / out_centroids: host or device.                                      */
+int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* offsets, int64_t n_classes,
+                      float* out_centroids, void* stream);
+
+/* --- K3: cosine top-k -------------------------------------------------------------------
+ * queries:      [Q, dim] fp32 (any norm), host or device.
+ * row_mask:     optional bitmask over row slots (bit r%32 of word r/32 set = row allowed),
+ *               ceil(rows/32) words, host or device; NULL = all rows.
+ * out_scores:   [Q, k] fp32 cosine, descending; ties broken by smaller row slot.
+ * out_rows:     [Q, k] int64 row slots; -1 (score -inf) where fewer than k rows qualify.
+ * out_scores64: optional [Q, k] fp64 scores (what the multi-GPU merge consumes), or NULL.
+ * stats:        optional.                                                                 */
+int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, const uint32_t* row_mask,
+                float* out_scores, int64_t* out_rows, double* out_scores64, rbod_search_stats* stats,
+                void* stream);
+
+/* --- K4: merge of per-shard top-k lists -------------------------------------------------
+ * scores64 / ids: [G, Q, k] as produced by an all-gather of each rank's rbod_search output
+ * (ids already global; id < 0 = empty).  Output: the global top-k per query, ordered by
+ * (score desc, id asc).  Device pointers only.                                            */
+int rbod_merge_topk(const double* scores64, const int64_t* ids, int32_t G, int64_t Q, int32_t k,
+                    float* out_scores, int64_t* out_ids, double* out_scores64, void* stream);
+
+/* --- test hook --------------------------------------------------------------------------
+ * Raw scores of the tcgen05 pass (before top-k and rescoring): out[q, r] for r < rows,
+ * fp32, device or host.  Small problems only (Q * rows <= 2^28).                          */
+int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBOD_H_ */

@@ -1,0 +1,397 @@
+// K4 family -- everything between the tensor-core pass and the answer:
+//
+//   merge_partials   per query, the per-slice candidate lists of K3 -> the kc best approximate
+//                    candidates and tau = the kc-th best approximate score (every row K3 dropped
+//                    scores <= tau).
+//   rescore          exact cosine of every (query, candidate) pair in fp64 on the stored values:
+//                    dot / (|q| * |g|), the formula of cosine_similarity
+//                    (33_run_all_experiments.py:76-77).
+//   select           per query: order candidates by (score desc, row asc), emit the top k, and
+//                    certify them: if tau + eps < (k-th exact score) no dropped row can belong to
+//                    the top k.  Uncertified queries are appended to a flag list.
+//   exact_collect /  exact fp64 sweep over the whole gallery for flagged queries only: collect
+//   select_collected every row whose exact score >= the query's provisional k-th score, then
+//                    select among those.  This is the guarantee behind "identical ids".
+//   merge_topk       (K4 proper) G sorted per-GPU lists -> global top k, after the NCCL
+//                    all-gather in the row-sharded multi-GPU search.
+//
+// All of it is small, latency/HBM-bound integer and fp64 work on CUDA cores.
+#include "rbod_common.cuh"
+#include "rbod_internal.h"
+
+namespace rbod {
+
+namespace {
+
+__device__ __forceinline__ bool beats(double sa, uint32_t ia, double sb, uint32_t ib) {
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+// ---------------------------------------------------------------------------------------------
+// merge_partials: one CTA per query, bitonic sort (descending) of packed keys in shared memory.
+// key = ordered(score) << 32 | ~idx   (ties: smaller row index first); 0 = padding.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+merge_partials_kernel(const float* __restrict__ part_score, const uint32_t* __restrict__ part_idx, int slices,
+                      int64_t q_pad, int kc, int m_pow2, uint32_t* __restrict__ cand_idx,
+                      float* __restrict__ cand_tau) {
+  extern __shared__ unsigned long long keys[];
+  const int64_t q = blockIdx.x;
+  const int m = slices * kc;
+  for (int i = threadIdx.x; i < m_pow2; i += blockDim.x) {
+    unsigned long long key = 0ull;
+    if (i < m) {
+      const int s = i / kc, j = i - s * kc;
+      const size_t off = ((size_t)s * q_pad + q) * kc + j;
+      const uint32_t idx = part_idx[off];
+      if (idx != 0xffffffffu)
+        key = (static_cast<unsigned long long>(f32_to_ordered(part_score[off])) << 32) |
+              static_cast<unsigned long long>(~idx);
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  for (int size = 2; size <= m_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (m_pow2 >> 1); i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if (desc ? (a < b) : (a > b)) { keys[lo] = b; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = threadIdx.x; j < kc; j += blockDim.x) {
+    const unsigned long long key = j < m_pow2 ? keys[j] : 0ull;
+    cand_idx[q * kc + j] = key ? ~static_cast<uint32_t>(key & 0xffffffffull) : 0xffffffffu;
+  }
+  if (threadIdx.x == 0) {
+    const unsigned long long key = (kc - 1) < m_pow2 ? keys[kc - 1] : 0ull;
+    cand_tau[q] = key ? ordered_to_f32(static_cast<uint32_t>(key >> 32)) : -INFINITY;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rescore: one warp per (query, candidate)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rescore_kernel(const float* __restrict__ q, const double* __restrict__ q_qq, const float* __restrict__ master32,
+               const uint16_t* __restrict__ rows16, int kind16, int dim, int64_t ld32, int64_t ld16,
+               const uint32_t* __restrict__ cand_idx, int64_t n_pairs, int kc, double* __restrict__ cand_score) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * 8;
+  for (int64_t p = w0; p < n_pairs; p += nw) {
+    const uint32_t idx = cand_idx[p];
+    if (idx == 0xffffffffu) {
+      if (lane == 0) cand_score[p] = -INFINITY;
+      continue;
+    }
+    const int64_t qi = p / kc;
+    const float* qv = q + qi * dim;
+    double dot = 0.0, gg = 0.0;
+    if (master32) {
+      const float* g = master32 + (int64_t)idx * ld32;
+      for (int c = lane; c < dim; c += 32) {
+        const double x = (double)g[c];
+        dot = fma((double)qv[c], x, dot);
+        gg = fma(x, x, gg);
+      }
+    } else {
+      const uint16_t* g = rows16 + (int64_t)idx * ld16;
+      for (int c = lane; c < dim; c += 32) {
+        const double x = (double)h16_to_f32(g[c], kind16);
+        dot = fma((double)qv[c], x, dot);
+        gg = fma(x, x, gg);
+      }
+    }
+    dot = warp_sum_f64(dot);
+    gg = warp_sum_f64(gg);
+    if (lane == 0) {
+      const double den = sqrt(q_qq[qi]) * sqrt(gg);
+      cand_score[p] = den > 0.0 ? dot / den : 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// select: one warp per query, rank by counting over kc <= 128 candidates
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict__ cand_idx,
+              const float* __restrict__ cand_tau, const float* __restrict__ q_dq, const float* __restrict__ stats,
+              int dp, int64_t Q, int kc, int k, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+              double* __restrict__ out_scores64, int* __restrict__ n_flag, int* __restrict__ flag_q,
+              double* __restrict__ flag_thr, float* __restrict__ max_eps) {
+  __shared__ double s_sc[4][K3_MAX_KC];
+  __shared__ uint32_t s_ix[4][K3_MAX_KC];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * 4 + w;
+  if (q >= Q) return;
+  for (int j = lane; j < kc; j += 32) {
+    s_sc[w][j] = cand_score[q * kc + j];
+    s_ix[w][j] = cand_idx[q * kc + j];
+  }
+  for (int j = lane; j < k; j += 32) {
+    out_scores[q * k + j] = -INFINITY;
+    out_rows[q * k + j] = -1;
+    if (out_scores64) out_scores64[q * k + j] = -INFINITY;
+  }
+  __syncwarp();
+  double kth = -INFINITY;  // exact score of rank k-1, if it exists
+  int have_kth = 0;
+  for (int j = lane; j < kc; j += 32) {
+    const double s = s_sc[w][j];
+    const uint32_t ix = s_ix[w][j];
+    if (ix == 0xffffffffu) continue;
+    int rank = 0;
+    for (int i = 0; i < kc; ++i) {
+      const uint32_t oi = s_ix[w][i];
+      if (oi != 0xffffffffu && beats(s_sc[w][i], oi, s, ix)) ++rank;
+    }
+    if (rank < k) {
+      out_scores[q * k + rank] = (float)s;
+      out_rows[q * k + rank] = (int64_t)ix;
+      if (out_scores64) out_scores64[q * k + rank] = s;
+      if (rank == k - 1) { kth = s; have_kth = 1; }
+    }
+  }
+  // broadcast the k-th score
+  const uint32_t who = __ballot_sync(FULL_MASK, have_kth);
+  const float tau = cand_tau[q];
+  if (tau == -INFINITY) return;  // nothing was dropped for this query: exact by construction
+  const float gmax = stats[0] * 1.000001f, gdev = stats[1] * 1.000001f;
+  // margin: query rounding * largest row + row rounding / norm deviation + fp32 accumulation
+  const float eps = q_dq[q] * gmax + gdev + (float)dp * 1.2e-7f * gmax + fabsf(tau) * 1e-6f + 1e-7f;
+  bool flagged = true;
+  if (who) {
+    const int src = __ffs(who) - 1;
+    const double kth_b = __shfl_sync(FULL_MASK, kth, src);
+    flagged = !((double)tau + (double)eps < kth_b);
+    kth = kth_b;
+  } else {
+    kth = -INFINITY;  // fewer than k valid candidates although rows were dropped: cannot happen
+  }
+  if (lane == 0) {
+    atomic_max_nonneg(max_eps, eps);
+    if (flagged) {
+      const int slot = atomicAdd(n_flag, 1);
+      flag_q[slot] = (int)q;
+      flag_thr[slot] = kth;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact fallback
+// ---------------------------------------------------------------------------------------------
+constexpr int EX_NMAX = 32;  // dim <= 1024
+
+__global__ void __launch_bounds__(256)
+exact_collect_kernel(const float* __restrict__ q, const double* __restrict__ q_qq,
+                     const float* __restrict__ master32, const uint16_t* __restrict__ rows16, int kind16, int dim,
+                     int64_t ld32, int64_t ld16, int64_t n_rows, const uint32_t* __restrict__ row_mask,
+                     const int* __restrict__ flag_q, const double* __restrict__ flag_thr, int f0, int nf, int cap,
+                     double* __restrict__ coll_score, uint32_t* __restrict__ coll_idx, int* __restrict__ coll_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * 8;
+  for (int64_t r = w0; r < n_rows; r += nw) {
+    if (row_mask && !((row_mask[r >> 5] >> (r & 31)) & 1u)) continue;
+    double g[EX_NMAX];
+    double gg = 0.0;
+#pragma unroll
+    for (int i = 0; i < EX_NMAX; ++i) {
+      const int c = lane + 32 * i;
+      double x = 0.0;
+      if (c < dim) x = master32 ? (double)master32[r * ld32 + c] : (double)h16_to_f32(rows16[r * ld16 + c], kind16);
+      g[i] = x;
+      gg = fma(x, x, gg);
+    }
+    gg = warp_sum_f64(gg);
+    const double gn = sqrt(gg);
+    for (int f = 0; f < nf; ++f) {
+      const int qi = flag_q[f0 + f];
+      const float* qv = q + (int64_t)qi * dim;
+      double dot = 0.0;
+#pragma unroll
+      for (int i = 0; i < EX_NMAX; ++i) {
+        const int c = lane + 32 * i;
+        if (c < dim) dot = fma((double)qv[c], g[i], dot);
+      }
+      dot = warp_sum_f64(dot);
+      if (lane == 0) {
+        const double den = sqrt(q_qq[qi]) * gn;
+        const double s = den > 0.0 ? dot / den : 0.0;
+        if (s >= flag_thr[f0 + f]) {
+          const int slot = atomicAdd(coll_cnt + f, 1);
+          if (slot < cap) {
+            coll_score[(size_t)f * cap + slot] = s;
+            coll_idx[(size_t)f * cap + slot] = (uint32_t)r;
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+select_collected_kernel(const double* __restrict__ coll_score, const uint32_t* __restrict__ coll_idx,
+                        const int* __restrict__ coll_cnt, const int* __restrict__ flag_q, int f0, int cap, int k,
+                        float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+                        double* __restrict__ out_scores64, int* __restrict__ overflow) {
+  const int f = blockIdx.x;
+  const int q = flag_q[f0 + f];
+  int cnt = coll_cnt[f];
+  if (cnt > cap) {
+    if (threadIdx.x == 0) atomicExch(overflow, 1);
+    cnt = cap;
+  }
+  const double* sc = coll_score + (size_t)f * cap;
+  const uint32_t* ix = coll_idx + (size_t)f * cap;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    out_scores[(int64_t)q * k + j] = -INFINITY;
+    out_rows[(int64_t)q * k + j] = -1;
+    if (out_scores64) out_scores64[(int64_t)q * k + j] = -INFINITY;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+    const double s = sc[j];
+    const uint32_t id = ix[j];
+    int rank = 0;
+    for (int i = 0; i < cnt; ++i)
+      if (beats(sc[i], ix[i], s, id)) ++rank;
+    if (rank < k) {
+      out_scores[(int64_t)q * k + rank] = (float)s;
+      out_rows[(int64_t)q * k + rank] = (int64_t)id;
+      if (out_scores64) out_scores64[(int64_t)q * k + rank] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// merge_topk: one warp per query, lane g walks the (sorted) list of shard g.  G <= 32.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(const double* __restrict__ scores64, const int64_t* __restrict__ ids, int G, int64_t Q, int k,
+                  float* __restrict__ out_scores, int64_t* __restrict__ out_ids, double* __restrict__ out_scores64) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  int pos = 0;
+  const double* sc = scores64 + ((size_t)lane * Q + q) * k;
+  const int64_t* id = ids + ((size_t)lane * Q + q) * k;
+  const long long kEmpty = 0x7fffffffffffffffll;
+  double hs = -INFINITY;
+  long long hi = kEmpty;
+  if (lane < G && k > 0 && id[0] >= 0) { hs = sc[0]; hi = id[0]; }
+  for (int j = 0; j < k; ++j) {
+    // warp arg-best over (score desc, id asc); empty heads lose
+    double bs = hs;
+    long long bi = hi;
+    int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double os = __shfl_xor_sync(FULL_MASK, bs, o);
+      const long long oi = __shfl_xor_sync(FULL_MASK, bi, o);
+      const int ol = __shfl_xor_sync(FULL_MASK, bl, o);
+      const bool take = (oi != kEmpty) && (bi == kEmpty || os > bs || (os == bs && (oi < bi || (oi == bi && ol < bl))));
+      if (take) { bs = os; bi = oi; bl = ol; }
+    }
+    if (lane == 0) {
+      const bool valid = bi != kEmpty;
+      out_scores[q * k + j] = valid ? (float)bs : -INFINITY;
+      out_ids[q * k + j] = valid ? (int64_t)bi : -1;
+      if (out_scores64) out_scores64[q * k + j] = valid ? bs : -INFINITY;
+    }
+    if (bi == kEmpty) continue;  // uniform: all lanes agree on the winner
+    if (lane == bl) {
+      ++pos;
+      if (pos < k && id[pos] >= 0) { hs = sc[pos]; hi = id[pos]; }
+      else { hs = -INFINITY; hi = kEmpty; }
+    }
+  }
+}
+
+}  // namespace
+
+int launch_merge_partials(const float* part_score, const uint32_t* part_idx, int slices, int64_t q_pad,
+                          int64_t Q, int kc, uint32_t* cand_idx, float* cand_tau, cudaStream_t st) {
+  if (Q <= 0) return RBOD_OK;
+  int m = slices * kc, p2 = 32;
+  while (p2 < m) p2 <<= 1;
+  if (p2 > 8192) return set_error(RBOD_E_INVAL, "merge_partials: %d candidates per query exceed 8192", m);
+  const size_t smem = (size_t)p2 * 8;
+  RBOD_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  merge_partials_kernel<<<(unsigned)Q, 256, smem, st>>>(part_score, part_idx, slices, q_pad, kc, p2, cand_idx,
+                                                        cand_tau);
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+int launch_rescore(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16, int kind16,
+                   int dim, int64_t ld32, int64_t ld16, int metric, const uint32_t* cand_idx, int64_t Q, int kc,
+                   double* cand_score, cudaStream_t st) {
+  (void)metric;
+  const int64_t n_pairs = Q * kc;
+  if (n_pairs <= 0) return RBOD_OK;
+  const int64_t want = (n_pairs + 7) / 8;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  rescore_kernel<<<grid, 256, 0, st>>>(q, q_qq, master32, rows16, kind16, dim, ld32, ld16, cand_idx, n_pairs, kc,
+                                       cand_score);
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
+                  const float* stats, int dp, int64_t Q, int kc, int k, float* out_scores, int64_t* out_rows,
+                  double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* max_eps,
+                  cudaStream_t st) {
+  if (Q <= 0) return RBOD_OK;
+  if (kc > K3_MAX_KC) return set_error(RBOD_E_INVAL, "select: kc %d > %d", kc, K3_MAX_KC);
+  select_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, st>>>(cand_score, cand_idx, cand_tau, q_dq, stats, dp, Q, kc, k,
+                                                         out_scores, out_rows, out_scores64, n_flag, flag_q,
+                                                         flag_thr, max_eps);
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+int launch_exact_collect(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
+                         int kind16, int dim, int64_t ld32, int64_t ld16, int metric, int64_t n_rows,
+                         const uint32_t* row_mask, const int* flag_q, const double* flag_thr, int f0, int nf,
+                         int cap, double* coll_score, uint32_t* coll_idx, int* coll_cnt, int num_sms,
+                         cudaStream_t st) {
+  (void)metric;
+  if (nf <= 0 || n_rows <= 0) return RBOD_OK;
+  if (dim > 32 * EX_NMAX) return set_error(RBOD_E_UNSUPPORTED, "exact fallback supports dim <= %d", 32 * EX_NMAX);
+  const int64_t want = (n_rows + 7) / 8;
+  const int grid = (int)(want < (int64_t)num_sms * 6 ? want : (int64_t)num_sms * 6);
+  exact_collect_kernel<<<grid, 256, 0, st>>>(q, q_qq, master32, rows16, kind16, dim, ld32, ld16, n_rows, row_mask,
+                                             flag_q, flag_thr, f0, nf, cap, coll_score, coll_idx, coll_cnt);
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+int launch_select_collected(const double* coll_score, const uint32_t* coll_idx, const int* coll_cnt,
+                            const int* flag_q, int f0, int nf, int cap, int k, float* out_scores,
+                            int64_t* out_rows, double* out_scores64, int* overflow, cudaStream_t st) {
+  if (nf <= 0) return RBOD_OK;
+  select_collected_kernel<<<nf, 256, 0, st>>>(coll_score, coll_idx, coll_cnt, flag_q, f0, cap, k, out_scores,
+                                              out_rows, out_scores64, overflow);
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+int launch_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t Q, int k, float* out_scores,
+                      int64_t* out_ids, double* out_scores64, cudaStream_t st) {
+  if (Q <= 0 || k <= 0) return RBOD_OK;
+  if (G < 1 || G > 32) return set_error(RBOD_E_UNSUPPORTED, "merge_topk: G=%d outside [1, 32]", G);
+  merge_topk_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(scores64, ids, G, Q, k, out_scores, out_ids,
+                                                            out_scores64);
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+}  // namespace rbod

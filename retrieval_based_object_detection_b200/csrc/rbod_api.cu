@@ -1,0 +1,708 @@
+// C ABI of librbod.so (see include/rbod.h for the contract and the reference call sites each
+// entry point replaces).  Host-side orchestration only: handle lifetime, host<->device staging,
+// work decomposition for the tcgen05 pass, and the certify / fallback loop.
+#include "rbod_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace rbod {
+
+int make_tmap_2d_sw128(CUtensorMap* out, const void* base, int64_t rows, int dp, int box_rows);
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int DevBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return RBOD_OK;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&p, want);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    p = nullptr;
+    return set_error(RBOD_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  }
+  cap = want;
+  return RBOD_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+int PinBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return RBOD_OK;
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+  cudaError_t e = cudaMallocHost(&p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    p = nullptr;
+    return set_error(RBOD_E_NOMEM, "cudaMallocHost of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  }
+  cap = bytes;
+  return RBOD_OK;
+}
+void PinBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+}
+
+static bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Returns a device view of `src` (bytes): the pointer itself when it already is device memory,
+// otherwise an async copy into `buf`.
+static int to_device(const void* src, size_t bytes, DevBuf& buf, cudaStream_t st, const void** out) {
+  if (bytes == 0 || is_device_ptr(src)) {
+    *out = src;
+    return RBOD_OK;
+  }
+  RBOD_TRY(buf.ensure(bytes));
+  RBOD_CUDA(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st));
+  *out = buf.p;
+  return RBOD_OK;
+}
+
+static int copy_out(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
+  if (bytes == 0 || dst == nullptr || dst == src_dev) return RBOD_OK;
+  RBOD_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDefault, st));
+  return RBOD_OK;
+}
+
+static size_t elem16_bytes() { return 2; }
+
+static size_t gallery_bytes(const rbod_gallery* g) {
+  size_t b = (size_t)g->capacity * g->dp * elem16_bytes();
+  if (g->master32) b += (size_t)g->capacity * g->dim * 4;
+  return b;
+}
+
+static int grow(rbod_gallery* g, int64_t need, cudaStream_t st) {
+  if (need <= g->capacity) return RBOD_OK;
+  int64_t cap = std::max<int64_t>(need, g->capacity + g->capacity / 2);
+  cap = std::max<int64_t>(cap, 1024);
+  cap = (cap + 63) / 64 * 64;
+  uint16_t* n16 = nullptr;
+  float* n32 = nullptr;
+  cudaError_t e = cudaMalloc(&n16, (size_t)cap * g->dp * 2);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(RBOD_E_NOMEM, "gallery: cudaMalloc of %zu bytes failed", (size_t)cap * g->dp * 2);
+  }
+  if (g->dtype == RBOD_F32) {
+    e = cudaMalloc(&n32, (size_t)cap * g->dim * 4);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(n16);
+      return set_error(RBOD_E_NOMEM, "gallery: cudaMalloc of %zu bytes failed", (size_t)cap * g->dim * 4);
+    }
+  }
+  // zero the new tail (keeps the dim..dp padding columns zero), then carry the old rows over
+  const size_t old16 = (size_t)g->rows * g->dp * 2;
+  RBOD_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(n16) + old16, 0, (size_t)cap * g->dp * 2 - old16, st));
+  if (g->rows > 0) {
+    RBOD_CUDA(cudaMemcpyAsync(n16, g->rows16, old16, cudaMemcpyDeviceToDevice, st));
+    if (n32)
+      RBOD_CUDA(cudaMemcpyAsync(n32, g->master32, (size_t)g->rows * g->dim * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  RBOD_CUDA(cudaStreamSynchronize(st));
+  if (g->rows16) cudaFree(g->rows16);
+  if (g->master32) cudaFree(g->master32);
+  g->rows16 = n16;
+  g->master32 = n32;
+  g->capacity = cap;
+  return RBOD_OK;
+}
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct SearchPlan {
+  int kc, slices, grid, num_qt, tiles_total, num_stages;
+  int64_t q_pad;
+  size_t smem;
+};
+
+static int plan_search(const rbod_gallery* g, int64_t Q, int k, int variant, int smem_optin, SearchPlan* P) {
+  int kc;
+  if (g->slack >= 0) kc = round_up(k + g->slack, 32);
+  else kc = k <= 10 ? 32 : (k <= 40 ? 64 : 128);
+  if (kc > K3_MAX_KC || kc < k)
+    return set_error(RBOD_E_UNSUPPORTED, "search: k=%d (+slack) needs %d candidates per query, max is %d", k, kc,
+                     K3_MAX_KC);
+  P->kc = kc;
+  P->q_pad = (Q + K3_TILE_M - 1) / K3_TILE_M * K3_TILE_M;
+  P->num_qt = (int)(P->q_pad / K3_TILE_M);
+  P->tiles_total = (int)((g->rows + K3_TILE_N - 1) / K3_TILE_N);
+  // slices: balance (units per CTA) x (tiles per unit); fewer slices on ties (less merge work)
+  const int max_slices = std::max(1, std::min({P->tiles_total, 8192 / kc, 64}));
+  double best = 1e300;
+  int best_s = 1;
+  for (int s = 1; s <= max_slices; ++s) {
+    const int64_t units = (int64_t)s * P->num_qt;
+    const int64_t per_cta = (units + g->num_sms - 1) / g->num_sms;
+    const double tiles_per_unit = std::ceil((double)P->tiles_total / s);
+    const double cost = (double)per_cta * (tiles_per_unit + 24.0);  // +24 ~ per-unit setup in tile units
+    if (cost < best * 0.97) { best = cost; best_s = s; }
+  }
+  P->slices = best_s;
+  const int64_t units = (int64_t)P->slices * P->num_qt;
+  P->grid = (int)std::min<int64_t>(units, g->num_sms);
+  int stages = 8;
+  while (stages > 1 && k3_smem_bytes(variant, kc, stages) > (size_t)smem_optin) --stages;
+  if (k3_smem_bytes(variant, kc, stages) > (size_t)smem_optin)
+    return set_error(RBOD_E_UNSUPPORTED, "search: variant %d with %d candidates does not fit shared memory",
+                     variant, kc);
+  P->num_stages = stages;
+  P->smem = k3_smem_bytes(variant, kc, stages);
+  return RBOD_OK;
+}
+
+}  // namespace rbod
+
+using namespace rbod;
+
+// =============================================================================================
+extern "C" {
+
+const char* rbod_last_error(void) { return g_err; }
+int rbod_abi_version(void) { return RBOD_ABI_VERSION; }
+
+int rbod_create(int32_t dim, int32_t dtype, int32_t metric, int64_t capacity_hint, int32_t device,
+                rbod_gallery** out) {
+  if (!out) return set_error(RBOD_E_INVAL, "rbod_create: out is NULL");
+  *out = nullptr;
+  if (dim < 1 || dim > 65536) return set_error(RBOD_E_INVAL, "rbod_create: dim %d out of range", dim);
+  if (dtype != RBOD_F32 && dtype != RBOD_BF16 && dtype != RBOD_F16)
+    return set_error(RBOD_E_INVAL, "rbod_create: unknown dtype %d", dtype);
+  if (metric != RBOD_COSINE && metric != RBOD_DOT)
+    return set_error(RBOD_E_INVAL, "rbod_create: unknown metric %d", metric);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_error(RBOD_E_IO, "rbod_create: no CUDA device available (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return set_error(RBOD_E_INVAL, "rbod_create: device %d of %d", device, ndev);
+  RBOD_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RBOD_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_error(RBOD_E_UNSUPPORTED, "rbod_create: device %d is sm_%d%d; this build is sm_100a only", device,
+                     prop.major, prop.minor);
+  rbod_gallery* g = new (std::nothrow) rbod_gallery();
+  if (!g) return set_error(RBOD_E_NOMEM, "rbod_create: out of host memory");
+  g->dim = dim;
+  g->dp = round_up(dim, K3_KBLOCK);
+  g->dtype = dtype;
+  g->metric = metric;
+  g->device = device;
+  // 16-bit search operand: the master itself for bf16/fp16 galleries; for fp32 galleries an fp16
+  // shadow (unit vectors are well inside fp16 range and it halves the rounding radius of bf16),
+  // bf16 when the rows are not normalised.
+  g->kind16 = dtype == RBOD_BF16 ? 1 : (dtype == RBOD_F16 ? 2 : (metric == RBOD_COSINE ? 2 : 1));
+  g->num_sms = prop.multiProcessorCount;
+  cudaError_t e = cudaMalloc(&g->stats, 2 * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    delete g;
+    return set_error(RBOD_E_NOMEM, "rbod_create: cudaMalloc failed");
+  }
+  cudaMemset(g->stats, 0, 2 * sizeof(float));
+  cudaEventCreate(&g->ev0);
+  cudaEventCreate(&g->ev1);
+  int rc = grow(g, std::max<int64_t>(capacity_hint, 1), nullptr);
+  if (rc != RBOD_OK) {
+    rbod_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return RBOD_OK;
+}
+
+int rbod_destroy(rbod_gallery* g) {
+  if (!g) return RBOD_OK;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  if (g->rows16) cudaFree(g->rows16);
+  if (g->master32) cudaFree(g->master32);
+  if (g->stats) cudaFree(g->stats);
+  DevBuf* bufs[] = {&g->stage_rows, &g->stage_slots, &g->stage_norms, &g->q32, &g->q16, &g->q_dq, &g->q_qq,
+                    &g->part_score, &g->part_idx, &g->cand_idx, &g->cand_tau, &g->cand_score, &g->out_scores,
+                    &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->coll_score,
+                    &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->seg_idx, &g->seg_off, &g->seg_out,
+                    &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->gather_idx, &g->gather_out};
+  for (DevBuf* b : bufs) b->release();
+  g->pin_a.release();
+  g->pin_b.release();
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  cudaGetLastError();
+  delete g;
+  return RBOD_OK;
+}
+
+int64_t rbod_count(const rbod_gallery* g) { return g ? g->rows : (int64_t)set_error(RBOD_E_INVAL, "NULL handle"); }
+
+int rbod_info(const rbod_gallery* g, rbod_gallery_info* out) {
+  if (!g || !out) return set_error(RBOD_E_INVAL, "rbod_info: NULL argument");
+  RBOD_CUDA(cudaSetDevice(g->device));
+  memset(out, 0, sizeof(*out));
+  out->dim = g->dim;
+  out->dim_padded = g->dp;
+  out->dtype = g->dtype;
+  out->metric = g->metric;
+  out->device = g->device;
+  out->rows = g->rows;
+  out->capacity = g->capacity;
+  size_t ws = 0;
+  const DevBuf* bufs[] = {&g->stage_rows, &g->q32, &g->q16, &g->part_score, &g->part_idx, &g->cand_idx,
+                          &g->cand_score, &g->out_scores, &g->out_rows, &g->out_scores64, &g->coll_score,
+                          &g->coll_idx, &g->mask_dev, &g->dump, &g->seg_idx, &g->seg_out, &g->seg_partials,
+                          &g->gather_out};
+  for (const DevBuf* b : bufs) ws += b->cap;
+  out->bytes_device = (int64_t)(gallery_bytes(g) + ws);
+  float st[2] = {0, 0};
+  RBOD_CUDA(cudaMemcpy(st, g->stats, sizeof(st), cudaMemcpyDeviceToHost));
+  out->max_row_norm = st[0];
+  out->max_row_dev = st[1];
+  return RBOD_OK;
+}
+
+int rbod_truncate(rbod_gallery* g, int64_t rows) {
+  if (!g) return set_error(RBOD_E_INVAL, "rbod_truncate: NULL handle");
+  if (rows < 0 || rows > g->rows) return set_error(RBOD_E_RANGE, "rbod_truncate: %lld not in [0, %lld]",
+                                                   (long long)rows, (long long)g->rows);
+  g->rows = rows;
+  if (rows == 0) {
+    RBOD_CUDA(cudaSetDevice(g->device));
+    RBOD_CUDA(cudaMemset(g->stats, 0, 2 * sizeof(float)));
+  }
+  return RBOD_OK;
+}
+
+int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
+  if (!g || !key) return set_error(RBOD_E_INVAL, "rbod_set_option: NULL argument");
+  if (!strcmp(key, "k3_variant")) {
+    if (value != 0 && value != 1) return set_error(RBOD_E_INVAL, "k3_variant must be 0 or 1");
+    g->k3_variant = (int)value;
+  } else if (!strcmp(key, "slack")) {
+    if (value < -1 || value > 118) return set_error(RBOD_E_INVAL, "slack must be in [-1, 118]");
+    g->slack = (int)value;
+  } else if (!strcmp(key, "time_k3")) {
+    g->time_k3 = value != 0;
+  } else {
+    return set_error(RBOD_E_INVAL, "rbod_set_option: unknown key '%s'", key);
+  }
+  return RBOD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int rbod_upsert(rbod_gallery* g, const float* rows, int64_t n, const int64_t* row_slots, float* out_norms,
+                int32_t flags, void* stream) {
+  if (!g) return set_error(RBOD_E_INVAL, "rbod_upsert: NULL handle");
+  if (n < 0 || (n > 0 && !rows)) return set_error(RBOD_E_INVAL, "rbod_upsert: bad rows/n");
+  if (n == 0) return RBOD_OK;
+  RBOD_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (row_slots && is_device_ptr(row_slots))
+    return set_error(RBOD_E_INVAL, "rbod_upsert: row_slots must be a host pointer (or NULL to append)");
+
+  int64_t new_rows = g->rows + n;
+  if (row_slots) {
+    int64_t mx = -1, fresh = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      if (row_slots[i] < 0) return set_error(RBOD_E_RANGE, "rbod_upsert: negative slot at %lld", (long long)i);
+      if (row_slots[i] >= g->rows) ++fresh;
+      mx = std::max(mx, row_slots[i]);
+    }
+    new_rows = std::max(g->rows, mx + 1);
+    if (mx + 1 > g->rows + fresh)
+      return set_error(RBOD_E_RANGE, "rbod_upsert: slots would leave holes (max slot %lld, rows %lld)",
+                       (long long)mx, (long long)g->rows);
+  }
+  RBOD_TRY(grow(g, new_rows, st));
+
+  const int normalize = (g->metric == RBOD_COSINE) && !(flags & RBOD_UPSERT_RAW);
+  const int cosine = g->metric == RBOD_COSINE;
+  const bool rows_dev = is_device_ptr(rows);
+  const bool norms_dev = out_norms && is_device_ptr(out_norms);
+  // chunking bounds the staging buffers for host input
+  const int64_t chunk_rows = rows_dev ? n : std::max<int64_t>(1, std::min<int64_t>(n, (256ll << 20) / ((int64_t)g->dim * 4)));
+  for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+    const int64_t m = std::min(chunk_rows, n - r0);
+    const float* src = rows + r0 * g->dim;
+    if (!rows_dev) {
+      RBOD_TRY(g->stage_rows.ensure((size_t)m * g->dim * 4));
+      RBOD_CUDA(cudaMemcpyAsync(g->stage_rows.p, src, (size_t)m * g->dim * 4, cudaMemcpyHostToDevice, st));
+      src = g->stage_rows.as<float>();
+    }
+    const int64_t* slots_dev = nullptr;
+    if (row_slots) {
+      RBOD_TRY(g->stage_slots.ensure((size_t)m * 8));
+      RBOD_CUDA(cudaMemcpyAsync(g->stage_slots.p, row_slots + r0, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+      slots_dev = g->stage_slots.as<int64_t>();
+    }
+    float* norms_dst = nullptr;
+    if (out_norms) {
+      if (norms_dev) norms_dst = out_norms + r0;
+      else {
+        RBOD_TRY(g->stage_norms.ensure((size_t)m * 4));
+        norms_dst = g->stage_norms.as<float>();
+      }
+    }
+    RBOD_TRY(launch_l2norm_pack(src, m, g->dim, slots_dev, g->rows + r0, normalize, cosine, g->master32, g->dim,
+                                g->rows16, g->dp, g->kind16, norms_dst, g->stats, g->num_sms, st));
+    if (out_norms && !norms_dev)
+      RBOD_CUDA(cudaMemcpyAsync(out_norms + r0, norms_dst, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    if (!rows_dev || row_slots) RBOD_CUDA(cudaStreamSynchronize(st));  // staging buffers are reused
+  }
+  g->rows = new_rows;
+  if (out_norms && !norms_dev) RBOD_CUDA(cudaStreamSynchronize(st));
+  return RBOD_OK;
+}
+
+int rbod_get_rows(rbod_gallery* g, const int64_t* rows, int64_t n, float* out, void* stream) {
+  if (!g) return set_error(RBOD_E_INVAL, "rbod_get_rows: NULL handle");
+  if (n < 0 || (n > 0 && (!rows || !out))) return set_error(RBOD_E_INVAL, "rbod_get_rows: bad arguments");
+  if (n == 0) return RBOD_OK;
+  RBOD_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const void* rows_dev = nullptr;
+  RBOD_TRY(to_device(rows, (size_t)n * 8, g->gather_idx, st, &rows_dev));
+  const bool out_dev = is_device_ptr(out);
+  float* dst = out;
+  if (!out_dev) {
+    RBOD_TRY(g->gather_out.ensure((size_t)n * g->dim * 4));
+    dst = g->gather_out.as<float>();
+  }
+  RBOD_TRY(g->flags.ensure(64));
+  RBOD_CUDA(cudaMemsetAsync(g->flags.p, 0, 64, st));
+  RBOD_TRY(launch_gather_rows(g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp,
+                              static_cast<const int64_t*>(rows_dev), n, g->rows, dst, g->flags.as<int>() + 2, st));
+  if (!out_dev) RBOD_CUDA(cudaMemcpyAsync(out, dst, (size_t)n * g->dim * 4, cudaMemcpyDeviceToHost, st));
+  int err = 0;
+  RBOD_CUDA(cudaMemcpyAsync(&err, g->flags.as<int>() + 2, 4, cudaMemcpyDeviceToHost, st));
+  RBOD_CUDA(cudaStreamSynchronize(st));
+  if (err) return set_error(RBOD_E_RANGE, "rbod_get_rows: row index outside [0, %lld)", (long long)g->rows);
+  return RBOD_OK;
+}
+
+int rbod_l2norm_pack(const float* in, int64_t n, int32_t dim, int32_t out_dtype, void* out, int64_t out_ld,
+                     float* out_norms, void* stream) {
+  if (n < 0 || dim < 1 || (n > 0 && (!in || !out))) return set_error(RBOD_E_INVAL, "rbod_l2norm_pack: bad arguments");
+  if (out_ld < dim) return set_error(RBOD_E_INVAL, "rbod_l2norm_pack: out_ld < dim");
+  if (n == 0) return RBOD_OK;
+  if (!is_device_ptr(in) || !is_device_ptr(out) || (out_norms && !is_device_ptr(out_norms)))
+    return set_error(RBOD_E_INVAL, "rbod_l2norm_pack: device pointers only");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  RBOD_CUDA(cudaGetDevice(&dev));
+  RBOD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (out_dtype == RBOD_F32)
+    return launch_l2norm_pack(in, n, dim, nullptr, 0, 1, 1, static_cast<float*>(out), out_ld, nullptr, 0, 1,
+                              out_norms, nullptr, sms, st);
+  if (out_dtype == RBOD_BF16 || out_dtype == RBOD_F16)
+    return launch_l2norm_pack(in, n, dim, nullptr, 0, 1, 1, nullptr, 0, static_cast<uint16_t*>(out), out_ld,
+                              out_dtype == RBOD_BF16 ? 1 : 2, out_norms, nullptr, sms, st);
+  return set_error(RBOD_E_INVAL, "rbod_l2norm_pack: unknown out_dtype %d", out_dtype);
+}
+
+// ---------------------------------------------------------------------------------------------
+int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* offsets, int64_t n_classes,
+                      float* out_centroids, void* stream) {
+  if (!g) return set_error(RBOD_E_INVAL, "rbod_segment_mean: NULL handle");
+  if (n_classes < 0 || (n_classes > 0 && (!offsets || !out_centroids)))
+    return set_error(RBOD_E_INVAL, "rbod_segment_mean: bad arguments");
+  if (n_classes == 0) return RBOD_OK;
+  if (n_classes > (1ll << 30)) return set_error(RBOD_E_INVAL, "rbod_segment_mean: too many classes");
+  RBOD_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t first = 0, total = 0;
+  if (is_device_ptr(offsets)) {
+    RBOD_CUDA(cudaMemcpyAsync(&first, offsets, 8, cudaMemcpyDeviceToHost, st));
+    RBOD_CUDA(cudaMemcpyAsync(&total, offsets + n_classes, 8, cudaMemcpyDeviceToHost, st));
+    RBOD_CUDA(cudaStreamSynchronize(st));
+  } else {
+    first = offsets[0];
+    total = offsets[n_classes];
+    for (int64_t c = 0; c < n_classes; ++c)
+      if (offsets[c + 1] < offsets[c]) return set_error(RBOD_E_INVAL, "rbod_segment_mean: offsets not monotone");
+  }
+  if (first < 0 || total < first) return set_error(RBOD_E_INVAL, "rbod_segment_mean: bad offsets");
+  if (!row_idx && total > g->rows) return set_error(RBOD_E_RANGE, "rbod_segment_mean: offsets exceed row count");
+  const void *idx_dev = nullptr, *off_dev = nullptr;
+  if (row_idx) RBOD_TRY(to_device(row_idx, (size_t)total * 8, g->seg_idx, st, &idx_dev));
+  RBOD_TRY(to_device(offsets, (size_t)(n_classes + 1) * 8, g->seg_off, st, &off_dev));
+  const bool out_dev = is_device_ptr(out_centroids);
+  float* dst = out_centroids;
+  if (!out_dev) {
+    RBOD_TRY(g->seg_out.ensure((size_t)n_classes * g->dim * 4));
+    dst = g->seg_out.as<float>();
+  }
+  const int64_t items_upper = (total - first) / 1024 + n_classes + 1;
+  const int64_t parts_upper = 2 * ((total - first) / 1024) + 2;
+  if (items_upper > 0x7fffffff) return set_error(RBOD_E_INVAL, "rbod_segment_mean: problem too large");
+  RBOD_TRY(g->seg_partials.ensure((size_t)parts_upper * g->dim * 8));
+  RBOD_TRY(g->seg_prefix.ensure((size_t)(2 * n_classes + 2) * 4));
+  RBOD_TRY(g->seg_arrive.ensure((size_t)n_classes * 4));
+  RBOD_TRY(g->flags.ensure(64));
+  RBOD_CUDA(cudaMemsetAsync(g->flags.p, 0, 64, st));
+  RBOD_TRY(launch_segment_mean(g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp, g->rows,
+                               static_cast<const int64_t*>(idx_dev), static_cast<const int64_t*>(off_dev), n_classes,
+                               items_upper, g->seg_partials.as<double>(), g->seg_prefix.as<int>(),
+                               g->seg_arrive.as<unsigned int>(), dst, g->flags.as<int>() + 2, st));
+  if (!out_dev)
+    RBOD_CUDA(cudaMemcpyAsync(out_centroids, dst, (size_t)n_classes * g->dim * 4, cudaMemcpyDeviceToHost, st));
+  int err = 0;
+  RBOD_CUDA(cudaMemcpyAsync(&err, g->flags.as<int>() + 2, 4, cudaMemcpyDeviceToHost, st));
+  RBOD_CUDA(cudaStreamSynchronize(st));
+  if (err) return set_error(RBOD_E_RANGE, "rbod_segment_mean: row index outside [0, %lld)", (long long)g->rows);
+  return RBOD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint32_t* mask_dev, float* dump,
+                  int64_t dump_ld, cudaStream_t st) {
+  K3Launch L;
+  memset(&L, 0, sizeof(L));
+  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, g->rows16, g->rows, g->dp, K3_TILE_N));
+  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_a, g->q16.p, P.q_pad, g->dp, K3_TILE_M));
+  L.q16 = g->q16.as<uint16_t>();
+  L.dp = g->dp;
+  L.n_rows = g->rows;
+  L.tiles_total = P.tiles_total;
+  L.num_qt = P.num_qt;
+  L.slices = P.slices;
+  L.q_valid = Q;
+  L.q_pad = P.q_pad;
+  L.kc = P.kc;
+  L.num_stages = P.num_stages;
+  L.variant = g->k3_variant;
+  L.a_fmt = g->kind16 == 1 ? 1 : 0;
+  L.b_fmt = g->kind16 == 1 ? 1 : 0;
+  L.part_score = g->part_score.as<float>();
+  L.part_idx = g->part_idx.as<uint32_t>();
+  L.row_mask = mask_dev;
+  L.dump = dump;
+  L.dump_ld = dump_ld;
+  L.grid = P.grid;
+  L.smem_bytes = P.smem;
+  return launch_k3(L, st);
+}
+
+static int prepare_queries(rbod_gallery* g, const float* queries, int64_t Q, const SearchPlan& P, cudaStream_t st,
+                           const float** q_dev) {
+  const void* qd = nullptr;
+  RBOD_TRY(to_device(queries, (size_t)Q * g->dim * 4, g->q32, st, &qd));
+  *q_dev = static_cast<const float*>(qd);
+  RBOD_TRY(g->q16.ensure((size_t)P.q_pad * g->dp * 2));
+  RBOD_TRY(g->q_dq.ensure((size_t)P.q_pad * 4));
+  RBOD_TRY(g->q_qq.ensure((size_t)P.q_pad * 8));
+  return launch_prep_queries(*q_dev, Q, P.q_pad, g->dim, g->dp, g->kind16, g->q16.as<uint16_t>(),
+                             g->q_dq.as<float>(), g->q_qq.as<double>(), st);
+}
+
+int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, const uint32_t* row_mask,
+                float* out_scores, int64_t* out_rows, double* out_scores64, rbod_search_stats* stats,
+                void* stream) {
+  if (!g) return set_error(RBOD_E_INVAL, "rbod_search: NULL handle");
+  if (Q < 0 || k < 1 || (Q > 0 && (!queries || !out_scores || !out_rows)))
+    return set_error(RBOD_E_INVAL, "rbod_search: bad arguments");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (Q == 0) return RBOD_OK;
+  if (g->metric != RBOD_COSINE)
+    return set_error(RBOD_E_UNSUPPORTED, "rbod_search: only COSINE collections are searchable in this build");
+  if (g->dp > K3_MAX_DP)
+    return set_error(RBOD_E_UNSUPPORTED, "rbod_search: dim %d > %d not supported by the tcgen05 pass", g->dim,
+                     K3_MAX_DP);
+  if (Q > (1ll << 24)) return set_error(RBOD_E_INVAL, "rbod_search: Q too large");
+  if (g->rows >= 0xffffffffll) return set_error(RBOD_E_UNSUPPORTED, "rbod_search: more than 2^32-2 rows per shard");
+  RBOD_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int smem_optin = k3_configure(g->device);
+  if (smem_optin < 0) return smem_optin;
+
+  const size_t nout = (size_t)Q * k;
+  RBOD_TRY(g->out_scores.ensure(nout * 4));
+  RBOD_TRY(g->out_rows.ensure(nout * 8));
+  RBOD_TRY(g->out_scores64.ensure(nout * 8));
+  float* d_scores = is_device_ptr(out_scores) ? out_scores : g->out_scores.as<float>();
+  int64_t* d_rows = is_device_ptr(out_rows) ? out_rows : g->out_rows.as<int64_t>();
+  double* d_scores64 = (out_scores64 && is_device_ptr(out_scores64)) ? out_scores64 : g->out_scores64.as<double>();
+
+  SearchPlan P;
+  RBOD_TRY(plan_search(g, Q, k, g->k3_variant, smem_optin, &P));
+  if (stats) {
+    stats->queries = Q;
+    stats->candidates = P.kc;
+    stats->slices = P.slices;
+  }
+
+  RBOD_TRY(g->flags.ensure(64));
+  RBOD_CUDA(cudaMemsetAsync(g->flags.p, 0, 64, st));
+  int* d_flags = g->flags.as<int>();
+  int64_t launches = 0;
+
+  if (g->rows == 0) {
+    // empty collection: every slot is "no result"
+    std::vector<float> hs(nout, -INFINITY);
+    std::vector<int64_t> hr(nout, -1);
+    std::vector<double> hd(nout, -INFINITY);
+    RBOD_CUDA(cudaMemcpyAsync(out_scores, hs.data(), nout * 4, cudaMemcpyDefault, st));
+    RBOD_CUDA(cudaMemcpyAsync(out_rows, hr.data(), nout * 8, cudaMemcpyDefault, st));
+    if (out_scores64) RBOD_CUDA(cudaMemcpyAsync(out_scores64, hd.data(), nout * 8, cudaMemcpyDefault, st));
+    RBOD_CUDA(cudaStreamSynchronize(st));
+    return RBOD_OK;
+  }
+
+  const void* mask_dev = nullptr;
+  if (row_mask) RBOD_TRY(to_device(row_mask, (size_t)((g->rows + 31) / 32) * 4, g->mask_dev, st, &mask_dev));
+
+  const float* q_dev = nullptr;
+  RBOD_TRY(prepare_queries(g, queries, Q, P, st, &q_dev));
+  ++launches;
+
+  const size_t part_elems = (size_t)P.slices * P.q_pad * P.kc;
+  RBOD_TRY(g->part_score.ensure(part_elems * 4));
+  RBOD_TRY(g->part_idx.ensure(part_elems * 4));
+  RBOD_TRY(g->cand_idx.ensure((size_t)Q * P.kc * 4));
+  RBOD_TRY(g->cand_tau.ensure((size_t)Q * 4));
+  RBOD_TRY(g->cand_score.ensure((size_t)Q * P.kc * 8));
+  RBOD_TRY(g->flag_q.ensure((size_t)Q * 4));
+  RBOD_TRY(g->flag_thr.ensure((size_t)Q * 8));
+
+  if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev0, st));
+  RBOD_TRY(run_k3(g, P, Q, static_cast<const uint32_t*>(mask_dev), nullptr, 0, st));
+  if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev1, st));
+  ++launches;
+
+  RBOD_TRY(launch_merge_partials(g->part_score.as<float>(), g->part_idx.as<uint32_t>(), P.slices, P.q_pad, Q, P.kc,
+                                 g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(), st));
+  RBOD_TRY(launch_rescore(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp,
+                          g->metric, g->cand_idx.as<uint32_t>(), Q, P.kc, g->cand_score.as<double>(), st));
+  RBOD_TRY(launch_select(g->cand_score.as<double>(), g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(),
+                         g->q_dq.as<float>(), g->stats, g->dp, Q, P.kc, k, d_scores, d_rows, d_scores64, d_flags,
+                         g->flag_q.as<int>(), g->flag_thr.as<double>(), reinterpret_cast<float*>(d_flags + 3), st));
+  launches += 3;
+
+  int hflags[4] = {0, 0, 0, 0};
+  RBOD_CUDA(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+  RBOD_CUDA(cudaStreamSynchronize(st));
+  const int n_flag = hflags[0];
+  float max_eps;
+  memcpy(&max_eps, &hflags[3], 4);
+
+  if (n_flag > 0) {
+    const int cap = 4096, batch = 32;
+    RBOD_TRY(g->coll_score.ensure((size_t)batch * cap * 8));
+    RBOD_TRY(g->coll_idx.ensure((size_t)batch * cap * 4));
+    RBOD_TRY(g->coll_cnt.ensure((size_t)batch * 4));
+    for (int f0 = 0; f0 < n_flag; f0 += batch) {
+      const int nf = std::min(batch, n_flag - f0);
+      RBOD_CUDA(cudaMemsetAsync(g->coll_cnt.p, 0, (size_t)batch * 4, st));
+      RBOD_TRY(launch_exact_collect(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim,
+                                    g->dp, g->metric, g->rows, static_cast<const uint32_t*>(mask_dev),
+                                    g->flag_q.as<int>(), g->flag_thr.as<double>(), f0, nf, cap,
+                                    g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
+                                    g->num_sms, st));
+      RBOD_TRY(launch_select_collected(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(),
+                                       g->coll_cnt.as<int>(), g->flag_q.as<int>(), f0, nf, cap, k, d_scores, d_rows,
+                                       d_scores64, d_flags + 1, st));
+      launches += 2;
+    }
+    RBOD_CUDA(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+  }
+
+  RBOD_TRY(copy_out(out_scores, d_scores, nout * 4, st));
+  RBOD_TRY(copy_out(out_rows, d_rows, nout * 8, st));
+  if (out_scores64) RBOD_TRY(copy_out(out_scores64, d_scores64, nout * 8, st));
+  RBOD_CUDA(cudaStreamSynchronize(st));
+  if (hflags[1])
+    return set_error(RBOD_E_OVERFLOW, "rbod_search: more than 4096 rows tie around the k-th score of a query");
+
+  if (stats) {
+    stats->fallback_queries = n_flag;
+    stats->k3_launches = 1;
+    stats->total_launches = launches;
+    stats->max_eps = max_eps;
+    if (g->time_k3) {
+      float ms = 0.f;
+      RBOD_CUDA(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
+      stats->k3_ms = ms;
+    }
+  }
+  return RBOD_OK;
+}
+
+int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* out, void* stream) {
+  if (!g || !queries || !out || Q < 1) return set_error(RBOD_E_INVAL, "rbod_debug_scores: bad arguments");
+  if (g->rows < 1) return set_error(RBOD_E_INVAL, "rbod_debug_scores: empty gallery");
+  if (g->dp > K3_MAX_DP) return set_error(RBOD_E_UNSUPPORTED, "rbod_debug_scores: dim too large");
+  if ((double)Q * (double)g->rows > (double)(1ll << 28))
+    return set_error(RBOD_E_INVAL, "rbod_debug_scores: Q * rows > 2^28");
+  RBOD_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int smem_optin = k3_configure(g->device);
+  if (smem_optin < 0) return smem_optin;
+  SearchPlan P;
+  RBOD_TRY(plan_search(g, Q, 1, g->k3_variant, smem_optin, &P));
+  const float* q_dev = nullptr;
+  RBOD_TRY(prepare_queries(g, queries, Q, P, st, &q_dev));
+  const size_t part_elems = (size_t)P.slices * P.q_pad * P.kc;
+  RBOD_TRY(g->part_score.ensure(part_elems * 4));
+  RBOD_TRY(g->part_idx.ensure(part_elems * 4));
+  const int64_t ld = g->rows;
+  const bool out_dev = is_device_ptr(out);
+  float* dst = out;
+  if (!out_dev) {
+    RBOD_TRY(g->dump.ensure((size_t)Q * ld * 4));
+    dst = g->dump.as<float>();
+  }
+  RBOD_CUDA(cudaMemsetAsync(dst, 0xff, (size_t)Q * ld * 4, st));  // NaN pattern: unwritten cells show up
+  RBOD_TRY(run_k3(g, P, Q, nullptr, dst, ld, st));
+  if (!out_dev) RBOD_CUDA(cudaMemcpyAsync(out, dst, (size_t)Q * ld * 4, cudaMemcpyDeviceToHost, st));
+  RBOD_CUDA(cudaStreamSynchronize(st));
+  return RBOD_OK;
+}
+
+int rbod_merge_topk(const double* scores64, const int64_t* ids, int32_t G, int64_t Q, int32_t k,
+                    float* out_scores, int64_t* out_ids, double* out_scores64, void* stream) {
+  if (!scores64 || !ids || !out_scores || !out_ids || Q < 0 || k < 1)
+    return set_error(RBOD_E_INVAL, "rbod_merge_topk: bad arguments");
+  if (!is_device_ptr(scores64) || !is_device_ptr(ids) || !is_device_ptr(out_scores) || !is_device_ptr(out_ids) ||
+      (out_scores64 && !is_device_ptr(out_scores64)))
+    return set_error(RBOD_E_INVAL, "rbod_merge_topk: device pointers only");
+  return launch_merge_topk(scores64, ids, G, Q, k, out_scores, out_ids, out_scores64,
+                           static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// Internal declarations shared by the rbod translation units (host side).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdarg>
+#include <cstddef>
+
+#include "../../include/rbod.h"
+
+namespace rbod {
+
+// ---- error plumbing (rbod_api.cu) -------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+#define RBOD_CUDA(expr)                                                                            \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::rbod::set_error(RBOD_E_IO, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                               __FILE__, __LINE__);                                                \
+  } while (0)
+#define RBOD_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != RBOD_OK) return _rc; \
+  } while (0)
+
+// ---- growable device / pinned buffers ---------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);  // contents are NOT preserved on growth
+  void release();
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+// ---- K3 geometry ------------------------------------------------------------------------
+constexpr int K3_TILE_M = 128;       // queries per CTA (TMEM lanes)
+constexpr int K3_TILE_N = 64;        // gallery rows per accumulator buffer
+constexpr int K3_KBLOCK = 64;        // 16-bit elements per 128-byte swizzle row
+constexpr int K3_KB_PER_STAGE = 4;   // k-blocks per pipeline stage
+constexpr int K3_MAX_DP = 768;       // A operand must fit 384 TMEM columns
+constexpr int K3_THREADS = 192;      // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int K3_MAX_KC = 128;
+
+struct K3Launch {
+  CUtensorMap tmap_b;     // gallery [rows, dp] 16-bit, box {64, 64}, SWIZZLE_128B
+  CUtensorMap tmap_a;     // queries [Qpad, dp] 16-bit, box {64, 128} (variant 1 only)
+  const uint16_t* q16;    // [Qpad, dp]
+  int dp;
+  int64_t n_rows;         // valid gallery rows
+  int tiles_total;        // ceil(n_rows / K3_TILE_N)
+  int num_qt;             // Qpad / 128
+  int slices;
+  int64_t q_valid;
+  int64_t q_pad;
+  int kc;                 // candidates per (query, slice); multiple of 32
+  int num_stages;
+  int variant;            // 0 = A in TMEM, 1 = A streamed through smem
+  int a_fmt, b_fmt;       // 0 = f16, 1 = bf16
+  float* part_score;      // [slices][q_pad][kc]
+  uint32_t* part_idx;     // [slices][q_pad][kc]
+  const uint32_t* row_mask;
+  float* dump;            // optional raw scores [q_pad][dump_ld]
+  int64_t dump_ld;
+  int grid;
+  size_t smem_bytes;
+};
+
+// kernels (each returns RBOD_OK or sets the error) -----------------------------------------
+// K1
+int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots_dev, int64_t slot0,
+                       int normalize, int cosine, float* master32, int64_t ld32, uint16_t* out16, int64_t ld16,
+                       int kind16, float* out_norms, float* stats, int num_sms, cudaStream_t st);
+int launch_gather_rows(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32,
+                       int64_t ld16, const int64_t* rows, int64_t n, int64_t n_valid, float* out, int* err_flag,
+                       cudaStream_t st);
+// K2
+int launch_segment_mean(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32,
+                        int64_t ld16, int64_t n_valid, const int64_t* row_idx, const int64_t* offsets,
+                        int64_t n_classes, int64_t n_items_upper, double* partials, int* chunk_prefix,
+                        unsigned int* arrive_cnt, float* out, int* err_flag, cudaStream_t st);
+// K3
+int k3_configure(int device);
+size_t k3_smem_bytes(int variant, int kc, int num_stages);
+int launch_k3(const K3Launch& L, cudaStream_t st);
+// query preparation: normalise, round to 16 bit, per-query error radius and |q|^2
+int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16, uint16_t* q16,
+                        float* q_dq, double* q_qq, cudaStream_t st);
+// K4 family
+int launch_merge_partials(const float* part_score, const uint32_t* part_idx, int slices, int64_t q_pad,
+                          int64_t Q, int kc, uint32_t* cand_idx, float* cand_tau, cudaStream_t st);
+int launch_rescore(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16, int kind16,
+                   int dim, int64_t ld32, int64_t ld16, int metric, const uint32_t* cand_idx, int64_t Q, int kc,
+                   double* cand_score, cudaStream_t st);
+int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
+                  const float* stats, int dp, int64_t Q, int kc, int k, float* out_scores, int64_t* out_rows,
+                  double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* max_eps,
+                  cudaStream_t st);
+int launch_exact_collect(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
+                         int kind16, int dim, int64_t ld32, int64_t ld16, int metric, int64_t n_rows,
+                         const uint32_t* row_mask, const int* flag_q, const double* flag_thr, int f0, int nf,
+                         int cap, double* coll_score, uint32_t* coll_idx, int* coll_cnt, int num_sms,
+                         cudaStream_t st);
+int launch_select_collected(const double* coll_score, const uint32_t* coll_idx, const int* coll_cnt,
+                            const int* flag_q, int f0, int nf, int cap, int k, float* out_scores,
+                            int64_t* out_rows, double* out_scores64, int* overflow, cudaStream_t st);
+int launch_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t Q, int k, float* out_scores,
+                      int64_t* out_ids, double* out_scores64, cudaStream_t st);
+
+}  // namespace rbod
+
+struct rbod_gallery {
+  int dim = 0, dp = 0, dtype = 0, metric = 0, device = 0;
+  int kind16 = 1;  // 16-bit search operand: 1 = bf16, 2 = fp16
+  int64_t rows = 0, capacity = 0;
+  float* master32 = nullptr;    // [capacity, dim]  (dtype == RBOD_F32 only)
+  uint16_t* rows16 = nullptr;   // [capacity, dp]
+  float* stats = nullptr;       // device [2]: max ||row16||, max ||row16 - unit(master)||
+  int num_sms = 148;
+  // options
+  int k3_variant = 0;
+  int slack = -1;  // -1 = automatic
+  int time_k3 = 0;
+  // workspaces
+  rbod::DevBuf stage_rows, stage_slots, stage_norms;          // upsert staging
+  rbod::DevBuf q32, q16, q_dq, q_qq;                          // query prep
+  rbod::DevBuf part_score, part_idx, cand_idx, cand_tau, cand_score;
+  rbod::DevBuf out_scores, out_rows, out_scores64;
+  rbod::DevBuf flags;      // ints: [0]=n_flag [1]=overflow [2]=err; float max_eps at [3]
+  rbod::DevBuf flag_q, flag_thr;
+  rbod::DevBuf coll_score, coll_idx, coll_cnt;
+  rbod::DevBuf mask_dev, dump;
+  rbod::DevBuf seg_idx, seg_off, seg_out, seg_partials, seg_prefix, seg_arrive;
+  rbod::DevBuf gather_idx, gather_out;
+  rbod::PinBuf pin_a, pin_b;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};

@@ -1,0 +1,98 @@
+"""Row-sharded multi-GPU search: one process per GPU, gallery rows block-partitioned over ranks.
+
+Each rank searches its own rows (K3 + exact rescoring -> local top-k with float64 scores), the
+(Q, k) lists are exchanged with ONE all-gather over NCCL/NVLink, and every rank merges the G lists
+with K4 (``rbod_merge_topk``).  Scores travel as float64 so the merged order is exactly the
+(score desc, id asc) order a single GPU would produce.  No other collective is on the data path.
+
+The reference has no multi-GPU path at all; this implements BASELINE.json's
+"shard the gallery by rows ... merge the global top-k with an NCCL allgather".
+"""
+from __future__ import annotations
+
+import sys
+from typing import Callable, Optional, Tuple
+
+
+def shard_range(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block partition: rank r owns global rows [start, end).  Sizes differ by <= 1."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"shard_range: rank {rank} of world {world}")
+    base, rem = divmod(int(n_rows), world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def all_gather_stack(t, group=None):
+    """[...]-tensor per rank -> [G, ...] on every rank (NCCL: one all_gather_into_tensor)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    t = t.contiguous()
+    if t.is_cuda:
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    return torch.stack(parts, 0)
+
+
+class ShardedGallery:
+    """A gallery whose rows are split over the ranks of a torch.distributed process group.
+
+    ``local_search`` / ``merge`` are injectable so the host-side logic (partitioning, id offsets,
+    gather layout) is testable on CPU with the gloo backend; the defaults call librbod.so.
+    """
+
+    def __init__(self, dim: int, n_rows_total: int, dtype: str = "bf16", metric: str = "cosine", group=None,
+                 device: Optional[int] = None, local_search: Optional[Callable] = None,
+                 merge: Optional[Callable] = None, create_local: bool = True):
+        import torch.distributed as dist
+
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.dim = dim
+        self.n_rows_total = int(n_rows_total)
+        self.row_start, self.row_end = shard_range(self.n_rows_total, self.rank, self.world)
+        self._local_search = local_search
+        self._merge = merge
+        self.local = None
+        if create_local:
+            from .gallery import Gallery
+
+            self.local = Gallery(dim, dtype=dtype, metric=metric, capacity=self.row_end - self.row_start,
+                                 device=self.rank if device is None else device)
+
+    @property
+    def local_rows(self) -> int:
+        return self.row_end - self.row_start
+
+    def upsert_local(self, rows):
+        """Appends this rank's rows (global ids row_start + local slot)."""
+        return self.local.upsert(rows)
+
+    def search(self, queries, k: int):
+        """Global top-k on every rank: (scores f32 [Q,k], global ids i64 [Q,k], scores f64 [Q,k])."""
+        import torch
+
+        if self._local_search is not None:
+            s64, rows = self._local_search(queries, k)
+        else:
+            res = self.local.search(queries, k, want_scores64=True)
+            s64, rows = res.scores64, res.rows
+            if not isinstance(s64, torch.Tensor):
+                s64, rows = torch.from_numpy(s64), torch.from_numpy(rows)
+        ids = torch.where(rows >= 0, rows + self.row_start, rows)
+        if self.world == 1:
+            g_s, g_i = s64.unsqueeze(0), ids.unsqueeze(0)
+        else:
+            g_s = all_gather_stack(s64, self.group)
+            g_i = all_gather_stack(ids, self.group)
+        if self._merge is not None:
+            return self._merge(g_s, g_i, k)
+        from .gallery import merge_topk
+
+        return merge_topk(g_s, g_i, k)

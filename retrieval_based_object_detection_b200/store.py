@@ -1,0 +1,531 @@
+"""Host side of a collection: point ids, payloads, filters, persistence, upsert staging.
+
+This is the part of the (third-party) Qdrant server the reference scripts rely on that is NOT
+arithmetic: everything here is bookkeeping in Python; every vector operation goes to a
+``Gallery`` (librbod.so).  Behaviours reproduced, with the reference call sites that need them:
+
+* upsert-overwrites-by-id with deterministic md5 ids   31_…py:42-43,177-179; 32_…py:29-31,41-42
+* ids are unsigned ints or UUID strings, returned canonical (hyphenated)
+* scroll pages ordered by id (ints first, then UUIDs), ``limit`` default 10, ``next_page_offset``
+                                                       32_…py:78-82,123-131; 33_…py:96-106,139-145
+* ``Filter(must=[FieldCondition(key, match=MatchValue(value))])`` = AND of payload equalities;
+  a ``None`` payload value never matches                 32_…py:125-129; 33_…py:98-103,117-137
+* state survives the process (the scripts are separate processes talking to one server):
+  ``meta.json`` + snapshot (``points.json``, ``vectors.npy``) + an append-only ``wal.jsonl``.
+
+Single-point upserts (31_…py:179 sends one RPC per image) are appended to the WAL and kept in a
+host staging dict; they reach the GPU in one batched K1 launch on the first read that needs
+vectors, so read-your-writes holds without a kernel launch per point.
+"""
+from __future__ import annotations
+
+import base64
+import copy
+import json
+import os
+import shutil
+import uuid
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Set
+
+import numpy as np
+
+FORMAT_VERSION = 1
+_FLUSH_THRESHOLD = 65536  # staged rows that force a device flush
+
+
+class CollectionNotFound(Exception):
+    """Raised for operations on a collection that does not exist (the server's 404)."""
+
+    def __init__(self, name: str):
+        super().__init__(f"Not found: Collection `{name}` doesn't exist!")
+        self.status_code = 404
+        self.collection = name
+
+
+def canonical_id(pid) -> Any:
+    """Qdrant point id rules: unsigned 64-bit int, or a UUID given in any textual form."""
+    if isinstance(pid, bool):
+        raise ValueError(f"invalid point id {pid!r}")
+    if isinstance(pid, (int, np.integer)):
+        v = int(pid)
+        if v < 0 or v >= 1 << 64:
+            raise ValueError(f"point id {v} is not an unsigned 64-bit integer")
+        return v
+    if isinstance(pid, uuid.UUID):
+        return str(pid)
+    if isinstance(pid, str):
+        try:
+            return str(uuid.UUID(pid))
+        except ValueError as exc:
+            raise ValueError(f"point id {pid!r} is neither an unsigned integer nor a UUID") from exc
+    raise ValueError(f"unsupported point id type {type(pid).__name__}")
+
+
+def id_sort_key(pid):
+    return (0, pid) if isinstance(pid, int) else (1, uuid.UUID(pid).int)
+
+
+def _vkey(value):
+    """Index key that keeps True / 1 / 1.0 / "1" apart (python would merge the first three)."""
+    return (type(value).__name__, value)
+
+
+def _indexable(value) -> bool:
+    return isinstance(value, (str, bool, int, float)) and value is not None
+
+
+class Collection:
+    """One collection: host metadata + (lazily) a device gallery."""
+
+    def __init__(self, directory: Optional[str], name: str, dim: int, distance: str, dtype: str = "f32",
+                 device: int = 0):
+        self.directory = directory  # None = in-memory only
+        self.name = name
+        self.dim = int(dim)
+        self.distance = distance
+        self.dtype = dtype
+        self.device = device
+        self.ids: List[Any] = []
+        self.slot_of: Dict[Any, int] = {}
+        self.payloads: List[dict] = []
+        self.index: Dict[str, Dict[Any, Set[int]]] = {}
+        self.pending: Dict[int, np.ndarray] = {}
+        self.snapshot_vectors: Optional[np.ndarray] = None  # stored rows loaded from disk, not yet on device
+        self.gallery = None
+        self._order: Optional[List[int]] = None
+        self._dirty = False
+        self._wal = None
+
+    # ------------------------------------------------------------------ persistence
+    @staticmethod
+    def meta_path(directory: str) -> str:
+        return os.path.join(directory, "meta.json")
+
+    @classmethod
+    def create(cls, directory: Optional[str], name: str, dim: int, distance: str, dtype: str, device: int):
+        col = cls(directory, name, dim, distance, dtype, device)
+        if directory is not None:
+            os.makedirs(directory, exist_ok=True)
+            col._write_meta()
+            open(os.path.join(directory, "wal.jsonl"), "w").close()
+        return col
+
+    @classmethod
+    def open(cls, directory: str, device: int):
+        with open(cls.meta_path(directory), encoding="utf-8") as f:
+            meta = json.load(f)
+        col = cls(directory, meta["name"], meta["dim"], meta["distance"], meta.get("dtype", "f32"), device)
+        ppath, vpath = os.path.join(directory, "points.json"), os.path.join(directory, "vectors.npy")
+        if os.path.exists(ppath) and os.path.exists(vpath):
+            with open(ppath, encoding="utf-8") as f:
+                pts = json.load(f)
+            vec = np.load(vpath)
+            if vec.shape != (len(pts), col.dim):
+                raise RuntimeError(f"collection {col.name!r}: snapshot shape {vec.shape} != ({len(pts)}, {col.dim})")
+            for pid, payload in pts:
+                col._add_point(pid if isinstance(pid, int) else str(pid), payload)
+            col.snapshot_vectors = np.ascontiguousarray(vec, dtype=np.float32)
+        wal = os.path.join(directory, "wal.jsonl")
+        if os.path.exists(wal):
+            with open(wal, encoding="utf-8") as f:
+                for line in f:
+                    line = line.strip()
+                    if not line:
+                        continue
+                    try:
+                        rec = json.loads(line)
+                    except json.JSONDecodeError:
+                        break  # torn tail of an interrupted append
+                    if rec.get("op") == "upsert":
+                        vec = np.frombuffer(base64.b64decode(rec["vec"]), dtype=np.float32)
+                        col._stage(rec["id"], vec, rec["payload"])
+                    elif rec.get("op") == "delete":
+                        col._wal_deletes = getattr(col, "_wal_deletes", []) + [rec["id"]]
+        return col
+
+    def _write_meta(self) -> None:
+        meta = {"name": self.name, "dim": self.dim, "distance": self.distance, "dtype": self.dtype,
+                "format": FORMAT_VERSION}
+        tmp = self.meta_path(self.directory) + ".tmp"
+        with open(tmp, "w", encoding="utf-8") as f:
+            json.dump(meta, f)
+        os.replace(tmp, self.meta_path(self.directory))
+
+    def _wal_append(self, rec: dict) -> None:
+        if self.directory is None:
+            return
+        if self._wal is None:
+            self._wal = open(os.path.join(self.directory, "wal.jsonl"), "a", encoding="utf-8")
+        self._wal.write(json.dumps(rec, separators=(",", ":")) + "\n")
+        self._wal.flush()
+
+    def save(self) -> None:
+        """Snapshot stored vectors + points and truncate the WAL (needs the device copy)."""
+        if self.directory is None or not self._dirty:
+            return
+        if self.gallery is None:
+            return  # nothing materialised in this process: the WAL already holds every change
+        vec = self.stored_vectors(range(len(self.ids))) if self.ids else np.zeros((0, self.dim), np.float32)
+        tmp_v, tmp_p = os.path.join(self.directory, "vectors.tmp.npy"), os.path.join(self.directory, "points.tmp.json")
+        np.save(tmp_v, vec)
+        with open(tmp_p, "w", encoding="utf-8") as f:
+            json.dump([[pid, pl] for pid, pl in zip(self.ids, self.payloads)], f)
+        os.replace(tmp_v, os.path.join(self.directory, "vectors.npy"))
+        os.replace(tmp_p, os.path.join(self.directory, "points.json"))
+        if self._wal is not None:
+            self._wal.close()
+            self._wal = None
+        open(os.path.join(self.directory, "wal.jsonl"), "w").close()
+        self._dirty = False
+
+    def close(self) -> None:
+        try:
+            self.save()
+        finally:
+            if self._wal is not None:
+                self._wal.close()
+                self._wal = None
+            if self.gallery is not None:
+                self.gallery.close()
+                self.gallery = None
+
+    # ------------------------------------------------------------------ points
+    def __len__(self) -> int:
+        return len(self.ids)
+
+    def _index_add(self, slot: int, payload: dict) -> None:
+        for key, value in payload.items():
+            values = value if isinstance(value, (list, tuple)) else [value]
+            for v in values:
+                if _indexable(v):
+                    self.index.setdefault(key, {}).setdefault(_vkey(v), set()).add(slot)
+
+    def _index_remove(self, slot: int, payload: dict) -> None:
+        for key, value in payload.items():
+            values = value if isinstance(value, (list, tuple)) else [value]
+            for v in values:
+                if _indexable(v):
+                    s = self.index.get(key, {}).get(_vkey(v))
+                    if s is not None:
+                        s.discard(slot)
+
+    def _add_point(self, pid, payload: Optional[dict]) -> int:
+        payload = copy.deepcopy(payload) if payload else {}
+        slot = self.slot_of.get(pid)
+        if slot is None:
+            slot = len(self.ids)
+            self.ids.append(pid)
+            self.payloads.append(payload)
+            self.slot_of[pid] = slot
+            self._order = None
+        else:
+            self._index_remove(slot, self.payloads[slot])
+            self.payloads[slot] = payload
+        self._index_add(slot, payload)
+        return slot
+
+    def _stage(self, pid, vec: np.ndarray, payload: Optional[dict]) -> int:
+        slot = self._add_point(pid, payload)
+        self.pending[slot] = np.array(vec, dtype=np.float32, copy=True)
+        self._dirty = True
+        return slot
+
+    def upsert(self, pid, vector, payload: Optional[dict]) -> None:
+        pid = canonical_id(pid)
+        vec = np.asarray(vector, dtype=np.float32).reshape(-1)
+        if vec.shape[0] != self.dim:
+            raise ValueError(f"Wrong input: Vector dimension error: expected dim: {self.dim}, got {vec.shape[0]}")
+        if payload is not None and not isinstance(payload, dict):
+            raise ValueError("payload must be a dict or None")
+        self._wal_append({"op": "upsert", "id": pid, "payload": payload or {},
+                          "vec": base64.b64encode(vec.tobytes()).decode("ascii")})
+        self._stage(pid, vec, payload)
+        if len(self.pending) >= _FLUSH_THRESHOLD:
+            self.flush()
+
+    def upsert_many(self, pids: Sequence, vectors: np.ndarray, payloads: Optional[Sequence[Optional[dict]]]) -> None:
+        for i, pid in enumerate(pids):
+            self.upsert(pid, vectors[i], None if payloads is None else payloads[i])
+
+    # ------------------------------------------------------------------ device
+    def _ensure_gallery(self):
+        if self.gallery is None:
+            from .gallery import Gallery
+
+            metric = "cosine" if self.distance == "Cosine" else "dot"
+            self.gallery = Gallery(self.dim, dtype=self.dtype, metric=metric, capacity=max(len(self.ids), 1024),
+                                   device=self.device)
+            if self.snapshot_vectors is not None and len(self.snapshot_vectors):
+                self.gallery.upsert(self.snapshot_vectors, raw=True)
+            self.snapshot_vectors = None
+        return self.gallery
+
+    def flush(self) -> None:
+        """Pushes staged upserts to the GPU in one K1 launch (snapshot rows go first, untouched)."""
+        g = self._ensure_gallery()
+        if self.pending:
+            slots = np.fromiter(sorted(self.pending), dtype=np.int64, count=len(self.pending))
+            rows = np.stack([self.pending[int(s)] for s in slots])
+            g.upsert(rows, slots=slots)
+            self.pending.clear()
+        for pid in getattr(self, "_wal_deletes", []):
+            self._delete_now(pid)
+        self._wal_deletes = []
+
+    def stored_vectors(self, slots: Iterable[int]) -> np.ndarray:
+        """Stored (normalised) float32 vectors of the given slots, from the device."""
+        slots = np.fromiter(slots, dtype=np.int64)
+        if len(slots) == 0:
+            return np.zeros((0, self.dim), dtype=np.float32)
+        self.flush()
+        return self.gallery.get_rows(slots)
+
+    def _delete_now(self, pid) -> bool:
+        slot = self.slot_of.get(pid)
+        if slot is None:
+            return False
+        last = len(self.ids) - 1
+        self._index_remove(slot, self.payloads[slot])
+        if slot != last:
+            row = self.gallery.get_rows(np.array([last], dtype=np.int64))
+            self.gallery.upsert(row, slots=np.array([slot], dtype=np.int64), raw=True)
+            moved = self.ids[last]
+            self._index_remove(last, self.payloads[last])
+            self.ids[slot], self.payloads[slot] = moved, self.payloads[last]
+            self.slot_of[moved] = slot
+            self._index_add(slot, self.payloads[slot])
+        self.ids.pop()
+        self.payloads.pop()
+        del self.slot_of[pid]
+        self.gallery.truncate(last)
+        self._order = None
+        self._dirty = True
+        return True
+
+    def delete(self, pids: Iterable) -> int:
+        self.flush()
+        n = 0
+        for pid in pids:
+            pid = canonical_id(pid)
+            if pid in self.slot_of:
+                self._wal_append({"op": "delete", "id": pid})
+                n += int(self._delete_now(pid))
+        return n
+
+    # ------------------------------------------------------------------ filters / scroll
+    def ordered_slots(self) -> List[int]:
+        if self._order is None:
+            self._order = sorted(range(len(self.ids)), key=lambda s: id_sort_key(self.ids[s]))
+        return self._order
+
+    def _match_slots(self, cond) -> Set[int]:
+        """Slots satisfying one condition object (duck-typed on the qdrant_client.models classes)."""
+        if hasattr(cond, "must") or hasattr(cond, "should") or hasattr(cond, "must_not"):
+            res = self.filter_slots(cond)
+            return set(range(len(self.ids))) if res is None else res
+        if hasattr(cond, "has_id"):
+            out = set()
+            for pid in cond.has_id:
+                s = self.slot_of.get(canonical_id(pid))
+                if s is not None:
+                    out.add(s)
+            return out
+        if hasattr(cond, "is_null"):
+            key = cond.is_null.key if hasattr(cond.is_null, "key") else cond.is_null
+            return {s for s, p in enumerate(self.payloads) if key in p and p[key] is None}
+        if hasattr(cond, "is_empty"):
+            key = cond.is_empty.key if hasattr(cond.is_empty, "key") else cond.is_empty
+            return {s for s, p in enumerate(self.payloads) if p.get(key) in (None, [], ())}
+        key = getattr(cond, "key", None)
+        if key is None:
+            raise ValueError(f"unsupported filter condition {cond!r}")
+        match = getattr(cond, "match", None)
+        rng = getattr(cond, "range", None)
+        if match is not None:
+            by_value = self.index.get(key, {})
+            if hasattr(match, "value"):
+                if match.value is None:
+                    return set()
+                return set(by_value.get(_vkey(match.value), ()))
+            if hasattr(match, "any"):
+                out: Set[int] = set()
+                for v in match.any:
+                    out |= by_value.get(_vkey(v), set())
+                return out
+            if hasattr(match, "except_"):
+                banned: Set[int] = set()
+                for v in match.except_:
+                    banned |= by_value.get(_vkey(v), set())
+                have = set()
+                for s in by_value.values():
+                    have |= s
+                return have - banned
+            if hasattr(match, "text"):
+                return {s for s, p in enumerate(self.payloads) if isinstance(p.get(key), str) and match.text in p[key]}
+            raise ValueError(f"unsupported match {match!r}")
+        if rng is not None:
+            def ok(v):
+                if isinstance(v, bool) or not isinstance(v, (int, float)):
+                    return False
+                for name, op in (("gt", lambda a, b: a > b), ("gte", lambda a, b: a >= b),
+                                 ("lt", lambda a, b: a < b), ("lte", lambda a, b: a <= b)):
+                    bound = getattr(rng, name, None)
+                    if bound is not None and not op(v, bound):
+                        return False
+                return True
+            return {s for s, p in enumerate(self.payloads) if ok(p.get(key))}
+        raise ValueError(f"filter condition on {key!r} has neither match nor range")
+
+    def filter_slots(self, flt) -> Optional[Set[int]]:
+        """Set of slots passing ``flt`` (None = no filter = every slot)."""
+        if flt is None:
+            return None
+        result: Optional[Set[int]] = None
+        must = getattr(flt, "must", None) or []
+        should = getattr(flt, "should", None) or []
+        must_not = getattr(flt, "must_not", None) or []
+        for group in (must, should, must_not):
+            if not isinstance(group, (list, tuple)):
+                raise ValueError("filter clauses must be lists of conditions")
+        for cond in must:
+            s = self._match_slots(cond)
+            result = s if result is None else (result & s)
+            if not result:
+                return set()
+        if should:
+            any_of: Set[int] = set()
+            for cond in should:
+                any_of |= self._match_slots(cond)
+            result = any_of if result is None else (result & any_of)
+        if must_not:
+            if result is None:
+                result = set(range(len(self.ids)))
+            for cond in must_not:
+                result -= self._match_slots(cond)
+        return result
+
+    def scroll(self, flt=None, limit: int = 10, offset=None):
+        """-> (slots of this page in id order, next_page_offset id or None)."""
+        allowed = self.filter_slots(flt)
+        order = self.ordered_slots()
+        start = 0
+        if offset is not None:
+            key = id_sort_key(canonical_id(offset))
+            lo, hi = 0, len(order)
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if id_sort_key(self.ids[order[mid]]) < key:
+                    lo = mid + 1
+                else:
+                    hi = mid
+            start = lo
+        page: List[int] = []
+        nxt = None
+        for s in order[start:]:
+            if allowed is not None and s not in allowed:
+                continue
+            if len(page) == limit:
+                nxt = self.ids[s]
+                break
+            page.append(s)
+        return page, nxt
+
+    def row_mask(self, allowed: Optional[Set[int]]) -> Optional[np.ndarray]:
+        """uint32 bitmask over row slots for the device search (None = all rows)."""
+        if allowed is None:
+            return None
+        n = len(self.ids)
+        bits = np.zeros((n + 31) // 32 * 32, dtype=np.uint8)
+        if allowed:
+            bits[np.fromiter(allowed, dtype=np.int64)] = 1
+        return np.packbits(bits, bitorder="little").view(np.uint32).copy()
+
+    def search(self, queries: np.ndarray, k: int, flt=None):
+        """-> (scores [Q,k] float32, slots [Q,k] int64) via the device (K3 + exact rescoring)."""
+        self.flush()
+        mask = self.row_mask(self.filter_slots(flt))
+        res = self.gallery.search(np.ascontiguousarray(queries, dtype=np.float32), k, row_mask=mask)
+        return res.scores, res.rows
+
+
+class StoreRoot:
+    """All collections under one directory (one emulated "server"); ``None`` = in-memory."""
+
+    def __init__(self, directory: Optional[str], dtype: str = "f32", device: int = 0):
+        self.directory = directory
+        self.dtype = dtype
+        self.device = device
+        self.open_collections: Dict[str, Collection] = {}
+        if directory is not None:
+            os.makedirs(directory, exist_ok=True)
+
+    def _dir(self, name: str) -> str:
+        if not name or "/" in name or "\\" in name or name in (".", ".."):
+            raise ValueError(f"invalid collection name {name!r}")
+        return os.path.join(self.directory, name)
+
+    def names(self) -> List[str]:
+        if self.directory is None:
+            return sorted(self.open_collections)
+        out = []
+        for entry in sorted(os.listdir(self.directory)):
+            if os.path.isfile(Collection.meta_path(os.path.join(self.directory, entry))):
+                out.append(entry)
+        return out
+
+    def exists(self, name: str) -> bool:
+        return name in self.names()
+
+    def get(self, name: str) -> Collection:
+        col = self.open_collections.get(name)
+        if col is not None:
+            return col
+        if self.directory is None or not os.path.isfile(Collection.meta_path(self._dir(name))):
+            raise CollectionNotFound(name)
+        col = Collection.open(self._dir(name), self.device)
+        self.open_collections[name] = col
+        return col
+
+    def create(self, name: str, dim: int, distance: str, dtype: Optional[str] = None) -> Collection:
+        if self.exists(name):
+            raise ValueError(f"Wrong input: Collection `{name}` already exists!")
+        directory = None if self.directory is None else self._dir(name)
+        col = Collection.create(directory, name, dim, distance, dtype or self.dtype, self.device)
+        self.open_collections[name] = col
+        return col
+
+    def delete(self, name: str) -> bool:
+        col = self.open_collections.pop(name, None)
+        existed = col is not None
+        if col is not None:
+            col._dirty = False
+            col.close()
+        if self.directory is not None and os.path.isdir(self._dir(name)):
+            shutil.rmtree(self._dir(name))
+            existed = True
+        return existed
+
+    def rename(self, old: str, new: str) -> None:
+        if not self.exists(old):
+            raise CollectionNotFound(old)
+        if self.exists(new):
+            raise ValueError(f"Wrong input: Collection `{new}` already exists!")
+        col = self.open_collections.pop(old, None)
+        if self.directory is None:
+            col.name = new
+            self.open_collections[new] = col
+            return
+        if col is not None:
+            col.save()
+            col.close()
+        os.rename(self._dir(old), self._dir(new))
+        with open(Collection.meta_path(self._dir(new)), encoding="utf-8") as f:
+            meta = json.load(f)
+        meta["name"] = new
+        with open(Collection.meta_path(self._dir(new)), "w", encoding="utf-8") as f:
+            json.dump(meta, f)
+
+    def close(self) -> None:
+        for col in list(self.open_collections.values()):
+            col.close()
+        self.open_collections.clear()
