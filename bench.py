@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Headline benchmark: top-10 cosine queries/s on a 10M x 768 bf16 gallery (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rows R --queries Q --k K]
+
+A step = one pass of the hot path over one batch of synthetic queries: rbod_search (query prep,
+K3 tcgen05 cosine top-k, slice merge, fp64 rescoring, certification) on a gallery that is already
+resident in HBM.  ``value`` times the step with device-resident queries/outputs; ``e2e`` times the
+same call through the C ABI with HOST (pinned) query and result buffers, copies inside the timed
+region.  ``roofline`` describes the dominant kernel (K3), timed live with CUDA events on its launch
+stream.  ``cpu_baseline`` is the numpy float64 oracle port on a bounded sample of the same workload
+(the one place besides tests/smoke where oracle/ is executed; it is never the thing shipped).
+
+N > 1 (torchrun, one rank per GPU): the 10M rows are block-partitioned over the ranks, every rank
+searches its shard for the same query batch, one NCCL all-gather of the (Q, k) lists, K4 merge.
+Timing = CUDA events bracketed by barrier + synchronize, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "top-10 cosine queries/s on 10M x 768"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--queries", type=int, default=10_000)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a) -> str:
+    return (f"{a.rows / 1e6:g}M x {a.dim} {a.dtype} gallery (synthetic unit-norm rows), "
+            f"{a.queries}-query batch, exact top-{a.k} cosine")
+
+
+# --------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi while the timed region runs
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU legs (oracle port) -- bounded sample, scaled to the metric's unit
+# --------------------------------------------------------------------------------------------
+def cpu_sample_qps(a, budget_s: float = 12.0):
+    """Times the float64 numpy oracle (cosine_topk: GEMM + (score desc, id asc) top-k) on a row sample
+    of the gallery and scales queries/s linearly to the full row count."""
+    import numpy as np
+
+    from oracle import oracle_np as O
+
+    threads = os.cpu_count() or 1
+    n_s = min(a.rows, 200_000)
+    g = O.l2_normalize_store(O.synthetic_unit_rows(n_s, a.dim, seed=0), a.dtype if a.dtype != "fp16" else "f16")[0]
+    q_probe = O.synthetic_unit_rows(32, a.dim, seed=1)
+    t0 = time.perf_counter()
+    O.cosine_topk(q_probe, g, a.k)
+    t_probe = time.perf_counter() - t0
+    q_s = int(max(32, min(a.queries, 32 * budget_s / max(t_probe, 1e-3))))
+    q = O.synthetic_unit_rows(q_s, a.dim, seed=2)
+    t0 = time.perf_counter()
+    O.cosine_topk(q, g, a.k)
+    t = time.perf_counter() - t0
+    qps_full = q_s / t * (n_s / a.rows)
+    sample = (f"{q_s} queries x {n_s} rows x {a.dim} (float64 GEMM + lexsort top-{a.k}) in {t:.2f} s; "
+              f"queries/s scaled by {n_s}/{a.rows} rows")
+    return qps_full, threads, sample, t
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU arithmetic for this path (numpy float64 cosine, as
+    33_run_all_experiments.py:76-77, batched; the Qdrant server itself is not installable offline),
+    on the box's host cores, each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = []
+    sample = ""
+    threads = os.cpu_count() or 1
+    total = a.warmup + a.steps
+    budget = max(2.0, min(12.0, 150.0 / max(total, 1)))
+    for i in range(total):
+        qps, threads, sample, t = cpu_sample_qps(a, budget_s=budget)
+        if i >= a.warmup:
+            per_step.append((qps, t))
+    value = statistics.mean(q for q, _ in per_step)
+    ms = statistics.mean(t for _, t in per_step) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "CPU; each step is a bounded row/query sample, scaled"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p.get("bf16_tflops_sustained", 1422.9), p.get("bf16_tflops", 1691.8), p.get("hbm_gbs", 6555.8), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from retrieval_based_object_detection_b200 import Gallery, ShardedGallery, merge_topk, shard_range
+    from retrieval_based_object_detection_b200.sharded import all_gather_stack
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- build the resident gallery: synthetic unit-norm rows, generated on device, stored by K1
+    r0, r1 = shard_range(a.rows, rank, world)
+    n_local = r1 - r0
+    g = Gallery(a.dim, dtype=a.dtype, capacity=n_local, device=local_rank)
+    gen = torch.Generator(dev).manual_seed(1234 + rank)
+    t_build0 = time.perf_counter()
+    chunk = 500_000
+    for s in range(0, n_local, chunk):
+        m = min(chunk, n_local - s)
+        g.upsert(torch.randn(m, a.dim, device=dev, generator=gen))
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build0
+    g.set_option("time_k3", 1)
+
+    qgen = torch.Generator(dev).manual_seed(99)          # same queries on every rank
+    q_dev = torch.randn(a.queries, a.dim, device=dev, generator=qgen)
+    q_host = torch.empty((a.queries, a.dim), dtype=torch.float32).pin_memory()
+    q_host.copy_(q_dev)
+    out_dev = (torch.empty((a.queries, a.k), dtype=torch.float32, device=dev),
+               torch.empty((a.queries, a.k), dtype=torch.int64, device=dev),
+               torch.empty((a.queries, a.k), dtype=torch.float64, device=dev))
+    out_host = (torch.empty((a.queries, a.k), dtype=torch.float32).pin_memory(),
+                torch.empty((a.queries, a.k), dtype=torch.int64).pin_memory(),
+                torch.empty((a.queries, a.k), dtype=torch.float64).pin_memory())
+    out_host_np = tuple(t.numpy() for t in out_host)
+
+    launches = {"n": 0}
+    k3_ms = []
+    fallback = []
+
+    def step_device():
+        res = g.search(q_dev, a.k, out=out_dev)
+        launches["n"] += res.stats["total_launches"]
+        k3_ms.append(res.stats["k3_ms"])
+        fallback.append(res.stats["fallback_queries"])
+        if world > 1:
+            ids = torch.where(out_dev[1] >= 0, out_dev[1] + r0, out_dev[1])
+            g_s = all_gather_stack(out_dev[2], None)
+            g_i = all_gather_stack(ids, None)
+            merged = merge_topk(g_s, g_i, a.k)
+            launches["n"] += 2       # id offset + K4 merge (NCCL's own kernels not counted)
+            return merged, res.stats
+        return out_dev, res.stats
+
+    def step_host():
+        res = g.search(q_host.numpy(), a.k, out=out_host_np)
+        launches["n"] += res.stats["total_launches"]
+        if world > 1:
+            s64 = torch.from_numpy(out_host_np[2]).to(dev, non_blocking=True)
+            ids = torch.from_numpy(out_host_np[1]).to(dev, non_blocking=True)
+            ids = torch.where(ids >= 0, ids + r0, ids)
+            merged = merge_topk(all_gather_stack(s64, None), all_gather_stack(ids, None), a.k)
+            launches["n"] += 2
+            return [m.cpu() for m in merged]
+        return out_host_np
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    last_stats = None
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    k3_ms.clear()
+    fallback.clear()
+    ms_dev = timed(lambda: step_device(), a.steps)
+    n_launch_timed = launches["n"]
+    k3_timed = list(k3_ms)
+    _, last_stats = step_device()
+    for _ in range(2):
+        step_host()
+    ms_e2e = timed(lambda: step_host(), a.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    sus, burst, hbm, src = load_peaks()
+    value = a.queries * a.steps / (ms_dev / 1e3)
+    e2e_value = a.queries * a.steps / (ms_e2e / 1e3)
+    k3_avg_ms = statistics.mean(k3_timed) if k3_timed else 0.0
+    flops_per_launch = 2.0 * a.queries * n_local * a.dim
+    achieved = flops_per_launch / (k3_avg_ms / 1e3) / 1e12 if k3_avg_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "k3_cosine_topk_kernel", "achieved": achieved, "peak": sus,
+                "unit": "TFLOP/s", "frac": achieved / sus, "traffic": None,
+                "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
+                "algorithmic": f"2*Q*N_local*D = {flops_per_launch:.3e} flop per launch", "kernel_ms": k3_avg_ms,
+                "kernel_share_of_step": k3_avg_ms * a.steps / ms_dev if ms_dev > 0 else None}
+    prof = os.path.join(ROOT, "profiles", "k3_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        qps, threads, sample, _ = cpu_sample_qps(a)
+        cpu = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(a), "gallery_rows_total": a.rows, "rows_per_gpu": n_local, "dim": a.dim,
+                   "queries_per_step": a.queries, "k": a.k, "parallelism": f"row-shard x{world} + allgather merge",
+                   "l2": "gallery operand per GPU is far larger than the 126 MB L2; no flush between steps",
+                   "candidates_per_query": last_stats["candidates"], "slices": last_stats["slices"],
+                   "fallback_queries_per_step": statistics.mean(fallback) if fallback else 0,
+                   "gallery_build_s": round(t_build, 2)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": a.queries * a.dim * 4,
+                "d2h_bytes_per_step": a.queries * a.k * (4 + 8 + 8), "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": n_launch_timed,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()
