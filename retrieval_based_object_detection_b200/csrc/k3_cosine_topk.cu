@@ -146,20 +146,21 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
-        const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
-        const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
-        for (int t = t0; t < t1; ++t) {
-          for (int ch = 0; ch < num_chunks; ++ch) {
-            const int kb0 = ch * K3_KB_PER_STAGE;
-            const int nkb = min(K3_KB_PER_STAGE, P.num_kb - kb0);
-            mbar_wait(&bars->empty[stage], phase ^ 1u, 1);
-            const uint32_t bytes = nkb * (B_KBLOCK_BYTES + (P.variant == 1 ? A_KBLOCK_BYTES : 0));
-            mbar_arrive_expect_tx(&bars->full[stage], bytes);
+    // The whole warp walks the schedule (warp-uniform control flow); one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t kb_bytes = B_KBLOCK_BYTES + (P.variant == 1 ? A_KBLOCK_BYTES : 0);
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
+      const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
+      const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
+      for (int t = t0; t < t1; ++t) {
+        for (int ch = 0; ch < num_chunks; ++ch) {
+          const int kb0 = ch * K3_KB_PER_STAGE;
+          const int nkb = min(K3_KB_PER_STAGE, P.num_kb - kb0);
+          mbar_wait(&bars->empty[stage], phase ^ 1u, 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bars->full[stage], nkb * kb_bytes);
             uint8_t* sb = stage_base + (size_t)stage * stage_bytes;
             for (int j = 0; j < nkb; ++j)
               tma_load_2d(sb + j * B_KBLOCK_BYTES, &P.tmap_b, &bars->full[stage], (kb0 + j) * K3_KBLOCK,
@@ -170,59 +171,68 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
                 tma_load_2d(sa + j * A_KBLOCK_BYTES, &P.tmap_a, &bars->full[stage], (kb0 + j) * K3_KBLOCK,
                             qt * K3_TILE_M);
             }
-            if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0, unit_par = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        const int slice = u / P.num_qt;
-        const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
-        const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
-        if (P.variant == 0) {
-          mbar_wait(&bars->a_ready, unit_par, 2);
-          unit_par ^= 1u;
+    // Warp-converged loop; elect.sync picks the issuing lane so descriptors stay in uniform registers.
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0, unit_par = 0;
+    const uint32_t tmem_b = __shfl_sync(FULL_MASK, tmem_base, 0);
+    const uint32_t smem_stage0 = __shfl_sync(FULL_MASK, smem_u32(stage_base), 0);
+    const uint64_t desc_hi = make_smem_desc_sw128(0);  // everything except the start address
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int slice = u / P.num_qt;
+      const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
+      const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
+      if (P.variant == 0) {
+        mbar_wait(&bars->a_ready, unit_par, 2);
+        unit_par ^= 1u;
+        tc_fence_after();
+      }
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&bars->tempty[acc], acc_phase ^ 1u, 3);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_b + ACC_COL0 + acc * K3_TILE_N;
+        for (int ch = 0; ch < num_chunks; ++ch) {
+          const int kb0 = ch * K3_KB_PER_STAGE;
+          const int nkb = min(K3_KB_PER_STAGE, P.num_kb - kb0);
+          mbar_wait(&bars->full[stage], phase, 4);
           tc_fence_after();
-        }
-        for (int t = t0; t < t1; ++t) {
-          mbar_wait(&bars->tempty[acc], acc_phase ^ 1u, 3);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + ACC_COL0 + acc * K3_TILE_N;
-          for (int ch = 0; ch < num_chunks; ++ch) {
-            const int kb0 = ch * K3_KB_PER_STAGE;
-            const int nkb = min(K3_KB_PER_STAGE, P.num_kb - kb0);
-            mbar_wait(&bars->full[stage], phase, 4);
-            tc_fence_after();
-            const uint32_t sb = smem_u32(stage_base + (size_t)stage * stage_bytes);
+          if (elect_one()) {
+            const uint32_t sb = smem_stage0 + (uint32_t)stage * (uint32_t)stage_bytes;
             const uint32_t sa = sb + K3_KB_PER_STAGE * B_KBLOCK_BYTES;
             for (int j = 0; j < nkb; ++j) {
-              const uint64_t bdesc0 = make_smem_desc_sw128(sb + j * B_KBLOCK_BYTES);
-              const uint64_t adesc0 = make_smem_desc_sw128(sa + j * A_KBLOCK_BYTES);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const int k16 = (kb0 + j) * 4 + kk;  // index of this K=16 step within the row
-                const uint64_t bdesc = bdesc0 + (uint64_t)(kk * 2);  // +32 bytes (>>4) inside the swizzle row
-                if (P.variant == 0) {
-                  mma_f16_ts(d_tmem, tmem_base + (uint32_t)k16 * 8u, bdesc, P.idesc, k16 > 0 ? 1u : 0u);
-                } else {
-                  mma_f16_ss(d_tmem, adesc0 + (uint64_t)(kk * 2), bdesc, P.idesc, k16 > 0 ? 1u : 0u);
-                }
+              const uint64_t bdesc0 = desc_hi | (uint64_t)(((sb + j * B_KBLOCK_BYTES) >> 4) & 0x3fffu);
+              const uint64_t adesc0 = desc_hi | (uint64_t)(((sa + j * A_KBLOCK_BYTES) >> 4) & 0x3fffu);
+              const int k16 = (kb0 + j) * 4;  // index of the first K=16 step of this k-block
+              if (P.variant == 0) {
+                const uint32_t a_tmem = tmem_b + (uint32_t)k16 * 8u;
+                mma_f16_ts(d_tmem, a_tmem, bdesc0, P.idesc, k16 > 0 ? 1u : 0u);
+                mma_f16_ts(d_tmem, a_tmem + 8u, bdesc0 + 2u, P.idesc, 1u);
+                mma_f16_ts(d_tmem, a_tmem + 16u, bdesc0 + 4u, P.idesc, 1u);
+                mma_f16_ts(d_tmem, a_tmem + 24u, bdesc0 + 6u, P.idesc, 1u);
+              } else {
+                mma_f16_ss(d_tmem, adesc0, bdesc0, P.idesc, k16 > 0 ? 1u : 0u);
+                mma_f16_ss(d_tmem, adesc0 + 2u, bdesc0 + 2u, P.idesc, 1u);
+                mma_f16_ss(d_tmem, adesc0 + 4u, bdesc0 + 4u, P.idesc, 1u);
+                mma_f16_ss(d_tmem, adesc0 + 6u, bdesc0 + 6u, P.idesc, 1u);
               }
             }
             mma_commit(&bars->empty[stage]);
-            if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
+            if (ch == num_chunks - 1) mma_commit(&bars->tfull[acc]);
           }
-          mma_commit(&bars->tfull[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1u;
+          __syncwarp();
+          if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
         }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
       }
     }
   } else {

@@ -66,6 +66,18 @@ __device__ __forceinline__ float h16_to_f32(uint16_t h, int kind) {
   return __half2float(__ushort_as_half(h));
 }
 
+// One lane of a fully converged warp returns true.  Using elect.sync (instead of lane == 0) lets
+// ptxas keep tcgen05 / TMA operands in uniform registers without a uniformisation loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------
