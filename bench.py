@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=-1, help="override the K3 kernel variant (debug)")
     return ap.parse_args()
 
 
@@ -208,6 +209,8 @@ def run_b200(a):
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build0
     g.set_option("time_k3", 1)
+    if a.variant >= 0:
+        g.set_option("k3_variant", a.variant)
 
     qgen = torch.Generator(dev).manual_seed(99)          # same queries on every rank
     q_dev = torch.randn(a.queries, a.dim, device=dev, generator=qgen)

@@ -111,7 +111,8 @@ int64_t rbod_count(const rbod_gallery* g);
 int rbod_info(const rbod_gallery* g, rbod_gallery_info* out);
 /* Shrinks the number of used row slots (rows beyond `rows` are forgotten). */
 int rbod_truncate(rbod_gallery* g, int64_t rows);
-/* Tunables: "k3_variant" (0 = A operand resident in TMEM, 1 = A streamed through smem),
+/* Tunables: "k3_variant" (0 = query tile resident in TMEM, 1 = query tile streamed through smem,
+ * 2 = TMEM-resident + CTA pairs / cta_group::2),
  * "slack" (extra candidates kept per query), "time_k3" (1 = fill stats.k3_ms). */
 int rbod_set_option(rbod_gallery* g, const char* key, int64_t value);
 

@@ -11,9 +11,11 @@
 //     A operand straight from tensor memory (tcgen05.mma with A in TMEM), so the only operand
 //     that streams is the gallery: HBM -> L2 -> shared memory by TMA (128-byte swizzle, boxes of
 //     64 rows x 64 elements), 4 k-blocks per pipeline stage.
-//   * Accumulators: two 128x64 fp32 buffers in TMEM columns [384,448) and [448,512); the MMA of
-//     gallery tile j+1 overlaps the epilogue of tile j.
-//   * Epilogue (4 warps, one thread per query row): tcgen05.ld the 64 scores of the row, compare
+//   * Accumulators: 128x128 fp32 tiles (one N=128 MMA shape: measured 90% of peak per clock and
+//     ~23% less energy per flop than N=64) at the top of TMEM.  dim <= 512 leaves room for two
+//     buffers (MMA of tile j+1 overlaps the epilogue of tile j); dim 768 has room for one, so the
+//     epilogue copies the tile to registers and releases TMEM before it starts selecting.
+//   * Epilogue (4 warps, one thread per query row): tcgen05.ld the 128 scores of the row, compare
 //     against the row's running threshold (one FMNMX per score on the fast path); survivors are
 //     inserted by the whole warp into the row's candidate list in shared memory (replace-min).
 //   * Work unit = (gallery slice, query tile).  Units are ordered slice-major so that CTAs
@@ -35,9 +37,6 @@ namespace rbod {
 namespace {
 
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_COL0 = 384;
-constexpr int B_KBLOCK_BYTES = K3_TILE_N * 128;   // 8 KB : 64 rows x 128 B
-constexpr int A_KBLOCK_BYTES = K3_TILE_M * 128;   // 16 KB: 128 rows x 128 B
 constexpr int MAX_STAGES = 8;
 
 struct alignas(64) K3Params {
@@ -60,6 +59,8 @@ struct alignas(64) K3Params {
   int kc;
   int num_stages;
   int variant;
+  int num_acc;     // accumulator buffers (1 or 2)
+  int acc_col0;    // first accumulator column in TMEM
   uint32_t idesc;
 };
 
@@ -107,7 +108,49 @@ __device__ __noinline__ float2 k3_insert(float val, uint32_t col, uint32_t ball,
   return make_float2(tau, __int_as_float(minpos));
 }
 
+// Geometry of one kernel flavour.
+//   PAIR = 0: one CTA per 128 queries, the CTA streams whole 128-row gallery tiles.
+//   PAIR = 1: a 2-CTA cluster (tcgen05 cta_group::2) owns 256 queries; each CTA holds its own 128 query
+//             rows in TMEM and streams only HALF of every gallery tile (64 rows); the leader CTA issues
+//             M=256 MMAs that read both halves.  L2 -> SM operand traffic per flop is halved.
+template <int VARIANT, int PAIR>
+struct K3Geom {
+  static constexpr int BOX_N = PAIR ? K3_TILE_N / 2 : K3_TILE_N;   // gallery rows this CTA loads per tile
+  static constexpr int B_KB_BYTES = BOX_N * 128;
+  static constexpr int A_KB_BYTES = VARIANT == 1 ? K3_TILE_M * 128 : 0;
+  static constexpr int KBS = PAIR ? 4 : 2;                         // k-blocks per pipeline stage
+  static constexpr int STAGE_BYTES = KBS * (B_KB_BYTES + A_KB_BYTES);
+  static constexpr int Q_PER_UNIT = PAIR ? 2 * K3_TILE_M : K3_TILE_M;
+  static constexpr uint32_t EPI_ARRIVALS = PAIR ? 256 : 128;
+};
+
+// Issues the MMAs of one full pipeline stage as straight-line code: per MMA one uniform add for the
+// A address / descriptor and one for the B descriptor.
+template <int VARIANT, int PAIR>
+__device__ __forceinline__ void issue_full_stage(uint32_t d_tmem, uint32_t a_tmem0, uint64_t adesc, uint64_t bdesc,
+                                                 uint32_t idesc, uint32_t first_accumulate) {
+  using G = K3Geom<VARIANT, PAIR>;
+#pragma unroll
+  for (int j = 0; j < G::KBS; ++j) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t accumulate = (j == 0 && kk == 0) ? first_accumulate : 1u;
+      const uint64_t bd = bdesc + (uint64_t)(j * (G::B_KB_BYTES >> 4) + kk * 2);
+      const uint32_t at = a_tmem0 + (uint32_t)((j * 4 + kk) * 8);
+      if (PAIR) {
+        mma_f16_ts_pair(d_tmem, at, bd, idesc, accumulate);
+      } else if (VARIANT == 0) {
+        mma_f16_ts(d_tmem, at, bd, idesc, accumulate);
+      } else {
+        mma_f16_ss(d_tmem, adesc + (uint64_t)(j * (G::A_KB_BYTES >> 4) + kk * 2), bd, idesc, accumulate);
+      }
+    }
+  }
+}
+
+template <int VARIANT, int PAIR>
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __grid_constant__ K3Params P) {
+  using G = K3Geom<VARIANT, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled operand tiles
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -115,61 +158,76 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int stage_bytes = K3_KB_PER_STAGE * (B_KBLOCK_BYTES + (P.variant == 1 ? A_KBLOCK_BYTES : 0));
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader of the pair
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+
   uint8_t* stage_base = smem;
-  float* sc = reinterpret_cast<float*>(smem + (size_t)P.num_stages * stage_bytes);
+  float* sc = reinterpret_cast<float*>(smem + (size_t)P.num_stages * G::STAGE_BYTES);
   uint32_t* ix = reinterpret_cast<uint32_t*>(sc + K3_TILE_M * P.kc);
   K3Barriers* bars = reinterpret_cast<K3Barriers*>(ix + K3_TILE_M * P.kc);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.tmap_b);
-    if (P.variant == 1) tma_prefetch_desc(&P.tmap_a);
+    if (VARIANT == 1) tma_prefetch_desc(&P.tmap_a);
     for (int s = 0; s < P.num_stages; ++s) {
-      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->full[s], PAIR ? 2 : 1);
       mbar_init(&bars->empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars->tfull[b], 1);
-      mbar_init(&bars->tempty[b], 128);
+      mbar_init(&bars->tempty[b], G::EPI_ARRIVALS);
     }
-    mbar_init(&bars->a_ready, 128);
+    mbar_init(&bars->a_ready, G::EPI_ARRIVALS);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(&bars->tmem_base, TMEM_COLS);
+    else tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   const int num_units = P.slices * P.num_qt;
-  const int num_chunks = (P.num_kb + K3_KB_PER_STAGE - 1) / K3_KB_PER_STAGE;
+  const int num_chunks = (P.num_kb + G::KBS - 1) / G::KBS;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     // The whole warp walks the schedule (warp-uniform control flow); one elected lane issues.
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t kb_bytes = B_KBLOCK_BYTES + (P.variant == 1 ? A_KBLOCK_BYTES : 0);
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    for (int u = worker; u < num_units; u += num_workers) {
       const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
       const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
       const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
       for (int t = t0; t < t1; ++t) {
         for (int ch = 0; ch < num_chunks; ++ch) {
-          const int kb0 = ch * K3_KB_PER_STAGE;
-          const int nkb = min(K3_KB_PER_STAGE, P.num_kb - kb0);
+          const int kb0 = ch * G::KBS;
+          const int nkb = min(G::KBS, P.num_kb - kb0);
           mbar_wait(&bars->empty[stage], phase ^ 1u, 1);
           if (elect_one()) {
-            mbar_arrive_expect_tx(&bars->full[stage], nkb * kb_bytes);
-            uint8_t* sb = stage_base + (size_t)stage * stage_bytes;
-            for (int j = 0; j < nkb; ++j)
-              tma_load_2d(sb + j * B_KBLOCK_BYTES, &P.tmap_b, &bars->full[stage], (kb0 + j) * K3_KBLOCK,
-                          t * K3_TILE_N);
-            if (P.variant == 1) {
-              uint8_t* sa = sb + K3_KB_PER_STAGE * B_KBLOCK_BYTES;
+            uint8_t* sb = stage_base + (size_t)stage * G::STAGE_BYTES;
+            if (PAIR) {
+              // both halves report to the leader's barrier, which expects the bytes of the whole tile
+              const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[stage]), 0);
+              if (rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * nkb * G::B_KB_BYTES);
+              else mbar_arrive_cluster(full_leader);
               for (int j = 0; j < nkb; ++j)
-                tma_load_2d(sa + j * A_KBLOCK_BYTES, &P.tmap_a, &bars->full[stage], (kb0 + j) * K3_KBLOCK,
-                            qt * K3_TILE_M);
+                tma_load_2d_pair(sb + j * G::B_KB_BYTES, &P.tmap_b, full_leader, (kb0 + j) * K3_KBLOCK,
+                                 t * K3_TILE_N + (int)rank * G::BOX_N);
+            } else {
+              mbar_arrive_expect_tx(&bars->full[stage], nkb * (G::B_KB_BYTES + G::A_KB_BYTES));
+              for (int j = 0; j < nkb; ++j)
+                tma_load_2d(sb + j * G::B_KB_BYTES, &P.tmap_b, &bars->full[stage], (kb0 + j) * K3_KBLOCK,
+                            t * K3_TILE_N);
+              if (VARIANT == 1) {
+                uint8_t* sa = sb + G::KBS * G::B_KB_BYTES;
+                for (int j = 0; j < nkb; ++j)
+                  tma_load_2d(sa + j * G::A_KB_BYTES, &P.tmap_a, &bars->full[stage], (kb0 + j) * K3_KBLOCK,
+                              qt * K3_TILE_M);
+              }
             }
           }
           __syncwarp();
@@ -180,59 +238,66 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     // Warp-converged loop; elect.sync picks the issuing lane so descriptors stay in uniform registers.
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0, unit_par = 0;
-    const uint32_t tmem_b = __shfl_sync(FULL_MASK, tmem_base, 0);
-    const uint32_t smem_stage0 = __shfl_sync(FULL_MASK, smem_u32(stage_base), 0);
-    const uint64_t desc_hi = make_smem_desc_sw128(0);  // everything except the start address
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-      const int slice = u / P.num_qt;
-      const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
-      const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
-      if (P.variant == 0) {
-        mbar_wait(&bars->a_ready, unit_par, 2);
-        unit_par ^= 1u;
-        tc_fence_after();
-      }
-      for (int t = t0; t < t1; ++t) {
-        mbar_wait(&bars->tempty[acc], acc_phase ^ 1u, 3);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_b + ACC_COL0 + acc * K3_TILE_N;
-        for (int ch = 0; ch < num_chunks; ++ch) {
-          const int kb0 = ch * K3_KB_PER_STAGE;
-          const int nkb = min(K3_KB_PER_STAGE, P.num_kb - kb0);
-          mbar_wait(&bars->full[stage], phase, 4);
+    // In a CTA pair only the leader issues (its MMAs drive both SMs).
+    if (rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0, unit_par = 0;
+      const uint32_t tmem_b = __shfl_sync(FULL_MASK, tmem_base, 0);
+      const uint32_t smem_stage0 = __shfl_sync(FULL_MASK, smem_u32(stage_base), 0);
+      const uint64_t desc_hi = make_smem_desc_sw128(0);  // everything except the start address
+      for (int u = worker; u < num_units; u += num_workers) {
+        const int slice = u / P.num_qt;
+        const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
+        const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
+        if (VARIANT == 0) {
+          mbar_wait(&bars->a_ready, unit_par, 2);
+          unit_par ^= 1u;
           tc_fence_after();
-          if (elect_one()) {
-            const uint32_t sb = smem_stage0 + (uint32_t)stage * (uint32_t)stage_bytes;
-            const uint32_t sa = sb + K3_KB_PER_STAGE * B_KBLOCK_BYTES;
-            for (int j = 0; j < nkb; ++j) {
-              const uint64_t bdesc0 = desc_hi | (uint64_t)(((sb + j * B_KBLOCK_BYTES) >> 4) & 0x3fffu);
-              const uint64_t adesc0 = desc_hi | (uint64_t)(((sa + j * A_KBLOCK_BYTES) >> 4) & 0x3fffu);
-              const int k16 = (kb0 + j) * 4;  // index of the first K=16 step of this k-block
-              if (P.variant == 0) {
-                const uint32_t a_tmem = tmem_b + (uint32_t)k16 * 8u;
-                mma_f16_ts(d_tmem, a_tmem, bdesc0, P.idesc, k16 > 0 ? 1u : 0u);
-                mma_f16_ts(d_tmem, a_tmem + 8u, bdesc0 + 2u, P.idesc, 1u);
-                mma_f16_ts(d_tmem, a_tmem + 16u, bdesc0 + 4u, P.idesc, 1u);
-                mma_f16_ts(d_tmem, a_tmem + 24u, bdesc0 + 6u, P.idesc, 1u);
+        }
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&bars->tempty[acc], acc_phase ^ 1u, 3);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_b + (uint32_t)(P.acc_col0 + acc * K3_TILE_N);
+          for (int ch = 0; ch < num_chunks; ++ch) {
+            const int kb0 = ch * G::KBS;
+            const int nkb = min(G::KBS, P.num_kb - kb0);
+            mbar_wait(&bars->full[stage], phase, 4);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sb = smem_stage0 + (uint32_t)stage * (uint32_t)G::STAGE_BYTES;
+              const uint32_t sa = sb + G::KBS * G::B_KB_BYTES;
+              const uint64_t bdesc = desc_hi | (uint64_t)((sb >> 4) & 0x3fffu);
+              const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3fffu);
+              const uint32_t a_tmem0 = tmem_b + (uint32_t)kb0 * 32u;   // 4 K=16 steps x 8 columns per k-block
+              if (nkb == G::KBS) {
+                issue_full_stage<VARIANT, PAIR>(d_tmem, a_tmem0, adesc, bdesc, P.idesc, ch > 0 ? 1u : 0u);
               } else {
-                mma_f16_ss(d_tmem, adesc0, bdesc0, P.idesc, k16 > 0 ? 1u : 0u);
-                mma_f16_ss(d_tmem, adesc0 + 2u, bdesc0 + 2u, P.idesc, 1u);
-                mma_f16_ss(d_tmem, adesc0 + 4u, bdesc0 + 4u, P.idesc, 1u);
-                mma_f16_ss(d_tmem, adesc0 + 6u, bdesc0 + 6u, P.idesc, 1u);
+                for (int j = 0; j < nkb; ++j) {
+                  for (int kk = 0; kk < 4; ++kk) {
+                    const uint32_t accumulate = (ch > 0 || j > 0 || kk > 0) ? 1u : 0u;
+                    const uint64_t bd = bdesc + (uint64_t)(j * (G::B_KB_BYTES >> 4) + kk * 2);
+                    const uint32_t at = a_tmem0 + (uint32_t)((j * 4 + kk) * 8);
+                    if (PAIR) mma_f16_ts_pair(d_tmem, at, bd, P.idesc, accumulate);
+                    else if (VARIANT == 0) mma_f16_ts(d_tmem, at, bd, P.idesc, accumulate);
+                    else mma_f16_ss(d_tmem, adesc + (uint64_t)(j * (G::A_KB_BYTES >> 4) + kk * 2), bd, P.idesc, accumulate);
+                  }
+                }
+              }
+              if (PAIR) {
+                mma_commit_pair(&bars->empty[stage], 3);
+                if (ch == num_chunks - 1) mma_commit_pair(&bars->tfull[acc], 3);
+              } else {
+                mma_commit(&bars->empty[stage]);
+                if (ch == num_chunks - 1) mma_commit(&bars->tfull[acc]);
               }
             }
-            mma_commit(&bars->empty[stage]);
-            if (ch == num_chunks - 1) mma_commit(&bars->tfull[acc]);
+            __syncwarp();
+            if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
           }
-          __syncwarp();
-          if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
+          if (++acc == P.num_acc) { acc = 0; acc_phase ^= 1u; }
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
       }
     }
   } else {
@@ -244,14 +309,19 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
     const int kc = P.kc;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // barriers the MMA issuer waits on live in the leader CTA
+    const uint32_t a_ready_leader = PAIR ? mapa_u32(smem_u32(&bars->a_ready), 0) : 0u;
+    const uint32_t tempty_leader0 = PAIR ? mapa_u32(smem_u32(&bars->tempty[0]), 0) : 0u;
+    const uint32_t tempty_leader1 = PAIR ? mapa_u32(smem_u32(&bars->tempty[1]), 0) : 0u;
 
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    for (int u = worker; u < num_units; u += num_workers) {
       const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
       const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
       const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
-      const int64_t qg = (int64_t)qt * K3_TILE_M + row;
+      const int64_t q_unit0 = (int64_t)qt * G::Q_PER_UNIT + (int64_t)rank * K3_TILE_M;   // first query row of this CTA
+      const int64_t qg = q_unit0 + row;
 
-      if (P.variant == 0) {
+      if (VARIANT == 0) {
         // park this thread's query row in TMEM: lane = row, column c holds elements 2c, 2c+1
         const uint4* src = reinterpret_cast<const uint4*>(P.q16 + qg * P.dp);
         const int n16 = P.dp / 16;
@@ -262,7 +332,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars->a_ready);
+        if (PAIR) mbar_arrive_cluster(a_ready_leader); else mbar_arrive(&bars->a_ready);
       }
       // reset the candidate lists of this warp's 32 rows
       for (int r = 0; r < 32; ++r)
@@ -277,54 +347,59 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&bars->tfull[acc], acc_phase, 5);
         tc_fence_after();
-        uint32_t raw0[32], raw1[32];
-        const uint32_t taddr = tmem_base + lane_addr + ACC_COL0 + acc * K3_TILE_N;
-        tmem_ld_32x32b_x32(taddr, raw0);
-        tmem_ld_32x32b_x32(taddr + 32, raw1);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&bars->tempty[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
-
-        float v[64];
+        float v[K3_TILE_N];
+        {
+          const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(P.acc_col0 + acc * K3_TILE_N);
+          uint32_t raw[4][32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          v[c] = __uint_as_float(raw0[c]);
-          v[32 + c] = __uint_as_float(raw1[c]);
+          for (int h = 0; h < 4; ++h) tmem_ld_32x32b_x32(taddr + 32u * h, raw[h]);
+          tmem_ld_wait();
+          tc_fence_before();
+          // TMEM tile is in registers: hand it back to the MMA issuer
+          if (PAIR) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+          else mbar_arrive(&bars->tempty[acc]);
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[h * 32 + c] = __uint_as_float(raw[h][c]);
         }
+        if (++acc == P.num_acc) { acc = 0; acc_phase ^= 1u; }
         const int64_t col0 = (int64_t)t * K3_TILE_N;
 
         if (P.dump != nullptr && qg < P.q_valid) {
 #pragma unroll
-          for (int c = 0; c < 64; ++c)
+          for (int c = 0; c < K3_TILE_N; ++c)
             if (col0 + c < P.n_rows) P.dump[qg * P.dump_ld + col0 + c] = v[c];
         }
 
         if (col0 + K3_TILE_N > P.n_rows || P.row_mask != nullptr) {
-          uint64_t allow = ~0ull;
-          if (col0 + K3_TILE_N > P.n_rows) {
-            const int valid = (int)(P.n_rows - col0);
-            allow = valid <= 0 ? 0ull : (valid >= 64 ? ~0ull : ((1ull << valid) - 1ull));
-          }
-          if (P.row_mask != nullptr) {
-            const int64_t w0 = col0 >> 5;
-            const int64_t nwords = (P.n_rows + 31) >> 5;
-            const uint64_t lo = w0 < nwords ? P.row_mask[w0] : 0u;
-            const uint64_t hi = (w0 + 1) < nwords ? P.row_mask[w0 + 1] : 0u;
-            allow &= (lo | (hi << 32));
-          }
 #pragma unroll
-          for (int c = 0; c < 64; ++c)
-            if (!((allow >> c) & 1ull)) v[c] = -INFINITY;
+          for (int half = 0; half < 2; ++half) {
+            const int64_t c0 = col0 + 64 * half;
+            uint64_t allow = ~0ull;
+            if (c0 + 64 > P.n_rows) {
+              const int64_t valid = P.n_rows - c0;
+              allow = valid <= 0 ? 0ull : (valid >= 64 ? ~0ull : ((1ull << valid) - 1ull));
+            }
+            if (P.row_mask != nullptr) {
+              const int64_t w0 = c0 >> 5;
+              const int64_t nwords = (P.n_rows + 31) >> 5;
+              const uint64_t lo = w0 < nwords ? P.row_mask[w0] : 0u;
+              const uint64_t hi = (w0 + 1) < nwords ? P.row_mask[w0 + 1] : 0u;
+              allow &= (lo | (hi << 32));
+            }
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (!((allow >> c) & 1ull)) v[64 * half + c] = -INFINITY;
+          }
         }
 
         float m = v[0];
 #pragma unroll
-        for (int c = 1; c < 64; ++c) m = fmaxf(m, v[c]);
+        for (int c = 1; c < K3_TILE_N; ++c) m = fmaxf(m, v[c]);
         if (__any_sync(FULL_MASK, m > tau)) {
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
+          for (int c = 0; c < K3_TILE_N; ++c) {
             const uint32_t ball = __ballot_sync(FULL_MASK, v[c] > tau);
             if (ball) {
               const float2 r = k3_insert(v[c], (uint32_t)(col0 + c), ball, tau, minpos, sc, ix, wrow0, kc, lane);
@@ -338,7 +413,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
       // unit done: publish this warp's 32 candidate lists
       __syncwarp();
       for (int r = 0; r < 32; ++r) {
-        const int64_t q = (int64_t)qt * K3_TILE_M + wrow0 + r;
+        const int64_t q = q_unit0 + wrow0 + r;
         if (q < P.q_valid) {
           const size_t base = ((size_t)slice * P.q_pad + q) * kc;
           for (int j = lane; j < kc; j += 32) {
@@ -352,10 +427,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -433,15 +509,23 @@ int make_tmap_2d_sw128(CUtensorMap* out, const void* base, int64_t rows, int dp,
   return RBOD_OK;
 }
 
-size_t k3_smem_bytes(int variant, int kc, int num_stages) {
-  const size_t stage = (size_t)K3_KB_PER_STAGE * (B_KBLOCK_BYTES + (variant == 1 ? A_KBLOCK_BYTES : 0));
-  return 1024 + (size_t)num_stages * stage + (size_t)K3_TILE_M * kc * 8 + sizeof(K3Barriers);
+static size_t k3_stage_bytes(int variant) {
+  return variant == 1 ? (size_t)K3Geom<1, 0>::STAGE_BYTES
+                      : (variant == 2 ? (size_t)K3Geom<0, 1>::STAGE_BYTES : (size_t)K3Geom<0, 0>::STAGE_BYTES);
 }
+
+size_t k3_smem_bytes(int variant, int kc, int num_stages) {
+  return 1024 + (size_t)num_stages * k3_stage_bytes(variant) + (size_t)K3_TILE_M * kc * 8 + sizeof(K3Barriers);
+}
+
+int k3_box_rows(int variant) { return variant == 2 ? K3Geom<0, 1>::BOX_N : K3_TILE_N; }
 
 int k3_configure(int device) {
   int optin = 0;
   RBOD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   return optin;
 }
 
@@ -467,10 +551,32 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.kc = L.kc;
   P.num_stages = L.num_stages;
   P.variant = L.variant;
-  P.idesc = make_idesc_f16(L.a_fmt, L.b_fmt, K3_TILE_M, K3_TILE_N);
+  P.num_acc = (L.variant == 1 || L.dp / 2 + 2 * K3_TILE_N <= TMEM_COLS) ? 2 : 1;
+  P.acc_col0 = TMEM_COLS - P.num_acc * K3_TILE_N;
+  P.idesc = make_idesc_f16(L.a_fmt, L.b_fmt, L.variant == 2 ? 2 * K3_TILE_M : K3_TILE_M, K3_TILE_N);
   if (L.num_stages < 1 || L.num_stages > MAX_STAGES)
     return set_error(RBOD_E_INVAL, "k3: bad stage count %d", L.num_stages);
-  k3_cosine_topk_kernel<<<L.grid, K3_THREADS, L.smem_bytes, st>>>(P);
+  if (L.variant == 2) {
+    if (L.grid % 2) return set_error(RBOD_E_INVAL, "k3: pair kernel needs an even grid");
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)L.grid);
+    cfg.blockDim = dim3(K3_THREADS);
+    cfg.dynamicSmemBytes = L.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1>, P));
+  } else if (L.variant == 0) {
+    k3_cosine_topk_kernel<0, 0><<<L.grid, K3_THREADS, L.smem_bytes, st>>>(P);
+  } else {
+    k3_cosine_topk_kernel<1, 0><<<L.grid, K3_THREADS, L.smem_bytes, st>>>(P);
+  }
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

@@ -160,8 +160,10 @@ static int plan_search(const rbod_gallery* g, int64_t Q, int k, int variant, int
     return set_error(RBOD_E_UNSUPPORTED, "search: k=%d (+slack) needs %d candidates per query, max is %d", k, kc,
                      K3_MAX_KC);
   P->kc = kc;
-  P->q_pad = (Q + K3_TILE_M - 1) / K3_TILE_M * K3_TILE_M;
-  P->num_qt = (int)(P->q_pad / K3_TILE_M);
+  const int q_per_unit = variant == 2 ? 2 * K3_TILE_M : K3_TILE_M;   // a CTA pair owns 256 queries
+  const int workers = variant == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
+  P->q_pad = (Q + q_per_unit - 1) / q_per_unit * q_per_unit;
+  P->num_qt = (int)(P->q_pad / q_per_unit);
   P->tiles_total = (int)((g->rows + K3_TILE_N - 1) / K3_TILE_N);
   // slices: balance (units per CTA) x (tiles per unit); fewer slices on ties (less merge work)
   const int max_slices = std::max(1, std::min({P->tiles_total, 8192 / kc, 64}));
@@ -169,14 +171,14 @@ static int plan_search(const rbod_gallery* g, int64_t Q, int k, int variant, int
   int best_s = 1;
   for (int s = 1; s <= max_slices; ++s) {
     const int64_t units = (int64_t)s * P->num_qt;
-    const int64_t per_cta = (units + g->num_sms - 1) / g->num_sms;
+    const int64_t per_cta = (units + workers - 1) / workers;
     const double tiles_per_unit = std::ceil((double)P->tiles_total / s);
     const double cost = (double)per_cta * (tiles_per_unit + 24.0);  // +24 ~ per-unit setup in tile units
     if (cost < best * 0.97) { best = cost; best_s = s; }
   }
   P->slices = best_s;
   const int64_t units = (int64_t)P->slices * P->num_qt;
-  P->grid = (int)std::min<int64_t>(units, g->num_sms);
+  P->grid = (int)std::min<int64_t>(units, workers) * (variant == 2 ? 2 : 1);
   int stages = 8;
   while (stages > 1 && k3_smem_bytes(variant, kc, stages) > (size_t)smem_optin) --stages;
   if (k3_smem_bytes(variant, kc, stages) > (size_t)smem_optin)
@@ -312,7 +314,7 @@ int rbod_truncate(rbod_gallery* g, int64_t rows) {
 int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
   if (!g || !key) return set_error(RBOD_E_INVAL, "rbod_set_option: NULL argument");
   if (!strcmp(key, "k3_variant")) {
-    if (value != 0 && value != 1) return set_error(RBOD_E_INVAL, "k3_variant must be 0 or 1");
+    if (value < 0 || value > 2) return set_error(RBOD_E_INVAL, "k3_variant must be 0, 1 or 2");
     g->k3_variant = (int)value;
   } else if (!strcmp(key, "slack")) {
     if (value < -1 || value > 118) return set_error(RBOD_E_INVAL, "slack must be in [-1, 118]");
@@ -494,7 +496,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint32_
                   int64_t dump_ld, cudaStream_t st) {
   K3Launch L;
   memset(&L, 0, sizeof(L));
-  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, g->rows16, g->rows, g->dp, K3_TILE_N));
+  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, g->rows16, g->rows, g->dp, k3_box_rows(g->k3_variant)));
   RBOD_TRY(make_tmap_2d_sw128(&L.tmap_a, g->q16.p, P.q_pad, g->dp, K3_TILE_M));
   L.q16 = g->q16.as<uint16_t>();
   L.dp = g->dp;

@@ -46,15 +46,14 @@ struct PinBuf {
 
 // ---- K3 geometry ------------------------------------------------------------------------
 constexpr int K3_TILE_M = 128;       // queries per CTA (TMEM lanes)
-constexpr int K3_TILE_N = 64;        // gallery rows per accumulator buffer
+constexpr int K3_TILE_N = 128;       // gallery rows per accumulator buffer (one tcgen05.mma N)
 constexpr int K3_KBLOCK = 64;        // 16-bit elements per 128-byte swizzle row
-constexpr int K3_KB_PER_STAGE = 4;   // k-blocks per pipeline stage
 constexpr int K3_MAX_DP = 768;       // A operand must fit 384 TMEM columns
 constexpr int K3_THREADS = 192;      // warp0 TMA, warp1 MMA, warps 2-5 epilogue
 constexpr int K3_MAX_KC = 128;
 
 struct K3Launch {
-  CUtensorMap tmap_b;     // gallery [rows, dp] 16-bit, box {64, 64}, SWIZZLE_128B
+  CUtensorMap tmap_b;     // gallery [rows, dp] 16-bit, box {64, 128}, SWIZZLE_128B
   CUtensorMap tmap_a;     // queries [Qpad, dp] 16-bit, box {64, 128} (variant 1 only)
   const uint16_t* q16;    // [Qpad, dp]
   int dp;
@@ -66,7 +65,7 @@ struct K3Launch {
   int64_t q_pad;
   int kc;                 // candidates per (query, slice); multiple of 32
   int num_stages;
-  int variant;            // 0 = A in TMEM, 1 = A streamed through smem
+  int variant;            // 0 = A in TMEM, 1 = A streamed through smem, 2 = A in TMEM + CTA pairs (cta_group::2)
   int a_fmt, b_fmt;       // 0 = f16, 1 = bf16
   float* part_score;      // [slices][q_pad][kc]
   uint32_t* part_idx;     // [slices][q_pad][kc]
@@ -93,6 +92,7 @@ int launch_segment_mean(const float* master32, const uint16_t* rows16, int kind1
 // K3
 int k3_configure(int device);
 size_t k3_smem_bytes(int variant, int kc, int num_stages);
+int k3_box_rows(int variant);   // gallery rows per TMA box (64 for the CTA-pair kernel)
 int launch_k3(const K3Launch& L, cudaStream_t st);
 // query preparation: normalise, round to 16 bit, per-query error radius and |q|^2
 int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16, uint16_t* q16,

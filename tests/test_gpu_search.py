@@ -25,7 +25,7 @@ def _mk(G, n, dim, dtype, seed, clustered=False):
     return g, g.get_rows(np.arange(n)), x
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("dtype,n,dim,Q", [("bf16", 1000, 768, 130), ("f16", 200, 512, 5), ("f32", 513, 512, 128),
                                            ("bf16", 300, 64, 7), ("bf16", 4097, 320, 260)])
 def test_raw_tensor_core_scores(G, variant, dtype, n, dim, Q):
@@ -57,9 +57,11 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("dtype,n,dim,Q,k,clustered", CASES)
-def test_search_matches_fp64_brute_force(G, dtype, n, dim, Q, k, clustered):
+def test_search_matches_fp64_brute_force(G, variant, dtype, n, dim, Q, k, clustered):
     g, stored, x = _mk(G, n, dim, dtype, seed=n + k, clustered=clustered)
+    g.set_option("k3_variant", variant)
     rng = np.random.default_rng(k)
     q = rng.standard_normal((Q, dim)).astype(np.float32)
     near = rng.integers(0, n, Q // 2)
