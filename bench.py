@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=-1, help="override the K3 kernel variant (debug)")
+    ap.add_argument("--opt", action="append", default=[], help="library tunable key=value (debug), repeatable")
     return ap.parse_args()
 
 
@@ -211,6 +212,9 @@ def run_b200(a):
     g.set_option("time_k3", 1)
     if a.variant >= 0:
         g.set_option("k3_variant", a.variant)
+    for kv in a.opt:
+        key, _, val = kv.partition("=")
+        g.set_option(key, int(val))
 
     qgen = torch.Generator(dev).manual_seed(99)          # same queries on every rank
     q_dev = torch.randn(a.queries, a.dim, device=dev, generator=qgen)

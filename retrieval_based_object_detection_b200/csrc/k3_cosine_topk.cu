@@ -38,6 +38,7 @@ namespace {
 
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
+constexpr int A_TILE_KB_BYTES = K3_TILE_M * 128;   // one k-block of a 128-row query tile in smem: 16 KB
 
 struct alignas(64) K3Params {
   CUtensorMap tmap_b;
@@ -59,6 +60,12 @@ struct alignas(64) K3Params {
   int kc;
   int num_stages;
   int variant;
+  int* sync_counters;   // [groups][sync_windows] issue-progress counters (nullptr = no throttle)
+  int sync_window;      // tiles per progress window
+  int sync_lead;        // windows a CTA may run ahead of the slowest CTA of its group
+  int sync_span;        // groups per slice (a slice's units may fall into several rounds)
+  int sync_windows;     // counters per group
+  int a_tmem_kb;   // k-blocks of the query tile held in TMEM; the rest sits in shared memory (resident)
   int num_acc;     // accumulator buffers (1 or 2)
   int acc_col0;    // first accumulator column in TMEM
   uint32_t idesc;
@@ -117,7 +124,7 @@ template <int VARIANT, int PAIR>
 struct K3Geom {
   static constexpr int BOX_N = PAIR ? K3_TILE_N / 2 : K3_TILE_N;   // gallery rows this CTA loads per tile
   static constexpr int B_KB_BYTES = BOX_N * 128;
-  static constexpr int A_KB_BYTES = VARIANT == 1 ? K3_TILE_M * 128 : 0;
+  static constexpr int A_KB_BYTES = VARIANT == 1 ? A_TILE_KB_BYTES : 0;   // streamed A (variant 1 only)
   static constexpr int KBS = PAIR ? 4 : 2;                         // k-blocks per pipeline stage
   static constexpr int STAGE_BYTES = KBS * (B_KB_BYTES + A_KB_BYTES);
   static constexpr int Q_PER_UNIT = PAIR ? 2 * K3_TILE_M : K3_TILE_M;
@@ -125,8 +132,9 @@ struct K3Geom {
 };
 
 // Issues the MMAs of one full pipeline stage as straight-line code: per MMA one uniform add for the
-// A address / descriptor and one for the B descriptor.
-template <int VARIANT, int PAIR>
+// A address / descriptor and one for the B descriptor.  A_SMEM: the A operand of this stage comes from
+// shared memory (streamed tile in variant 1, resident tail of the query tile otherwise).
+template <int VARIANT, int PAIR, int A_SMEM>
 __device__ __forceinline__ void issue_full_stage(uint32_t d_tmem, uint32_t a_tmem0, uint64_t adesc, uint64_t bdesc,
                                                  uint32_t idesc, uint32_t first_accumulate) {
   using G = K3Geom<VARIANT, PAIR>;
@@ -137,12 +145,13 @@ __device__ __forceinline__ void issue_full_stage(uint32_t d_tmem, uint32_t a_tme
       const uint32_t accumulate = (j == 0 && kk == 0) ? first_accumulate : 1u;
       const uint64_t bd = bdesc + (uint64_t)(j * (G::B_KB_BYTES >> 4) + kk * 2);
       const uint32_t at = a_tmem0 + (uint32_t)((j * 4 + kk) * 8);
-      if (PAIR) {
-        mma_f16_ts_pair(d_tmem, at, bd, idesc, accumulate);
-      } else if (VARIANT == 0) {
-        mma_f16_ts(d_tmem, at, bd, idesc, accumulate);
+      const uint64_t ad = adesc + (uint64_t)(j * (A_TILE_KB_BYTES >> 4) + kk * 2);
+      if (A_SMEM) {
+        if (PAIR) mma_f16_ss_pair(d_tmem, ad, bd, idesc, accumulate);
+        else mma_f16_ss(d_tmem, ad, bd, idesc, accumulate);
       } else {
-        mma_f16_ss(d_tmem, adesc + (uint64_t)(j * (G::A_KB_BYTES >> 4) + kk * 2), bd, idesc, accumulate);
+        if (PAIR) mma_f16_ts_pair(d_tmem, at, bd, idesc, accumulate);
+        else mma_f16_ts(d_tmem, at, bd, idesc, accumulate);
       }
     }
   }
@@ -163,7 +172,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
   const int num_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   uint8_t* stage_base = smem;
-  float* sc = reinterpret_cast<float*>(smem + (size_t)P.num_stages * G::STAGE_BYTES);
+  uint8_t* a_tail = smem + (size_t)P.num_stages * G::STAGE_BYTES;       // resident query-tile tail (k-blocks >= a_tmem_kb)
+  const int tail_kb = VARIANT == 1 ? 0 : (P.num_kb - P.a_tmem_kb);
+  float* sc = reinterpret_cast<float*>(a_tail + (size_t)tail_kb * A_TILE_KB_BYTES);
   uint32_t* ix = reinterpret_cast<uint32_t*>(sc + K3_TILE_M * P.kc);
   K3Barriers* bars = reinterpret_cast<K3Barriers*>(ix + K3_TILE_M * P.kc);
 
@@ -202,7 +213,45 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
       const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
       const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
       const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
+      // L2 sharing throttle: the CTAs that stream this slice in this round form a group; nobody
+      // issues window w before every member has issued window w - lead.  That keeps the group's
+      // working set (lead + 1 windows) hot in L2, so each gallery tile is fetched from HBM once per
+      // group instead of once per CTA.  Dependencies only point to the same or earlier rounds.
+      int* cnt = nullptr;
+      int gsize = 0;
+      if (P.sync_counters != nullptr && rank == 0) {
+        const int round = u / num_workers;
+        const int first_round = (slice * P.num_qt) / num_workers;
+        const int lo = max(slice * P.num_qt, round * num_workers);
+        const int hi = min((slice + 1) * P.num_qt, (round + 1) * num_workers);
+        gsize = hi - lo;
+        cnt = P.sync_counters + ((size_t)slice * P.sync_span + (round - first_round)) * P.sync_windows;
+      }
       for (int t = t0; t < t1; ++t) {
+        if (cnt != nullptr && gsize > 1 && (t - t0) % P.sync_window == 0) {
+          const int w = (t - t0) / P.sync_window;
+          if (elect_one()) {
+            if (w > 0) {
+              __threadfence();
+              atomicAdd(cnt + (w - 1), 1);
+            }
+            if (w >= P.sync_lead) {
+              const volatile int* flag = cnt + (w - P.sync_lead);
+              if (*flag < gsize) {
+                const uint64_t w0 = global_timer_ns();
+                while (*flag < gsize) {
+                  __nanosleep(128);
+                  if (global_timer_ns() - w0 > 4000000000ull) {
+                    printf("rbod: L2 throttle watchdog: block %d unit %d window %d count %d/%d\n", (int)blockIdx.x, u,
+                           w, *flag, gsize);
+                    __trap();
+                  }
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
         for (int ch = 0; ch < num_chunks; ++ch) {
           const int kb0 = ch * G::KBS;
           const int nkb = min(G::KBS, P.num_kb - kb0);
@@ -246,6 +295,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
       uint32_t acc_phase = 0, unit_par = 0;
       const uint32_t tmem_b = __shfl_sync(FULL_MASK, tmem_base, 0);
       const uint32_t smem_stage0 = __shfl_sync(FULL_MASK, smem_u32(stage_base), 0);
+      const uint32_t smem_tail0 = __shfl_sync(FULL_MASK, smem_u32(a_tail), 0);
       const uint64_t desc_hi = make_smem_desc_sw128(0);  // everything except the start address
       for (int u = worker; u < num_units; u += num_workers) {
         const int slice = u / P.num_qt;
@@ -267,21 +317,32 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
             tc_fence_after();
             if (elect_one()) {
               const uint32_t sb = smem_stage0 + (uint32_t)stage * (uint32_t)G::STAGE_BYTES;
-              const uint32_t sa = sb + G::KBS * G::B_KB_BYTES;
               const uint64_t bdesc = desc_hi | (uint64_t)((sb >> 4) & 0x3fffu);
+              const uint32_t first = ch > 0 ? 1u : 0u;
+              // A operand of this stage: streamed tile (variant 1), TMEM columns, or the smem-resident tail
+              const bool a_smem = VARIANT == 1 || kb0 >= P.a_tmem_kb;
+              const uint32_t sa = VARIANT == 1 ? sb + G::KBS * G::B_KB_BYTES
+                                               : smem_tail0 + (uint32_t)(kb0 - P.a_tmem_kb) * (uint32_t)A_TILE_KB_BYTES;
               const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3fffu);
               const uint32_t a_tmem0 = tmem_b + (uint32_t)kb0 * 32u;   // 4 K=16 steps x 8 columns per k-block
               if (nkb == G::KBS) {
-                issue_full_stage<VARIANT, PAIR>(d_tmem, a_tmem0, adesc, bdesc, P.idesc, ch > 0 ? 1u : 0u);
+                if (a_smem) issue_full_stage<VARIANT, PAIR, 1>(d_tmem, a_tmem0, adesc, bdesc, P.idesc, first);
+                else issue_full_stage<VARIANT, PAIR, 0>(d_tmem, a_tmem0, adesc, bdesc, P.idesc, first);
               } else {
                 for (int j = 0; j < nkb; ++j) {
+                  const bool js = VARIANT == 1 || (kb0 + j) >= P.a_tmem_kb;
                   for (int kk = 0; kk < 4; ++kk) {
                     const uint32_t accumulate = (ch > 0 || j > 0 || kk > 0) ? 1u : 0u;
                     const uint64_t bd = bdesc + (uint64_t)(j * (G::B_KB_BYTES >> 4) + kk * 2);
                     const uint32_t at = a_tmem0 + (uint32_t)((j * 4 + kk) * 8);
-                    if (PAIR) mma_f16_ts_pair(d_tmem, at, bd, P.idesc, accumulate);
-                    else if (VARIANT == 0) mma_f16_ts(d_tmem, at, bd, P.idesc, accumulate);
-                    else mma_f16_ss(d_tmem, adesc + (uint64_t)(j * (G::A_KB_BYTES >> 4) + kk * 2), bd, P.idesc, accumulate);
+                    const uint64_t ad = adesc + (uint64_t)(j * (A_TILE_KB_BYTES >> 4) + kk * 2);
+                    if (js) {
+                      if (PAIR) mma_f16_ss_pair(d_tmem, ad, bd, P.idesc, accumulate);
+                      else mma_f16_ss(d_tmem, ad, bd, P.idesc, accumulate);
+                    } else {
+                      if (PAIR) mma_f16_ts_pair(d_tmem, at, bd, P.idesc, accumulate);
+                      else mma_f16_ts(d_tmem, at, bd, P.idesc, accumulate);
+                    }
                   }
                 }
               }
@@ -322,13 +383,25 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
       const int64_t qg = q_unit0 + row;
 
       if (VARIANT == 0) {
-        // park this thread's query row in TMEM: lane = row, column c holds elements 2c, 2c+1
+        // Park this thread's query row.  K-blocks < a_tmem_kb go to TMEM (lane = row, column c holds
+        // elements 2c, 2c+1); the rest goes to shared memory in the K-major 128B-swizzled layout the MMA
+        // descriptor expects: row r at r*128 B inside its k-block, 16-byte chunk c at position c ^ (r & 7).
         const uint4* src = reinterpret_cast<const uint4*>(P.q16 + qg * P.dp);
-        const int n16 = P.dp / 16;
-        for (int c = 0; c < n16; ++c) {
+        const int n16_tmem = P.a_tmem_kb * 4;
+        for (int c = 0; c < n16_tmem; ++c) {
           const uint4 x0 = __ldg(src + 2 * c), x1 = __ldg(src + 2 * c + 1);
           const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
           tmem_st_32x32b_x8(tmem_base + lane_addr + (uint32_t)c * 8u, r);
+        }
+        if (tail_kb > 0) {
+          for (int kb = 0; kb < tail_kb; ++kb) {
+            uint8_t* dst = a_tail + (size_t)kb * A_TILE_KB_BYTES + row * 128;
+            const uint4* s8 = src + (size_t)(P.a_tmem_kb + kb) * 8;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = __ldg(s8 + c);
+          }
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async proxy
         }
         tmem_st_wait();
         tc_fence_before();
@@ -514,8 +587,37 @@ static size_t k3_stage_bytes(int variant) {
                       : (variant == 2 ? (size_t)K3Geom<0, 1>::STAGE_BYTES : (size_t)K3Geom<0, 0>::STAGE_BYTES);
 }
 
-size_t k3_smem_bytes(int variant, int kc, int num_stages) {
-  return 1024 + (size_t)num_stages * k3_stage_bytes(variant) + (size_t)K3_TILE_M * kc * 8 + sizeof(K3Barriers);
+size_t k3_smem_bytes(int variant, int kc, int num_stages, int tail_kb) {
+  return 1024 + (size_t)num_stages * k3_stage_bytes(variant) + (size_t)tail_kb * A_TILE_KB_BYTES +
+         (size_t)K3_TILE_M * kc * 8 + sizeof(K3Barriers);
+}
+
+// Chooses where the query tile lives and how deep the gallery pipeline is.
+//   dp <= 512            : whole tile in TMEM (<= 256 columns), two accumulator buffers.
+//   dp  > 512, room left : first 8 k-blocks in TMEM, the tail resident in shared memory, two buffers.
+//   dp  > 512, smem short: whole tile in TMEM (384 columns), one accumulator buffer.
+int k3_plan(int variant, int kc, int dp, int smem_optin, int allow_hybrid, int* num_stages, int* a_tmem_kb,
+            size_t* smem_bytes) {
+  const int num_kb = dp / K3_KBLOCK;
+  auto fit = [&](int tail_kb) {
+    int st = MAX_STAGES;
+    while (st > 0 && k3_smem_bytes(variant, kc, st, tail_kb) > (size_t)smem_optin) --st;
+    return st;
+  };
+  int tmem_kb = num_kb, tail = 0;
+  if (variant == 1) {
+    tmem_kb = 0;
+  } else if (num_kb > 8 && allow_hybrid) {
+    if (fit(num_kb - 8) >= 3) { tmem_kb = 8; tail = num_kb - 8; }
+  }
+  const int st = fit(tail);
+  if (st < 1 || (variant != 1 && st < 2))
+    return set_error(RBOD_E_UNSUPPORTED, "search: variant %d with %d candidates per query does not fit shared memory",
+                     variant, kc);
+  *num_stages = st;
+  *a_tmem_kb = tmem_kb;
+  *smem_bytes = k3_smem_bytes(variant, kc, st, tail);
+  return RBOD_OK;
 }
 
 int k3_box_rows(int variant) { return variant == 2 ? K3Geom<0, 1>::BOX_N : K3_TILE_N; }
@@ -551,7 +653,13 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.kc = L.kc;
   P.num_stages = L.num_stages;
   P.variant = L.variant;
-  P.num_acc = (L.variant == 1 || L.dp / 2 + 2 * K3_TILE_N <= TMEM_COLS) ? 2 : 1;
+  P.sync_counters = L.sync_counters;
+  P.sync_window = L.sync_window;
+  P.sync_lead = L.sync_lead;
+  P.sync_span = L.sync_span;
+  P.sync_windows = L.sync_windows;
+  P.a_tmem_kb = L.a_tmem_kb;
+  P.num_acc = (L.variant == 1 || L.a_tmem_kb * 32 + 2 * K3_TILE_N <= TMEM_COLS) ? 2 : 1;
   P.acc_col0 = TMEM_COLS - P.num_acc * K3_TILE_N;
   P.idesc = make_idesc_f16(L.a_fmt, L.b_fmt, L.variant == 2 ? 2 * K3_TILE_M : K3_TILE_M, K3_TILE_N);
   if (L.num_stages < 1 || L.num_stages > MAX_STAGES)

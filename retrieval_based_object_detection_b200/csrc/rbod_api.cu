@@ -147,7 +147,7 @@ static int grow(rbod_gallery* g, int64_t need, cudaStream_t st) {
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct SearchPlan {
-  int kc, slices, grid, num_qt, tiles_total, num_stages;
+  int kc, slices, grid, num_qt, tiles_total, num_stages, a_tmem_kb;
   int64_t q_pad;
   size_t smem;
 };
@@ -179,13 +179,7 @@ static int plan_search(const rbod_gallery* g, int64_t Q, int k, int variant, int
   P->slices = best_s;
   const int64_t units = (int64_t)P->slices * P->num_qt;
   P->grid = (int)std::min<int64_t>(units, workers) * (variant == 2 ? 2 : 1);
-  int stages = 8;
-  while (stages > 1 && k3_smem_bytes(variant, kc, stages) > (size_t)smem_optin) --stages;
-  if (k3_smem_bytes(variant, kc, stages) > (size_t)smem_optin)
-    return set_error(RBOD_E_UNSUPPORTED, "search: variant %d with %d candidates does not fit shared memory",
-                     variant, kc);
-  P->num_stages = stages;
-  P->smem = k3_smem_bytes(variant, kc, stages);
+  RBOD_TRY(k3_plan(variant, kc, g->dp, smem_optin, g->hybrid, &P->num_stages, &P->a_tmem_kb, &P->smem));
   return RBOD_OK;
 }
 
@@ -260,7 +254,7 @@ int rbod_destroy(rbod_gallery* g) {
   DevBuf* bufs[] = {&g->stage_rows, &g->stage_slots, &g->stage_norms, &g->q32, &g->q16, &g->q_dq, &g->q_qq,
                     &g->part_score, &g->part_idx, &g->cand_idx, &g->cand_tau, &g->cand_score, &g->out_scores,
                     &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->coll_score,
-                    &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->seg_idx, &g->seg_off, &g->seg_out,
+                    &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->sync_counters, &g->seg_idx, &g->seg_off, &g->seg_out,
                     &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->gather_idx, &g->gather_out};
   for (DevBuf* b : bufs) b->release();
   g->pin_a.release();
@@ -321,6 +315,16 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
     g->slack = (int)value;
   } else if (!strcmp(key, "time_k3")) {
     g->time_k3 = value != 0;
+  } else if (!strcmp(key, "hybrid")) {
+    g->hybrid = value != 0;
+  } else if (!strcmp(key, "l2_sync")) {
+    g->l2_sync = value != 0;
+  } else if (!strcmp(key, "sync_window")) {
+    if (value < 1 || value > 4096) return set_error(RBOD_E_INVAL, "sync_window must be in [1, 4096]");
+    g->sync_window = (int)value;
+  } else if (!strcmp(key, "sync_lead")) {
+    if (value < 1 || value > 64) return set_error(RBOD_E_INVAL, "sync_lead must be in [1, 64]");
+    g->sync_lead = (int)value;
   } else {
     return set_error(RBOD_E_INVAL, "rbod_set_option: unknown key '%s'", key);
   }
@@ -508,6 +512,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint32_
   L.q_pad = P.q_pad;
   L.kc = P.kc;
   L.num_stages = P.num_stages;
+  L.a_tmem_kb = P.a_tmem_kb;
   L.variant = g->k3_variant;
   L.a_fmt = g->kind16 == 1 ? 1 : 0;
   L.b_fmt = g->kind16 == 1 ? 1 : 0;
@@ -518,6 +523,18 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint32_
   L.dump_ld = dump_ld;
   L.grid = P.grid;
   L.smem_bytes = P.smem;
+  if (g->l2_sync && dump == nullptr) {
+    const int workers = g->k3_variant == 2 ? P.grid / 2 : P.grid;
+    const int max_tiles = (P.tiles_total + P.slices - 1) / P.slices + 1;
+    L.sync_window = std::max(1, g->sync_window);
+    L.sync_lead = std::max(1, g->sync_lead);
+    L.sync_span = P.num_qt / std::max(1, workers) + 2;
+    L.sync_windows = max_tiles / L.sync_window + 2;
+    const size_t n = (size_t)P.slices * L.sync_span * L.sync_windows;
+    RBOD_TRY(g->sync_counters.ensure(n * sizeof(int)));
+    RBOD_CUDA(cudaMemsetAsync(g->sync_counters.p, 0, n * sizeof(int), st));
+    L.sync_counters = g->sync_counters.as<int>();
+  }
   return launch_k3(L, st);
 }
 

@@ -206,6 +206,16 @@ __device__ __forceinline__ void mma_f16_ts_pair(uint32_t tmem_d, uint32_t tmem_a
       ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem, both CTAs] (+)= A[smem, each CTA its 128 rows] * B[smem, each CTA half the columns]^T ; leader CTA only
+__device__ __forceinline__ void mma_f16_ss_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives (once all prior MMAs of this thread are done) on the barrier at the same smem offset in
 // every CTA of `cta_mask`
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask) {

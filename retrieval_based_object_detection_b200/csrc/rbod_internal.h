@@ -65,6 +65,7 @@ struct K3Launch {
   int64_t q_pad;
   int kc;                 // candidates per (query, slice); multiple of 32
   int num_stages;
+  int a_tmem_kb;          // k-blocks of the query tile kept in TMEM (rest resident in smem)
   int variant;            // 0 = A in TMEM, 1 = A streamed through smem, 2 = A in TMEM + CTA pairs (cta_group::2)
   int a_fmt, b_fmt;       // 0 = f16, 1 = bf16
   float* part_score;      // [slices][q_pad][kc]
@@ -72,6 +73,8 @@ struct K3Launch {
   const uint32_t* row_mask;
   float* dump;            // optional raw scores [q_pad][dump_ld]
   int64_t dump_ld;
+  int* sync_counters;     // zeroed [slices * sync_span * sync_windows] ints, or nullptr
+  int sync_window, sync_lead, sync_span, sync_windows;
   int grid;
   size_t smem_bytes;
 };
@@ -91,7 +94,8 @@ int launch_segment_mean(const float* master32, const uint16_t* rows16, int kind1
                         unsigned int* arrive_cnt, float* out, int* err_flag, cudaStream_t st);
 // K3
 int k3_configure(int device);
-size_t k3_smem_bytes(int variant, int kc, int num_stages);
+int k3_plan(int variant, int kc, int dp, int smem_optin, int allow_hybrid, int* num_stages, int* a_tmem_kb,
+            size_t* smem_bytes);
 int k3_box_rows(int variant);   // gallery rows per TMA box (64 for the CTA-pair kernel)
 int launch_k3(const K3Launch& L, cudaStream_t st);
 // query preparation: normalise, round to 16 bit, per-query error radius and |q|^2
@@ -132,6 +136,9 @@ struct rbod_gallery {
   int k3_variant = 0;
   int slack = -1;  // -1 = automatic
   int time_k3 = 0;
+  int hybrid = 1;         // allow the query tile to be split between TMEM and resident smem
+  int l2_sync = 1;        // producer throttle that keeps slice-mates within an L2 window
+  int sync_window = 16, sync_lead = 4;
   // workspaces
   rbod::DevBuf stage_rows, stage_slots, stage_norms;          // upsert staging
   rbod::DevBuf q32, q16, q_dq, q_qq;                          // query prep
@@ -140,7 +147,7 @@ struct rbod_gallery {
   rbod::DevBuf flags;      // ints: [0]=n_flag [1]=overflow [2]=err; float max_eps at [3]
   rbod::DevBuf flag_q, flag_thr;
   rbod::DevBuf coll_score, coll_idx, coll_cnt;
-  rbod::DevBuf mask_dev, dump;
+  rbod::DevBuf mask_dev, dump, sync_counters;
   rbod::DevBuf seg_idx, seg_off, seg_out, seg_partials, seg_prefix, seg_arrive;
   rbod::DevBuf gather_idx, gather_out;
   rbod::PinBuf pin_a, pin_b;
