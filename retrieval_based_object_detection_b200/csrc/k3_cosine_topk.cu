@@ -16,8 +16,8 @@
 //     buffers (MMA of tile j+1 overlaps the epilogue of tile j); dim 768 has room for one, so the
 //     epilogue copies the tile to registers and releases TMEM before it starts selecting.
 //   * Epilogue (4 warps, one thread per query row): tcgen05.ld the 128 scores of the row, compare
-//     against the row's running threshold (one FMNMX per score on the fast path); survivors are
-//     inserted by the whole warp into the row's candidate list in shared memory (replace-min).
+//     against the row's running threshold (one FMNMX per score on the fast path); survivors replace
+//     the root of the row's min-heap of candidates in shared memory (transposed, conflict-free).
 //   * Work unit = (gallery slice, query tile).  Units are ordered slice-major so that CTAs
 //     running at the same time stream the same gallery slice and share it through L2.
 // Output: per (slice, query) the `kc` best approximate scores and their row indices.  The K4
@@ -81,38 +81,29 @@ struct K3Barriers {
   uint32_t pad;
 };
 
-// Whole-warp insertion of the lanes flagged in `ball` (each with its own val / col) into the
-// candidate lists of their rows.  Returns the calling lane's updated (threshold, min slot).
-__device__ __noinline__ float2 k3_insert(float val, uint32_t col, uint32_t ball, float tau, int minpos, float* sc,
-                                         uint32_t* ix, int wrow0, int kc, int lane) {
-  while (ball) {
-    const int l = __ffs(ball) - 1;
-    ball &= ball - 1;
-    float* rs = sc + (wrow0 + l) * kc;
-    uint32_t* ri = ix + (wrow0 + l) * kc;
-    if (lane == l) {
-      rs[minpos] = val;
-      ri[minpos] = col;
-    }
-    __syncwarp();
-    float lm = INFINITY;
-    int lp = 0;
-    for (int j = lane; j < kc; j += 32) {
-      const float x = rs[j];
-      if (x < lm) { lm = x; lp = j; }
-    }
-    const uint32_t key = f32_to_ordered(lm);
-    const uint32_t mn = __reduce_min_sync(FULL_MASK, key);
-    const uint32_t who = __ballot_sync(FULL_MASK, key == mn);
-    const int src = __ffs(who) - 1;
-    const int p = __shfl_sync(FULL_MASK, lp, src);
-    if (lane == l) {
-      tau = ordered_to_f32(mn);
-      minpos = p;
-    }
-    __syncwarp();
+// Per-row candidate list = a min-heap of `kc` (score, row index) pairs kept by the row's own thread.
+// Storage is transposed -- entry j of row r lives at [j * 128 + r] -- so whatever heap positions the
+// 32 lanes of a warp touch, they always hit 32 different banks.  Replacing the root with a better
+// candidate and sifting it down keeps the kc best scores seen so far; the root is the threshold.
+// Unused slots hold -inf, so the threshold stays -inf until the list is full.
+__device__ __noinline__ float k3_heap_replace_root(float* sc, uint32_t* ix, int kc, float s, uint32_t id) {
+  int j = 0;
+  while (true) {
+    const int l = 2 * j + 1;
+    if (l >= kc) break;
+    const int r = l + 1;
+    const float sl = sc[l * K3_TILE_M];
+    const float sr = r < kc ? sc[r * K3_TILE_M] : INFINITY;
+    const int m = sr < sl ? r : l;
+    const float sm = fminf(sl, sr);
+    if (!(sm < s)) break;
+    sc[j * K3_TILE_M] = sm;
+    ix[j * K3_TILE_M] = ix[m * K3_TILE_M];
+    j = m;
   }
-  return make_float2(tau, __int_as_float(minpos));
+  sc[j * K3_TILE_M] = s;
+  ix[j * K3_TILE_M] = id;
+  return sc[0];
 }
 
 // Geometry of one kernel flavour.
@@ -128,7 +119,7 @@ struct K3Geom {
   static constexpr int KBS = PAIR ? 4 : 2;                         // k-blocks per pipeline stage
   static constexpr int STAGE_BYTES = KBS * (B_KB_BYTES + A_KB_BYTES);
   static constexpr int Q_PER_UNIT = PAIR ? 2 * K3_TILE_M : K3_TILE_M;
-  static constexpr uint32_t EPI_ARRIVALS = PAIR ? 256 : 128;
+  static constexpr uint32_t EPI_ARRIVALS = PAIR ? 8 : 4;   // one arrival per epilogue warp
 };
 
 // Issues the MMAs of one full pipeline stage as straight-line code: per MMA one uniform add for the
@@ -405,17 +396,19 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         }
         tmem_st_wait();
         tc_fence_before();
-        if (PAIR) mbar_arrive_cluster(a_ready_leader); else mbar_arrive(&bars->a_ready);
-      }
-      // reset the candidate lists of this warp's 32 rows
-      for (int r = 0; r < 32; ++r)
-        for (int j = lane; j < kc; j += 32) {
-          sc[(wrow0 + r) * kc + j] = -INFINITY;
-          ix[(wrow0 + r) * kc + j] = 0xffffffffu;
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(a_ready_leader); else mbar_arrive(&bars->a_ready);
         }
-      __syncwarp();
+      }
+      // reset this row's candidate heap
+      float* my_sc = sc + row;
+      uint32_t* my_ix = ix + row;
+      for (int j = 0; j < kc; ++j) {
+        my_sc[j * K3_TILE_M] = -INFINITY;
+        my_ix[j * K3_TILE_M] = 0xffffffffu;
+      }
       float tau = -INFINITY;
-      int minpos = 0;
 
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&bars->tfull[acc], acc_phase, 5);
@@ -428,9 +421,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
           for (int h = 0; h < 4; ++h) tmem_ld_32x32b_x32(taddr + 32u * h, raw[h]);
           tmem_ld_wait();
           tc_fence_before();
-          // TMEM tile is in registers: hand it back to the MMA issuer
-          if (PAIR) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
-          else mbar_arrive(&bars->tempty[acc]);
+          __syncwarp();
+          // TMEM tile is in registers: hand it back to the MMA issuer (one arrival per warp)
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+            else mbar_arrive(&bars->tempty[acc]);
+          }
 #pragma unroll
           for (int h = 0; h < 4; ++h)
 #pragma unroll
@@ -467,35 +463,39 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
           }
         }
 
-        float m = v[0];
+        // group maxima (16 columns each) -> row maximum; almost always everything is below the threshold
+        float gm[K3_TILE_N / 16];
 #pragma unroll
-        for (int c = 1; c < K3_TILE_N; ++c) m = fmaxf(m, v[c]);
-        if (__any_sync(FULL_MASK, m > tau)) {
+        for (int gi = 0; gi < K3_TILE_N / 16; ++gi) {
+          float a = fmaxf(v[16 * gi], v[16 * gi + 1]);
 #pragma unroll
-          for (int c = 0; c < K3_TILE_N; ++c) {
-            const uint32_t ball = __ballot_sync(FULL_MASK, v[c] > tau);
-            if (ball) {
-              const float2 r = k3_insert(v[c], (uint32_t)(col0 + c), ball, tau, minpos, sc, ix, wrow0, kc, lane);
-              tau = r.x;
-              minpos = __float_as_int(r.y);
+          for (int c = 2; c < 16; ++c) a = fmaxf(a, v[16 * gi + c]);
+          gm[gi] = a;
+        }
+        float m = gm[0];
+#pragma unroll
+        for (int gi = 1; gi < K3_TILE_N / 16; ++gi) m = fmaxf(m, gm[gi]);
+        if (m > tau) {
+#pragma unroll
+          for (int gi = 0; gi < K3_TILE_N / 16; ++gi) {
+            if (gm[gi] > tau) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                if (v[16 * gi + c] > tau)
+                  tau = k3_heap_replace_root(my_sc, my_ix, kc, v[16 * gi + c], (uint32_t)(col0 + 16 * gi + c));
             }
           }
         }
       }
 
-      // unit done: publish this warp's 32 candidate lists
-      __syncwarp();
-      for (int r = 0; r < 32; ++r) {
-        const int64_t q = q_unit0 + wrow0 + r;
-        if (q < P.q_valid) {
-          const size_t base = ((size_t)slice * P.q_pad + q) * kc;
-          for (int j = lane; j < kc; j += 32) {
-            P.part_score[base + j] = sc[(wrow0 + r) * kc + j];
-            P.part_idx[base + j] = ix[(wrow0 + r) * kc + j];
-          }
+      // unit done: publish this row's candidates (heap order; the merge kernel sorts)
+      if (qg < P.q_valid) {
+        const size_t base = ((size_t)slice * P.q_pad + qg) * kc;
+        for (int j = 0; j < kc; ++j) {
+          P.part_score[base + j] = my_sc[j * K3_TILE_M];
+          P.part_idx[base + j] = my_ix[j * K3_TILE_M];
         }
       }
-      __syncwarp();
     }
   }
 
