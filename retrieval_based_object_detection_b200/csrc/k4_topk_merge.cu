@@ -122,7 +122,7 @@ rescore_kernel(const float* __restrict__ q, const double* __restrict__ q_qq, con
 __global__ void __launch_bounds__(128)
 select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict__ cand_idx,
               const float* __restrict__ cand_tau, const float* __restrict__ q_dq, const float* __restrict__ stats,
-              int dp, int64_t Q, int kc, int k, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+              int master16, int dp, int64_t Q, int kc, int k, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
               double* __restrict__ out_scores64, int* __restrict__ n_flag, int* __restrict__ flag_q,
               double* __restrict__ flag_thr, float* __restrict__ max_eps) {
   __shared__ double s_sc[4][K3_MAX_KC];
@@ -162,9 +162,17 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
   const uint32_t who = __ballot_sync(FULL_MASK, have_kth);
   const float tau = cand_tau[q];
   if (tau == -INFINITY) return;  // nothing was dropped for this query: exact by construction
+  // Certification margin: every row the tensor-core pass dropped has approximate score <= tau, and
+  //   |approx - exact cosine| <= ||q16 - unit(q)|| * max||g16||      (query rounding, Cauchy-Schwarz)
+  //                            + dp * 2^-23 * max||g16||              (fp32 accumulation in the tensor core)
+  //                            + row term
+  // The row term is ||g16 - unit(G)|| for fp32 masters (their 16-bit shadow is rounded independently);
+  // for 16-bit masters g16 IS the stored row and only its norm deviates from 1 by d = stats[1], which
+  // scales the score instead of adding to it: (|tau| + e) * d / (1 - d).
   const float gmax = stats[0] * 1.000001f, gdev = stats[1] * 1.000001f;
-  // margin: query rounding * largest row + row rounding / norm deviation + fp32 accumulation
-  const float eps = q_dq[q] * gmax + gdev + (float)dp * 1.2e-7f * gmax + fabsf(tau) * 1e-6f + 1e-7f;
+  const float e = q_dq[q] * gmax + (float)dp * 1.2e-7f * gmax;
+  const float row_term = master16 ? (fabsf(tau) + e) * gdev / (1.0f - gdev) : gdev;
+  const float eps = e + row_term + fabsf(tau) * 1e-6f + 1e-7f;
   bool flagged = true;
   if (who) {
     const int src = __ffs(who) - 1;
@@ -346,12 +354,12 @@ int launch_rescore(const float* q, const double* q_qq, const float* master32, co
 }
 
 int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
-                  const float* stats, int dp, int64_t Q, int kc, int k, float* out_scores, int64_t* out_rows,
+                  const float* stats, int master16, int dp, int64_t Q, int kc, int k, float* out_scores, int64_t* out_rows,
                   double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* max_eps,
                   cudaStream_t st) {
   if (Q <= 0) return RBOD_OK;
   if (kc > K3_MAX_KC) return set_error(RBOD_E_INVAL, "select: kc %d > %d", kc, K3_MAX_KC);
-  select_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, st>>>(cand_score, cand_idx, cand_tau, q_dq, stats, dp, Q, kc, k,
+  select_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, st>>>(cand_score, cand_idx, cand_tau, q_dq, stats, master16, dp, Q, kc, k,
                                                          out_scores, out_rows, out_scores64, n_flag, flag_q,
                                                          flag_thr, max_eps);
   RBOD_CUDA(cudaGetLastError());

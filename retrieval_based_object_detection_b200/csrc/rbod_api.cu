@@ -315,6 +315,9 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
     g->slack = (int)value;
   } else if (!strcmp(key, "time_k3")) {
     g->time_k3 = value != 0;
+  } else if (!strcmp(key, "q_kind")) {
+    if (value < 0 || value > 2) return set_error(RBOD_E_INVAL, "q_kind must be 0 (auto), 1 (bf16) or 2 (fp16)");
+    g->q_kind = (int)value;
   } else if (!strcmp(key, "hybrid")) {
     g->hybrid = value != 0;
   } else if (!strcmp(key, "l2_sync")) {
@@ -496,6 +499,11 @@ int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* of
 }
 
 // ---------------------------------------------------------------------------------------------
+// 16-bit type the (unit-norm) queries are rounded to for the tensor-core pass.  fp16 has 3 more
+// mantissa bits than bf16 and unit vectors never leave its range, so it is the default even for
+// bf16 galleries (kind::f16 MMAs take the two operand formats independently).
+static int query_kind(const rbod_gallery* g) { return g->q_kind ? g->q_kind : 2; }
+
 static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint32_t* mask_dev, float* dump,
                   int64_t dump_ld, cudaStream_t st) {
   K3Launch L;
@@ -514,7 +522,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint32_
   L.num_stages = P.num_stages;
   L.a_tmem_kb = P.a_tmem_kb;
   L.variant = g->k3_variant;
-  L.a_fmt = g->kind16 == 1 ? 1 : 0;
+  L.a_fmt = query_kind(g) == 1 ? 1 : 0;
   L.b_fmt = g->kind16 == 1 ? 1 : 0;
   L.part_score = g->part_score.as<float>();
   L.part_idx = g->part_idx.as<uint32_t>();
@@ -546,7 +554,7 @@ static int prepare_queries(rbod_gallery* g, const float* queries, int64_t Q, con
   RBOD_TRY(g->q16.ensure((size_t)P.q_pad * g->dp * 2));
   RBOD_TRY(g->q_dq.ensure((size_t)P.q_pad * 4));
   RBOD_TRY(g->q_qq.ensure((size_t)P.q_pad * 8));
-  return launch_prep_queries(*q_dev, Q, P.q_pad, g->dim, g->dp, g->kind16, g->q16.as<uint16_t>(),
+  return launch_prep_queries(*q_dev, Q, P.q_pad, g->dim, g->dp, query_kind(g), g->q16.as<uint16_t>(),
                              g->q_dq.as<float>(), g->q_qq.as<double>(), st);
 }
 
@@ -629,7 +637,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   RBOD_TRY(launch_rescore(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp,
                           g->metric, g->cand_idx.as<uint32_t>(), Q, P.kc, g->cand_score.as<double>(), st));
   RBOD_TRY(launch_select(g->cand_score.as<double>(), g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(),
-                         g->q_dq.as<float>(), g->stats, g->dp, Q, P.kc, k, d_scores, d_rows, d_scores64, d_flags,
+                         g->q_dq.as<float>(), g->stats, g->dtype != RBOD_F32, g->dp, Q, P.kc, k, d_scores, d_rows, d_scores64, d_flags,
                          g->flag_q.as<int>(), g->flag_thr.as<double>(), reinterpret_cast<float*>(d_flags + 3), st));
   launches += 3;
 

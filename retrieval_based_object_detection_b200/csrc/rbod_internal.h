@@ -108,7 +108,7 @@ int launch_rescore(const float* q, const double* q_qq, const float* master32, co
                    int dim, int64_t ld32, int64_t ld16, int metric, const uint32_t* cand_idx, int64_t Q, int kc,
                    double* cand_score, cudaStream_t st);
 int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
-                  const float* stats, int dp, int64_t Q, int kc, int k, float* out_scores, int64_t* out_rows,
+                  const float* stats, int master16, int dp, int64_t Q, int kc, int k, float* out_scores, int64_t* out_rows,
                   double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* max_eps,
                   cudaStream_t st);
 int launch_exact_collect(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
@@ -136,6 +136,7 @@ struct rbod_gallery {
   int k3_variant = 0;
   int slack = -1;  // -1 = automatic
   int time_k3 = 0;
+  int q_kind = 0;         // 16-bit type queries are rounded to: 0 = automatic, 1 = bf16, 2 = fp16
   int hybrid = 1;         // allow the query tile to be split between TMEM and resident smem
   int l2_sync = 1;        // producer throttle that keeps slice-mates within an L2 window
   int sync_window = 16, sync_lead = 4;
