@@ -315,9 +315,6 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
     g->slack = (int)value;
   } else if (!strcmp(key, "time_k3")) {
     g->time_k3 = value != 0;
-  } else if (!strcmp(key, "q_kind")) {
-    if (value < 0 || value > 2) return set_error(RBOD_E_INVAL, "q_kind must be 0 (auto), 1 (bf16) or 2 (fp16)");
-    g->q_kind = (int)value;
   } else if (!strcmp(key, "hybrid")) {
     g->hybrid = value != 0;
   } else if (!strcmp(key, "l2_sync")) {
@@ -499,10 +496,10 @@ int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* of
 }
 
 // ---------------------------------------------------------------------------------------------
-// 16-bit type the (unit-norm) queries are rounded to for the tensor-core pass.  fp16 has 3 more
-// mantissa bits than bf16 and unit vectors never leave its range, so it is the default even for
-// bf16 galleries (kind::f16 MMAs take the two operand formats independently).
-static int query_kind(const rbod_gallery* g) { return g->q_kind ? g->q_kind : 2; }
+// 16-bit type the (unit-norm) queries are rounded to for the tensor-core pass: the gallery's own.
+// (Measured on B200: a kind::f16 MMA whose instruction descriptor mixes an fp16 A with a bf16 B
+// raises "illegal instruction", so both operands must share one format.)
+static int query_kind(const rbod_gallery* g) { return g->kind16; }
 
 static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint32_t* mask_dev, float* dump,
                   int64_t dump_ld, cudaStream_t st) {

@@ -136,7 +136,6 @@ struct rbod_gallery {
   int k3_variant = 0;
   int slack = -1;  // -1 = automatic
   int time_k3 = 0;
-  int q_kind = 0;         // 16-bit type queries are rounded to: 0 = automatic, 1 = bf16, 2 = fp16
   int hybrid = 1;         // allow the query tile to be split between TMEM and resident smem
   int l2_sync = 1;        // producer throttle that keeps slice-mates within an L2 window
   int sync_window = 16, sync_lead = 4;

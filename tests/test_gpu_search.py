@@ -35,7 +35,7 @@ def test_raw_tensor_core_scores(G, variant, dtype, n, dim, Q):
     q = O.synthetic_unit_rows(Q, dim, seed=99)
     got = g.debug_scores(q)
     kind = "bf16" if dtype == "bf16" else "f16"        # fp32 galleries search an fp16 shadow
-    qn = O.l2_normalize_store(q, "f16")[0].astype(np.float64)   # queries are always rounded to fp16
+    qn = O.l2_normalize_store(q, kind)[0].astype(np.float64)
     g16 = O.round_store(stored, kind).astype(np.float64)
     want = qn @ g16.T
     assert got.shape == (Q, n) and not np.isnan(got).any()
