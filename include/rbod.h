@@ -90,14 +90,18 @@ typedef struct rbod_gallery_info {
 
 typedef struct rbod_search_stats {
   int64_t queries;          /* Q                                                         */
-  int64_t fallback_queries; /* queries whose top-k was not certified by the tensor-core  */
-                            /* pass and went through the exact fp64 sweep                */
-  int64_t k3_launches;      /* kernel launches of the tcgen05 pass                       */
+  int64_t fallback_queries; /* queries whose top-k was not certified by the first        */
+                            /* tensor-core pass (they get a collecting second pass)      */
+  int64_t k3_launches;      /* kernel launches of the tcgen05 pass (1, or 2 with the     */
+                            /* collecting pass)                                          */
   int64_t total_launches;   /* all kernel launches issued by this call                   */
   int32_t candidates;       /* candidates kept per query before rescoring (k + slack)    */
   int32_t slices;           /* gallery slices the tcgen05 pass was split into            */
   float max_eps;            /* largest certification margin used                         */
-  float k3_ms;              /* device time of the tcgen05 pass (CUDA events), 0 if off   */
+  float k3_ms;              /* device time of the first tcgen05 pass (CUDA events), 0 if */
+                            /* off                                                       */
+  int64_t sweep_queries;    /* queries that needed the exact fp64 sweep over the gallery */
+                            /* (tie cluster wider than the collecting pass records)      */
 } rbod_search_stats;
 
 const char* rbod_last_error(void);
@@ -112,8 +116,10 @@ int rbod_info(const rbod_gallery* g, rbod_gallery_info* out);
 /* Shrinks the number of used row slots (rows beyond `rows` are forgotten). */
 int rbod_truncate(rbod_gallery* g, int64_t rows);
 /* Tunables: "k3_variant" (0 = query tile resident in TMEM, 1 = query tile streamed through smem,
- * 2 = TMEM-resident + CTA pairs / cta_group::2),
- * "slack" (extra candidates kept per query), "time_k3" (1 = fill stats.k3_ms). */
+ * 2 = TMEM-resident + CTA pairs / cta_group::2), "slack" (extra candidates kept per query),
+ * "time_k3" (1 = fill stats.k3_ms), "tau_share" (slices of a query share their threshold),
+ * "collect_pass" (tensor-core second pass for uncertified queries), "l2_sync" / "sync_window" /
+ * "sync_lead" (L2-sharing producer throttle), "hybrid" (query tile split TMEM / smem). */
 int rbod_set_option(rbod_gallery* g, const char* key, int64_t value);
 
 /* --- K1: normalise + pack on upsert ----------------------------------------------------

@@ -47,6 +47,11 @@ struct alignas(64) K3Params {
   float* part_score;
   uint32_t* part_idx;
   const uint32_t* row_mask;
+  uint32_t* tau_shared;   // [q_pad] per-query lower bound on the kc-th best score, as ordered keys (nullptr = off)
+  const float* collect_thr;   // collect mode: [q_pad] fixed per-query thresholds; every row scoring above is recorded
+  uint32_t* coll_idx;         //   [q_pad][coll_cap] recorded row indices
+  int* coll_cnt;              //   [q_pad] rows recorded (may exceed coll_cap: overflow, caller falls back)
+  int coll_cap;
   float* dump;
   int64_t dump_ld;
   int64_t n_rows;
@@ -68,6 +73,7 @@ struct alignas(64) K3Params {
   int a_tmem_kb;   // k-blocks of the query tile held in TMEM; the rest sits in shared memory (resident)
   int num_acc;     // accumulator buffers (1 or 2)
   int acc_col0;    // first accumulator column in TMEM
+  int debug_epi;   // bring-up only: 1 = epilogue loads the tile but selects nothing, 2 = does not even load it
   uint32_t idesc;
 };
 
@@ -408,11 +414,38 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         my_sc[j * K3_TILE_M] = -INFINITY;
         my_ix[j * K3_TILE_M] = 0xffffffffu;
       }
-      float tau = -INFINITY;
+      // Threshold shared between the units (gallery slices) of one query.  A unit publishes the root of its
+      // heap once the heap is full: kc rows score at least that much, so no row below it can be among the
+      // kc best of the whole gallery, whichever slice it sits in.  Other units start from, and
+      // periodically re-read, the best published bound, which removes almost all heap traffic after the
+      // first slice of a query has warmed up.
+      uint32_t* tau_cell = P.tau_shared != nullptr ? P.tau_shared + qg : nullptr;
+      float tau = tau_cell != nullptr ? ordered_to_f32(ld_relaxed_u32(tau_cell)) : -INFINITY;
+      float tau_published = tau;
+      const bool collect = P.collect_thr != nullptr;
+      if (collect) tau = qg < P.q_valid ? P.collect_thr[qg] : INFINITY;
 
       for (int t = t0; t < t1; ++t) {
+        if (tau_cell != nullptr && ((t - t0) & (K3_TAU_REFRESH - 1)) == K3_TAU_REFRESH - 1) {
+          const float root = my_sc[0];
+          if (root > tau_published) {
+            atomicMax(tau_cell, f32_to_ordered(root));
+            tau_published = root;
+          }
+          tau = fmaxf(tau, ordered_to_f32(ld_relaxed_u32(tau_cell)));
+        }
         mbar_wait(&bars->tfull[acc], acc_phase, 5);
         tc_fence_after();
+        if (P.debug_epi == 2) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+            else mbar_arrive(&bars->tempty[acc]);
+          }
+          if (++acc == P.num_acc) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
         float v[K3_TILE_N];
         {
           const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(P.acc_col0 + acc * K3_TILE_N);
@@ -475,21 +508,32 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         float m = gm[0];
 #pragma unroll
         for (int gi = 1; gi < K3_TILE_N / 16; ++gi) m = fmaxf(m, gm[gi]);
+        if (P.debug_epi == 1) {
+          if (m == 12345.678f) tau = m;   // keep the loads and maxima alive
+          continue;
+        }
         if (m > tau) {
 #pragma unroll
           for (int gi = 0; gi < K3_TILE_N / 16; ++gi) {
             if (gm[gi] > tau) {
 #pragma unroll
               for (int c = 0; c < 16; ++c)
-                if (v[16 * gi + c] > tau)
-                  tau = k3_heap_replace_root(my_sc, my_ix, kc, v[16 * gi + c], (uint32_t)(col0 + 16 * gi + c));
+                if (v[16 * gi + c] > tau) {
+                  if (collect) {
+                    const int slot = atomicAdd(P.coll_cnt + qg, 1);
+                    if (slot < P.coll_cap) P.coll_idx[(size_t)qg * P.coll_cap + slot] = (uint32_t)(col0 + 16 * gi + c);
+                  } else {
+                    tau = fmaxf(tau, k3_heap_replace_root(my_sc, my_ix, kc, v[16 * gi + c], (uint32_t)(col0 + 16 * gi + c)));
+                  }
+                }
             }
           }
         }
       }
 
       // unit done: publish this row's candidates (heap order; the merge kernel sorts)
-      if (qg < P.q_valid) {
+      if (tau_cell != nullptr && my_sc[0] > tau_published) atomicMax(tau_cell, f32_to_ordered(my_sc[0]));
+      if (qg < P.q_valid && !collect) {
         const size_t base = ((size_t)slice * P.q_pad + qg) * kc;
         for (int j = 0; j < kc; ++j) {
           P.part_score[base + j] = my_sc[j * K3_TILE_M];
@@ -512,12 +556,14 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
 // dq = || fp(q16) - q/|q| ||_2 (the query's share of the certification margin).
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16,
-                    uint16_t* __restrict__ q16, float* __restrict__ q_dq, double* __restrict__ q_qq) {
+                    uint16_t* __restrict__ q16, float* __restrict__ q_dq, double* __restrict__ q_qq,
+                    uint32_t* __restrict__ tau_shared) {
   const int lane = threadIdx.x & 31;
   const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int64_t nw = (int64_t)gridDim.x * 8;
   for (int64_t i = w0; i < q_pad; i += nw) {
     uint16_t* dst = q16 + i * dp;
+    if (lane == 0 && tau_shared != nullptr) tau_shared[i] = f32_to_ordered(-INFINITY);
     if (i >= Q) {
       for (int c = lane; c < dp; c += 32) dst[c] = 0;
       continue;
@@ -640,6 +686,11 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.part_score = L.part_score;
   P.part_idx = L.part_idx;
   P.row_mask = L.row_mask;
+  P.tau_shared = L.tau_shared;
+  P.collect_thr = L.collect_thr;
+  P.coll_idx = L.coll_idx;
+  P.coll_cnt = L.coll_cnt;
+  P.coll_cap = L.coll_cap;
   P.dump = L.dump;
   P.dump_ld = L.dump_ld;
   P.n_rows = L.n_rows;
@@ -659,6 +710,7 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.sync_span = L.sync_span;
   P.sync_windows = L.sync_windows;
   P.a_tmem_kb = L.a_tmem_kb;
+  P.debug_epi = L.debug_epi;
   P.num_acc = (L.variant == 1 || L.a_tmem_kb * 32 + 2 * K3_TILE_N <= TMEM_COLS) ? 2 : 1;
   P.acc_col0 = TMEM_COLS - P.num_acc * K3_TILE_N;
   P.idesc = make_idesc_f16(L.a_fmt, L.b_fmt, L.variant == 2 ? 2 * K3_TILE_M : K3_TILE_M, K3_TILE_N);
@@ -690,10 +742,10 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
 }
 
 int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16, uint16_t* q16,
-                        float* q_dq, double* q_qq, cudaStream_t st) {
+                        float* q_dq, double* q_qq, uint32_t* tau_shared, cudaStream_t st) {
   const int64_t want = (q_pad + 7) / 8;
   const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
-  prep_queries_kernel<<<grid, 256, 0, st>>>(q, Q, q_pad, dim, dp, kind16, q16, q_dq, q_qq);
+  prep_queries_kernel<<<grid, 256, 0, st>>>(q, Q, q_pad, dim, dp, kind16, q16, q_dq, q_qq, tau_shared);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

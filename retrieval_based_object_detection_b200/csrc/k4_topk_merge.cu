@@ -124,7 +124,7 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
               const float* __restrict__ cand_tau, const float* __restrict__ q_dq, const float* __restrict__ stats,
               int master16, int dp, int64_t Q, int kc, int k, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
               double* __restrict__ out_scores64, int* __restrict__ n_flag, int* __restrict__ flag_q,
-              double* __restrict__ flag_thr, float* __restrict__ max_eps) {
+              double* __restrict__ flag_thr, float* __restrict__ flag_lo, float* __restrict__ max_eps) {
   __shared__ double s_sc[4][K3_MAX_KC];
   __shared__ uint32_t s_ix[4][K3_MAX_KC];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -188,6 +188,11 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
       const int slot = atomicAdd(n_flag, 1);
       flag_q[slot] = (int)q;
       flag_thr[slot] = kth;
+      // Threshold for the collecting second pass: every row whose exact score reaches kth has an
+      // approximate score above lo (same error model, applied from the exact side).
+      const float kf = (float)kth;
+      const float lo = master16 ? kf - fabsf(kf) * gdev - e : kf - e - gdev;
+      flag_lo[slot] = kth == -INFINITY ? -INFINITY : lo - fabsf(kf) * 2e-6f - 2e-7f;
     }
   }
 }
@@ -254,6 +259,7 @@ select_collected_kernel(const double* __restrict__ coll_score, const uint32_t* _
   const int q = flag_q[f0 + f];
   int cnt = coll_cnt[f];
   if (cnt > cap) {
+    if (overflow == nullptr) return;   // caller re-runs this query through the exact sweep
     if (threadIdx.x == 0) atomicExch(overflow, 1);
     cnt = cap;
   }
@@ -275,6 +281,68 @@ select_collected_kernel(const double* __restrict__ coll_score, const uint32_t* _
       out_scores[(int64_t)q * k + rank] = (float)s;
       out_rows[(int64_t)q * k + rank] = (int64_t)id;
       if (out_scores64) out_scores64[(int64_t)q * k + rank] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// second pass for uncertified queries (tensor-core collect): pack their 16-bit rows into a dense
+// query matrix, then rescore whatever the collecting K3 launch recorded.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_flagged_kernel(const uint16_t* __restrict__ q16, int dp, const int* __restrict__ flag_q, int f0, int nf,
+                      int64_t nf_pad, uint16_t* __restrict__ fq16, int* __restrict__ coll_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * 8;
+  for (int64_t f = w0; f < nf_pad; f += nw) {
+    uint4* dst = reinterpret_cast<uint4*>(fq16 + f * dp);
+    if (f < nf) {
+      const uint4* src = reinterpret_cast<const uint4*>(q16 + (int64_t)flag_q[f0 + f] * dp);
+      for (int c = lane; c < dp / 8; c += 32) dst[c] = src[c];
+    } else {
+      for (int c = lane; c < dp / 8; c += 32) dst[c] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (lane == 0) coll_cnt[f] = 0;
+  }
+}
+
+// one warp per (flagged query, recorded row); grid.y = flagged query
+__global__ void __launch_bounds__(256)
+rescore_collected_kernel(const float* __restrict__ q, const double* __restrict__ q_qq,
+                         const float* __restrict__ master32, const uint16_t* __restrict__ rows16, int kind16,
+                         int dim, int64_t ld32, int64_t ld16, const int* __restrict__ flag_q, int f0, int cap,
+                         const uint32_t* __restrict__ coll_idx, const int* __restrict__ coll_cnt,
+                         double* __restrict__ coll_score) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.y;
+  const int cnt = min(coll_cnt[f], cap);
+  const int qi = flag_q[f0 + f];
+  const float* qv = q + (int64_t)qi * dim;
+  const double qn = sqrt(q_qq[qi]);
+  for (int j = blockIdx.x * 8 + (threadIdx.x >> 5); j < cnt; j += gridDim.x * 8) {
+    const uint32_t idx = coll_idx[(size_t)f * cap + j];
+    double dot = 0.0, gg = 0.0;
+    if (master32) {
+      const float* g = master32 + (int64_t)idx * ld32;
+      for (int c = lane; c < dim; c += 32) {
+        const double x = (double)g[c];
+        dot = fma((double)qv[c], x, dot);
+        gg = fma(x, x, gg);
+      }
+    } else {
+      const uint16_t* g = rows16 + (int64_t)idx * ld16;
+      for (int c = lane; c < dim; c += 32) {
+        const double x = (double)h16_to_f32(g[c], kind16);
+        dot = fma((double)qv[c], x, dot);
+        gg = fma(x, x, gg);
+      }
+    }
+    dot = warp_sum_f64(dot);
+    gg = warp_sum_f64(gg);
+    if (lane == 0) {
+      const double den = qn * sqrt(gg);
+      coll_score[(size_t)f * cap + j] = den > 0.0 ? dot / den : 0.0;
     }
   }
 }
@@ -355,13 +423,13 @@ int launch_rescore(const float* q, const double* q_qq, const float* master32, co
 
 int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
                   const float* stats, int master16, int dp, int64_t Q, int kc, int k, float* out_scores, int64_t* out_rows,
-                  double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* max_eps,
+                  double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* flag_lo, float* max_eps,
                   cudaStream_t st) {
   if (Q <= 0) return RBOD_OK;
   if (kc > K3_MAX_KC) return set_error(RBOD_E_INVAL, "select: kc %d > %d", kc, K3_MAX_KC);
   select_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, st>>>(cand_score, cand_idx, cand_tau, q_dq, stats, master16, dp, Q, kc, k,
                                                          out_scores, out_rows, out_scores64, n_flag, flag_q,
-                                                         flag_thr, max_eps);
+                                                         flag_thr, flag_lo, max_eps);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }
@@ -388,6 +456,31 @@ int launch_select_collected(const double* coll_score, const uint32_t* coll_idx, 
   if (nf <= 0) return RBOD_OK;
   select_collected_kernel<<<nf, 256, 0, st>>>(coll_score, coll_idx, coll_cnt, flag_q, f0, cap, k, out_scores,
                                               out_rows, out_scores64, overflow);
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+int launch_gather_flagged(const uint16_t* q16, int dp, const int* flag_q, int f0, int nf, int64_t nf_pad,
+                          uint16_t* fq16, int* coll_cnt, cudaStream_t st) {
+  if (nf_pad <= 0) return RBOD_OK;
+  const int64_t want = (nf_pad + 7) / 8;
+  gather_flagged_kernel<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(q16, dp, flag_q, f0, nf, nf_pad,
+                                                                                    fq16, coll_cnt);
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+int launch_rescore_collected(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
+                             int kind16, int dim, int64_t ld32, int64_t ld16, const int* flag_q, int f0, int nf,
+                             int cap, const uint32_t* coll_idx, const int* coll_cnt, double* coll_score,
+                             cudaStream_t st) {
+  if (nf <= 0) return RBOD_OK;
+  for (int y0 = 0; y0 < nf; y0 += 32768) {   // grid.y limit
+    const int ny = nf - y0 < 32768 ? nf - y0 : 32768;
+    rescore_collected_kernel<<<dim3(4, (unsigned)ny), 256, 0, st>>>(
+        q, q_qq, master32, rows16, kind16, dim, ld32, ld16, flag_q, f0 + y0, cap, coll_idx + (size_t)y0 * cap,
+        coll_cnt + y0, coll_score + (size_t)y0 * cap);
+  }
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

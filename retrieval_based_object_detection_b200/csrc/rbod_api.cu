@@ -166,7 +166,7 @@ static int plan_search(const rbod_gallery* g, int64_t Q, int k, int variant, int
   P->num_qt = (int)(P->q_pad / q_per_unit);
   P->tiles_total = (int)((g->rows + K3_TILE_N - 1) / K3_TILE_N);
   // slices: balance (units per CTA) x (tiles per unit); fewer slices on ties (less merge work)
-  const int max_slices = std::max(1, std::min({P->tiles_total, 8192 / kc, 64}));
+  const int max_slices = std::max(1, std::min({P->tiles_total, 8192 / kc, 2 * workers}));
   double best = 1e300;
   int best_s = 1;
   for (int s = 1; s <= max_slices; ++s) {
@@ -251,9 +251,9 @@ int rbod_destroy(rbod_gallery* g) {
   if (g->rows16) cudaFree(g->rows16);
   if (g->master32) cudaFree(g->master32);
   if (g->stats) cudaFree(g->stats);
-  DevBuf* bufs[] = {&g->stage_rows, &g->stage_slots, &g->stage_norms, &g->q32, &g->q16, &g->q_dq, &g->q_qq,
+  DevBuf* bufs[] = {&g->stage_rows, &g->stage_slots, &g->stage_norms, &g->q32, &g->q16, &g->q_dq, &g->q_qq, &g->tau_shared,
                     &g->part_score, &g->part_idx, &g->cand_idx, &g->cand_tau, &g->cand_score, &g->out_scores,
-                    &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->coll_score,
+                    &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->flag_lo, &g->fq16, &g->coll_score,
                     &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->sync_counters, &g->seg_idx, &g->seg_off, &g->seg_out,
                     &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->gather_idx, &g->gather_out};
   for (DevBuf* b : bufs) b->release();
@@ -315,6 +315,12 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
     g->slack = (int)value;
   } else if (!strcmp(key, "time_k3")) {
     g->time_k3 = value != 0;
+  } else if (!strcmp(key, "collect_pass")) {
+    g->collect_pass = value != 0;
+  } else if (!strcmp(key, "tau_share")) {
+    g->tau_share = value != 0;
+  } else if (!strcmp(key, "debug_epi")) {
+    g->debug_epi = (int)value;   // bring-up only: results are wrong when non-zero
   } else if (!strcmp(key, "hybrid")) {
     g->hybrid = value != 0;
   } else if (!strcmp(key, "l2_sync")) {
@@ -501,13 +507,26 @@ int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* of
 // raises "illegal instruction", so both operands must share one format.)
 static int query_kind(const rbod_gallery* g) { return g->kind16; }
 
-static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint32_t* mask_dev, float* dump,
-                  int64_t dump_ld, cudaStream_t st) {
+struct K3Collect {
+  const float* thr;
+  uint32_t* idx;
+  int* cnt;
+  int cap;
+};
+
+static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_t* q16, const uint32_t* mask_dev,
+                  const K3Collect* collect, float* dump, int64_t dump_ld, cudaStream_t st) {
   K3Launch L;
   memset(&L, 0, sizeof(L));
   RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, g->rows16, g->rows, g->dp, k3_box_rows(g->k3_variant)));
-  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_a, g->q16.p, P.q_pad, g->dp, K3_TILE_M));
-  L.q16 = g->q16.as<uint16_t>();
+  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_a, q16, P.q_pad, g->dp, K3_TILE_M));
+  L.q16 = q16;
+  if (collect) {
+    L.collect_thr = collect->thr;
+    L.coll_idx = collect->idx;
+    L.coll_cnt = collect->cnt;
+    L.coll_cap = collect->cap;
+  }
   L.dp = g->dp;
   L.n_rows = g->rows;
   L.tiles_total = P.tiles_total;
@@ -519,11 +538,13 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint32_
   L.num_stages = P.num_stages;
   L.a_tmem_kb = P.a_tmem_kb;
   L.variant = g->k3_variant;
+  L.debug_epi = g->debug_epi;
   L.a_fmt = query_kind(g) == 1 ? 1 : 0;
   L.b_fmt = g->kind16 == 1 ? 1 : 0;
   L.part_score = g->part_score.as<float>();
   L.part_idx = g->part_idx.as<uint32_t>();
   L.row_mask = mask_dev;
+  L.tau_shared = (g->tau_share && dump == nullptr && collect == nullptr) ? g->tau_shared.as<uint32_t>() : nullptr;
   L.dump = dump;
   L.dump_ld = dump_ld;
   L.grid = P.grid;
@@ -551,8 +572,9 @@ static int prepare_queries(rbod_gallery* g, const float* queries, int64_t Q, con
   RBOD_TRY(g->q16.ensure((size_t)P.q_pad * g->dp * 2));
   RBOD_TRY(g->q_dq.ensure((size_t)P.q_pad * 4));
   RBOD_TRY(g->q_qq.ensure((size_t)P.q_pad * 8));
+  RBOD_TRY(g->tau_shared.ensure((size_t)P.q_pad * 4));
   return launch_prep_queries(*q_dev, Q, P.q_pad, g->dim, g->dp, query_kind(g), g->q16.as<uint16_t>(),
-                             g->q_dq.as<float>(), g->q_qq.as<double>(), st);
+                             g->q_dq.as<float>(), g->q_qq.as<double>(), g->tau_shared.as<uint32_t>(), st);
 }
 
 int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, const uint32_t* row_mask,
@@ -623,9 +645,10 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   RBOD_TRY(g->cand_score.ensure((size_t)Q * P.kc * 8));
   RBOD_TRY(g->flag_q.ensure((size_t)Q * 4));
   RBOD_TRY(g->flag_thr.ensure((size_t)Q * 8));
+  RBOD_TRY(g->flag_lo.ensure((size_t)P.q_pad * 4 + 1024));   // read as [q_pad of the second pass]
 
   if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev0, st));
-  RBOD_TRY(run_k3(g, P, Q, static_cast<const uint32_t*>(mask_dev), nullptr, 0, st));
+  RBOD_TRY(run_k3(g, P, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st));
   if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev1, st));
   ++launches;
 
@@ -635,7 +658,8 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
                           g->metric, g->cand_idx.as<uint32_t>(), Q, P.kc, g->cand_score.as<double>(), st));
   RBOD_TRY(launch_select(g->cand_score.as<double>(), g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(),
                          g->q_dq.as<float>(), g->stats, g->dtype != RBOD_F32, g->dp, Q, P.kc, k, d_scores, d_rows, d_scores64, d_flags,
-                         g->flag_q.as<int>(), g->flag_thr.as<double>(), reinterpret_cast<float*>(d_flags + 3), st));
+                         g->flag_q.as<int>(), g->flag_thr.as<double>(), g->flag_lo.as<float>(),
+                         reinterpret_cast<float*>(d_flags + 3), st));
   launches += 3;
 
   int hflags[4] = {0, 0, 0, 0};
@@ -645,13 +669,61 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   float max_eps;
   memcpy(&max_eps, &hflags[3], 4);
 
-  if (n_flag > 0) {
+  int n_sweep = n_flag;   // queries that still need the exact fp64 sweep
+  int64_t k3_launches = 1;
+  if (n_flag > 0 && g->collect_pass) {
+    // Second tensor-core pass over the uncertified queries only: record every row whose approximate
+    // score can still reach the query's provisional k-th exact score, rescore those exactly, select.
+    const int cap = K3_COLLECT_CAP;
+    SearchPlan P2;
+    RBOD_TRY(plan_search(g, n_flag, k, g->k3_variant, smem_optin, &P2));
+    RBOD_TRY(g->fq16.ensure((size_t)P2.q_pad * g->dp * 2));
+    RBOD_TRY(g->coll_cnt.ensure((size_t)P2.q_pad * 4));
+    RBOD_TRY(g->coll_idx.ensure((size_t)P2.q_pad * cap * 4));
+    RBOD_TRY(g->coll_score.ensure((size_t)n_flag * cap * 8));
+    RBOD_TRY(launch_gather_flagged(g->q16.as<uint16_t>(), g->dp, g->flag_q.as<int>(), 0, n_flag, P2.q_pad,
+                                   g->fq16.as<uint16_t>(), g->coll_cnt.as<int>(), st));
+    K3Collect C;
+    C.thr = g->flag_lo.as<float>();
+    C.idx = g->coll_idx.as<uint32_t>();
+    C.cnt = g->coll_cnt.as<int>();
+    C.cap = cap;
+    RBOD_TRY(run_k3(g, P2, n_flag, g->fq16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), &C, nullptr, 0, st));
+    RBOD_TRY(launch_rescore_collected(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim,
+                                      g->dp, g->flag_q.as<int>(), 0, n_flag, cap, g->coll_idx.as<uint32_t>(),
+                                      g->coll_cnt.as<int>(), g->coll_score.as<double>(), st));
+    RBOD_TRY(launch_select_collected(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
+                                     g->flag_q.as<int>(), 0, n_flag, cap, k, d_scores, d_rows, d_scores64, nullptr,
+                                     st));
+    launches += 4;
+    ++k3_launches;
+    // queries whose list overflowed (a tie cluster wider than `cap`) keep going to the exact sweep
+    std::vector<int> cnt_h(n_flag), fq_h(n_flag);
+    std::vector<double> thr_h(n_flag);
+    RBOD_CUDA(cudaMemcpyAsync(cnt_h.data(), g->coll_cnt.p, (size_t)n_flag * 4, cudaMemcpyDeviceToHost, st));
+    RBOD_CUDA(cudaMemcpyAsync(fq_h.data(), g->flag_q.p, (size_t)n_flag * 4, cudaMemcpyDeviceToHost, st));
+    RBOD_CUDA(cudaMemcpyAsync(thr_h.data(), g->flag_thr.p, (size_t)n_flag * 8, cudaMemcpyDeviceToHost, st));
+    RBOD_CUDA(cudaStreamSynchronize(st));
+    n_sweep = 0;
+    for (int f = 0; f < n_flag; ++f)
+      if (cnt_h[f] > cap) {
+        fq_h[n_sweep] = fq_h[f];
+        thr_h[n_sweep] = thr_h[f];
+        ++n_sweep;
+      }
+    if (n_sweep > 0) {
+      RBOD_CUDA(cudaMemcpyAsync(g->flag_q.p, fq_h.data(), (size_t)n_sweep * 4, cudaMemcpyHostToDevice, st));
+      RBOD_CUDA(cudaMemcpyAsync(g->flag_thr.p, thr_h.data(), (size_t)n_sweep * 8, cudaMemcpyHostToDevice, st));
+      RBOD_CUDA(cudaStreamSynchronize(st));   // the host vectors go out of scope below
+    }
+  }
+  if (n_sweep > 0) {
     const int cap = 4096, batch = 32;
     RBOD_TRY(g->coll_score.ensure((size_t)batch * cap * 8));
     RBOD_TRY(g->coll_idx.ensure((size_t)batch * cap * 4));
     RBOD_TRY(g->coll_cnt.ensure((size_t)batch * 4));
-    for (int f0 = 0; f0 < n_flag; f0 += batch) {
-      const int nf = std::min(batch, n_flag - f0);
+    for (int f0 = 0; f0 < n_sweep; f0 += batch) {
+      const int nf = std::min(batch, n_sweep - f0);
       RBOD_CUDA(cudaMemsetAsync(g->coll_cnt.p, 0, (size_t)batch * 4, st));
       RBOD_TRY(launch_exact_collect(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim,
                                     g->dp, g->metric, g->rows, static_cast<const uint32_t*>(mask_dev),
@@ -675,7 +747,8 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
 
   if (stats) {
     stats->fallback_queries = n_flag;
-    stats->k3_launches = 1;
+    stats->k3_launches = k3_launches;
+    stats->sweep_queries = n_sweep;
     stats->total_launches = launches;
     stats->max_eps = max_eps;
     if (g->time_k3) {
@@ -712,7 +785,7 @@ int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* o
     dst = g->dump.as<float>();
   }
   RBOD_CUDA(cudaMemsetAsync(dst, 0xff, (size_t)Q * ld * 4, st));  // NaN pattern: unwritten cells show up
-  RBOD_TRY(run_k3(g, P, Q, nullptr, dst, ld, st));
+  RBOD_TRY(run_k3(g, P, Q, g->q16.as<uint16_t>(), nullptr, nullptr, dst, ld, st));
   if (!out_dev) RBOD_CUDA(cudaMemcpyAsync(out, dst, (size_t)Q * ld * 4, cudaMemcpyDeviceToHost, st));
   RBOD_CUDA(cudaStreamSynchronize(st));
   return RBOD_OK;

@@ -51,6 +51,12 @@ __device__ __forceinline__ float warp_max_f32(float v) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // atomic max on non-negative floats (bit pattern order == value order)
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
   atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));

@@ -51,6 +51,8 @@ constexpr int K3_KBLOCK = 64;        // 16-bit elements per 128-byte swizzle row
 constexpr int K3_MAX_DP = 768;       // A operand must fit 384 TMEM columns
 constexpr int K3_THREADS = 192;      // warp0 TMA, warp1 MMA, warps 2-5 epilogue
 constexpr int K3_MAX_KC = 128;
+constexpr int K3_COLLECT_CAP = 1024; // rows a collecting pass records per query before it reports overflow
+constexpr int K3_TAU_REFRESH = 32;   // tiles between two looks at the threshold shared by a query's slices
 
 struct K3Launch {
   CUtensorMap tmap_b;     // gallery [rows, dp] 16-bit, box {64, 128}, SWIZZLE_128B
@@ -71,10 +73,16 @@ struct K3Launch {
   float* part_score;      // [slices][q_pad][kc]
   uint32_t* part_idx;     // [slices][q_pad][kc]
   const uint32_t* row_mask;
+  uint32_t* tau_shared;   // [q_pad] ordered-key thresholds shared across slices, preset to key(-inf); or nullptr
+  const float* collect_thr;   // collect mode (second pass for uncertified queries), see k3_cosine_topk.cu
+  uint32_t* coll_idx;
+  int* coll_cnt;
+  int coll_cap;
   float* dump;            // optional raw scores [q_pad][dump_ld]
   int64_t dump_ld;
   int* sync_counters;     // zeroed [slices * sync_span * sync_windows] ints, or nullptr
   int sync_window, sync_lead, sync_span, sync_windows;
+  int debug_epi;          // bring-up: 1 = epilogue selects nothing, 2 = epilogue does not read the tile
   int grid;
   size_t smem_bytes;
 };
@@ -100,7 +108,7 @@ int k3_box_rows(int variant);   // gallery rows per TMA box (64 for the CTA-pair
 int launch_k3(const K3Launch& L, cudaStream_t st);
 // query preparation: normalise, round to 16 bit, per-query error radius and |q|^2
 int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16, uint16_t* q16,
-                        float* q_dq, double* q_qq, cudaStream_t st);
+                        float* q_dq, double* q_qq, uint32_t* tau_shared, cudaStream_t st);
 // K4 family
 int launch_merge_partials(const float* part_score, const uint32_t* part_idx, int slices, int64_t q_pad,
                           int64_t Q, int kc, uint32_t* cand_idx, float* cand_tau, cudaStream_t st);
@@ -109,8 +117,14 @@ int launch_rescore(const float* q, const double* q_qq, const float* master32, co
                    double* cand_score, cudaStream_t st);
 int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
                   const float* stats, int master16, int dp, int64_t Q, int kc, int k, float* out_scores, int64_t* out_rows,
-                  double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* max_eps,
+                  double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* flag_lo, float* max_eps,
                   cudaStream_t st);
+int launch_gather_flagged(const uint16_t* q16, int dp, const int* flag_q, int f0, int nf, int64_t nf_pad,
+                          uint16_t* fq16, int* coll_cnt, cudaStream_t st);
+int launch_rescore_collected(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
+                             int kind16, int dim, int64_t ld32, int64_t ld16, const int* flag_q, int f0, int nf,
+                             int cap, const uint32_t* coll_idx, const int* coll_cnt, double* coll_score,
+                             cudaStream_t st);
 int launch_exact_collect(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
                          int kind16, int dim, int64_t ld32, int64_t ld16, int metric, int64_t n_rows,
                          const uint32_t* row_mask, const int* flag_q, const double* flag_thr, int f0, int nf,
@@ -136,16 +150,19 @@ struct rbod_gallery {
   int k3_variant = 0;
   int slack = -1;  // -1 = automatic
   int time_k3 = 0;
+  int debug_epi = 0;
+  int collect_pass = 1;   // uncertified queries get a collecting tensor-core pass before the fp64 sweep
+  int tau_share = 1;      // slices of one query share their candidate threshold through global memory
   int hybrid = 1;         // allow the query tile to be split between TMEM and resident smem
   int l2_sync = 1;        // producer throttle that keeps slice-mates within an L2 window
   int sync_window = 16, sync_lead = 4;
   // workspaces
   rbod::DevBuf stage_rows, stage_slots, stage_norms;          // upsert staging
-  rbod::DevBuf q32, q16, q_dq, q_qq;                          // query prep
+  rbod::DevBuf q32, q16, q_dq, q_qq, tau_shared;              // query prep
   rbod::DevBuf part_score, part_idx, cand_idx, cand_tau, cand_score;
   rbod::DevBuf out_scores, out_rows, out_scores64;
   rbod::DevBuf flags;      // ints: [0]=n_flag [1]=overflow [2]=err; float max_eps at [3]
-  rbod::DevBuf flag_q, flag_thr;
+  rbod::DevBuf flag_q, flag_thr, flag_lo, fq16;
   rbod::DevBuf coll_score, coll_idx, coll_cnt;
   rbod::DevBuf mask_dev, dump, sync_counters;
   rbod::DevBuf seg_idx, seg_off, seg_out, seg_partials, seg_prefix, seg_arrive;
