@@ -25,6 +25,11 @@ namespace rbod {
 namespace {
 
 constexpr int K1_WARPS = 8;
+constexpr int K1_PREFETCH_ROWS = 2;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 __device__ __forceinline__ void finish_row_stats(float s16, float sy, float sd, bool master_is_f32, bool cosine,
                                                  float& wmax_norm, float& wmax_dev) {
@@ -60,6 +65,13 @@ l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const i
 
   for (int64_t row = warp0; row < n; row += nwarps) {
     const float4* src = reinterpret_cast<const float4*>(in + row * dim);
+    // pull the row this warp handles two iterations from now into L2 (one 128-byte line per lane): the
+    // demand loads below then see L2 latency instead of HBM latency, which is what the 2 resident CTAs
+    // per SM (100 registers per thread) cannot hide on their own
+    {
+      const int64_t ahead = row + K1_PREFETCH_ROWS * nwarps;
+      if (ahead < n && lane < NV * 4) prefetch_l2(in + ahead * dim + lane * 32);
+    }
     float4 v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = __ldcs(src + lane + 32 * i);
