@@ -1,0 +1,78 @@
+"""Multi-GPU search path (row shards -> local top-k -> all-gather -> K4 merge), host logic on CPU:
+two gloo ranks, the local search and the merge answered by the oracle (injected), results compared with
+a single brute force over the whole gallery.  The NCCL/K4 version runs in bench.py --gpus N on B200s."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle_np as O
+from retrieval_based_object_detection_b200.sharded import ShardedGallery, shard_range
+
+
+def test_shard_range_partitions_exactly():
+    for n, w in ((10, 3), (7, 8), (10_000_000, 8), (0, 2), (1, 1)):
+        ranges = [shard_range(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = [b - a for a, b in ranges]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 3, 3)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, dim, Q, k, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = O.synthetic_unit_rows(n, dim, seed=0)
+        x[n // 2 + 3] = x[5]                                  # an exact tie across the two shards
+        stored = O.l2_normalize_store(x, "bf16")[0]
+        q = O.synthetic_unit_rows(Q, dim, seed=1)
+        q[0] = x[5]
+
+        def local_search(queries, kk):                        # what Gallery.search returns for this rank's rows
+            a, b = shard_range(n, rank, world)
+            s, i = O.cosine_topk(np.asarray(queries), stored[a:b], kk)
+            return torch.from_numpy(s), torch.from_numpy(i)
+
+        def merge(g_s, g_i, kk):                              # what rbod_merge_topk does
+            s, i = O.merge_topk(g_s.numpy(), g_i.numpy(), kk)
+            return torch.from_numpy(s.astype(np.float32)), torch.from_numpy(i), torch.from_numpy(s)
+
+        sg = ShardedGallery(dim, n, dtype="bf16", local_search=local_search, merge=merge, create_local=False)
+        assert (sg.row_start, sg.row_end) == shard_range(n, rank, world)
+        s32, ids, s64 = sg.search(q, k)
+        np.save(os.path.join(out_dir, f"ids_{rank}.npy"), ids.numpy())
+        np.save(os.path.join(out_dir, f"s64_{rank}.npy"), s64.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,k", [(301, 10), (7, 5)])
+def test_two_rank_search_equals_single_brute_force(tmp_path, n, k):
+    dim, Q, world = 64, 9, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, dim, Q, k, str(tmp_path)), nprocs=world, join=True)
+    x = O.synthetic_unit_rows(n, dim, seed=0)
+    x[n // 2 + 3] = x[5]
+    stored = O.l2_normalize_store(x, "bf16")[0]
+    q = O.synthetic_unit_rows(Q, dim, seed=1)
+    q[0] = x[5]
+    ws, wi = O.cosine_topk(q, stored, k)
+    for r in range(world):
+        ids, s64 = np.load(tmp_path / f"ids_{r}.npy"), np.load(tmp_path / f"s64_{r}.npy")
+        assert np.array_equal(ids, wi)                        # every rank holds the same global answer
+        fin = np.isfinite(ws)
+        assert np.allclose(s64[fin], ws[fin], rtol=0, atol=1e-15)
+    assert list(wi[0][:2]) == [5, n // 2 + 3]                 # the cross-shard tie resolves to the smaller global id

@@ -1,0 +1,235 @@
+"""Host side of the drop-in ``qdrant_client`` (ids, payload filters, scroll paging, staging, persistence, error
+behaviour) on CPU.  Vector arithmetic is answered by the Gallery test double (tests/fakes/fake_gallery.py = the
+oracle); the same scenarios run against librbod.so in tests/test_gpu_shim.py.
+
+Behaviours and the reference call sites that rely on them are listed in SURVEY.md §8(b)/(c).
+"""
+import hashlib
+import uuid
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as O
+from fakes import fake_gallery
+
+
+@pytest.fixture()
+def client(store_dir, monkeypatch):
+    import retrieval_based_object_detection_b200 as pkg
+    import retrieval_based_object_detection_b200.gallery as gallery
+
+    monkeypatch.setattr(gallery, "Gallery", fake_gallery.FakeGallery)
+    monkeypatch.setattr(pkg, "Gallery", fake_gallery.FakeGallery)
+    from qdrant_client import QdrantClient
+
+    return QdrantClient(host="localhost", port=6333)
+
+
+def _models():
+    from qdrant_client import models
+
+    return models
+
+
+def _payload(cls, i, data_type="original_images", seg=False, aug=False):
+    # the 8 keys of 31_clip_embedding_and_save_vector.py:166-175
+    return {"data_type": data_type, "is_cropped": True, "is_segmented": seg, "is_augmented": aug, "class_name": cls,
+            "is_delegate": False, "delegate_type": None, "img_path": f"dataset_cropped/{data_type}/{cls}/{i}.png"}
+
+
+def _fill(client, name="thesis", n=60, dim=512, classes=("cup", "dog", "tree")):
+    m = _models()
+    client.recreate_collection(collection_name=name, vectors_config=m.VectorParams(size=dim, distance=m.Distance.COSINE))
+    rng = np.random.default_rng(0)
+    vecs = rng.standard_normal((n, dim)).astype(np.float32) * 3.0
+    ids = []
+    for i in range(n):
+        cls = classes[i % len(classes)]
+        pl = _payload(cls, i, data_type="natural_images" if i % 2 else "original_images", seg=(i % 4 == 0))
+        pid = hashlib.md5(pl["img_path"].encode()).hexdigest()            # 31:42-43
+        ids.append(pid)
+        client.upsert(collection_name=name, points=[m.PointStruct(id=pid, vector=vecs[i].tolist(), payload=pl)])
+    return vecs, ids
+
+
+def test_collection_admin_matches_qdrant_manager_calls(client):
+    m = _models()
+    assert client.get_collections().collections == []
+    assert client.recreate_collection(collection_name="a", vectors_config=m.VectorParams(size=512, distance=m.Distance.COSINE))
+    client.recreate_collection(collection_name="b", vectors_config=m.VectorParams(size=8, distance=m.Distance.DOT))
+    assert [c.name for c in client.get_collections().collections] == ["a", "b"]
+    assert client.get_collection("a").points_count == 0                   # util/qdrant_manager.py:46-47
+    assert client.count("a", exact=True).count == 0                        # 32:67
+    client.rename_collection(old_collection_name="a", new_collection_name="c")   # util/qdrant_manager.py:99
+    assert [c.name for c in client.get_collections().collections] == ["b", "c"]
+    with pytest.raises(Exception):
+        client.get_collection("a")                                          # unknown collection raises (404)
+    with pytest.raises(Exception):
+        client.create_collection("b", vectors_config=m.VectorParams(size=8, distance=m.Distance.DOT))
+    client.recreate_collection(collection_name="b", vectors_config=m.VectorParams(size=4, distance=m.Distance.COSINE))
+    assert client.get_collection("b").config.params.vectors.size == 4      # recreate = drop + create
+    assert client.delete_collection("b") and not client.delete_collection("b")
+    for bad in ("", "x/y", ".."):
+        with pytest.raises(ValueError):
+            client.create_collection(bad, vectors_config=m.VectorParams(size=4, distance=m.Distance.COSINE))
+
+
+def test_ids_are_canonical_and_upsert_overwrites(client):
+    m = _models()
+    client.recreate_collection(collection_name="t", vectors_config=m.VectorParams(size=4, distance=m.Distance.COSINE))
+    hex_id = hashlib.md5(b"some/path.png").hexdigest()
+    client.upsert("t", points=[m.PointStruct(id=hex_id, vector=[1, 0, 0, 0], payload={"v": 1})])
+    client.upsert("t", points=[m.PointStruct(id=str(uuid.UUID(hex_id)), vector=[0, 2, 0, 0], payload={"v": 2})])
+    client.upsert("t", points=[m.PointStruct(id=7, vector=[0, 0, 3, 0], payload=None)])
+    assert client.count("t").count == 2                                    # same UUID in two spellings = one point
+    recs, nxt = client.scroll("t", with_vectors=True)
+    assert nxt is None and [r.id for r in recs] == [7, str(uuid.UUID(hex_id))]    # ints first, then UUIDs; hyphenated
+    assert recs[1].payload == {"v": 2} and recs[0].payload == {}
+    assert np.allclose(recs[1].vector, [0, 1, 0, 0]) and np.allclose(recs[0].vector, [0, 0, 1, 0])   # normalised
+    for bad in ("not-a-uuid", -1, 1 << 64, 1.5, True):
+        with pytest.raises(ValueError):
+            client.upsert("t", points=[m.PointStruct(id=bad, vector=[1, 0, 0, 0], payload={})])
+    with pytest.raises(ValueError):
+        client.upsert("t", points=[m.PointStruct(id=1, vector=[1, 0, 0], payload={})])          # wrong dimension
+
+
+def test_scroll_filters_paging_and_access_patterns(client):
+    m = _models()
+    vecs, ids = _fill(client)
+    # 32:78-82 -- no filter, limit 9999, [0] index, payload.get
+    results = client.scroll(collection_name="thesis", limit=9999, with_payload=True)[0]
+    assert len(results) == 60
+    assert sorted({p.payload.get("class_name") for p in results if p.payload.get("is_delegate") != True}) == \
+        ["cup", "dog", "tree"]
+    assert results[0].vector is None
+    assert [r.id for r in results] == sorted((str(uuid.UUID(i)) for i in ids), key=lambda s: uuid.UUID(s).int)
+    # default limit is 10 (33:96-106 relies on it returning at least the one match)
+    page, nxt = client.scroll(collection_name="thesis")
+    assert len(page) == 10 and nxt == results[10].id
+    seen = [r.id for r in page]
+    while nxt is not None:
+        page, nxt = client.scroll(collection_name="thesis", offset=nxt, limit=7)
+        seen += [r.id for r in page]
+    assert seen == [r.id for r in results]
+    # 32:123-131 -- AND of equalities, bools and strings
+    flt = m.Filter(must=[m.FieldCondition(key="class_name", match=m.MatchValue(value="dog")),
+                         m.FieldCondition(key="is_delegate", match=m.MatchValue(value=False)),
+                         m.FieldCondition(key="is_cropped", match=m.MatchValue(value=True)),
+                         m.FieldCondition(key="is_segmented", match=m.MatchValue(value=False)),
+                         m.FieldCondition(key="is_augmented", match=m.MatchValue(value=False))])
+    recs, _ = client.scroll(collection_name="thesis", scroll_filter=flt, with_vectors=True, with_payload=True, limit=10000)
+    want = [i for i in range(60) if i % 3 == 1 and i % 4 != 0]
+    assert sorted(r.payload["img_path"] for r in recs) == sorted(_payload("dog", i, "natural_images" if i % 2 else "original_images")["img_path"] for i in want)
+    stored = O.l2_normalize_store(vecs, "f32")[0]
+    by_path = {r.payload["img_path"]: np.array(r.vector) for r in recs}
+    for i in want:
+        p = _payload("dog", i, "natural_images" if i % 2 else "original_images")["img_path"]
+        assert np.array_equal(by_path[p].astype(np.float32), stored[i])    # scroll returns the stored (normalised) row
+        assert isinstance(recs[0].vector, list) and isinstance(recs[0].vector[0], float)
+    # a None payload value never matches; True does not match 1; unknown key matches nothing
+    none = m.Filter(must=[m.FieldCondition(key="delegate_type", match=m.MatchValue(value=None))])
+    assert client.scroll("thesis", scroll_filter=none)[0] == []
+    one = m.Filter(must=[m.FieldCondition(key="is_cropped", match=m.MatchValue(value=1))])
+    assert client.scroll("thesis", scroll_filter=one)[0] == []
+    assert client.scroll("thesis", scroll_filter=m.Filter(must=[m.FieldCondition(key="nope", match=m.MatchValue(value="x"))]))[0] == []
+    assert client.count("thesis", count_filter=flt).count == len(want)
+    with pytest.raises(ValueError):
+        client.scroll("thesis", limit=0)
+
+
+def test_delegate_round_trip_like_script_32_and_33(client):
+    """The arithmetic chain of 32 (scroll -> numpy delegate -> upsert) and 33 (scroll limit=1 -> cosine)."""
+    from oracle import ref_loader as R
+
+    m = _models()
+    vecs, ids = _fill(client)
+    flt = m.Filter(must=[m.FieldCondition(key="class_name", match=m.MatchValue(value="cup")),
+                         m.FieldCondition(key="is_delegate", match=m.MatchValue(value=False))])
+    results, _ = client.scroll(collection_name="thesis", scroll_filter=flt, with_vectors=True, with_payload=True, limit=10000)
+    vectors_np = np.array([r.vector for r in results])                     # 32:137
+    assert vectors_np.dtype == np.float64 and vectors_np.shape == (20, 512)
+    mean = O.compute_average(vectors_np)
+    if R.available():
+        assert np.array_equal(mean, R.delegate_module().compute_average(vectors_np))
+    payload = {"class_name": "cup", "is_delegate": True, "delegate_type": "average"}
+    pid = hashlib.md5("cup::average::x::False::False".encode()).hexdigest()          # 32:29-31
+    client.upsert(collection_name="thesis", points=[m.PointStruct(id=pid, vector=mean.tolist(), payload=payload)])
+    got, _ = client.scroll(collection_name="thesis", with_vectors=True, limit=1, scroll_filter=m.Filter(must=[
+        m.FieldCondition(key="delegate_type", match=m.MatchValue(value="average")),
+        m.FieldCondition(key="is_delegate", match=m.MatchValue(value=True)),
+        m.FieldCondition(key="class_name", match=m.MatchValue(value="cup"))]))
+    assert len(got) == 1
+    want = O.l2_normalize_store(mean.astype(np.float32)[None], "f32")[0][0]
+    assert np.array_equal(np.array(got[0].vector, dtype=np.float32), want)
+    # the batched K2 entry point gives the same delegate for every class in one call
+    names, cents = client.build_delegates("thesis", group_key="class_name",
+                                          scroll_filter=m.Filter(must=[m.FieldCondition(key="is_delegate", match=m.MatchValue(value=False))]))
+    assert names == ["cup", "dog", "tree"] and np.array_equal(cents[0], want)
+    # 33:151 on stored vectors: a member compared with itself gives the reference's known answer
+    v = np.array(results[0].vector)
+    assert O.cosine_similarity(v, v) in (1.0, 1.0000000000000002, 0.9999999999999999)
+
+
+def test_search_api_filters_thresholds_and_ties(client):
+    m = _models()
+    vecs, ids = _fill(client)
+    stored = O.l2_normalize_store(vecs, "f32")[0]
+    hits = client.search("thesis", query_vector=vecs[5].tolist(), limit=3, with_vectors=True)
+    assert hits[0].id == str(uuid.UUID(ids[5])) and abs(hits[0].score - 1.0) < 1e-6
+    assert [h.score for h in hits] == sorted((h.score for h in hits), reverse=True)
+    ws, wi = O.cosine_topk(vecs[5:6], stored, 3)
+    # slots are insertion order here, so oracle row i <-> ids[i]
+    assert [h.id for h in hits] == [str(uuid.UUID(ids[i])) for i in wi[0]]
+    flt = m.Filter(must=[m.FieldCondition(key="class_name", match=m.MatchValue(value="tree"))])
+    hits = client.query_points("thesis", query=vecs[5].tolist(), query_filter=flt, limit=50).points
+    assert len(hits) == 20 and all(h.payload["class_name"] == "tree" for h in hits)
+    assert client.search("thesis", vecs[5].tolist(), limit=5, score_threshold=0.999)[0].id == str(uuid.UUID(ids[5]))
+    assert len(client.search("thesis", vecs[5].tolist(), limit=5, score_threshold=0.999)) == 1
+    assert [h.id for h in client.search("thesis", vecs[5].tolist(), limit=2, offset=1)] == \
+        [h.id for h in client.search("thesis", vecs[5].tolist(), limit=3)][1:]
+    scores, idlists = client.search_batch("thesis", queries=vecs[:4], k=2)
+    assert scores.shape == (4, 2) and [l[0] for l in idlists] == [str(uuid.UUID(i)) for i in ids[:4]]
+    with pytest.raises(ValueError):
+        client.search("thesis", [1.0, 2.0], limit=1)
+
+
+def test_state_survives_processes_and_deletes(client, store_dir):
+    """The scripts are separate processes talking to one server: WAL + snapshot must carry everything."""
+    import qdrant_client as qc
+
+    m = _models()
+    vecs, ids = _fill(client, n=12)
+    recs_before, _ = client.scroll("thesis", limit=100, with_vectors=True)
+    qc._close_all()                                                        # "process exit" with a device copy: snapshot
+    c2 = qc.QdrantClient(host="localhost", port=6333)
+    assert c2.count("thesis").count == 12
+    # a second "process" that only upserts (31_…py) never touches the device: its points live in the WAL
+    c2.upsert("thesis", points=[m.PointStruct(id=3, vector=(np.arange(512) + 1.0).tolist(), payload={"class_name": "new"})])
+    qc._ROOTS.clear()                                                      # drop without close(): crash-like
+    c3 = qc.QdrantClient(host="localhost", port=6333)
+    assert c3.count("thesis").count == 13
+    recs_after, _ = c3.scroll("thesis", limit=100, with_vectors=True)
+    assert recs_after[0].id == 3 and recs_after[0].payload == {"class_name": "new"}
+    assert [(r.id, r.payload, r.vector) for r in recs_after[1:]] == [(r.id, r.payload, r.vector) for r in recs_before]
+    c3.delete("thesis", points_selector=[3, ids[0]])
+    assert c3.count("thesis").count == 11
+    assert str(uuid.UUID(ids[0])) not in [r.id for r in c3.scroll("thesis", limit=100)[0]]
+    qc._close_all()
+    c4 = qc.QdrantClient(host="localhost", port=6333)
+    left, _ = c4.scroll("thesis", limit=100, with_vectors=True)
+    assert len(left) == 11 and {r.id for r in left} == {r.id for r in recs_before} - {str(uuid.UUID(ids[0]))}
+    want = {r.id: r.vector for r in recs_before}
+    assert all(r.vector == want[r.id] for r in left)
+    # another (host, port) is another server
+    assert qc.QdrantClient(host="localhost", port=7000).get_collections().collections == []
+
+
+def test_single_point_upserts_are_batched_into_one_device_flush(client):
+    m = _models()
+    _fill(client, n=30)
+    col = client._root.get("thesis")
+    assert col.gallery is None and len(col.pending) == 30                  # 30 RPC-style upserts, no device work yet
+    client.scroll("thesis", with_vectors=True, limit=1)                    # first read that needs vectors
+    assert [c for c in col.gallery.calls if c[0] == "upsert"] == [("upsert", 30)]
+    assert not col.pending
