@@ -4,13 +4,14 @@
 // scrolled at :123-137, followed by the renormalisation the COSINE collection applies when the
 // mean is upserted (:41-42).
 //
-// Work decomposition: a work item is (class, chunk of <= SEG_CHUNK rows).  A one-block planning
-// kernel turns the CSR offsets into an exclusive prefix of item counts; the main kernel launches
-// an upper bound of items and each CTA finds its (class, chunk) by binary search, so skewed class
-// sizes spread over many CTAs with no host round trip.  Inside a CTA the 4 warps take rows
-// round-robin, lanes cover the row with 128-bit loads, and every lane accumulates its columns in
-// fp64 registers; warps are combined through shared memory.  Single-chunk classes are finished
-// in place; multi-chunk classes park an fp64 partial per chunk and the last CTA to arrive adds
+// Work decomposition: a work item is (class, chunk of <= K2_SEG_CHUNK rows) and belongs to ONE WARP.
+// A one-block planning kernel turns the CSR offsets into an exclusive prefix of item counts; the
+// main kernel launches an upper bound of items and each warp finds its (class, chunk) by binary
+// search, so skewed class sizes spread over many warps with no host round trip.  Lanes cover the
+// row with 128-bit loads, two rows in flight per warp, and every lane accumulates its columns in
+// fp64 registers -- no shared memory, no block barrier, so a warp that is normalising and writing
+// its class never stalls the warps that are still streaming.  Single-chunk classes are finished
+// in place; multi-chunk classes park an fp64 partial per chunk and the last warp to arrive adds
 // the partials in chunk order (deterministic) and finishes.
 //
 // Numerics (mirrored by oracle/oracle_np.py::segment_mean_renorm): m = fp32(sum_fp64 / len),
@@ -22,14 +23,17 @@ namespace rbod {
 
 namespace {
 
-constexpr int SEG_CHUNK = 1024;
+constexpr int SEG_CHUNK = K2_SEG_CHUNK;
 constexpr int SEG_WARPS = 4;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 constexpr int SEG_THREADS = SEG_WARPS * 32;
 
 // prefix[c]  = number of items before class c            (c = 0..C)
 // prefix[C+1+c] = number of parked partial slots before class c (multi-chunk classes only)
-__global__ void seg_plan_kernel(const int64_t* __restrict__ offsets, int64_t C, int* __restrict__ prefix,
-                                unsigned int* __restrict__ arrive) {
+__global__ void seg_plan_kernel(const int64_t* __restrict__ offsets, int64_t C, int* __restrict__ prefix) {
   __shared__ int s_items[1024];
   __shared__ int s_parts[1024];
   __shared__ int carry_items, carry_parts;
@@ -42,7 +46,6 @@ __global__ void seg_plan_kernel(const int64_t* __restrict__ offsets, int64_t C, 
       const int64_t len = offsets[c + 1] - offsets[c];
       items = len > 0 ? (int)((len + SEG_CHUNK - 1) / SEG_CHUNK) : 1;  // empty class: 1 item writes zeros
       parts = items > 1 ? items : 0;
-      arrive[c] = 0u;
     }
     s_items[threadIdx.x] = items;
     s_parts[threadIdx.x] = parts;
@@ -67,19 +70,67 @@ __global__ void seg_plan_kernel(const int64_t* __restrict__ offsets, int64_t C, 
   if (threadIdx.x == 0) { prefix[C] = carry_items; prefix[2 * C + 1] = carry_parts; }
 }
 
-// VEC = 4: dim == 128 * NG, 128-bit loads.  VEC = 1: dim <= 32 * NG, scalar loads.
-template <int VEC, int NG>
+// One WARP per work item (class, chunk).  VEC = 4: dim == 128 * NG, 128-bit loads; VEC = 1: dim <= 32 * NG,
+// scalar loads.  Lane l owns columns {(l + 32 g) * VEC + e}; rows are streamed UN at a time (2 fp32 rows or
+// 4 16-bit rows = 6 KB in flight per warp at dim 768) with the next UN rows prefetched into L2.  No shared
+// memory and no block barrier: while one warp normalises and writes its class, its neighbours keep streaming.
+//
+// Classes longer than one chunk are reduced over a fixed binary tree whose nodes live in the chunks' own
+// partial slots (node (level, i) is stored in the slot of its leftmost leaf): a warp stores its sum, sets the
+// parent's bit in that slot's flag word, and the second of two siblings to arrive adds left + right and climbs.
+// The shape of the tree depends only on the chunk count, so the sum is deterministic, and no warp ever waits.
+template <int IS16, int NG>
+struct K2Row {
+  uint2 v[NG];
+  __device__ __forceinline__ void load(const uint16_t* rows16, int64_t r, int64_t ld, int lane) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) v[g] = __ldcs(reinterpret_cast<const uint2*>(rows16 + r * ld) + lane + 32 * g);
+  }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) v[g] = make_uint2(0u, 0u);
+  }
+  __device__ __forceinline__ void add_to(double* acc, int kind16) const {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      acc[4 * g + 0] += (double)h16_to_f32((uint16_t)(v[g].x & 0xffffu), kind16);
+      acc[4 * g + 1] += (double)h16_to_f32((uint16_t)(v[g].x >> 16), kind16);
+      acc[4 * g + 2] += (double)h16_to_f32((uint16_t)(v[g].y & 0xffffu), kind16);
+      acc[4 * g + 3] += (double)h16_to_f32((uint16_t)(v[g].y >> 16), kind16);
+    }
+  }
+};
+template <int NG>
+struct K2Row<0, NG> {
+  float4 v[NG];
+  __device__ __forceinline__ void load(const float* master32, int64_t r, int64_t ld, int lane) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) v[g] = __ldcs(reinterpret_cast<const float4*>(master32 + r * ld) + lane + 32 * g);
+  }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void add_to(double* acc, int) const {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      acc[4 * g + 0] += (double)v[g].x;
+      acc[4 * g + 1] += (double)v[g].y;
+      acc[4 * g + 2] += (double)v[g].z;
+      acc[4 * g + 3] += (double)v[g].w;
+    }
+  }
+};
+
+template <int VEC, int NG, int IS16>
 __global__ void __launch_bounds__(SEG_THREADS)
 seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__ rows16, int kind16, int dim,
                 int64_t ld32, int64_t ld16, int64_t n_valid, const int64_t* __restrict__ row_idx,
                 const int64_t* __restrict__ offsets, int64_t C, const int* __restrict__ prefix,
-                double* __restrict__ partials, unsigned int* __restrict__ arrive, float* __restrict__ out,
+                double* __restrict__ partials, unsigned int* __restrict__ node_bits, float* __restrict__ out,
                 int* __restrict__ err_flag) {
-  extern __shared__ double s_acc[];  // [SEG_WARPS][dim]
-  __shared__ double s_red[SEG_WARPS];
-  __shared__ int s_last;
-
-  const int item = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * SEG_WARPS + warp;
   if (item >= prefix[C]) return;
   // largest c with prefix[c] <= item
   int64_t lo = 0, hi = C - 1;
@@ -94,121 +145,143 @@ seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__
   const int64_t r0 = seg0 + (int64_t)chunk * SEG_CHUNK;
   const int64_t r1 = (r0 + SEG_CHUNK < seg1) ? r0 + SEG_CHUNK : seg1;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NACC = VEC * NG;
   double acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
 
-  for (int64_t i = r0 + warp; i < r1; i += SEG_WARPS) {
+  auto row_of = [&](int64_t i) -> int64_t {
     const int64_t r = row_idx ? row_idx[i] : i;
     if (r < 0 || r >= n_valid) {
       if (lane == 0) atomicExch(err_flag, 1);
-      continue;
+      return -1;
     }
-    if constexpr (VEC == 4) {
-      if (master32) {
-        const float4* src = reinterpret_cast<const float4*>(master32 + r * ld32);
-        float4 v[NG];
+    return r;
+  };
+
+  if constexpr (VEC == 4) {
+    constexpr int UN = IS16 ? 4 : 2;
+    constexpr int LINES = IS16 ? NG * 2 : NG * 4;   // 128-byte lines per row
+    int64_t i = r0;
+    for (; i + UN <= r1; i += UN) {
+      int64_t rr[UN];
 #pragma unroll
-        for (int g = 0; g < NG; ++g) v[g] = __ldcs(src + lane + 32 * g);
+      for (int u = 0; u < UN; ++u) rr[u] = row_of(i + u);
+      if (i + 2 * UN <= r1 && lane < LINES) {
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          acc[4 * g + 0] += (double)v[g].x;
-          acc[4 * g + 1] += (double)v[g].y;
-          acc[4 * g + 2] += (double)v[g].z;
-          acc[4 * g + 3] += (double)v[g].w;
-        }
-      } else {
-        const uint2* src = reinterpret_cast<const uint2*>(rows16 + r * ld16);
-        uint2 v[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) v[g] = __ldcs(src + lane + 32 * g);
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          acc[4 * g + 0] += (double)h16_to_f32((uint16_t)(v[g].x & 0xffffu), kind16);
-          acc[4 * g + 1] += (double)h16_to_f32((uint16_t)(v[g].x >> 16), kind16);
-          acc[4 * g + 2] += (double)h16_to_f32((uint16_t)(v[g].y & 0xffffu), kind16);
-          acc[4 * g + 3] += (double)h16_to_f32((uint16_t)(v[g].y >> 16), kind16);
+        for (int u = 0; u < UN; ++u) {
+          const int64_t pr = row_idx ? row_idx[i + UN + u] : i + UN + u;
+          if (pr >= 0 && pr < n_valid) {
+            if (IS16) prefetch_l2(rows16 + pr * ld16 + lane * 64);
+            else prefetch_l2(master32 + pr * ld32 + lane * 32);
+          }
         }
       }
-    } else {
+      K2Row<IS16, NG> row[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (rr[u] >= 0) {
+          if constexpr (IS16) row[u].load(rows16, rr[u], ld16, lane);
+          else row[u].load(master32, rr[u], ld32, lane);
+        } else {
+          row[u].zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) row[u].add_to(acc, kind16);
+    }
+    for (; i < r1; ++i) {
+      const int64_t r = row_of(i);
+      if (r < 0) continue;
+      K2Row<IS16, NG> row;
+      if constexpr (IS16) row.load(rows16, r, ld16, lane);
+      else row.load(master32, r, ld32, lane);
+      row.add_to(acc, kind16);
+    }
+  } else {
+    for (int64_t i = r0; i < r1; ++i) {
+      const int64_t r = row_of(i);
+      if (r < 0) continue;
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
         const int col = lane + 32 * g;
         if (col < dim) {
-          const float x = master32 ? master32[r * ld32 + col] : h16_to_f32(rows16[r * ld16 + col], kind16);
+          const float x = IS16 ? h16_to_f32(rows16[r * ld16 + col], kind16) : master32[r * ld32 + col];
           acc[g] += (double)x;
         }
       }
     }
   }
 
-  // park per-warp sums: column of acc[...] for this lane
-  double* mine = s_acc + (size_t)warp * dim;
-  if constexpr (VEC == 4) {
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) mine[(lane + 32 * g) * 4 + e] = acc[4 * g + e];
-    }
-  } else {
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      const int col = lane + 32 * g;
-      if (col < dim) mine[col] = acc[g];
-    }
-  }
-  __syncthreads();
-  // combine warps in fixed order into s_acc[0][*]
-  for (int col = threadIdx.x; col < dim; col += SEG_THREADS) {
-    double s = s_acc[col];
-#pragma unroll
-    for (int w = 1; w < SEG_WARPS; ++w) s += s_acc[(size_t)w * dim + col];
-    s_acc[col] = s;
-  }
-  __syncthreads();
+  // column index of accumulator a of this lane
+  auto col_of = [&](int a) -> int { return VEC == 4 ? (lane + 32 * (a >> 2)) * 4 + (a & 3) : lane + 32 * a; };
 
   if (nchunks > 1) {
     const int part0 = prefix[C + 1 + c];
-    double* dst = partials + (size_t)(part0 + chunk) * dim;
-    for (int col = threadIdx.x; col < dim; col += SEG_THREADS) dst[col] = s_acc[col];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned int prev = atomicAdd(arrive + c, 1u);
-      s_last = (prev == (unsigned int)(nchunks - 1));
+    double* slots = partials + (size_t)part0 * dim;
+    unsigned int* bits = node_bits + part0;
+    int idx = chunk;      // node index on its level
+    int level = 0;
+    int count = nchunks;  // nodes on this level
+    while (count > 1) {
+      if ((idx ^ 1) >= count) {   // no sibling on this level: the node is its own parent
+        idx >>= 1;
+        ++level;
+        count = (count + 1) >> 1;
+        continue;
+      }
+      // publish this node's sum in the slot of its leftmost leaf, then claim the parent
+      double* mine = slots + (size_t)((int64_t)idx << level) * dim;
+#pragma unroll
+      for (int a = 0; a < NACC; ++a)
+        if (col_of(a) < dim) mine[col_of(a)] = acc[a];
+      __threadfence();
+      __syncwarp();
+      const int parent_leaf = (idx >> 1) << (level + 1);
+      unsigned int prev = 0;
+      if (lane == 0) prev = atomicOr(bits + parent_leaf, 1u << level);
+      prev = __shfl_sync(FULL_MASK, prev, 0);
+      if (!(prev & (1u << level))) return;   // first of the two siblings: the other one carries on
+      __threadfence();
+      const double* other = slots + (size_t)((int64_t)(idx ^ 1) << level) * dim;
+      if (idx & 1) {   // left + right, whoever arrives last
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+          if (col_of(a) < dim) acc[a] = __ldcg(other + col_of(a)) + acc[a];
+      } else {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+          if (col_of(a) < dim) acc[a] = acc[a] + __ldcg(other + col_of(a));
+      }
+      idx >>= 1;
+      ++level;
+      count = (count + 1) >> 1;
     }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const double* src = partials + (size_t)part0 * dim;
-    for (int col = threadIdx.x; col < dim; col += SEG_THREADS) {
-      double s = 0.0;
-      for (int j = 0; j < nchunks; ++j) s += __ldcg(src + (size_t)j * dim + col);
-      s_acc[col] = s;
-    }
-    __syncthreads();
   }
 
   // finish: m = fp32(sum / len); out = K1 normalisation of m
   const int64_t len = seg1 - seg0;
-  const double inv_len = len > 0 ? 1.0 / (double)len : 0.0;
   double ss = 0.0;
-  for (int col = threadIdx.x; col < dim; col += SEG_THREADS) {
-    const float m = len > 0 ? (float)(s_acc[col] / (double)len) : 0.0f;
-    (void)inv_len;
-    s_acc[col] = (double)m;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    const float m = (len > 0 && col_of(a) < dim) ? (float)(acc[a] / (double)len) : 0.0f;
+    acc[a] = (double)m;
     ss = fma((double)m, (double)m, ss);
   }
   ss = warp_sum_f64(ss);
-  if (lane == 0) s_red[warp] = ss;
-  __syncthreads();
-  double tot = 0.0;
+  const double r = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+  float* o = out + c * dim;
+  if constexpr (VEC == 4) {
 #pragma unroll
-  for (int w = 0; w < SEG_WARPS; ++w) tot += s_red[w];
-  const double r = tot > 0.0 ? 1.0 / sqrt(tot) : 0.0;
-  for (int col = threadIdx.x; col < dim; col += SEG_THREADS) out[c * dim + col] = (float)(s_acc[col] * r);
+    for (int g = 0; g < NG; ++g)
+      reinterpret_cast<float4*>(o)[lane + 32 * g] =
+          make_float4((float)(acc[4 * g + 0] * r), (float)(acc[4 * g + 1] * r), (float)(acc[4 * g + 2] * r),
+                      (float)(acc[4 * g + 3] * r));
+  } else {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+      if (col_of(a) < dim) o[col_of(a)] = (float)(acc[a] * r);
+  }
 }
 
 }  // namespace
@@ -218,21 +291,24 @@ int launch_segment_mean(const float* master32, const uint16_t* rows16, int kind1
                         int64_t n_classes, int64_t n_items_upper, double* partials, int* chunk_prefix,
                         unsigned int* arrive_cnt, float* out, int* err_flag, cudaStream_t st) {
   if (n_classes <= 0) return RBOD_OK;
-  seg_plan_kernel<<<1, 1024, 0, st>>>(offsets, n_classes, chunk_prefix, arrive_cnt);
+  seg_plan_kernel<<<1, 1024, 0, st>>>(offsets, n_classes, chunk_prefix);
   RBOD_CUDA(cudaGetLastError());
-  const size_t smem = (size_t)SEG_WARPS * dim * sizeof(double);
-  const int grid = (int)n_items_upper;
+  const int grid = (int)((n_items_upper + SEG_WARPS - 1) / SEG_WARPS);
   const bool vec_ok = dim % 128 == 0 && dim / 128 <= 8 &&
                       (master32 ? (reinterpret_cast<uintptr_t>(master32) % 16 == 0 && ld32 % 4 == 0)
                                 : (reinterpret_cast<uintptr_t>(rows16) % 8 == 0 && ld16 % 4 == 0));
 #define RBOD_K2_LAUNCH(VEC, NG)                                                                              \
   do {                                                                                                       \
-    RBOD_CUDA(cudaFuncSetAttribute(seg_mean_kernel<VEC, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                   (int)smem));                                                              \
-    seg_mean_kernel<VEC, NG><<<grid, SEG_THREADS, smem, st>>>(master32, rows16, kind16, dim, ld32, ld16,      \
-                                                              n_valid, row_idx, offsets, n_classes,          \
-                                                              chunk_prefix, partials, arrive_cnt, out,       \
-                                                              err_flag);                                     \
+    if (master32)                                                                                            \
+      seg_mean_kernel<VEC, NG, 0><<<grid, SEG_THREADS, 0, st>>>(master32, rows16, kind16, dim, ld32, ld16,    \
+                                                                n_valid, row_idx, offsets, n_classes,        \
+                                                                chunk_prefix, partials, arrive_cnt, out,     \
+                                                                err_flag);                                   \
+    else                                                                                                     \
+      seg_mean_kernel<VEC, NG, 1><<<grid, SEG_THREADS, 0, st>>>(master32, rows16, kind16, dim, ld32, ld16,    \
+                                                                n_valid, row_idx, offsets, n_classes,        \
+                                                                chunk_prefix, partials, arrive_cnt, out,     \
+                                                                err_flag);                                   \
   } while (0)
   if (vec_ok) {
     switch (dim / 128) {

@@ -52,6 +52,9 @@ struct alignas(64) K3Params {
   uint32_t* coll_idx;         //   [q_pad][coll_cap] recorded row indices
   int* coll_cnt;              //   [q_pad] rows recorded (may exceed coll_cap: overflow, caller falls back)
   int coll_cap;
+  float* groupmax_out;        // sample mode: [slices][q_pad] row maxima over the unit's tiles (no candidate lists)
+  int group_stride;           // > 0: unit `slice` visits tiles slice, slice + stride, ... (at most group_tiles of them)
+  int group_tiles;
   float* dump;
   int64_t dump_ld;
   int64_t n_rows;
@@ -110,6 +113,25 @@ __device__ __noinline__ float k3_heap_replace_root(float* sc, uint32_t* ix, int 
   sc[j * K3_TILE_M] = s;
   ix[j * K3_TILE_M] = id;
   return sc[0];
+}
+
+// Tiles a work unit visits: t0, t0 + step, ... (n of them).  Normal launches cut the gallery into `slices`
+// contiguous ranges; sample launches (group_stride > 0) give unit `slice` a strided comb of tiles, which stays
+// representative when the gallery is stored in class order.
+struct K3TileRange { int t0, n, step; };
+__device__ __forceinline__ K3TileRange k3_unit_tiles(const K3Params& P, int slice) {
+  K3TileRange r;
+  if (P.group_stride > 0) {
+    r.t0 = slice;
+    r.step = P.group_stride;
+    const int avail = slice < P.tiles_total ? (P.tiles_total - slice + r.step - 1) / r.step : 0;
+    r.n = min(P.group_tiles, avail);
+  } else {
+    r.t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
+    r.n = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices) - r.t0;
+    r.step = 1;
+  }
+  return r;
 }
 
 // Geometry of one kernel flavour.
@@ -208,8 +230,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
     uint32_t phase = 0;
     for (int u = worker; u < num_units; u += num_workers) {
       const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
-      const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
-      const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
+      const K3TileRange tr = k3_unit_tiles(P, slice);
       // L2 sharing throttle: the CTAs that stream this slice in this round form a group; nobody
       // issues window w before every member has issued window w - lead.  That keeps the group's
       // working set (lead + 1 windows) hot in L2, so each gallery tile is fetched from HBM once per
@@ -224,9 +245,10 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         gsize = hi - lo;
         cnt = P.sync_counters + ((size_t)slice * P.sync_span + (round - first_round)) * P.sync_windows;
       }
-      for (int t = t0; t < t1; ++t) {
-        if (cnt != nullptr && gsize > 1 && (t - t0) % P.sync_window == 0) {
-          const int w = (t - t0) / P.sync_window;
+      for (int ti = 0; ti < tr.n; ++ti) {
+        const int t = tr.t0 + ti * tr.step;
+        if (cnt != nullptr && gsize > 1 && ti % P.sync_window == 0) {
+          const int w = ti / P.sync_window;
           if (elect_one()) {
             if (w > 0) {
               __threadfence();
@@ -296,14 +318,13 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
       const uint64_t desc_hi = make_smem_desc_sw128(0);  // everything except the start address
       for (int u = worker; u < num_units; u += num_workers) {
         const int slice = u / P.num_qt;
-        const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
-        const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
+        const K3TileRange tr = k3_unit_tiles(P, slice);
         if (VARIANT == 0) {
           mbar_wait(&bars->a_ready, unit_par, 2);
           unit_par ^= 1u;
           tc_fence_after();
         }
-        for (int t = t0; t < t1; ++t) {
+        for (int ti = 0; ti < tr.n; ++ti) {
           mbar_wait(&bars->tempty[acc], acc_phase ^ 1u, 3);
           tc_fence_after();
           const uint32_t d_tmem = tmem_b + (uint32_t)(P.acc_col0 + acc * K3_TILE_N);
@@ -374,8 +395,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
 
     for (int u = worker; u < num_units; u += num_workers) {
       const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
-      const int t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
-      const int t1 = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices);
+      const K3TileRange tr = k3_unit_tiles(P, slice);
       const int64_t q_unit0 = (int64_t)qt * G::Q_PER_UNIT + (int64_t)rank * K3_TILE_M;   // first query row of this CTA
       const int64_t qg = q_unit0 + row;
 
@@ -425,8 +445,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
       const bool collect = P.collect_thr != nullptr;
       if (collect) tau = qg < P.q_valid ? P.collect_thr[qg] : INFINITY;
 
-      for (int t = t0; t < t1; ++t) {
-        if (tau_cell != nullptr && ((t - t0) & (K3_TAU_REFRESH - 1)) == K3_TAU_REFRESH - 1) {
+      const bool groupmax = P.groupmax_out != nullptr;
+      float gmax_run = -INFINITY;
+      for (int ti = 0; ti < tr.n; ++ti) {
+        const int t = tr.t0 + ti * tr.step;
+        if (tau_cell != nullptr && (ti & (K3_TAU_REFRESH - 1)) == K3_TAU_REFRESH - 1) {
           const float root = my_sc[0];
           if (root > tau_published) {
             atomicMax(tau_cell, f32_to_ordered(root));
@@ -512,6 +535,10 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
           if (m == 12345.678f) tau = m;   // keep the loads and maxima alive
           continue;
         }
+        if (groupmax) {
+          gmax_run = fmaxf(gmax_run, m);
+          continue;
+        }
         if (m > tau) {
 #pragma unroll
           for (int gi = 0; gi < K3_TILE_N / 16; ++gi) {
@@ -533,7 +560,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
 
       // unit done: publish this row's candidates (heap order; the merge kernel sorts)
       if (tau_cell != nullptr && my_sc[0] > tau_published) atomicMax(tau_cell, f32_to_ordered(my_sc[0]));
-      if (qg < P.q_valid && !collect) {
+      if (groupmax) P.groupmax_out[(size_t)slice * P.q_pad + qg] = gmax_run;
+      if (qg < P.q_valid && !collect && !groupmax) {
         const size_t base = ((size_t)slice * P.q_pad + qg) * kc;
         for (int j = 0; j < kc; ++j) {
           P.part_score[base + j] = my_sc[j * K3_TILE_M];
@@ -691,6 +719,9 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.coll_idx = L.coll_idx;
   P.coll_cnt = L.coll_cnt;
   P.coll_cap = L.coll_cap;
+  P.groupmax_out = L.groupmax_out;
+  P.group_stride = L.group_stride;
+  P.group_tiles = L.group_tiles;
   P.dump = L.dump;
   P.dump_ld = L.dump_ld;
   P.n_rows = L.n_rows;
@@ -716,27 +747,34 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.idesc = make_idesc_f16(L.a_fmt, L.b_fmt, L.variant == 2 ? 2 * K3_TILE_M : K3_TILE_M, K3_TILE_N);
   if (L.num_stages < 1 || L.num_stages > MAX_STAGES)
     return set_error(RBOD_E_INVAL, "k3: bad stage count %d", L.num_stages);
+  if (L.variant == 2 && L.grid % 2) return set_error(RBOD_E_INVAL, "k3: pair kernel needs an even grid");
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)L.grid);
+  cfg.blockDim = dim3(K3_THREADS);
+  cfg.dynamicSmemBytes = L.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (L.variant == 2) {
-    if (L.grid % 2) return set_error(RBOD_E_INVAL, "k3: pair kernel needs an even grid");
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)L.grid);
-    cfg.blockDim = dim3(K3_THREADS);
-    cfg.dynamicSmemBytes = L.smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1>, P));
-  } else if (L.variant == 0) {
-    k3_cosine_topk_kernel<0, 0><<<L.grid, K3_THREADS, L.smem_bytes, st>>>(P);
-  } else {
-    k3_cosine_topk_kernel<1, 0><<<L.grid, K3_THREADS, L.smem_bytes, st>>>(P);
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (L.sync_counters != nullptr) {
+    // The L2-sharing throttle makes CTAs of one launch wait for each other: ask for a cooperative launch so
+    // the runtime guarantees (or refuses) co-residency of the whole grid (grid <= number of SMs, 1 CTA per SM).
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (L.variant == 2) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1>, P));
+  else if (L.variant == 0) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0>, P));
+  else RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<1, 0>, P));
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

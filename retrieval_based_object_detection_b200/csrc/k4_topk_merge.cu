@@ -33,8 +33,8 @@ __device__ __forceinline__ bool beats(double sa, uint32_t ia, double sb, uint32_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 merge_partials_kernel(const float* __restrict__ part_score, const uint32_t* __restrict__ part_idx, int slices,
-                      int64_t q_pad, int kc, int m_pow2, uint32_t* __restrict__ cand_idx,
-                      float* __restrict__ cand_tau) {
+                      int64_t q_pad, int kc, int m_pow2, const float* __restrict__ tau_init,
+                      uint32_t* __restrict__ cand_idx, float* __restrict__ cand_tau) {
   extern __shared__ unsigned long long keys[];
   const int64_t q = blockIdx.x;
   const int m = slices * kc;
@@ -69,8 +69,29 @@ merge_partials_kernel(const float* __restrict__ part_score, const uint32_t* __re
   }
   if (threadIdx.x == 0) {
     const unsigned long long key = (kc - 1) < m_pow2 ? keys[kc - 1] : 0ull;
-    cand_tau[q] = key ? ordered_to_f32(static_cast<uint32_t>(key >> 32)) : -INFINITY;
+    float tau = key ? ordered_to_f32(static_cast<uint32_t>(key >> 32)) : -INFINITY;
+    // rows below the pre-sampled starting threshold were dropped without ever entering a list
+    if (tau_init != nullptr) tau = fmaxf(tau, tau_init[q]);
+    cand_tau[q] = tau;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tau_init: starting threshold of a query = the smallest of its `groups` sample-group maxima.  Every
+// group holds one row scoring at least that much, and with N / (rows per group) = 16 * kc the expected
+// number of gallery rows above it is ~ 16 * kc * H(groups): far fewer than N, so the candidate heaps
+// skip their cold start, yet (with probability 1 - (kc / (16 kc))^groups) more than kc.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tau_init_kernel(const float* __restrict__ groupmax, int groups, int64_t q_pad, uint32_t* __restrict__ tau_shared,
+                float* __restrict__ tau_init) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= q_pad) return;
+  float t = groupmax[q];
+  for (int g = 1; g < groups; ++g) t = fminf(t, groupmax[(size_t)g * q_pad + q]);
+  if (!(t > -INFINITY)) t = -INFINITY;   // an empty (or fully masked) group: no starting threshold
+  tau_init[q] = t;
+  tau_shared[q] = f32_to_ordered(t);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -394,15 +415,24 @@ merge_topk_kernel(const double* __restrict__ scores64, const int64_t* __restrict
 }  // namespace
 
 int launch_merge_partials(const float* part_score, const uint32_t* part_idx, int slices, int64_t q_pad,
-                          int64_t Q, int kc, uint32_t* cand_idx, float* cand_tau, cudaStream_t st) {
+                          int64_t Q, int kc, const float* tau_init, uint32_t* cand_idx, float* cand_tau,
+                          cudaStream_t st) {
   if (Q <= 0) return RBOD_OK;
   int m = slices * kc, p2 = 32;
   while (p2 < m) p2 <<= 1;
   if (p2 > 8192) return set_error(RBOD_E_INVAL, "merge_partials: %d candidates per query exceed 8192", m);
   const size_t smem = (size_t)p2 * 8;
   RBOD_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  merge_partials_kernel<<<(unsigned)Q, 256, smem, st>>>(part_score, part_idx, slices, q_pad, kc, p2, cand_idx,
-                                                        cand_tau);
+  merge_partials_kernel<<<(unsigned)Q, 256, smem, st>>>(part_score, part_idx, slices, q_pad, kc, p2, tau_init,
+                                                        cand_idx, cand_tau);
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+int launch_tau_init(const float* groupmax, int groups, int64_t q_pad, uint32_t* tau_shared, float* tau_init,
+                    cudaStream_t st) {
+  if (q_pad <= 0) return RBOD_OK;
+  tau_init_kernel<<<(unsigned)((q_pad + 255) / 256), 256, 0, st>>>(groupmax, groups, q_pad, tau_shared, tau_init);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

@@ -253,7 +253,7 @@ int rbod_destroy(rbod_gallery* g) {
   if (g->stats) cudaFree(g->stats);
   DevBuf* bufs[] = {&g->stage_rows, &g->stage_slots, &g->stage_norms, &g->q32, &g->q16, &g->q_dq, &g->q_qq, &g->tau_shared,
                     &g->part_score, &g->part_idx, &g->cand_idx, &g->cand_tau, &g->cand_score, &g->out_scores,
-                    &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->flag_lo, &g->fq16, &g->coll_score,
+                    &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->flag_lo, &g->fq16, &g->groupmax, &g->tau_init, &g->coll_score,
                     &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->sync_counters, &g->seg_idx, &g->seg_off, &g->seg_out,
                     &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->gather_idx, &g->gather_out};
   for (DevBuf* b : bufs) b->release();
@@ -315,6 +315,8 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
     g->slack = (int)value;
   } else if (!strcmp(key, "time_k3")) {
     g->time_k3 = value != 0;
+  } else if (!strcmp(key, "presample")) {
+    g->presample = value != 0;
   } else if (!strcmp(key, "collect_pass")) {
     g->collect_pass = value != 0;
   } else if (!strcmp(key, "tau_share")) {
@@ -480,12 +482,13 @@ int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* of
     RBOD_TRY(g->seg_out.ensure((size_t)n_classes * g->dim * 4));
     dst = g->seg_out.as<float>();
   }
-  const int64_t items_upper = (total - first) / 1024 + n_classes + 1;
-  const int64_t parts_upper = 2 * ((total - first) / 1024) + 2;
+  const int64_t items_upper = (total - first) / K2_SEG_CHUNK + n_classes + 1;
+  const int64_t parts_upper = 2 * ((total - first) / K2_SEG_CHUNK) + 2;
   if (items_upper > 0x7fffffff) return set_error(RBOD_E_INVAL, "rbod_segment_mean: problem too large");
   RBOD_TRY(g->seg_partials.ensure((size_t)parts_upper * g->dim * 8));
   RBOD_TRY(g->seg_prefix.ensure((size_t)(2 * n_classes + 2) * 4));
-  RBOD_TRY(g->seg_arrive.ensure((size_t)n_classes * 4));
+  RBOD_TRY(g->seg_arrive.ensure((size_t)parts_upper * 4));   // one flag word per partial slot (tree reduction)
+  RBOD_CUDA(cudaMemsetAsync(g->seg_arrive.p, 0, (size_t)parts_upper * 4, st));
   RBOD_TRY(g->flags.ensure(64));
   RBOD_CUDA(cudaMemsetAsync(g->flags.p, 0, 64, st));
   RBOD_TRY(launch_segment_mean(g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp, g->rows,
@@ -514,8 +517,14 @@ struct K3Collect {
   int cap;
 };
 
+struct K3Sample {
+  float* groupmax;   // [groups][q_pad]
+  int stride, tiles;
+};
+
 static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_t* q16, const uint32_t* mask_dev,
-                  const K3Collect* collect, float* dump, int64_t dump_ld, cudaStream_t st) {
+                  const K3Collect* collect, float* dump, int64_t dump_ld, cudaStream_t st,
+                  const K3Sample* sample = nullptr) {
   K3Launch L;
   memset(&L, 0, sizeof(L));
   RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, g->rows16, g->rows, g->dp, k3_box_rows(g->k3_variant)));
@@ -544,12 +553,18 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.part_score = g->part_score.as<float>();
   L.part_idx = g->part_idx.as<uint32_t>();
   L.row_mask = mask_dev;
-  L.tau_shared = (g->tau_share && dump == nullptr && collect == nullptr) ? g->tau_shared.as<uint32_t>() : nullptr;
+  L.tau_shared = (g->tau_share && dump == nullptr && collect == nullptr && sample == nullptr)
+                     ? g->tau_shared.as<uint32_t>() : nullptr;
+  if (sample) {
+    L.groupmax_out = sample->groupmax;
+    L.group_stride = sample->stride;
+    L.group_tiles = sample->tiles;
+  }
   L.dump = dump;
   L.dump_ld = dump_ld;
   L.grid = P.grid;
   L.smem_bytes = P.smem;
-  if (g->l2_sync && dump == nullptr) {
+  if (g->l2_sync && dump == nullptr && sample == nullptr) {
     const int workers = g->k3_variant == 2 ? P.grid / 2 : P.grid;
     const int max_tiles = (P.tiles_total + P.slices - 1) / P.slices + 1;
     L.sync_window = std::max(1, g->sync_window);
@@ -648,12 +663,35 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   RBOD_TRY(g->flag_lo.ensure((size_t)P.q_pad * 4 + 1024));   // read as [q_pad of the second pass]
 
   if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev0, st));
+  // Threshold pre-pass: row maxima over K3_SAMPLE_GROUPS strided samples of the gallery give every query a
+  // starting threshold, so the candidate heaps of the main pass skip their cold start (see tau_init_kernel).
+  const float* tau_init = nullptr;
+  const int sample_tiles = std::max(1, P.tiles_total / (K3_SAMPLE_RATIO * P.kc));
+  if (g->tau_share && g->presample && P.tiles_total >= 10 * P.kc &&
+      P.tiles_total / sample_tiles >= K3_SAMPLE_GROUPS) {
+    SearchPlan PA = P;
+    PA.slices = K3_SAMPLE_GROUPS;
+    const int workers = g->k3_variant == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
+    PA.grid = (int)std::min<int64_t>((int64_t)PA.slices * PA.num_qt, workers) * (g->k3_variant == 2 ? 2 : 1);
+    RBOD_TRY(g->groupmax.ensure((size_t)K3_SAMPLE_GROUPS * P.q_pad * 4));
+    RBOD_TRY(g->tau_init.ensure((size_t)P.q_pad * 4));
+    K3Sample S;
+    S.groupmax = g->groupmax.as<float>();
+    S.tiles = sample_tiles;
+    S.stride = P.tiles_total / sample_tiles;
+    RBOD_TRY(run_k3(g, PA, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st,
+                    &S));
+    RBOD_TRY(launch_tau_init(g->groupmax.as<float>(), K3_SAMPLE_GROUPS, P.q_pad, g->tau_shared.as<uint32_t>(),
+                             g->tau_init.as<float>(), st));
+    tau_init = g->tau_init.as<float>();
+    launches += 2;
+  }
   RBOD_TRY(run_k3(g, P, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st));
   if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev1, st));
   ++launches;
 
   RBOD_TRY(launch_merge_partials(g->part_score.as<float>(), g->part_idx.as<uint32_t>(), P.slices, P.q_pad, Q, P.kc,
-                                 g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(), st));
+                                 tau_init, g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(), st));
   RBOD_TRY(launch_rescore(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp,
                           g->metric, g->cand_idx.as<uint32_t>(), Q, P.kc, g->cand_score.as<double>(), st));
   RBOD_TRY(launch_select(g->cand_score.as<double>(), g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(),

@@ -44,6 +44,8 @@ struct PinBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
+constexpr int K2_SEG_CHUNK = 256;    // rows per K2 work item (one warp)
+
 // ---- K3 geometry ------------------------------------------------------------------------
 constexpr int K3_TILE_M = 128;       // queries per CTA (TMEM lanes)
 constexpr int K3_TILE_N = 128;       // gallery rows per accumulator buffer (one tcgen05.mma N)
@@ -52,6 +54,8 @@ constexpr int K3_MAX_DP = 768;       // A operand must fit 384 TMEM columns
 constexpr int K3_THREADS = 192;      // warp0 TMA, warp1 MMA, warps 2-5 epilogue
 constexpr int K3_MAX_KC = 128;
 constexpr int K3_COLLECT_CAP = 1024; // rows a collecting pass records per query before it reports overflow
+constexpr int K3_SAMPLE_GROUPS = 4;  // threshold pre-pass: groups whose row maxima are compared
+constexpr int K3_SAMPLE_RATIO = 16;  // rows per group = N / (ratio * kc)
 constexpr int K3_TAU_REFRESH = 32;   // tiles between two looks at the threshold shared by a query's slices
 
 struct K3Launch {
@@ -78,6 +82,8 @@ struct K3Launch {
   uint32_t* coll_idx;
   int* coll_cnt;
   int coll_cap;
+  float* groupmax_out;        // sample mode: [slices][q_pad] row maxima (threshold pre-pass)
+  int group_stride, group_tiles;
   float* dump;            // optional raw scores [q_pad][dump_ld]
   int64_t dump_ld;
   int* sync_counters;     // zeroed [slices * sync_span * sync_windows] ints, or nullptr
@@ -111,7 +117,10 @@ int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int d
                         float* q_dq, double* q_qq, uint32_t* tau_shared, cudaStream_t st);
 // K4 family
 int launch_merge_partials(const float* part_score, const uint32_t* part_idx, int slices, int64_t q_pad,
-                          int64_t Q, int kc, uint32_t* cand_idx, float* cand_tau, cudaStream_t st);
+                          int64_t Q, int kc, const float* tau_init, uint32_t* cand_idx, float* cand_tau,
+                          cudaStream_t st);
+int launch_tau_init(const float* groupmax, int groups, int64_t q_pad, uint32_t* tau_shared, float* tau_init,
+                    cudaStream_t st);
 int launch_rescore(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16, int kind16,
                    int dim, int64_t ld32, int64_t ld16, int metric, const uint32_t* cand_idx, int64_t Q, int kc,
                    double* cand_score, cudaStream_t st);
@@ -151,6 +160,7 @@ struct rbod_gallery {
   int slack = -1;  // -1 = automatic
   int time_k3 = 0;
   int debug_epi = 0;
+  int presample = 1;      // threshold pre-pass over a strided sample of the gallery (needs tau_share)
   int collect_pass = 1;   // uncertified queries get a collecting tensor-core pass before the fp64 sweep
   int tau_share = 1;      // slices of one query share their candidate threshold through global memory
   int hybrid = 1;         // allow the query tile to be split between TMEM and resident smem
@@ -162,7 +172,7 @@ struct rbod_gallery {
   rbod::DevBuf part_score, part_idx, cand_idx, cand_tau, cand_score;
   rbod::DevBuf out_scores, out_rows, out_scores64;
   rbod::DevBuf flags;      // ints: [0]=n_flag [1]=overflow [2]=err; float max_eps at [3]
-  rbod::DevBuf flag_q, flag_thr, flag_lo, fq16;
+  rbod::DevBuf flag_q, flag_thr, flag_lo, fq16, groupmax, tau_init;
   rbod::DevBuf coll_score, coll_idx, coll_cnt;
   rbod::DevBuf mask_dev, dump, sync_counters;
   rbod::DevBuf seg_idx, seg_off, seg_out, seg_partials, seg_prefix, seg_arrive;

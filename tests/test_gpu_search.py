@@ -134,6 +134,33 @@ def test_k100_bf16_uncertified_queries_take_the_collect_pass(G, tau_share):
     g.close()
 
 
+@pytest.mark.parametrize("dtype,ordered", [("bf16", False), ("f32", True), ("f16", True)])
+def test_threshold_prepass_keeps_the_answer_exact(G, dtype, ordered):
+    """Galleries large enough for the sampled starting thresholds (>= 320 tiles), random and stored in class
+    order (the adversarial layout for a sample): ids identical to the brute force, with and without it."""
+    n, dim, Q, k = 60000, 256, 300, 10
+    x, labels, _ = O.synthetic_clustered(n, dim, 40, seed=4)
+    if ordered:
+        x = x[np.argsort(labels, kind="stable")]
+    g = G(dim, dtype=dtype, capacity=n)
+    g.upsert(x)
+    stored = g.get_rows(np.arange(n))
+    rng = np.random.default_rng(1)
+    q = x[rng.integers(0, n, Q)] + 0.2 * rng.standard_normal((Q, dim)).astype(np.float32) / np.sqrt(dim)
+    mask = rng.random(n) < 0.5
+    ws, wi = O.cosine_topk(q, stored, k)
+    wms, wmi = O.cosine_topk(q, stored, k, row_mask=mask)
+    for presample in (1, 0):
+        g.set_option("presample", presample)
+        res = g.search(q, k, want_scores64=True)
+        assert np.array_equal(res.rows, wi), (presample, (res.rows != wi).any(axis=1).sum())
+        assert np.allclose(res.scores64, ws, rtol=1e-5, atol=1e-9)
+        assert res.stats["total_launches"] >= (7 if presample else 5)      # pre-pass = K3 sample launch + tau_init
+        resm = g.search(q, k, row_mask=O.pack_row_mask(mask), want_scores64=True)
+        assert np.array_equal(resm.rows, wmi)
+    g.close()
+
+
 def test_row_mask_and_zero_vectors(G):
     n, dim, k, Q = 5000, 768, 10, 40
     g, stored, x = _mk(G, n, dim, "bf16", seed=8)
