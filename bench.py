@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=-1, help="override the K3 kernel variant (debug)")
     ap.add_argument("--opt", action="append", default=[], help="library tunable key=value (debug), repeatable")
+    ap.add_argument("--sweep", default="", help="comma list of batch sizes: per-size p50 latency and q/s on the "
+                    "resident gallery (config C5's query sweep), printed as one JSON line instead of the headline")
     return ap.parse_args()
 
 
@@ -227,6 +229,38 @@ def run_b200(a):
                 torch.empty((a.queries, a.k), dtype=torch.int64).pin_memory(),
                 torch.empty((a.queries, a.k), dtype=torch.float64).pin_memory())
     out_host_np = tuple(t.numpy() for t in out_host)
+
+    if a.sweep:
+        rows_out = []
+        for Q in [int(x) for x in a.sweep.split(",")]:
+            qd = torch.randn(Q, a.dim, device=dev, generator=qgen)
+            od = (torch.empty((Q, a.k), dtype=torch.float32, device=dev), torch.empty((Q, a.k), dtype=torch.int64, device=dev),
+                  torch.empty((Q, a.k), dtype=torch.float64, device=dev))
+            for _ in range(3):
+                st = g.search(qd, a.k, out=od).stats
+            lat = []
+            iters = max(5, min(30, int(2000 / max(1.0, st["k3_ms"]))))
+            for _ in range(iters):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                st = g.search(qd, a.k, out=od).stats
+                e1.record()
+                torch.cuda.synchronize()
+                lat.append(e0.elapsed_time(e1))
+            p50 = statistics.median(lat)
+            flops, byts = 2.0 * Q * n_local * a.dim, n_local * a.dim * 2.0 + Q * a.dim * 2.0 + Q * a.k * 12.0
+            sus, burst, hbm, src = load_peaks()
+            rows_out.append({"Q": Q, "p50_ms": round(p50, 4), "min_ms": round(min(lat), 4), "qps": round(Q / p50 * 1e3, 1),
+                             "tflops": round(flops / p50 / 1e9, 1), "gbs": round(byts / p50 / 1e6, 1),
+                             "bound": "hbm" if byts / hbm / 1e9 > flops / burst / 1e12 else "tensor",
+                             "frac_of_bound": round(max(byts / hbm / 1e9, flops / burst / 1e12) / (p50 / 1e3), 3),
+                             "slices": st["slices"], "fallback": st["fallback_queries"], "iters": iters})
+        if rank == 0:
+            print(json.dumps({"sweep": rows_out, "rows_per_gpu": n_local, "dim": a.dim, "dtype": a.dtype, "k": a.k,
+                              "n_gpus": world, "peaks": "measured hbm_gbs / bf16_tflops (burst)"}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     launches = {"n": 0}
     k3_ms = []

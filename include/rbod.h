@@ -102,6 +102,8 @@ typedef struct rbod_search_stats {
                             /* off                                                       */
   int64_t sweep_queries;    /* queries that needed the exact fp64 sweep over the gallery */
                             /* (tie cluster wider than the collecting pass records)      */
+  int64_t presample_retries;/* > 0: the sampled starting thresholds were too high for    */
+                            /* this many queries and the call was redone without them    */
 } rbod_search_stats;
 
 const char* rbod_last_error(void);
@@ -118,7 +120,8 @@ int rbod_truncate(rbod_gallery* g, int64_t rows);
 /* Tunables: "k3_variant" (0 = query tile resident in TMEM, 1 = query tile streamed through smem,
  * 2 = TMEM-resident + CTA pairs / cta_group::2), "slack" (extra candidates kept per query),
  * "time_k3" (1 = fill stats.k3_ms), "tau_share" (slices of a query share their threshold),
- * "collect_pass" (tensor-core second pass for uncertified queries), "l2_sync" / "sync_window" /
+ * "collect_pass" (tensor-core second pass for uncertified queries), "presample" (sampled
+ * starting thresholds), "l2_sync" / "sync_window" /
  * "sync_lead" (L2-sharing producer throttle), "hybrid" (query tile split TMEM / smem). */
 int rbod_set_option(rbod_gallery* g, const char* key, int64_t value);
 

@@ -39,7 +39,8 @@ class GalleryInfo(ctypes.Structure):
 class SearchStats(ctypes.Structure):
     _fields_ = [("queries", ctypes.c_int64), ("fallback_queries", ctypes.c_int64), ("k3_launches", ctypes.c_int64),
                 ("total_launches", ctypes.c_int64), ("candidates", ctypes.c_int32), ("slices", ctypes.c_int32),
-                ("max_eps", ctypes.c_float), ("k3_ms", ctypes.c_float), ("sweep_queries", ctypes.c_int64)]
+                ("max_eps", ctypes.c_float), ("k3_ms", ctypes.c_float), ("sweep_queries", ctypes.c_int64),
+                ("presample_retries", ctypes.c_int64)]
 
 
 class RbodError(RuntimeError):

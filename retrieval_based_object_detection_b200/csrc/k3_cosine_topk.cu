@@ -122,9 +122,10 @@ struct K3TileRange { int t0, n, step; };
 __device__ __forceinline__ K3TileRange k3_unit_tiles(const K3Params& P, int slice) {
   K3TileRange r;
   if (P.group_stride > 0) {
-    r.t0 = slice;
+    // group g starts g/slices of a stride in, so even one-tile groups are spread over the whole gallery
+    r.t0 = (int)(((int64_t)slice * P.group_stride) / P.slices);
     r.step = P.group_stride;
-    const int avail = slice < P.tiles_total ? (P.tiles_total - slice + r.step - 1) / r.step : 0;
+    const int avail = r.t0 < P.tiles_total ? (P.tiles_total - r.t0 + r.step - 1) / r.step : 0;
     r.n = min(P.group_tiles, avail);
   } else {
     r.t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);

@@ -201,7 +201,11 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
     flagged = !((double)tau + (double)eps < kth_b);
     kth = kth_b;
   } else {
-    kth = -INFINITY;  // fewer than k valid candidates although rows were dropped: cannot happen
+    // Fewer than k candidates although rows were dropped: the pre-sampled starting threshold sat above this
+    // query's k-th best score (possible only when the sample misrepresents the gallery).  The host reruns the
+    // search without the pre-pass.
+    kth = -INFINITY;
+    if (lane == 0) atomicAdd(n_flag + 4, 1);
   }
   if (lane == 0) {
     atomic_max_nonneg(max_eps, eps);

@@ -700,9 +700,18 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
                          reinterpret_cast<float*>(d_flags + 3), st));
   launches += 3;
 
-  int hflags[4] = {0, 0, 0, 0};
+  int hflags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   RBOD_CUDA(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
   RBOD_CUDA(cudaStreamSynchronize(st));
+  if (hflags[4] > 0 && tau_init != nullptr) {
+    // a starting threshold cut below k candidates for some query: redo the call without the pre-pass
+    const int saved = g->presample;
+    g->presample = 0;
+    const int rc = rbod_search(g, queries, Q, k, row_mask, out_scores, out_rows, out_scores64, stats, stream);
+    g->presample = saved;
+    if (rc == RBOD_OK && stats) stats->presample_retries = hflags[4];
+    return rc;
+  }
   const int n_flag = hflags[0];
   float max_eps;
   memcpy(&max_eps, &hflags[3], 4);

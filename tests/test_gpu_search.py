@@ -161,6 +161,25 @@ def test_threshold_prepass_keeps_the_answer_exact(G, dtype, ordered):
     g.close()
 
 
+def test_prepass_threshold_too_high_is_retried(G):
+    """Every sampled tile holds a copy of the query: the starting threshold equals the best score, fewer than k
+    rows beat it, and the call must be redone without the pre-pass -- same exact answer."""
+    n, dim, k = 60000, 256, 10
+    x = O.synthetic_unit_rows(n, dim, seed=12)
+    tiles = (n + 127) // 128
+    for g_ in range(4):                                   # K3_SAMPLE_GROUPS one-tile groups, spread over the gallery
+        x[(g_ * tiles // 4) * 128 + 5] = x[77]
+    g = G(dim, dtype="bf16", capacity=n)
+    g.upsert(x)
+    stored = g.get_rows(np.arange(n))
+    q = np.stack([x[77], x[1234]]).astype(np.float32)
+    res = g.search(q, k, want_scores64=True)
+    ws, wi = OC.cosine_topk(q, stored, k)
+    assert np.array_equal(res.rows, wi)
+    assert res.stats["presample_retries"] >= 1
+    g.close()
+
+
 def test_row_mask_and_zero_vectors(G):
     n, dim, k, Q = 5000, 768, 10, 40
     g, stored, x = _mk(G, n, dim, "bf16", seed=8)
