@@ -135,7 +135,7 @@ def cpu_sample_qps(a, budget_s: float = 12.0):
     O.cosine_topk(q, g, a.k)
     t = time.perf_counter() - t0
     qps_full = q_s / t * (n_s / a.rows)
-    sample = (f"{q_s} queries x {n_s} rows x {a.dim} (float64 GEMM + lexsort top-{a.k}) in {t:.2f} s; "
+    sample = (f"{q_s} queries x {n_s} rows x {a.dim} (float64 GEMM + partition/lexsort top-{a.k}) in {t:.2f} s; "
               f"queries/s scaled by {n_s}/{a.rows} rows")
     return qps_full, threads, sample, t
 
@@ -343,10 +343,13 @@ def run_b200(a):
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
                 "algorithmic": f"2*Q*N_local*D = {flops_per_launch:.3e} flop per launch", "kernel_ms": k3_avg_ms,
                 "kernel_share_of_step": k3_avg_ms * a.steps / ms_dev if ms_dev > 0 else None}
+    # dram bytes per K3 launch from the committed ncu --set full capture -- only when it was taken on this shape
     prof = os.path.join(ROOT, "profiles", "k3_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            t = json.load(open(prof))
+            if (t.get("rows_per_gpu"), t.get("queries"), t.get("dim"), t.get("k")) == (n_local, a.queries, a.dim, a.k):
+                roofline["traffic"] = t.get("dram_bytes_per_launch")
         except Exception:
             pass
 

@@ -137,17 +137,21 @@ def cosine_similarity(a, b):
     return np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b))
 
 
-def cosine_matrix(queries: np.ndarray, stored: np.ndarray, rowwise: bool = False) -> np.ndarray:
+def cosine_matrix(queries: np.ndarray, stored: np.ndarray, rowwise: bool = False, _g64=None) -> np.ndarray:
     """cosine_similarity for every (query, stored row) pair, float64.
 
     ``rowwise=True`` evaluates each row with the same operation sequence, so bitwise-identical
     rows get bitwise-identical scores (needed when a test plants duplicates); the default uses one
     float64 GEMM.  A zero-norm operand scores 0 (the reference formula would give nan).
+    ``_g64`` = (float64 copy of ``stored``, its row norms), so a chunked caller widens the gallery once.
     """
     q = np.atleast_2d(np.asarray(queries, dtype=np.float32)).astype(np.float64)
-    g = np.atleast_2d(np.asarray(stored, dtype=np.float32)).astype(np.float64)
     qn = np.sqrt(np.einsum("ij,ij->i", q, q))
-    gn = np.sqrt(np.einsum("ij,ij->i", g, g))
+    if _g64 is not None:
+        g, gn = _g64
+    else:
+        g = np.atleast_2d(np.asarray(stored, dtype=np.float32)).astype(np.float64)
+        gn = np.sqrt(np.einsum("ij,ij->i", g, g))
     if rowwise:
         dots = np.stack([(g * q[i][None, :]).sum(axis=1) for i in range(q.shape[0])])
     else:
@@ -165,11 +169,18 @@ def topk_from_scores(scores: np.ndarray, k: int, ids=None, row_mask=None):
     out_i = np.full((Q, k), -1, dtype=np.int64)
     allowed = np.ones(N, dtype=bool) if row_mask is None else np.asarray(row_mask, dtype=bool)
     cols = np.nonzero(allowed)[0]
+    col_ids = ids[cols]
     for qi in range(Q):
         s = scores[qi, cols]
-        order = np.lexsort((ids[cols], -s))[:k]
+        if len(s) > 8 * k:
+            # same result as sorting everything: keep the rows tied with or above the k-th largest score
+            kth = np.partition(s, len(s) - k)[len(s) - k]
+            cand = np.nonzero(s >= kth)[0]
+            order = cand[np.lexsort((col_ids[cand], -s[cand]))][:k]
+        else:
+            order = np.lexsort((col_ids, -s))[:k]
         out_s[qi, : len(order)] = s[order]
-        out_i[qi, : len(order)] = ids[cols][order]
+        out_i[qi, : len(order)] = col_ids[order]
     return out_s, out_i
 
 
@@ -179,8 +190,10 @@ def cosine_topk(queries, stored, k: int, row_mask=None, rowwise: bool = False, c
     Q = queries.shape[0]
     out_s = np.empty((Q, k), dtype=np.float64)
     out_i = np.empty((Q, k), dtype=np.int64)
+    g64 = np.atleast_2d(np.asarray(stored, dtype=np.float32)).astype(np.float64)
+    g64 = (g64, np.sqrt(np.einsum("ij,ij->i", g64, g64)))
     for a in range(0, Q, chunk):
-        sc = cosine_matrix(queries[a : a + chunk], stored, rowwise=rowwise)
+        sc = cosine_matrix(queries[a : a + chunk], stored, rowwise=rowwise, _g64=g64)
         out_s[a : a + chunk], out_i[a : a + chunk] = topk_from_scores(sc, k, row_mask=row_mask)
     return out_s, out_i
 

@@ -69,7 +69,8 @@ def ncu_reports(tag):
                 v, u = float(vals[hdr.index(m)].replace(",", "")), units[hdr.index(m)]
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
             rd, wr = get("dram__bytes_read.sum"), get("dram__bytes_write.sum")
-            json.dump({"dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
+            json.dump({"rows_per_gpu": 10_000_000, "queries": 10_000, "dim": 768, "k": 10,   # bench.py defaults
+                       "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
                        "source": os.path.basename(rep), "command": "python bench.py --steps 1 --warmup 3 --no-cpu-baseline",
                        "tensor_pipe_active_pct": float(vals[hdr.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")])},
                       open(os.path.join(PROF, "k3_traffic.json"), "w"), indent=1)
