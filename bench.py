@@ -197,12 +197,20 @@ def run_b200(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line of the contract
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- build the resident gallery: synthetic unit-norm rows, generated on device, stored by K1
     r0, r1 = shard_range(a.rows, rank, world)
     n_local = r1 - r0
     g = Gallery(a.dim, dtype=a.dtype, capacity=n_local, device=local_rank)
+    g.set_option("time_k3", 1)
+    if a.variant >= 0:
+        g.set_option("k3_variant", a.variant)
+    for kv in a.opt:                                      # before the first upsert: some options shape the storage
+        key, _, val = kv.partition("=")
+        g.set_option(key, int(val))
     gen = torch.Generator(dev).manual_seed(1234 + rank)
     t_build0 = time.perf_counter()
     chunk = 500_000
@@ -211,12 +219,6 @@ def run_b200(a):
         g.upsert(torch.randn(m, a.dim, device=dev, generator=gen))
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build0
-    g.set_option("time_k3", 1)
-    if a.variant >= 0:
-        g.set_option("k3_variant", a.variant)
-    for kv in a.opt:
-        key, _, val = kv.partition("=")
-        g.set_option(key, int(val))
 
     qgen = torch.Generator(dev).manual_seed(99)          # same queries on every rank
     q_dev = torch.randn(a.queries, a.dim, device=dev, generator=qgen)
@@ -266,8 +268,15 @@ def run_b200(a):
     k3_ms = []
     fallback = []
 
+    diag = {"search_s": 0.0, "steps": 0, "sweep": 0, "retries": 0}
+
     def step_device():
+        t_s = time.perf_counter()
         res = g.search(q_dev, a.k, out=out_dev)
+        diag["search_s"] += time.perf_counter() - t_s          # rbod_search returns synchronised
+        diag["steps"] += 1
+        diag["sweep"] += res.stats["sweep_queries"]
+        diag["retries"] += res.stats["presample_retries"]
         launches["n"] += res.stats["total_launches"]
         k3_ms.append(res.stats["k3_ms"])
         fallback.append(res.stats["fallback_queries"])
@@ -318,7 +327,18 @@ def run_b200(a):
     launches["n"] = 0
     k3_ms.clear()
     fallback.clear()
+    diag.update(search_s=0.0, steps=0, sweep=0, retries=0)
     ms_dev = timed(lambda: step_device(), a.steps)
+    per_rank = {"rank": rank, "search_ms_per_step": round(diag["search_s"] / max(diag["steps"], 1) * 1e3, 3),
+                "k3_ms": round(statistics.mean(k3_ms), 3) if k3_ms else 0.0,
+                "uncertified_per_step": statistics.mean(fallback) if fallback else 0,
+                "sweep_queries": diag["sweep"], "presample_retries": diag["retries"]}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank)
+        per_rank = gathered
+    else:
+        per_rank = [per_rank]
     n_launch_timed = launches["n"]
     k3_timed = list(k3_ms)
     _, last_stats = step_device()
@@ -367,7 +387,7 @@ def run_b200(a):
                    "l2": "gallery operand per GPU is far larger than the 126 MB L2; no flush between steps",
                    "candidates_per_query": last_stats["candidates"], "slices": last_stats["slices"],
                    "fallback_queries_per_step": statistics.mean(fallback) if fallback else 0,
-                   "gallery_build_s": round(t_build, 2)},
+                   "gallery_build_s": round(t_build, 2), "options": a.opt, "per_rank": per_rank},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": a.queries * a.dim * 4,
                 "d2h_bytes_per_step": a.queries * a.k * (4 + 8 + 8), "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": n_launch_timed,

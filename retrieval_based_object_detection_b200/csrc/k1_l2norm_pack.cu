@@ -17,6 +17,12 @@
 // It also maintains two per-gallery maxima used by the search certification margin:
 //   stats[0] = max ||row16||            stats[1] = max ||row16 - target||
 // where target = unit(master row) for cosine collections and the master row for dot.
+//
+// bf16 collections can keep an fp16 SHADOW of the stored rows as the search operand (option
+// "shadow16"): fp16 carries 3 more mantissa bits, so queries rounded to fp16 sit 8x closer to the
+// exact unit query and the certification margin of the search shrinks accordingly.  A bf16 value
+// converts to fp16 exactly unless it is smaller than 2^-17 in magnitude (then off by < 2^-25);
+// stats[2] = max ||shadow row||, stats[3] = max ||shadow row - stored row|| account for that.
 #include "rbod_common.cuh"
 #include "rbod_internal.h"
 
@@ -56,12 +62,12 @@ template <int NV>
 __global__ void __launch_bounds__(K1_WARPS * 32)
 l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const int64_t* __restrict__ slots,
                        int64_t slot0, int normalize, int cosine, float* __restrict__ master32, int64_t ld32,
-                       uint16_t* __restrict__ out16, int64_t ld16, int kind16, float* __restrict__ out_norms,
-                       float* __restrict__ stats) {
+                       uint16_t* __restrict__ out16, int64_t ld16, int kind16, uint16_t* __restrict__ shadow16,
+                       float* __restrict__ out_norms, float* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * K1_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * K1_WARPS;
-  float wmax_norm = 0.f, wmax_dev = 0.f;
+  float wmax_norm = 0.f, wmax_dev = 0.f, wmax_snorm = 0.f, wmax_sdev = 0.f;
 
   for (int64_t row = warp0; row < n; row += nwarps) {
     const float4* src = reinterpret_cast<const float4*>(in + row * dim);
@@ -106,12 +112,24 @@ l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const i
       for (int i = 0; i < NV; ++i) dst[lane + 32 * i] = v[i];
     }
     uint2* dst16 = reinterpret_cast<uint2*>(out16 + slot * ld16);
+    uint2* dsts = shadow16 ? reinterpret_cast<uint2*>(shadow16 + slot * ld16) : nullptr;
+    float ssn = 0.f, ssd = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const uint16_t h0 = f32_to_h16(v[i].x, kind16), h1 = f32_to_h16(v[i].y, kind16);
       const uint16_t h2 = f32_to_h16(v[i].z, kind16), h3 = f32_to_h16(v[i].w, kind16);
       const float f0 = h16_to_f32(h0, kind16), f1 = h16_to_f32(h1, kind16);
       const float f2 = h16_to_f32(h2, kind16), f3 = h16_to_f32(h3, kind16);
+      if (dsts) {
+        const uint16_t s0 = f32_to_h16(f0, 2), s1 = f32_to_h16(f1, 2), s2 = f32_to_h16(f2, 2), s3 = f32_to_h16(f3, 2);
+        const float g0 = h16_to_f32(s0, 2), g1 = h16_to_f32(s1, 2), g2 = h16_to_f32(s2, 2), g3 = h16_to_f32(s3, 2);
+        ssn += g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3;
+        ssd += (g0 - f0) * (g0 - f0) + (g1 - f1) * (g1 - f1) + (g2 - f2) * (g2 - f2) + (g3 - f3) * (g3 - f3);
+        uint2 ps;
+        ps.x = static_cast<uint32_t>(s0) | (static_cast<uint32_t>(s1) << 16);
+        ps.y = static_cast<uint32_t>(s2) | (static_cast<uint32_t>(s3) << 16);
+        dsts[lane + 32 * i] = ps;
+      }
       s16 += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
       sy += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
       const float d0 = f0 - v[i].x, d1 = f1 - v[i].y, d2 = f2 - v[i].z, d3 = f3 - v[i].w;
@@ -122,10 +140,23 @@ l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const i
       if (out16) dst16[lane + 32 * i] = p;
     }
     finish_row_stats(s16, sy, sd, master32 != nullptr, cosine != 0, wmax_norm, wmax_dev);
+    if (dsts) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ssn += __shfl_xor_sync(FULL_MASK, ssn, o);
+        ssd += __shfl_xor_sync(FULL_MASK, ssd, o);
+      }
+      wmax_snorm = fmaxf(wmax_snorm, sqrtf(ssn));
+      wmax_sdev = fmaxf(wmax_sdev, sqrtf(ssd));
+    }
   }
   if (lane == 0 && stats) {
     atomic_max_nonneg(stats + 0, wmax_norm);
     atomic_max_nonneg(stats + 1, wmax_dev);
+    if (shadow16) {
+      atomic_max_nonneg(stats + 2, wmax_snorm);
+      atomic_max_nonneg(stats + 3, wmax_sdev);
+    }
   }
 }
 
@@ -133,12 +164,12 @@ l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const i
 __global__ void __launch_bounds__(K1_WARPS * 32)
 l2norm_pack_generic_kernel(const float* __restrict__ in, int64_t n, int dim, const int64_t* __restrict__ slots,
                            int64_t slot0, int normalize, int cosine, float* __restrict__ master32, int64_t ld32,
-                           uint16_t* __restrict__ out16, int64_t ld16, int kind16,
+                           uint16_t* __restrict__ out16, int64_t ld16, int kind16, uint16_t* __restrict__ shadow16,
                            float* __restrict__ out_norms, float* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * K1_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * K1_WARPS;
-  float wmax_norm = 0.f, wmax_dev = 0.f;
+  float wmax_norm = 0.f, wmax_dev = 0.f, wmax_snorm = 0.f, wmax_sdev = 0.f;
 
   for (int64_t row = warp0; row < n; row += nwarps) {
     const float* src = in + row * dim;
@@ -151,7 +182,7 @@ l2norm_pack_generic_kernel(const float* __restrict__ in, int64_t n, int dim, con
     if (lane == 0 && out_norms) out_norms[row] = (float)sqrt(ss);
     const double r = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
     const int64_t slot = slots ? slots[row] : slot0 + row;
-    float s16 = 0.f, sy = 0.f, sd = 0.f;
+    float s16 = 0.f, sy = 0.f, sd = 0.f, ssn = 0.f, ssd = 0.f;
     for (int i = lane; i < dim; i += 32) {
       float y = src[i];
       if (normalize) y = (float)((double)y * r);
@@ -159,15 +190,35 @@ l2norm_pack_generic_kernel(const float* __restrict__ in, int64_t n, int dim, con
       const uint16_t h = f32_to_h16(y, kind16);
       const float f = h16_to_f32(h, kind16);
       if (out16) out16[slot * ld16 + i] = h;
+      if (shadow16) {
+        const uint16_t sh = f32_to_h16(f, 2);
+        const float gsh = h16_to_f32(sh, 2);
+        shadow16[slot * ld16 + i] = sh;
+        ssn += gsh * gsh;
+        ssd += (gsh - f) * (gsh - f);
+      }
       s16 += f * f;
       sy += y * y;
       sd += (f - y) * (f - y);
     }
     finish_row_stats(s16, sy, sd, master32 != nullptr, cosine != 0, wmax_norm, wmax_dev);
+    if (shadow16) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ssn += __shfl_xor_sync(FULL_MASK, ssn, o);
+        ssd += __shfl_xor_sync(FULL_MASK, ssd, o);
+      }
+      wmax_snorm = fmaxf(wmax_snorm, sqrtf(ssn));
+      wmax_sdev = fmaxf(wmax_sdev, sqrtf(ssd));
+    }
   }
   if (lane == 0 && stats) {
     atomic_max_nonneg(stats + 0, wmax_norm);
     atomic_max_nonneg(stats + 1, wmax_dev);
+    if (shadow16) {
+      atomic_max_nonneg(stats + 2, wmax_snorm);
+      atomic_max_nonneg(stats + 3, wmax_sdev);
+    }
   }
 }
 
@@ -197,7 +248,7 @@ gather_rows_kernel(const float* __restrict__ master32, const uint16_t* __restric
 
 int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots_dev, int64_t slot0,
                           int normalize, int cosine, float* master32, int64_t ld32, uint16_t* out16,
-                          int64_t ld16, int kind16, float* out_norms, float* stats, int num_sms,
+                          int64_t ld16, int kind16, uint16_t* shadow16, float* out_norms, float* stats, int num_sms,
                           cudaStream_t st) {
   if (n <= 0) return RBOD_OK;
   const int64_t want = (n + K1_WARPS - 1) / K1_WARPS;
@@ -209,7 +260,7 @@ int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots
   case NV:                                                                                                 \
     l2norm_pack_vec_kernel<NV><<<grid, K1_WARPS * 32, 0, st>>>(in, n, dim, slots_dev, slot0, normalize,     \
                                                                cosine, master32, ld32, out16, ld16, kind16, \
-                                                               out_norms, stats);                          \
+                                                               shadow16, out_norms, stats);                \
     break;
   if (aligned && dim % 128 == 0 && dim / 128 >= 1 && dim / 128 <= 8) {
     switch (dim / 128) {
@@ -224,8 +275,8 @@ int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots
     }
   } else {
     l2norm_pack_generic_kernel<<<grid, K1_WARPS * 32, 0, st>>>(in, n, dim, slots_dev, slot0, normalize, cosine,
-                                                               master32, ld32, out16, ld16, kind16, out_norms,
-                                                               stats);
+                                                               master32, ld32, out16, ld16, kind16, shadow16,
+                                                               out_norms, stats);
   }
 #undef RBOD_K1_CASE
   RBOD_CUDA(cudaGetLastError());

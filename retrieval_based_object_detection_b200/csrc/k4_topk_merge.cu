@@ -143,7 +143,8 @@ rescore_kernel(const float* __restrict__ q, const double* __restrict__ q_qq, con
 __global__ void __launch_bounds__(128)
 select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict__ cand_idx,
               const float* __restrict__ cand_tau, const float* __restrict__ q_dq, const float* __restrict__ stats,
-              int master16, int dp, int64_t Q, int kc, int k, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+              int master16, int shadow, int dp, int64_t Q, int kc, int k, float* __restrict__ out_scores,
+              int64_t* __restrict__ out_rows,
               double* __restrict__ out_scores64, int* __restrict__ n_flag, int* __restrict__ flag_q,
               double* __restrict__ flag_thr, float* __restrict__ flag_lo, float* __restrict__ max_eps) {
   __shared__ double s_sc[4][K3_MAX_KC];
@@ -190,8 +191,10 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
   // The row term is ||g16 - unit(G)|| for fp32 masters (their 16-bit shadow is rounded independently);
   // for 16-bit masters g16 IS the stored row and only its norm deviates from 1 by d = stats[1], which
   // scales the score instead of adding to it: (|tau| + e) * d / (1 - d).
-  const float gmax = stats[0] * 1.000001f, gdev = stats[1] * 1.000001f;
-  const float e = q_dq[q] * gmax + (float)dp * 1.2e-7f * gmax;
+  // With an fp16 shadow as the search operand, the operand norm is stats[2] and its distance to the stored
+  // row, stats[3], adds to the query term.
+  const float gmax = (shadow ? stats[2] : stats[0]) * 1.000001f, gdev = stats[1] * 1.000001f;
+  const float e = q_dq[q] * gmax + (float)dp * 1.2e-7f * gmax + (shadow ? stats[3] * 1.000001f : 0.0f);
   const float row_term = master16 ? (fabsf(tau) + e) * gdev / (1.0f - gdev) : gdev;
   const float eps = e + row_term + fabsf(tau) * 1e-6f + 1e-7f;
   bool flagged = true;
@@ -456,12 +459,12 @@ int launch_rescore(const float* q, const double* q_qq, const float* master32, co
 }
 
 int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
-                  const float* stats, int master16, int dp, int64_t Q, int kc, int k, float* out_scores, int64_t* out_rows,
-                  double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* flag_lo, float* max_eps,
-                  cudaStream_t st) {
+                  const float* stats, int master16, int shadow, int dp, int64_t Q, int kc, int k, float* out_scores,
+                  int64_t* out_rows, double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* flag_lo,
+                  float* max_eps, cudaStream_t st) {
   if (Q <= 0) return RBOD_OK;
   if (kc > K3_MAX_KC) return set_error(RBOD_E_INVAL, "select: kc %d > %d", kc, K3_MAX_KC);
-  select_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, st>>>(cand_score, cand_idx, cand_tau, q_dq, stats, master16, dp, Q, kc, k,
+  select_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, st>>>(cand_score, cand_idx, cand_tau, q_dq, stats, master16, shadow, dp, Q, kc, k,
                                                          out_scores, out_rows, out_scores64, n_flag, flag_q,
                                                          flag_thr, flag_lo, max_eps);
   RBOD_CUDA(cudaGetLastError());

@@ -104,6 +104,7 @@ static size_t elem16_bytes() { return 2; }
 static size_t gallery_bytes(const rbod_gallery* g) {
   size_t b = (size_t)g->capacity * g->dp * elem16_bytes();
   if (g->master32) b += (size_t)g->capacity * g->dim * 4;
+  if (g->shadow16) b += (size_t)g->capacity * g->dp * 2;
   return b;
 }
 
@@ -112,34 +113,47 @@ static int grow(rbod_gallery* g, int64_t need, cudaStream_t st) {
   int64_t cap = std::max<int64_t>(need, g->capacity + g->capacity / 2);
   cap = std::max<int64_t>(cap, 1024);
   cap = (cap + 63) / 64 * 64;
-  uint16_t* n16 = nullptr;
+  uint16_t *n16 = nullptr, *nsh = nullptr;
   float* n32 = nullptr;
   cudaError_t e = cudaMalloc(&n16, (size_t)cap * g->dp * 2);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(RBOD_E_NOMEM, "gallery: cudaMalloc of %zu bytes failed", (size_t)cap * g->dp * 2);
   }
+  if (g->use_shadow) {
+    e = cudaMalloc(&nsh, (size_t)cap * g->dp * 2);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(n16);
+      return set_error(RBOD_E_NOMEM, "gallery: cudaMalloc of %zu bytes (fp16 shadow) failed", (size_t)cap * g->dp * 2);
+    }
+  }
   if (g->dtype == RBOD_F32) {
     e = cudaMalloc(&n32, (size_t)cap * g->dim * 4);
     if (e != cudaSuccess) {
       cudaGetLastError();
       cudaFree(n16);
+      if (nsh) cudaFree(nsh);
       return set_error(RBOD_E_NOMEM, "gallery: cudaMalloc of %zu bytes failed", (size_t)cap * g->dim * 4);
     }
   }
   // zero the new tail (keeps the dim..dp padding columns zero), then carry the old rows over
   const size_t old16 = (size_t)g->rows * g->dp * 2;
   RBOD_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(n16) + old16, 0, (size_t)cap * g->dp * 2 - old16, st));
+  if (nsh) RBOD_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(nsh) + old16, 0, (size_t)cap * g->dp * 2 - old16, st));
   if (g->rows > 0) {
     RBOD_CUDA(cudaMemcpyAsync(n16, g->rows16, old16, cudaMemcpyDeviceToDevice, st));
+    if (nsh && g->shadow16) RBOD_CUDA(cudaMemcpyAsync(nsh, g->shadow16, old16, cudaMemcpyDeviceToDevice, st));
     if (n32)
       RBOD_CUDA(cudaMemcpyAsync(n32, g->master32, (size_t)g->rows * g->dim * 4, cudaMemcpyDeviceToDevice, st));
   }
   RBOD_CUDA(cudaStreamSynchronize(st));
   if (g->rows16) cudaFree(g->rows16);
   if (g->master32) cudaFree(g->master32);
+  if (g->shadow16) cudaFree(g->shadow16);
   g->rows16 = n16;
   g->master32 = n32;
+  g->shadow16 = nsh;
   g->capacity = cap;
   return RBOD_OK;
 }
@@ -226,13 +240,13 @@ int rbod_create(int32_t dim, int32_t dtype, int32_t metric, int64_t capacity_hin
   // bf16 when the rows are not normalised.
   g->kind16 = dtype == RBOD_BF16 ? 1 : (dtype == RBOD_F16 ? 2 : (metric == RBOD_COSINE ? 2 : 1));
   g->num_sms = prop.multiProcessorCount;
-  cudaError_t e = cudaMalloc(&g->stats, 2 * sizeof(float));
+  cudaError_t e = cudaMalloc(&g->stats, 4 * sizeof(float));
   if (e != cudaSuccess) {
     cudaGetLastError();
     delete g;
     return set_error(RBOD_E_NOMEM, "rbod_create: cudaMalloc failed");
   }
-  cudaMemset(g->stats, 0, 2 * sizeof(float));
+  cudaMemset(g->stats, 0, 4 * sizeof(float));
   cudaEventCreate(&g->ev0);
   cudaEventCreate(&g->ev1);
   int rc = grow(g, std::max<int64_t>(capacity_hint, 1), nullptr);
@@ -250,6 +264,7 @@ int rbod_destroy(rbod_gallery* g) {
   cudaDeviceSynchronize();
   if (g->rows16) cudaFree(g->rows16);
   if (g->master32) cudaFree(g->master32);
+  if (g->shadow16) cudaFree(g->shadow16);
   if (g->stats) cudaFree(g->stats);
   DevBuf* bufs[] = {&g->stage_rows, &g->stage_slots, &g->stage_norms, &g->q32, &g->q16, &g->q_dq, &g->q_qq, &g->tau_shared,
                     &g->part_score, &g->part_idx, &g->cand_idx, &g->cand_tau, &g->cand_score, &g->out_scores,
@@ -300,7 +315,7 @@ int rbod_truncate(rbod_gallery* g, int64_t rows) {
   g->rows = rows;
   if (rows == 0) {
     RBOD_CUDA(cudaSetDevice(g->device));
-    RBOD_CUDA(cudaMemset(g->stats, 0, 2 * sizeof(float)));
+    RBOD_CUDA(cudaMemset(g->stats, 0, 4 * sizeof(float)));
   }
   return RBOD_OK;
 }
@@ -315,6 +330,19 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
     g->slack = (int)value;
   } else if (!strcmp(key, "time_k3")) {
     g->time_k3 = value != 0;
+  } else if (!strcmp(key, "shadow16")) {
+    // fp16 search operand for a bf16 collection (doubles its device memory); must be chosen while it is empty
+    if (g->dtype != RBOD_BF16) return set_error(RBOD_E_INVAL, "shadow16 applies to bf16 collections only");
+    if (g->rows != 0) return set_error(RBOD_E_INVAL, "shadow16 must be set before the first upsert");
+    if ((value != 0) != (g->use_shadow != 0)) {
+      g->use_shadow = value != 0;
+      if (g->shadow16) { cudaFree(g->shadow16); g->shadow16 = nullptr; }
+      if (g->use_shadow) {
+        RBOD_CUDA(cudaSetDevice(g->device));
+        RBOD_CUDA(cudaMalloc(&g->shadow16, (size_t)g->capacity * g->dp * 2));
+        RBOD_CUDA(cudaMemset(g->shadow16, 0, (size_t)g->capacity * g->dp * 2));
+      }
+    }
   } else if (!strcmp(key, "presample")) {
     g->presample = value != 0;
   } else if (!strcmp(key, "collect_pass")) {
@@ -394,7 +422,7 @@ int rbod_upsert(rbod_gallery* g, const float* rows, int64_t n, const int64_t* ro
       }
     }
     RBOD_TRY(launch_l2norm_pack(src, m, g->dim, slots_dev, g->rows + r0, normalize, cosine, g->master32, g->dim,
-                                g->rows16, g->dp, g->kind16, norms_dst, g->stats, g->num_sms, st));
+                                g->rows16, g->dp, g->kind16, g->shadow16, norms_dst, g->stats, g->num_sms, st));
     if (out_norms && !norms_dev)
       RBOD_CUDA(cudaMemcpyAsync(out_norms + r0, norms_dst, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     if (!rows_dev || row_slots) RBOD_CUDA(cudaStreamSynchronize(st));  // staging buffers are reused
@@ -443,10 +471,10 @@ int rbod_l2norm_pack(const float* in, int64_t n, int32_t dim, int32_t out_dtype,
   RBOD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (out_dtype == RBOD_F32)
     return launch_l2norm_pack(in, n, dim, nullptr, 0, 1, 1, static_cast<float*>(out), out_ld, nullptr, 0, 1,
-                              out_norms, nullptr, sms, st);
+                              nullptr, out_norms, nullptr, sms, st);
   if (out_dtype == RBOD_BF16 || out_dtype == RBOD_F16)
     return launch_l2norm_pack(in, n, dim, nullptr, 0, 1, 1, nullptr, 0, static_cast<uint16_t*>(out), out_ld,
-                              out_dtype == RBOD_BF16 ? 1 : 2, out_norms, nullptr, sms, st);
+                              out_dtype == RBOD_BF16 ? 1 : 2, nullptr, out_norms, nullptr, sms, st);
   return set_error(RBOD_E_INVAL, "rbod_l2norm_pack: unknown out_dtype %d", out_dtype);
 }
 
@@ -508,7 +536,8 @@ int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* of
 // 16-bit type the (unit-norm) queries are rounded to for the tensor-core pass: the gallery's own.
 // (Measured on B200: a kind::f16 MMA whose instruction descriptor mixes an fp16 A with a bf16 B
 // raises "illegal instruction", so both operands must share one format.)
-static int query_kind(const rbod_gallery* g) { return g->kind16; }
+static int query_kind(const rbod_gallery* g) { return g->use_shadow ? 2 : g->kind16; }
+static const uint16_t* search_operand(const rbod_gallery* g) { return g->use_shadow ? g->shadow16 : g->rows16; }
 
 struct K3Collect {
   const float* thr;
@@ -527,7 +556,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
                   const K3Sample* sample = nullptr) {
   K3Launch L;
   memset(&L, 0, sizeof(L));
-  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, g->rows16, g->rows, g->dp, k3_box_rows(g->k3_variant)));
+  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, search_operand(g), g->rows, g->dp, k3_box_rows(g->k3_variant)));
   RBOD_TRY(make_tmap_2d_sw128(&L.tmap_a, q16, P.q_pad, g->dp, K3_TILE_M));
   L.q16 = q16;
   if (collect) {
@@ -549,7 +578,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.variant = g->k3_variant;
   L.debug_epi = g->debug_epi;
   L.a_fmt = query_kind(g) == 1 ? 1 : 0;
-  L.b_fmt = g->kind16 == 1 ? 1 : 0;
+  L.b_fmt = query_kind(g) == 1 ? 1 : 0;
   L.part_score = g->part_score.as<float>();
   L.part_idx = g->part_idx.as<uint32_t>();
   L.row_mask = mask_dev;
@@ -695,7 +724,8 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   RBOD_TRY(launch_rescore(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp,
                           g->metric, g->cand_idx.as<uint32_t>(), Q, P.kc, g->cand_score.as<double>(), st));
   RBOD_TRY(launch_select(g->cand_score.as<double>(), g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(),
-                         g->q_dq.as<float>(), g->stats, g->dtype != RBOD_F32, g->dp, Q, P.kc, k, d_scores, d_rows, d_scores64, d_flags,
+                         g->q_dq.as<float>(), g->stats, g->dtype != RBOD_F32, g->use_shadow, g->dp, Q, P.kc, k, d_scores,
+                         d_rows, d_scores64, d_flags,
                          g->flag_q.as<int>(), g->flag_thr.as<double>(), g->flag_lo.as<float>(),
                          reinterpret_cast<float*>(d_flags + 3), st));
   launches += 3;

@@ -97,7 +97,7 @@ struct K3Launch {
 // K1
 int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots_dev, int64_t slot0,
                        int normalize, int cosine, float* master32, int64_t ld32, uint16_t* out16, int64_t ld16,
-                       int kind16, float* out_norms, float* stats, int num_sms, cudaStream_t st);
+                       int kind16, uint16_t* shadow16, float* out_norms, float* stats, int num_sms, cudaStream_t st);
 int launch_gather_rows(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32,
                        int64_t ld16, const int64_t* rows, int64_t n, int64_t n_valid, float* out, int* err_flag,
                        cudaStream_t st);
@@ -125,9 +125,9 @@ int launch_rescore(const float* q, const double* q_qq, const float* master32, co
                    int dim, int64_t ld32, int64_t ld16, int metric, const uint32_t* cand_idx, int64_t Q, int kc,
                    double* cand_score, cudaStream_t st);
 int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
-                  const float* stats, int master16, int dp, int64_t Q, int kc, int k, float* out_scores, int64_t* out_rows,
-                  double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* flag_lo, float* max_eps,
-                  cudaStream_t st);
+                  const float* stats, int master16, int shadow, int dp, int64_t Q, int kc, int k, float* out_scores,
+                  int64_t* out_rows, double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* flag_lo,
+                  float* max_eps, cudaStream_t st);
 int launch_gather_flagged(const uint16_t* q16, int dp, const int* flag_q, int f0, int nf, int64_t nf_pad,
                           uint16_t* fq16, int* coll_cnt, cudaStream_t st);
 int launch_rescore_collected(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
@@ -153,7 +153,10 @@ struct rbod_gallery {
   int64_t rows = 0, capacity = 0;
   float* master32 = nullptr;    // [capacity, dim]  (dtype == RBOD_F32 only)
   uint16_t* rows16 = nullptr;   // [capacity, dp]
-  float* stats = nullptr;       // device [2]: max ||row16||, max ||row16 - unit(master)||
+  uint16_t* shadow16 = nullptr; // [capacity, dp] fp16 copy of a bf16 gallery used as the search operand (option)
+  int use_shadow = 0;
+  float* stats = nullptr;       // device [4]: max ||row16||, max ||row16 - unit(master)||, max ||shadow||,
+                                // max ||shadow - row16||
   int num_sms = 148;
   // options
   int k3_variant = 0;

@@ -255,6 +255,8 @@ class Collection:
             metric = "cosine" if self.distance == "Cosine" else "dot"
             self.gallery = Gallery(self.dim, dtype=self.dtype, metric=metric, capacity=max(len(self.ids), 1024),
                                    device=self.device)
+            if self.dtype in ("bf16", "bfloat16") and os.environ.get("RBOD_BF16_SHADOW", "0") == "1":
+                self.gallery.set_option("shadow16", 1)    # fp16 search operand: tighter certification, 2x memory
             if self.snapshot_vectors is not None and len(self.snapshot_vectors):
                 self.gallery.upsert(self.snapshot_vectors, raw=True)
             self.snapshot_vectors = None

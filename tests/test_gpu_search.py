@@ -118,6 +118,36 @@ def test_wide_tie_cluster_goes_to_exact_sweep(G):
     g.close()
 
 
+def test_bf16_gallery_with_fp16_shadow_operand(G):
+    """Option shadow16: a bf16 collection searched through an fp16 copy.  Stored rows, ids and scores are
+    those of the bf16 gallery; the certification margin shrinks ~6x, so k=100 needs no second pass."""
+    n, dim, Q, k = 120000, 768, 200, 100
+    x = O.synthetic_unit_rows(n, dim, seed=21)
+    x[5, :40] *= 1e-6                                    # elements far below fp16's normal range
+    g = G(dim, dtype="bf16", capacity=n)
+    g.set_option("shadow16", 1)
+    g.upsert(x[: n // 2])
+    g.upsert(x[n // 2:])                                 # second upsert grows nothing but appends to both copies
+    stored = g.get_rows(np.arange(n))
+    want_rows = O.l2_normalize_store(x, "bf16")[0]          # the stored rows stay bf16 (<= 1 bf16 ulp from the oracle)
+    assert np.abs(stored.view(np.int32).astype(np.int64) - want_rows.view(np.int32).astype(np.int64)).max() <= 65536
+    q = O.synthetic_unit_rows(Q, dim, seed=77)
+    q[0] = x[5]
+    res = g.search(q, k, want_scores64=True)
+    ws, wi = O.cosine_topk(q, stored, k)
+    assert np.array_equal(res.rows, wi)
+    assert np.allclose(res.scores64, ws, rtol=1e-5, atol=1e-9)
+    assert res.stats["max_eps"] < 6e-4 and res.stats["fallback_queries"] <= 2
+    got = g.debug_scores(q[:4])                           # raw tensor-core scores come from the fp16 operand
+    qn = O.l2_normalize_store(q[:4], "f16")[0].astype(np.float64)
+    want = qn @ O.round_store(stored, "f16").astype(np.float64).T
+    assert np.abs(got - want).max() < 2e-5
+    from retrieval_based_object_detection_b200._native import RbodError
+    with pytest.raises(RbodError):
+        g.set_option("shadow16", 0)                       # only while the collection is empty
+    g.close()
+
+
 @pytest.mark.parametrize("tau_share", [0, 1])
 def test_k100_bf16_uncertified_queries_take_the_collect_pass(G, tau_share):
     """bf16 rounding leaves little slack at k=100 (kc=128): a good share of the queries is not certified by
@@ -255,3 +285,78 @@ def test_full_size_properties(G):
     top = torch.topk(allrows, k)
     assert np.array_equal(np.sort(top.indices.cpu().numpy()), np.sort(rows[0]))
     g.close()
+
+
+def _torch_topk_fp64(q, stored, k, chunk=250_000):
+    """Independent check on device: plain torch float64 cosine + top-k (continuous random data: no exact ties,
+    the tie rule itself is covered by the duplicate tests)."""
+    import torch
+
+    qq = q.double()
+    qn = qq.norm(dim=1, keepdim=True)
+    best_s = torch.zeros((q.shape[0], 0), dtype=torch.float64, device=q.device)
+    best_i = torch.zeros((q.shape[0], 0), dtype=torch.int64, device=q.device)
+    for a in range(0, stored.shape[0], chunk):
+        g = stored[a:a + chunk].double()
+        sc = (qq @ g.T) / (qn * g.norm(dim=1)[None, :])
+        top = torch.topk(sc, min(k, sc.shape[1]), dim=1)
+        s_all, i_all = torch.cat([best_s, top.values], 1), torch.cat([best_i, top.indices + a], 1)
+        o = torch.topk(s_all, min(k, s_all.shape[1]), dim=1).indices
+        best_s, best_i = torch.gather(s_all, 1, o), torch.gather(i_all, 1, o)
+    return best_s, best_i
+
+
+def test_config_c2_full_size_fp32_gallery(G):
+    """BASELINE config C2: 1M x 512 fp32 gallery, 10k-query batch, exact top-10 -- every query checked against
+    a torch float64 brute force on the device (ids identical, scores within 1e-5 relative)."""
+    import torch
+
+    n, dim, Q, k = 1_000_000, 512, 10_000, 10
+    g = G(dim, dtype="f32", capacity=n)
+    gen = torch.Generator("cuda").manual_seed(2)
+    centres = torch.nn.functional.normalize(torch.randn(1000, dim, device="cuda", generator=gen), dim=1)
+    for a in range(0, n, 250_000):      # clustered rows (class = row mod 1000), CLIP-like score range
+        lab = torch.arange(a, a + 250_000, device="cuda") % 1000
+        g.upsert(centres[lab] + 0.4 * torch.randn(250_000, dim, device="cuda", generator=gen) / dim ** 0.5)
+    stored = g.get_rows(torch.arange(n, device="cuda"))
+    q = centres[torch.randint(0, 1000, (Q,), device="cuda", generator=gen)] + \
+        0.4 * torch.randn(Q, dim, device="cuda", generator=gen) / dim ** 0.5
+    r = g.search(q, k, want_scores64=True)
+    assert r.stats["sweep_queries"] == 0
+    for a in range(0, Q, 2000):
+        ws, wi = _torch_topk_fp64(q[a:a + 2000], stored, k)
+        assert torch.equal(r.rows[a:a + 2000], wi), int((r.rows[a:a + 2000] != wi).any(dim=1).sum())
+        assert torch.allclose(r.scores64[a:a + 2000], ws, rtol=1e-5, atol=1e-9)
+    g.close()
+
+
+def test_config_c3_delegates_then_centroid_search(G):
+    """BASELINE config C3: per-class mean + renormalise over 1M labelled 768-d rows (10k classes, label-sorted
+    through a row index), then query-vs-centroid top-5."""
+    import torch
+
+    n, dim, C, Q, k = 1_000_000, 768, 10_000, 10_000, 5
+    g = G(dim, dtype="f32", capacity=n)
+    gen = torch.Generator("cuda").manual_seed(3)
+    centres = torch.nn.functional.normalize(torch.randn(C, dim, device="cuda", generator=gen), dim=1)
+    labels = torch.randint(0, C, (n,), device="cuda", generator=gen)
+    for a in range(0, n, 250_000):
+        g.upsert(centres[labels[a:a + 250_000]] + 0.4 * torch.randn(250_000, dim, device="cuda", generator=gen) / dim ** 0.5)
+    order = torch.argsort(labels, stable=True)
+    offsets = torch.zeros(C + 1, dtype=torch.int64, device="cuda")
+    offsets[1:] = torch.cumsum(torch.bincount(labels, minlength=C), 0)
+    cent = g.segment_mean(offsets, row_idx=order)
+    # float64 reference of compute_average (32:9-10) + stored (renormalised fp32) form, on device
+    stored = g.get_rows(torch.arange(n, device="cuda"))
+    sums = torch.zeros(C, dim, dtype=torch.float64, device="cuda").index_add_(0, labels, stored.double())
+    mean32 = (sums / (offsets[1:] - offsets[:-1]).clamp(min=1)[:, None].double()).float()
+    want = (mean32.double() / mean32.double().norm(dim=1, keepdim=True)).float()
+    assert float((cent - want).abs().max()) <= 2e-7
+    gc = G(dim, dtype="f32", capacity=C)
+    gc.upsert(cent)
+    q = stored[torch.randint(0, n, (Q,), device="cuda", generator=gen)]
+    r = gc.search(q, k, want_scores64=True)
+    ws, wi = _torch_topk_fp64(q, gc.get_rows(torch.arange(C, device="cuda")), k)
+    assert torch.equal(r.rows, wi) and torch.allclose(r.scores64, ws, rtol=1e-5, atol=1e-9)
+    g.close()
+    gc.close()

@@ -45,14 +45,14 @@ def build_gallery(a, dev):
     from retrieval_based_object_detection_b200 import Gallery
 
     g = Gallery(a.dim, dtype=a.dtype, capacity=a.rows, device=0)
+    for kv in a.opt:
+        key, _, val = kv.partition("=")
+        g.set_option(key, int(val))
     gen = torch.Generator(dev).manual_seed(1234)
     chunk = 500_000
     for s in range(0, a.rows, chunk):
         g.upsert(torch.randn(min(chunk, a.rows - s), a.dim, device=dev, generator=gen))
     torch.cuda.synchronize()
-    for kv in a.opt:
-        key, _, val = kv.partition("=")
-        g.set_option(key, int(val))
     return g
 
 
