@@ -150,6 +150,22 @@ int rbod_l2norm_pack(const float* in, int64_t n, int32_t dim, int32_t out_dtype,
 int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* offsets, int64_t n_classes,
                       float* out_centroids, void* stream);
 
+/* Other delegate types of 32_create_delegate_vector.py, one vector per class, float64 arithmetic on the
+ * stored rows like the reference, output in stored form (fp32, L2-normalised for COSINE collections):
+ *   RBOD_DELEGATE_AVERAGE  compute_average           :9-10   (same result as rbod_segment_mean)
+ *   RBOD_DELEGATE_CENTROID compute_centroid          :12-15  member nearest to the mean
+ *   RBOD_DELEGATE_WEIGHTED compute_weighted_average  :17-21  softmax(-alpha * distance to mean) weights
+ *   RBOD_DELEGATE_MEDOID   compute_medoid            :23-26  member with the smallest distance sum
+ * out_member_rows: optional [n_classes] int64, the row slot of the chosen member (centroid / medoid),
+ * -1 for the other kinds and for empty classes.  Pointers host or device.                            */
+#define RBOD_DELEGATE_AVERAGE 0
+#define RBOD_DELEGATE_CENTROID 1
+#define RBOD_DELEGATE_WEIGHTED 2
+#define RBOD_DELEGATE_MEDOID 3
+int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx, const int64_t* offsets,
+                           int64_t n_classes, double alpha, float* out_vectors, int64_t* out_member_rows,
+                           void* stream);
+
 /* --- K3: cosine top-k -------------------------------------------------------------------
  * queries:      [Q, dim] fp32 (any norm), host or device.
  * row_mask:     optional bitmask over row slots (bit r%32 of word r/32 set = row allowed),

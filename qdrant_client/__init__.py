@@ -239,11 +239,14 @@ class QdrantClient:
         return scores, ids
 
     # ------------------------------------------------------------------ delegates (K2)
-    def build_delegates(self, collection_name: str, group_key: str = "class_name", scroll_filter=None):
-        """Normalised per-group mean of stored vectors in ONE segmented launch (K2).
+    def build_delegates(self, collection_name: str, group_key: str = "class_name", scroll_filter=None,
+                        kind: str = "average", alpha: float = 2.0):
+        """Per-group delegate vectors of stored vectors in ONE segmented launch (K2 / K2b).
 
-        The batched counterpart of the per-class loop in 32_create_delegate_vector.py:119-147
-        (compute_average :9-10 + renormalise on upsert).  -> (group values, [G, dim] float32)."""
+        The batched counterpart of the per-class loop in 32_create_delegate_vector.py:119-156: ``kind`` is
+        "average" (compute_average :9-10), "centroid" (:12-15), "weighted" (:17-21, ``alpha``) or "medoid"
+        (:23-26); the result is the stored (renormalised) form the script's upsert would leave.
+        -> (group values, [G, dim] float32)."""
         col = self._root.get(collection_name)
         allowed = col.filter_slots(scroll_filter)
         groups: Dict[Any, List[int]] = {}
@@ -258,7 +261,9 @@ class QdrantClient:
         offsets = np.zeros(len(names) + 1, dtype=np.int64)
         np.cumsum([len(groups[n]) for n in names], out=offsets[1:])
         col.flush()
-        return names, col.gallery.segment_mean(offsets, row_idx=row_idx)
+        if kind == "average":
+            return names, col.gallery.segment_mean(offsets, row_idx=row_idx)
+        return names, col.gallery.segment_delegates(kind, offsets, row_idx=row_idx, alpha=alpha)[0]
 
     def close(self, **_ignored: Any) -> None:
         if self._key is None:

@@ -23,6 +23,7 @@ RBOD_E_UNSUPPORTED = -95
 RBOD_F32, RBOD_BF16, RBOD_F16 = 0, 1, 2
 RBOD_COSINE, RBOD_DOT = 0, 1
 RBOD_UPSERT_RAW = 1
+DELEGATE_KINDS = {"average": 0, "centroid": 1, "weighted": 2, "medoid": 3}
 
 DTYPES = {"f32": RBOD_F32, "fp32": RBOD_F32, "float32": RBOD_F32, "bf16": RBOD_BF16, "bfloat16": RBOD_BF16,
           "f16": RBOD_F16, "fp16": RBOD_F16, "float16": RBOD_F16}
@@ -67,6 +68,7 @@ SIGNATURES = {
     "rbod_get_rows": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "rbod_l2norm_pack": (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _P]),
     "rbod_segment_mean": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P]),
+    "rbod_segment_delegates": (ctypes.c_int, [_P, _I32, _P, _P, _I64, ctypes.c_double, _P, _P, _P]),
     "rbod_search": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, ctypes.POINTER(SearchStats), _P]),
     "rbod_merge_topk": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
     "rbod_debug_scores": (ctypes.c_int, [_P, _P, _I64, _P, _P]),

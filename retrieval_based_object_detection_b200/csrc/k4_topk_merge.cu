@@ -80,7 +80,8 @@ merge_partials_kernel(const float* __restrict__ part_score, const uint32_t* __re
 // tau_init: starting threshold of a query = the smallest of its `groups` sample-group maxima.  Every
 // group holds one row scoring at least that much, and with N / (rows per group) = 16 * kc the expected
 // number of gallery rows above it is ~ 16 * kc * H(groups): far fewer than N, so the candidate heaps
-// skip their cold start, yet (with probability 1 - (kc / (16 kc))^groups) more than kc.
+// skip their cold start, yet fewer than k rows beat it only with probability ~ (k / (16 kc))^groups
+// per query (8 groups: < 1e-9 even at k = 100, kc = 128); the host then redoes the call without it.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 tau_init_kernel(const float* __restrict__ groupmax, int groups, int64_t q_pad, uint32_t* __restrict__ tau_shared,

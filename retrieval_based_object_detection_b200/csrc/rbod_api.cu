@@ -270,7 +270,8 @@ int rbod_destroy(rbod_gallery* g) {
                     &g->part_score, &g->part_idx, &g->cand_idx, &g->cand_tau, &g->cand_score, &g->out_scores,
                     &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->flag_lo, &g->fq16, &g->groupmax, &g->tau_init, &g->coll_score,
                     &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->sync_counters, &g->seg_idx, &g->seg_off, &g->seg_out,
-                    &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->gather_idx, &g->gather_out};
+                    &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->seg_scratch, &g->seg_member, &g->gather_idx,
+                    &g->gather_out};
   for (DevBuf* b : bufs) b->release();
   g->pin_a.release();
   g->pin_b.release();
@@ -529,6 +530,77 @@ int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* of
   RBOD_CUDA(cudaMemcpyAsync(&err, g->flags.as<int>() + 2, 4, cudaMemcpyDeviceToHost, st));
   RBOD_CUDA(cudaStreamSynchronize(st));
   if (err) return set_error(RBOD_E_RANGE, "rbod_segment_mean: row index outside [0, %lld)", (long long)g->rows);
+  return RBOD_OK;
+}
+
+int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx, const int64_t* offsets,
+                           int64_t n_classes, double alpha, float* out_vectors, int64_t* out_member_rows,
+                           void* stream) {
+  if (!g) return set_error(RBOD_E_INVAL, "rbod_segment_delegates: NULL handle");
+  if (kind == RBOD_DELEGATE_AVERAGE) {
+    RBOD_TRY(rbod_segment_mean(g, row_idx, offsets, n_classes, out_vectors, stream));
+    if (out_member_rows && n_classes > 0) {
+      if (is_device_ptr(out_member_rows))
+        RBOD_CUDA(cudaMemsetAsync(out_member_rows, 0xff, (size_t)n_classes * 8, static_cast<cudaStream_t>(stream)));
+      else
+        for (int64_t c = 0; c < n_classes; ++c) out_member_rows[c] = -1;
+    }
+    return RBOD_OK;
+  }
+  if (kind != RBOD_DELEGATE_CENTROID && kind != RBOD_DELEGATE_WEIGHTED && kind != RBOD_DELEGATE_MEDOID)
+    return set_error(RBOD_E_INVAL, "rbod_segment_delegates: unknown kind %d", kind);
+  if (n_classes < 0 || (n_classes > 0 && (!offsets || !out_vectors)))
+    return set_error(RBOD_E_INVAL, "rbod_segment_delegates: bad arguments");
+  if (n_classes == 0) return RBOD_OK;
+  if (n_classes > 0x7fffffffll) return set_error(RBOD_E_INVAL, "rbod_segment_delegates: too many classes");
+  RBOD_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t first = 0, total = 0;
+  if (is_device_ptr(offsets)) {
+    RBOD_CUDA(cudaMemcpyAsync(&first, offsets, 8, cudaMemcpyDeviceToHost, st));
+    RBOD_CUDA(cudaMemcpyAsync(&total, offsets + n_classes, 8, cudaMemcpyDeviceToHost, st));
+    RBOD_CUDA(cudaStreamSynchronize(st));
+  } else {
+    first = offsets[0];
+    total = offsets[n_classes];
+    for (int64_t c = 0; c < n_classes; ++c)
+      if (offsets[c + 1] < offsets[c]) return set_error(RBOD_E_INVAL, "rbod_segment_delegates: offsets not monotone");
+  }
+  if (first < 0 || total < first) return set_error(RBOD_E_INVAL, "rbod_segment_delegates: bad offsets");
+  if (!row_idx && total > g->rows) return set_error(RBOD_E_RANGE, "rbod_segment_delegates: offsets exceed row count");
+  const void *idx_dev = nullptr, *off_dev = nullptr;
+  if (row_idx) RBOD_TRY(to_device(row_idx, (size_t)total * 8, g->seg_idx, st, &idx_dev));
+  RBOD_TRY(to_device(offsets, (size_t)(n_classes + 1) * 8, g->seg_off, st, &off_dev));
+  const bool out_dev = is_device_ptr(out_vectors);
+  float* dst = out_vectors;
+  if (!out_dev) {
+    RBOD_TRY(g->seg_out.ensure((size_t)n_classes * g->dim * 4));
+    dst = g->seg_out.as<float>();
+  }
+  int64_t* mem_dst = nullptr;
+  const bool mem_dev = out_member_rows && is_device_ptr(out_member_rows);
+  if (out_member_rows) {
+    if (mem_dev) mem_dst = out_member_rows;
+    else {
+      RBOD_TRY(g->seg_member.ensure((size_t)n_classes * 8));
+      mem_dst = g->seg_member.as<int64_t>();
+    }
+  }
+  RBOD_TRY(g->seg_scratch.ensure((size_t)std::max<int64_t>(total, 1) * 8));
+  RBOD_TRY(g->flags.ensure(64));
+  RBOD_CUDA(cudaMemsetAsync(g->flags.p, 0, 64, st));
+  RBOD_TRY(launch_segment_delegates(g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp, g->rows,
+                                    static_cast<const int64_t*>(idx_dev), static_cast<const int64_t*>(off_dev),
+                                    n_classes, kind, alpha, g->metric == RBOD_COSINE, g->seg_scratch.as<double>(), dst,
+                                    mem_dst, g->flags.as<int>() + 2, st));
+  if (!out_dev)
+    RBOD_CUDA(cudaMemcpyAsync(out_vectors, dst, (size_t)n_classes * g->dim * 4, cudaMemcpyDeviceToHost, st));
+  if (out_member_rows && !mem_dev)
+    RBOD_CUDA(cudaMemcpyAsync(out_member_rows, mem_dst, (size_t)n_classes * 8, cudaMemcpyDeviceToHost, st));
+  int err = 0;
+  RBOD_CUDA(cudaMemcpyAsync(&err, g->flags.as<int>() + 2, 4, cudaMemcpyDeviceToHost, st));
+  RBOD_CUDA(cudaStreamSynchronize(st));
+  if (err) return set_error(RBOD_E_RANGE, "rbod_segment_delegates: row index outside [0, %lld)", (long long)g->rows);
   return RBOD_OK;
 }
 

@@ -54,7 +54,7 @@ constexpr int K3_MAX_DP = 768;       // A operand must fit 384 TMEM columns
 constexpr int K3_THREADS = 192;      // warp0 TMA, warp1 MMA, warps 2-5 epilogue
 constexpr int K3_MAX_KC = 128;
 constexpr int K3_COLLECT_CAP = 1024; // rows a collecting pass records per query before it reports overflow
-constexpr int K3_SAMPLE_GROUPS = 4;  // threshold pre-pass: groups whose row maxima are compared
+constexpr int K3_SAMPLE_GROUPS = 8;  // threshold pre-pass: groups whose row maxima are compared
 constexpr int K3_SAMPLE_RATIO = 16;  // rows per group = N / (ratio * kc)
 constexpr int K3_TAU_REFRESH = 32;   // tiles between two looks at the threshold shared by a query's slices
 
@@ -106,6 +106,10 @@ int launch_segment_mean(const float* master32, const uint16_t* rows16, int kind1
                         int64_t ld16, int64_t n_valid, const int64_t* row_idx, const int64_t* offsets,
                         int64_t n_classes, int64_t n_items_upper, double* partials, int* chunk_prefix,
                         unsigned int* arrive_cnt, float* out, int* err_flag, cudaStream_t st);
+int launch_segment_delegates(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32,
+                             int64_t ld16, int64_t n_valid, const int64_t* row_idx, const int64_t* offsets,
+                             int64_t n_classes, int kind, double alpha, int cosine, double* scratch, float* out,
+                             int64_t* out_member, int* err_flag, cudaStream_t st);
 // K3
 int k3_configure(int device);
 int k3_plan(int variant, int kc, int dp, int smem_optin, int allow_hybrid, int* num_stages, int* a_tmem_kb,
@@ -178,7 +182,7 @@ struct rbod_gallery {
   rbod::DevBuf flag_q, flag_thr, flag_lo, fq16, groupmax, tau_init;
   rbod::DevBuf coll_score, coll_idx, coll_cnt;
   rbod::DevBuf mask_dev, dump, sync_counters;
-  rbod::DevBuf seg_idx, seg_off, seg_out, seg_partials, seg_prefix, seg_arrive;
+  rbod::DevBuf seg_idx, seg_off, seg_out, seg_partials, seg_prefix, seg_arrive, seg_scratch, seg_member;
   rbod::DevBuf gather_idx, gather_out;
   rbod::PinBuf pin_a, pin_b;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -146,6 +146,23 @@ class Gallery:
         N.check(self._lib.rbod_segment_mean(self._h, p_idx, p_off, C, p_out, _current_stream()))
         return out
 
+    def segment_delegates(self, kind: str, offsets, row_idx=None, alpha: float = 2.0):
+        """Per-class delegate of ``kind`` in {"average", "centroid", "weighted", "medoid"}
+        (32_create_delegate_vector.py:9-26) in stored form -> (vectors [C, dim] float32, member rows [C] int64,
+        -1 where the delegate is not a member)."""
+        if kind not in N.DELEGATE_KINDS:
+            raise ValueError(f"unknown delegate kind {kind!r}")
+        k_off, p_off = self._in(offsets, np.int64, "int64")
+        k_idx, p_idx = self._in(row_idx, np.int64, "int64")
+        C = int(k_off.shape[0]) - 1
+        if C < 0:
+            raise ValueError("segment_delegates: offsets must have at least one entry")
+        out, p_out = self._alloc_like(k_off, (C, self.dim), np.float32, "float32")
+        mem, p_mem = self._alloc_like(k_off, (C,), np.int64, "int64")
+        N.check(self._lib.rbod_segment_delegates(self._h, N.DELEGATE_KINDS[kind], p_idx, p_off, C, float(alpha), p_out,
+                                                 p_mem, _current_stream()))
+        return out, mem
+
     # -- K3 ---------------------------------------------------------------------------------
     def search(self, queries, k: int, row_mask=None, want_scores64: bool = False, out=None, stream=None) -> SearchResult:
         """Exact cosine top-k of ``queries`` [Q, dim] against the stored rows."""

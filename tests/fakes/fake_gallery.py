@@ -65,6 +65,13 @@ class FakeGallery:
         self.calls.append(("segment_mean", len(offsets) - 1))
         return O.segment_mean_renorm(self._rows, row_idx, offsets)
 
+    def segment_delegates(self, kind, offsets, row_idx=None, alpha=2.0):
+        fn = {"average": O.compute_average, "centroid": O.compute_centroid, "medoid": O.compute_medoid,
+              "weighted": lambda v: O.compute_weighted_average(v, alpha)}[kind]
+        offsets = np.asarray(offsets, dtype=np.int64)
+        row_idx = np.arange(offsets[-1]) if row_idx is None else np.asarray(row_idx, dtype=np.int64)
+        return O.segment_mean_renorm(self._rows, row_idx, offsets, average_fn=fn), np.full(len(offsets) - 1, -1)
+
     def search(self, queries, k, row_mask=None, want_scores64=False, out=None, stream=None):
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
         self.calls.append(("search", len(q), k))

@@ -137,6 +137,75 @@ def test_k2_matches_reference_golden(G, golden_dir):
         g.close()
 
 
+# ------------------------------------------------------------------ K2b: centroid / weighted / medoid
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("n,dim,ncls", [(1200, 512, 12), (900, 768, 5), (300, 100, 7)])
+def test_k2b_delegate_types_match_the_reference_functions(G, dtype, n, dim, ncls):
+    """compute_centroid / compute_weighted_average / compute_medoid (32:12-26) per class, in stored form."""
+    x, labels, _ = O.synthetic_clustered(n, dim, ncls, seed=n + 1)
+    g = G(dim, dtype=dtype, capacity=n)
+    g.upsert(x)
+    stored = g.get_rows(np.arange(n))
+    order = np.argsort(labels, kind="stable").astype(np.int64)
+    offsets = np.zeros(ncls + 1, np.int64)
+    np.cumsum(np.bincount(labels, minlength=ncls), out=offsets[1:])
+    for kind, fn in (("centroid", O.compute_centroid), ("weighted", O.compute_weighted_average),
+                     ("medoid", O.compute_medoid), ("average", O.compute_average)):
+        got, members = g.segment_delegates(kind, offsets, row_idx=order)
+        want = O.segment_mean_renorm(stored, order, offsets, average_fn=fn)
+        assert got.shape == (ncls, dim) and _ulp(got, want) <= 2, kind
+        if kind in ("centroid", "medoid"):
+            for c in range(ncls):
+                rows = order[offsets[c]:offsets[c + 1]]
+                v = stored[rows].astype(np.float64)
+                assert members[c] in rows and np.array_equal(stored[members[c]].astype(np.float64), fn(v)), (kind, c)
+        else:
+            assert np.all(members == -1)
+    g.close()
+
+
+def test_k2b_golden_empty_duplicates_and_device_io(G, golden_dir):
+    import os
+
+    import torch
+
+    z = np.load(os.path.join(golden_dir, "delegates.npz"))
+    for case in range(5):                                    # outputs of the reference's own functions
+        stored = z[f"in_{case}"]
+        g = G(stored.shape[1], dtype="f32", capacity=len(stored))
+        g.upsert(stored, raw=True)
+        for kind in ("centroid", "weighted", "medoid"):
+            got, _ = g.segment_delegates(kind, np.array([0, len(stored)], np.int64))
+            want = O.l2_normalize_store(z[f"{kind}_{case}"].astype(np.float32)[None], "f32")[0][0]
+            assert _ulp(got, want[None]) <= 2, (case, kind)
+        g.close()
+    n, dim = 400, 256
+    x = O.synthetic_unit_rows(n, dim, seed=9)
+    x[40] = x[10]
+    x[70] = x[10]                                            # duplicates: argmin ties resolve to the first member
+    x[10] = x[:100].mean(axis=0)                             # ... and make that member the one nearest the mean
+    x[40] = x[10]
+    x[70] = x[10]
+    g = G(dim, dtype="f32", capacity=n)
+    g.upsert(x)
+    stored = g.get_rows(np.arange(n))
+    offsets = np.array([0, 100, 100, 101, 400], np.int64)    # a class, an empty class, a single member, the rest
+    for kind, fn in (("centroid", O.compute_centroid), ("medoid", O.compute_medoid), ("weighted", O.compute_weighted_average)):
+        got, members = g.segment_delegates(kind, offsets)
+        want = O.segment_mean_renorm(stored, None, offsets, average_fn=fn)
+        assert _ulp(got, want) <= 2 and np.all(got[1] == 0)
+        if kind != "weighted":
+            assert list(members[:3]) == [10, -1, 100]
+        d_got, d_mem = g.segment_delegates(kind, torch.from_numpy(offsets).cuda())
+        assert d_got.is_cuda and np.array_equal(d_got.cpu().numpy(), got) and np.array_equal(d_mem.cpu().numpy(), members)
+    from retrieval_based_object_detection_b200._native import RbodError
+    with pytest.raises(RbodError):
+        g.segment_delegates("medoid", np.array([0, 3], np.int64), row_idx=np.array([0, 1, 99999], np.int64))
+    with pytest.raises(ValueError):
+        g.segment_delegates("mode", offsets)
+    g.close()
+
+
 # ------------------------------------------------------------------ K4 merge
 def test_k4_merge_topk(G):
     import torch

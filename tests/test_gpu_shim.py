@@ -84,6 +84,14 @@ def test_script_chain_on_device(store_dir, monkeypatch, dtype):
         want = O.segment_mean_renorm(stored_dev, np.array(rows), np.array([0, len(rows)]))[0]
         assert np.abs(cents[j] - want).max() <= 2e-7
 
+    for kind, fn in (("centroid", O.compute_centroid), ("weighted", O.compute_weighted_average), ("medoid", O.compute_medoid)):
+        _, vk = c.build_delegates("thesis", group_key="class_name", kind=kind,
+                                  scroll_filter=Filter(must=[FieldCondition(key="is_delegate", match=MatchValue(value=False))]))
+        rows = [col.slot_of[str(uuid.UUID(hashlib.md5(_payload(classes[3], i, "natural_images" if i % 2 else "original_images")["img_path"].encode()).hexdigest()))]
+                for i in np.flatnonzero(labels == 3)]
+        want = O.segment_mean_renorm(stored_dev, np.array(rows), np.array([0, len(rows)]), average_fn=fn)[0]
+        assert np.abs(vk[3] - want).max() <= 2e-7, kind
+
     # north-star search API: delegate-vector top-5 (config C1) with a payload filter evaluated on the device
     only_delegates = Filter(must=[FieldCondition(key="is_delegate", match=MatchValue(value=True))])
     hits = c.search("thesis", query_vector=test_vec.tolist(), query_filter=only_delegates, limit=5)

@@ -166,6 +166,10 @@ def test_delegate_round_trip_like_script_32_and_33(client):
     names, cents = client.build_delegates("thesis", group_key="class_name",
                                           scroll_filter=m.Filter(must=[m.FieldCondition(key="is_delegate", match=m.MatchValue(value=False))]))
     assert names == ["cup", "dog", "tree"] and np.array_equal(cents[0], want)
+    for kind, fn in (("centroid", O.compute_centroid), ("weighted", O.compute_weighted_average), ("medoid", O.compute_medoid)):
+        _, vecs_k = client.build_delegates("thesis", kind=kind, scroll_filter=m.Filter(must=[
+            m.FieldCondition(key="is_delegate", match=m.MatchValue(value=False))]))
+        assert np.array_equal(vecs_k[0], O.l2_normalize_store(fn(vectors_np).astype(np.float32)[None], "f32")[0][0])
     # 33:151 on stored vectors: a member compared with itself gives the reference's known answer
     v = np.array(results[0].vector)
     assert O.cosine_similarity(v, v) in (1.0, 1.0000000000000002, 0.9999999999999999)
