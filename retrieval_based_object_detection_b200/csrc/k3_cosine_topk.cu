@@ -581,10 +581,10 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
   }
 }
 
-// One warp per query: |q|^2 in fp64, unit query rounded to the 16-bit operand type, and
-// dq = || fp(q16) - q/|q| ||_2 (the query's share of the certification margin).
+// One warp per query: |q|^2 in fp64, (unit) query rounded to the 16-bit operand type, and
+// dq = || fp(q16) - target ||_2 (the query's share of the certification margin), target = q/|q| (COSINE) or q (DOT).
 __global__ void __launch_bounds__(256)
-prep_queries_kernel(const float* __restrict__ q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16,
+prep_queries_kernel(const float* __restrict__ q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16, int normalize,
                     uint16_t* __restrict__ q16, float* __restrict__ q_dq, double* __restrict__ q_qq,
                     uint32_t* __restrict__ tau_shared) {
   const int lane = threadIdx.x & 31;
@@ -604,13 +604,17 @@ prep_queries_kernel(const float* __restrict__ q, int64_t Q, int64_t q_pad, int d
       ss = fma(x, x, ss);
     }
     ss = warp_sum_f64(ss);
-    const double r = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+    // COSINE: the operand is the unit query; DOT: the query itself (fp16 operands saturate instead of overflowing,
+    // the clamp error lands in dq like any other rounding error)
+    const double r = normalize ? (ss > 0.0 ? 1.0 / sqrt(ss) : 0.0) : 1.0;
     double dd = 0.0;
     for (int c = lane; c < dp; c += 32) {
       uint16_t h = 0;
       if (c < dim) {
         const double u = (double)src[c] * r;
-        h = f32_to_h16((float)u, kind16);
+        float uf = (float)u;
+        if (kind16 == 2) uf = fminf(fmaxf(uf, -65504.0f), 65504.0f);
+        h = f32_to_h16(uf, kind16);
         const double e = (double)h16_to_f32(h, kind16) - u;
         dd = fma(e, e, dd);
       }
@@ -780,11 +784,11 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   return RBOD_OK;
 }
 
-int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16, uint16_t* q16,
-                        float* q_dq, double* q_qq, uint32_t* tau_shared, cudaStream_t st) {
+int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16, int normalize,
+                        uint16_t* q16, float* q_dq, double* q_qq, uint32_t* tau_shared, cudaStream_t st) {
   const int64_t want = (q_pad + 7) / 8;
   const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
-  prep_queries_kernel<<<grid, 256, 0, st>>>(q, Q, q_pad, dim, dp, kind16, q16, q_dq, q_qq, tau_shared);
+  prep_queries_kernel<<<grid, 256, 0, st>>>(q, Q, q_pad, dim, dp, kind16, normalize, q16, q_dq, q_qq, tau_shared);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

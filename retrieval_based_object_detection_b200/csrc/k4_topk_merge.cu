@@ -100,7 +100,7 @@ tau_init_kernel(const float* __restrict__ groupmax, int groups, int64_t q_pad, u
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 rescore_kernel(const float* __restrict__ q, const double* __restrict__ q_qq, const float* __restrict__ master32,
-               const uint16_t* __restrict__ rows16, int kind16, int dim, int64_t ld32, int64_t ld16,
+               const uint16_t* __restrict__ rows16, int kind16, int dim, int64_t ld32, int64_t ld16, int metric,
                const uint32_t* __restrict__ cand_idx, int64_t n_pairs, int kc, double* __restrict__ cand_score) {
   const int lane = threadIdx.x & 31;
   const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -133,7 +133,7 @@ rescore_kernel(const float* __restrict__ q, const double* __restrict__ q_qq, con
     gg = warp_sum_f64(gg);
     if (lane == 0) {
       const double den = sqrt(q_qq[qi]) * sqrt(gg);
-      cand_score[p] = den > 0.0 ? dot / den : 0.0;
+      cand_score[p] = metric == RBOD_DOT ? dot : (den > 0.0 ? dot / den : 0.0);
     }
   }
 }
@@ -144,7 +144,7 @@ rescore_kernel(const float* __restrict__ q, const double* __restrict__ q_qq, con
 __global__ void __launch_bounds__(128)
 select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict__ cand_idx,
               const float* __restrict__ cand_tau, const float* __restrict__ q_dq, const float* __restrict__ stats,
-              int master16, int shadow, int dp, int64_t Q, int kc, int k, float* __restrict__ out_scores,
+              const double* __restrict__ q_qq, int metric, int master16, int shadow, int dp, int64_t Q, int kc, int k, float* __restrict__ out_scores,
               int64_t* __restrict__ out_rows,
               double* __restrict__ out_scores64, int* __restrict__ n_flag, int* __restrict__ flag_q,
               double* __restrict__ flag_thr, float* __restrict__ flag_lo, float* __restrict__ max_eps) {
@@ -195,8 +195,12 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
   // With an fp16 shadow as the search operand, the operand norm is stats[2] and its distance to the stored
   // row, stats[3], adds to the query term.
   const float gmax = (shadow ? stats[2] : stats[0]) * 1.000001f, gdev = stats[1] * 1.000001f;
-  const float e = q_dq[q] * gmax + (float)dp * 1.2e-7f * gmax + (shadow ? stats[3] * 1.000001f : 0.0f);
-  const float row_term = master16 ? (fabsf(tau) + e) * gdev / (1.0f - gdev) : gdev;
+  // DOT collections: nothing is normalised, so every term scales with the query norm |q| and the row term is
+  // |q| * ||g16 - g|| (zero for 16-bit masters, whose operand is the stored row).
+  const float qn = metric == RBOD_DOT ? (float)sqrt(q_qq[q]) * 1.000001f + q_dq[q] : 1.0f;
+  const float e = q_dq[q] * gmax + (float)dp * 1.2e-7f * gmax * qn + (shadow ? stats[3] * 1.000001f * qn : 0.0f);
+  const float row_term = metric == RBOD_DOT ? (master16 ? 0.0f : qn * gdev)
+                                            : (master16 ? (fabsf(tau) + e) * gdev / (1.0f - gdev) : gdev);
   const float eps = e + row_term + fabsf(tau) * 1e-6f + 1e-7f;
   bool flagged = true;
   if (who) {
@@ -220,7 +224,7 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
       // Threshold for the collecting second pass: every row whose exact score reaches kth has an
       // approximate score above lo (same error model, applied from the exact side).
       const float kf = (float)kth;
-      const float lo = master16 ? kf - fabsf(kf) * gdev - e : kf - e - gdev;
+      const float lo = metric == RBOD_DOT ? kf - e - row_term : (master16 ? kf - fabsf(kf) * gdev - e : kf - e - gdev);
       flag_lo[slot] = kth == -INFINITY ? -INFINITY : lo - fabsf(kf) * 2e-6f - 2e-7f;
     }
   }
@@ -234,7 +238,7 @@ constexpr int EX_NMAX = 32;  // dim <= 1024
 __global__ void __launch_bounds__(256)
 exact_collect_kernel(const float* __restrict__ q, const double* __restrict__ q_qq,
                      const float* __restrict__ master32, const uint16_t* __restrict__ rows16, int kind16, int dim,
-                     int64_t ld32, int64_t ld16, int64_t n_rows, const uint32_t* __restrict__ row_mask,
+                     int64_t ld32, int64_t ld16, int metric, int64_t n_rows, const uint32_t* __restrict__ row_mask,
                      const int* __restrict__ flag_q, const double* __restrict__ flag_thr, int f0, int nf, int cap,
                      double* __restrict__ coll_score, uint32_t* __restrict__ coll_idx, int* __restrict__ coll_cnt) {
   const int lane = threadIdx.x & 31;
@@ -266,7 +270,7 @@ exact_collect_kernel(const float* __restrict__ q, const double* __restrict__ q_q
       dot = warp_sum_f64(dot);
       if (lane == 0) {
         const double den = sqrt(q_qq[qi]) * gn;
-        const double s = den > 0.0 ? dot / den : 0.0;
+        const double s = metric == RBOD_DOT ? dot : (den > 0.0 ? dot / den : 0.0);
         if (s >= flag_thr[f0 + f]) {
           const int slot = atomicAdd(coll_cnt + f, 1);
           if (slot < cap) {
@@ -340,7 +344,7 @@ gather_flagged_kernel(const uint16_t* __restrict__ q16, int dp, const int* __res
 __global__ void __launch_bounds__(256)
 rescore_collected_kernel(const float* __restrict__ q, const double* __restrict__ q_qq,
                          const float* __restrict__ master32, const uint16_t* __restrict__ rows16, int kind16,
-                         int dim, int64_t ld32, int64_t ld16, const int* __restrict__ flag_q, int f0, int cap,
+                         int dim, int64_t ld32, int64_t ld16, int metric, const int* __restrict__ flag_q, int f0, int cap,
                          const uint32_t* __restrict__ coll_idx, const int* __restrict__ coll_cnt,
                          double* __restrict__ coll_score) {
   const int lane = threadIdx.x & 31;
@@ -371,7 +375,7 @@ rescore_collected_kernel(const float* __restrict__ q, const double* __restrict__
     gg = warp_sum_f64(gg);
     if (lane == 0) {
       const double den = qn * sqrt(gg);
-      coll_score[(size_t)f * cap + j] = den > 0.0 ? dot / den : 0.0;
+      coll_score[(size_t)f * cap + j] = metric == RBOD_DOT ? dot : (den > 0.0 ? dot / den : 0.0);
     }
   }
 }
@@ -448,24 +452,23 @@ int launch_tau_init(const float* groupmax, int groups, int64_t q_pad, uint32_t* 
 int launch_rescore(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16, int kind16,
                    int dim, int64_t ld32, int64_t ld16, int metric, const uint32_t* cand_idx, int64_t Q, int kc,
                    double* cand_score, cudaStream_t st) {
-  (void)metric;
   const int64_t n_pairs = Q * kc;
   if (n_pairs <= 0) return RBOD_OK;
   const int64_t want = (n_pairs + 7) / 8;
   const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
-  rescore_kernel<<<grid, 256, 0, st>>>(q, q_qq, master32, rows16, kind16, dim, ld32, ld16, cand_idx, n_pairs, kc,
-                                       cand_score);
+  rescore_kernel<<<grid, 256, 0, st>>>(q, q_qq, master32, rows16, kind16, dim, ld32, ld16, metric, cand_idx, n_pairs,
+                                       kc, cand_score);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }
 
 int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
-                  const float* stats, int master16, int shadow, int dp, int64_t Q, int kc, int k, float* out_scores,
-                  int64_t* out_rows, double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* flag_lo,
-                  float* max_eps, cudaStream_t st) {
+                  const float* stats, const double* q_qq, int metric, int master16, int shadow, int dp, int64_t Q, int kc,
+                  int k, float* out_scores, int64_t* out_rows, double* out_scores64, int* n_flag, int* flag_q,
+                  double* flag_thr, float* flag_lo, float* max_eps, cudaStream_t st) {
   if (Q <= 0) return RBOD_OK;
   if (kc > K3_MAX_KC) return set_error(RBOD_E_INVAL, "select: kc %d > %d", kc, K3_MAX_KC);
-  select_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, st>>>(cand_score, cand_idx, cand_tau, q_dq, stats, master16, shadow, dp, Q, kc, k,
+  select_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, st>>>(cand_score, cand_idx, cand_tau, q_dq, stats, q_qq, metric, master16, shadow, dp, Q, kc, k,
                                                          out_scores, out_rows, out_scores64, n_flag, flag_q,
                                                          flag_thr, flag_lo, max_eps);
   RBOD_CUDA(cudaGetLastError());
@@ -477,12 +480,11 @@ int launch_exact_collect(const float* q, const double* q_qq, const float* master
                          const uint32_t* row_mask, const int* flag_q, const double* flag_thr, int f0, int nf,
                          int cap, double* coll_score, uint32_t* coll_idx, int* coll_cnt, int num_sms,
                          cudaStream_t st) {
-  (void)metric;
   if (nf <= 0 || n_rows <= 0) return RBOD_OK;
   if (dim > 32 * EX_NMAX) return set_error(RBOD_E_UNSUPPORTED, "exact fallback supports dim <= %d", 32 * EX_NMAX);
   const int64_t want = (n_rows + 7) / 8;
   const int grid = (int)(want < (int64_t)num_sms * 6 ? want : (int64_t)num_sms * 6);
-  exact_collect_kernel<<<grid, 256, 0, st>>>(q, q_qq, master32, rows16, kind16, dim, ld32, ld16, n_rows, row_mask,
+  exact_collect_kernel<<<grid, 256, 0, st>>>(q, q_qq, master32, rows16, kind16, dim, ld32, ld16, metric, n_rows, row_mask,
                                              flag_q, flag_thr, f0, nf, cap, coll_score, coll_idx, coll_cnt);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
@@ -509,14 +511,14 @@ int launch_gather_flagged(const uint16_t* q16, int dp, const int* flag_q, int f0
 }
 
 int launch_rescore_collected(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
-                             int kind16, int dim, int64_t ld32, int64_t ld16, const int* flag_q, int f0, int nf,
-                             int cap, const uint32_t* coll_idx, const int* coll_cnt, double* coll_score,
+                             int kind16, int dim, int64_t ld32, int64_t ld16, int metric, const int* flag_q, int f0,
+                             int nf, int cap, const uint32_t* coll_idx, const int* coll_cnt, double* coll_score,
                              cudaStream_t st) {
   if (nf <= 0) return RBOD_OK;
   for (int y0 = 0; y0 < nf; y0 += 32768) {   // grid.y limit
     const int ny = nf - y0 < 32768 ? nf - y0 : 32768;
     rescore_collected_kernel<<<dim3(4, (unsigned)ny), 256, 0, st>>>(
-        q, q_qq, master32, rows16, kind16, dim, ld32, ld16, flag_q, f0 + y0, cap, coll_idx + (size_t)y0 * cap,
+        q, q_qq, master32, rows16, kind16, dim, ld32, ld16, metric, flag_q, f0 + y0, cap, coll_idx + (size_t)y0 * cap,
         coll_cnt + y0, coll_score + (size_t)y0 * cap);
   }
   RBOD_CUDA(cudaGetLastError());

@@ -689,7 +689,8 @@ static int prepare_queries(rbod_gallery* g, const float* queries, int64_t Q, con
   RBOD_TRY(g->q_dq.ensure((size_t)P.q_pad * 4));
   RBOD_TRY(g->q_qq.ensure((size_t)P.q_pad * 8));
   RBOD_TRY(g->tau_shared.ensure((size_t)P.q_pad * 4));
-  return launch_prep_queries(*q_dev, Q, P.q_pad, g->dim, g->dp, query_kind(g), g->q16.as<uint16_t>(),
+  return launch_prep_queries(*q_dev, Q, P.q_pad, g->dim, g->dp, query_kind(g), g->metric == RBOD_COSINE,
+                             g->q16.as<uint16_t>(),
                              g->q_dq.as<float>(), g->q_qq.as<double>(), g->tau_shared.as<uint32_t>(), st);
 }
 
@@ -701,8 +702,6 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     return set_error(RBOD_E_INVAL, "rbod_search: bad arguments");
   if (stats) memset(stats, 0, sizeof(*stats));
   if (Q == 0) return RBOD_OK;
-  if (g->metric != RBOD_COSINE)
-    return set_error(RBOD_E_UNSUPPORTED, "rbod_search: only COSINE collections are searchable in this build");
   if (g->dp > K3_MAX_DP)
     return set_error(RBOD_E_UNSUPPORTED, "rbod_search: dim %d > %d not supported by the tcgen05 pass", g->dim,
                      K3_MAX_DP);
@@ -796,7 +795,8 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   RBOD_TRY(launch_rescore(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp,
                           g->metric, g->cand_idx.as<uint32_t>(), Q, P.kc, g->cand_score.as<double>(), st));
   RBOD_TRY(launch_select(g->cand_score.as<double>(), g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(),
-                         g->q_dq.as<float>(), g->stats, g->dtype != RBOD_F32, g->use_shadow, g->dp, Q, P.kc, k, d_scores,
+                         g->q_dq.as<float>(), g->stats, g->q_qq.as<double>(), g->metric, g->dtype != RBOD_F32,
+                         g->use_shadow, g->dp, Q, P.kc, k, d_scores,
                          d_rows, d_scores64, d_flags,
                          g->flag_q.as<int>(), g->flag_thr.as<double>(), g->flag_lo.as<float>(),
                          reinterpret_cast<float*>(d_flags + 3), st));
@@ -839,7 +839,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     C.cap = cap;
     RBOD_TRY(run_k3(g, P2, n_flag, g->fq16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), &C, nullptr, 0, st));
     RBOD_TRY(launch_rescore_collected(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim,
-                                      g->dp, g->flag_q.as<int>(), 0, n_flag, cap, g->coll_idx.as<uint32_t>(),
+                                      g->dp, g->metric, g->flag_q.as<int>(), 0, n_flag, cap, g->coll_idx.as<uint32_t>(),
                                       g->coll_cnt.as<int>(), g->coll_score.as<double>(), st));
     RBOD_TRY(launch_select_collected(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
                                      g->flag_q.as<int>(), 0, n_flag, cap, k, d_scores, d_rows, d_scores64, nullptr,

@@ -117,8 +117,8 @@ int k3_plan(int variant, int kc, int dp, int smem_optin, int allow_hybrid, int* 
 int k3_box_rows(int variant);   // gallery rows per TMA box (64 for the CTA-pair kernel)
 int launch_k3(const K3Launch& L, cudaStream_t st);
 // query preparation: normalise, round to 16 bit, per-query error radius and |q|^2
-int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16, uint16_t* q16,
-                        float* q_dq, double* q_qq, uint32_t* tau_shared, cudaStream_t st);
+int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16, int normalize,
+                        uint16_t* q16, float* q_dq, double* q_qq, uint32_t* tau_shared, cudaStream_t st);
 // K4 family
 int launch_merge_partials(const float* part_score, const uint32_t* part_idx, int slices, int64_t q_pad,
                           int64_t Q, int kc, const float* tau_init, uint32_t* cand_idx, float* cand_tau,
@@ -129,14 +129,14 @@ int launch_rescore(const float* q, const double* q_qq, const float* master32, co
                    int dim, int64_t ld32, int64_t ld16, int metric, const uint32_t* cand_idx, int64_t Q, int kc,
                    double* cand_score, cudaStream_t st);
 int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
-                  const float* stats, int master16, int shadow, int dp, int64_t Q, int kc, int k, float* out_scores,
-                  int64_t* out_rows, double* out_scores64, int* n_flag, int* flag_q, double* flag_thr, float* flag_lo,
-                  float* max_eps, cudaStream_t st);
+                  const float* stats, const double* q_qq, int metric, int master16, int shadow, int dp, int64_t Q, int kc,
+                  int k, float* out_scores, int64_t* out_rows, double* out_scores64, int* n_flag, int* flag_q,
+                  double* flag_thr, float* flag_lo, float* max_eps, cudaStream_t st);
 int launch_gather_flagged(const uint16_t* q16, int dp, const int* flag_q, int f0, int nf, int64_t nf_pad,
                           uint16_t* fq16, int* coll_cnt, cudaStream_t st);
 int launch_rescore_collected(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
-                             int kind16, int dim, int64_t ld32, int64_t ld16, const int* flag_q, int f0, int nf,
-                             int cap, const uint32_t* coll_idx, const int* coll_cnt, double* coll_score,
+                             int kind16, int dim, int64_t ld32, int64_t ld16, int metric, const int* flag_q, int f0,
+                             int nf, int cap, const uint32_t* coll_idx, const int* coll_cnt, double* coll_score,
                              cudaStream_t st);
 int launch_exact_collect(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
                          int kind16, int dim, int64_t ld32, int64_t ld16, int metric, int64_t n_rows,

@@ -197,8 +197,8 @@ def test_prepass_threshold_too_high_is_retried(G):
     n, dim, k = 60000, 256, 10
     x = O.synthetic_unit_rows(n, dim, seed=12)
     tiles = (n + 127) // 128
-    for g_ in range(4):                                   # K3_SAMPLE_GROUPS one-tile groups, spread over the gallery
-        x[(g_ * tiles // 4) * 128 + 5] = x[77]
+    for g_ in range(8):                                   # K3_SAMPLE_GROUPS one-tile groups, spread over the gallery
+        x[(g_ * tiles // 8) * 128 + 5] = x[77]
     g = G(dim, dtype="bf16", capacity=n)
     g.upsert(x)
     stored = g.get_rows(np.arange(n))
@@ -360,3 +360,23 @@ def test_config_c3_delegates_then_centroid_search(G):
     assert torch.equal(r.rows, wi) and torch.allclose(r.scores64, ws, rtol=1e-5, atol=1e-9)
     g.close()
     gc.close()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_dot_collection_search(G, dtype):
+    """Distance.DOT (util/qdrant_manager.py:61-66 offers it): nothing is normalised, score = q . g on the stored
+    rows, same exactness machinery.  (Third-party semantics: parity unpinned.)"""
+    n, dim, Q, k = 30000, 512, 150, 10
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((n, dim)) * rng.uniform(0.2, 3.0, (n, 1))).astype(np.float32)
+    g = G(dim, dtype=dtype, metric="dot", capacity=n)
+    g.upsert(x)
+    stored = g.get_rows(np.arange(n))
+    assert np.array_equal(stored, O.round_store(x, dtype))              # stored as given (rounded to the dtype)
+    q = (rng.standard_normal((Q, dim)) * rng.uniform(0.5, 20.0, (Q, 1))).astype(np.float32)
+    res = g.search(q, k, want_scores64=True)
+    sc = q.astype(np.float64) @ stored.astype(np.float64).T
+    ws, wi = O.topk_from_scores(sc, k)
+    assert np.array_equal(res.rows, wi), int((res.rows != wi).any(axis=1).sum())
+    assert np.allclose(res.scores64, ws, rtol=1e-9, atol=1e-9)
+    g.close()
