@@ -149,6 +149,16 @@ class QdrantClient:
                 col.upsert(p.id, vec, p.payload)
         return UpdateResult(operation_id=0, status=UpdateStatus.COMPLETED)
 
+    def upsert_embeddings(self, collection_name: str, ids, embeddings, payloads=None) -> UpdateResult:
+        """Batched upsert of embeddings held in a torch CUDA tensor [n, dim] (e.g. ``model.encode_image(batch)``):
+        the device-to-device counterpart of the per-image ``client.upsert`` at 31_…py:178-179 (§8 f3)."""
+        col = self._root.get(collection_name)
+        if hasattr(embeddings, "is_cuda") and embeddings.is_cuda:
+            col.upsert_device(list(ids), embeddings, payloads)
+        else:
+            col.upsert_many(list(ids), np.asarray(embeddings, dtype=np.float32), payloads)
+        return UpdateResult(operation_id=0, status=UpdateStatus.COMPLETED)
+
     def upload_collection(self, collection_name: str, vectors, payload=None, ids=None, **_ignored: Any) -> None:
         """Bulk path: vectors [n, dim] (numpy), ids default to 0..n-1 appended after existing ints."""
         col = self._root.get(collection_name)

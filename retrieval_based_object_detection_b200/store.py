@@ -247,6 +247,25 @@ class Collection:
         for i, pid in enumerate(pids):
             self.upsert(pid, vectors[i], None if payloads is None else payloads[i])
 
+    def upsert_device(self, pids: Sequence, vectors, payloads: Optional[Sequence[Optional[dict]]]) -> None:
+        """Bulk upsert of embeddings that already live on the GPU (torch CUDA tensor [n, dim], any float dtype):
+        rows go straight into K1 by device pointer.  They are not journalled row by row -- the next ``save()``
+        (client.close / interpreter exit) snapshots them."""
+        n = len(pids)
+        if tuple(vectors.shape) != (n, self.dim):
+            raise ValueError(f"Wrong input: Vector dimension error: expected [{n}, {self.dim}], got {tuple(vectors.shape)}")
+        self.flush()                       # keep slot order: earlier staged points reach the device first
+        canon = [canonical_id(p) for p in pids]
+        if len(set(canon)) != n:
+            raise ValueError("duplicate point ids in one upsert_device call")
+        slots = np.empty(n, dtype=np.int64)
+        for i, pid in enumerate(canon):
+            slots[i] = self._add_point(pid, None if payloads is None else payloads[i])
+        import torch
+
+        self._ensure_gallery().upsert(vectors.detach().to(torch.float32).contiguous(), slots=slots)
+        self._dirty = True
+
     # ------------------------------------------------------------------ device
     def _ensure_gallery(self):
         if self.gallery is None:

@@ -100,7 +100,8 @@ def test_script_chain_on_device(store_dir, monkeypatch, dtype):
     allowed = np.zeros(len(col), dtype=bool)
     allowed[[col.slot_of[h.id] for h in hits]] = True
     full = col.stored_vectors(range(len(col)))
-    ws, wi = O.cosine_topk(test_vec[None].astype(np.float32), full, 5, row_mask=allowed)
+    # centroid and medoid are usually the same member: identical rows must tie and resolve to the smaller slot
+    ws, wi = O.cosine_topk(test_vec[None].astype(np.float32), full, 5, row_mask=allowed, rowwise=True)
     assert [col.slot_of[h.id] for h in hits] == list(wi[0][:4])
     assert np.allclose([h.score for h in hits], ws[0][:4], rtol=1e-5)
     # batched tensor entry point against the brute force over members only
@@ -118,3 +119,49 @@ def test_script_chain_on_device(store_dir, monkeypatch, dtype):
     again, _ = c2.scroll(collection_name="thesis", scroll_filter=flt, with_vectors=True, limit=10000)
     assert [(r.id, r.vector) for r in again] == [(r.id, r.vector) for r in results]
     assert c2.delete_collection("thesis") and c2.get_collections().collections == []
+
+
+def test_batched_clip_ingest_feeds_k1_on_device(store_dir, tmp_path):
+    """§8 f3: images -> batched encode_image on the GPU -> rbod_upsert by device pointer; ids, payloads and stored
+    vectors are what the per-image loop of 31_…py:161-179 would have produced."""
+    import torch
+    from PIL import Image
+
+    import clip
+    import qdrant_client as qc
+    from qdrant_client.models import Distance, PointStruct, VectorParams
+    from retrieval_based_object_detection_b200 import ingest
+
+    rng = np.random.default_rng(0)
+    dirs = {}
+    for cls in ("cup", "dog"):
+        d = tmp_path / "dataset_cropped" / "natural_images" / cls
+        d.mkdir(parents=True)
+        for i in range(5):
+            Image.fromarray(rng.integers(0, 255, (40, 56, 3), dtype=np.uint8)).save(d / f"{cls}_{i}.png")
+        (d / "broken.png").write_bytes(b"not an image")                 # skipped, like 31:31-39
+        dirs[cls] = d
+    model, preprocess = clip.load("ViT-B/32", device="cuda")
+    c = qc.QdrantClient(host="localhost", port=6333)
+    c.recreate_collection(collection_name="batched", vectors_config=VectorParams(size=512, distance=Distance.COSINE))
+    counts = ingest.ingest_directory(c, "batched", model, preprocess, dirs, "natural", batch_size=4, workers=2)
+    assert counts == {"cup": 5, "dog": 5} and c.count("batched").count == 10
+    # the reference's loop, one image at a time, into a second collection
+    c.recreate_collection(collection_name="single", vectors_config=VectorParams(size=512, distance=Distance.COSINE))
+    for cls, d in dirs.items():
+        for f in sorted(d.glob("c*_?.png")) + sorted(d.glob("d*_?.png")):
+            x = preprocess(Image.open(f).convert("RGB")).unsqueeze(0).to("cuda")
+            with torch.no_grad():
+                v = model.encode_image(x).squeeze().cpu().numpy().tolist()
+            c.upsert(collection_name="single", points=[PointStruct(id=ingest.reference_point_id(f), vector=v,
+                     payload=ingest.reference_payload(f, cls, "natural", False, False))])
+    a, _ = c.scroll("batched", limit=100, with_vectors=True)
+    b, _ = c.scroll("single", limit=100, with_vectors=True)
+    assert [(r.id, r.payload) for r in a] == [(r.id, r.payload) for r in b]
+    va, vb = np.array([r.vector for r in a]), np.array([r.vector for r in b])
+    assert np.abs(va - vb).max() < 2e-3            # fp16 encoder: batch-of-4 and batch-of-1 GEMMs round differently
+    assert np.allclose(np.linalg.norm(va, axis=1), 1.0, atol=1e-6)
+    qc._close_all()                                # device-resident upserts are snapshotted on close
+    c2 = qc.QdrantClient(host="localhost", port=6333)
+    a2, _ = c2.scroll("batched", limit=100, with_vectors=True)
+    assert [(r.id, r.vector) for r in a2] == [(r.id, r.vector) for r in a]

@@ -237,3 +237,31 @@ def test_single_point_upserts_are_batched_into_one_device_flush(client):
     client.scroll("thesis", with_vectors=True, limit=1)                    # first read that needs vectors
     assert [c for c in col.gallery.calls if c[0] == "upsert"] == [("upsert", 30)]
     assert not col.pending
+
+
+def test_batched_ingest_builds_the_scripts_ids_and_payloads(client, tmp_path):
+    """§8 f3 on CPU: the batched ingest loop produces the ids (31:42-43) and payloads (31:166-175) of the script."""
+    import clip
+    from PIL import Image
+
+    from retrieval_based_object_detection_b200 import ingest
+
+    m = _models()
+    rng = np.random.default_rng(0)
+    d = tmp_path / "dataset_segmented" / "original_images" / "cup"
+    d.mkdir(parents=True)
+    for i in range(3):
+        Image.fromarray(rng.integers(0, 255, (32, 32, 3), dtype=np.uint8)).save(d / f"cup_{i}.png")
+    (d / "bad.jpg").write_bytes(b"garbage")
+    model, preprocess = clip.load("ViT-B/32", device="cpu")
+    client.recreate_collection(collection_name="t", vectors_config=m.VectorParams(size=512, distance=m.Distance.COSINE))
+    counts = ingest.ingest_directory(client, "t", model, preprocess, {"cup": d}, "original", is_segmented=True,
+                                     device="cpu", batch_size=2, workers=2)
+    assert counts == {"cup": 3}
+    recs, _ = client.scroll("t", limit=10, with_vectors=True)
+    assert sorted(r.id for r in recs) == sorted(str(uuid.UUID(hashlib.md5(str((d / f"cup_{i}.png").resolve()).encode()).hexdigest()))
+                                                for i in range(3))
+    assert all(r.payload == {"data_type": "original_images", "is_cropped": True, "is_segmented": True, "is_augmented": False,
+                             "class_name": "cup", "is_delegate": False, "delegate_type": None,
+                             "img_path": r.payload["img_path"]} and r.payload["img_path"].endswith(".png") for r in recs)
+    assert np.allclose(np.linalg.norm(np.array([r.vector for r in recs]), axis=1), 1.0, atol=1e-6)
