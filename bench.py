@@ -90,7 +90,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in open(self.path):
@@ -102,6 +102,10 @@ class ClockSampler:
                     mx.append(float(p[2]))
                 except ValueError:
                     continue
+                try:
+                    pw.append(float(p[3]))
+                except ValueError:
+                    pass
                 for name, val in zip(names, p[5:9]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
@@ -109,7 +113,7 @@ class ClockSampler:
         except Exception:
             pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "power_w": statistics.median(pw) if pw else None, "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------------

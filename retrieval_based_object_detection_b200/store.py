@@ -93,6 +93,8 @@ class Collection:
         self.snapshot_vectors: Optional[np.ndarray] = None  # stored rows loaded from disk, not yet on device
         self.gallery = None
         self._order: Optional[List[int]] = None
+        self._columns: Dict[str, Any] = {}     # key -> (int32 codes per slot, {value key -> code}); rebuilt lazily
+        self._columns_n = -1
         self._dirty = False
         self._wal = None
 
@@ -222,6 +224,7 @@ class Collection:
             self._index_remove(slot, self.payloads[slot])
             self.payloads[slot] = payload
         self._index_add(slot, payload)
+        self._columns_n = -1
         return slot
 
     def _stage(self, pid, vec: np.ndarray, payload: Optional[dict]) -> int:
@@ -320,6 +323,7 @@ class Collection:
         del self.slot_of[pid]
         self.gallery.truncate(last)
         self._order = None
+        self._columns_n = -1
         self._dirty = True
         return True
 
@@ -461,10 +465,53 @@ class Collection:
             bits[np.fromiter(allowed, dtype=np.int64)] = 1
         return np.packbits(bits, bitorder="little").view(np.uint32).copy()
 
+    def _column(self, key: str):
+        """Dictionary-encoded payload column: int32 code per slot (-1 = missing / None / not a scalar)."""
+        if self._columns_n != len(self.ids):
+            self._columns = {}
+            self._columns_n = len(self.ids)
+        col = self._columns.get(key)
+        if col is None:
+            codes = np.full(len(self.ids), -1, dtype=np.int32)
+            table: Dict[Any, int] = {}
+            for slot, p in enumerate(self.payloads):
+                v = p.get(key)
+                if _indexable(v):
+                    codes[slot] = table.setdefault(_vkey(v), len(table))
+            col = (codes, table)
+            self._columns[key] = col
+        return col
+
+    def filter_mask(self, flt) -> Optional[np.ndarray]:
+        """Filter -> uint32 row bitmask for the device search.  The filters the reference issues
+        (AND of payload equalities, 32:125-129, 33:98-103,117-137) compile to vectorised compares over
+        dictionary-encoded columns; anything else goes through the general evaluator."""
+        if flt is None:
+            return None
+        must = getattr(flt, "must", None) or []
+        simple = (not (getattr(flt, "should", None) or []) and not (getattr(flt, "must_not", None) or []) and
+                  all(getattr(c, "key", None) is not None and hasattr(getattr(c, "match", None), "value")
+                      and getattr(c, "range", None) is None for c in must))
+        if not simple:
+            return self.row_mask(self.filter_slots(flt))
+        n = len(self.ids)
+        allowed = np.ones(n, dtype=bool)
+        for cond in must:
+            codes, table = self._column(cond.key)
+            value = cond.match.value
+            code = table.get(_vkey(value)) if _indexable(value) else None
+            if code is None:
+                allowed[:] = False
+                break
+            allowed &= codes == code
+        bits = np.zeros((n + 31) // 32 * 32, dtype=np.uint8)
+        bits[:n] = allowed
+        return np.packbits(bits, bitorder="little").view(np.uint32).copy()
+
     def search(self, queries: np.ndarray, k: int, flt=None):
         """-> (scores [Q,k] float32, slots [Q,k] int64) via the device (K3 + exact rescoring)."""
         self.flush()
-        mask = self.row_mask(self.filter_slots(flt))
+        mask = self.filter_mask(flt)
         res = self.gallery.search(np.ascontiguousarray(queries, dtype=np.float32), k, row_mask=mask)
         return res.scores, res.rows
 

@@ -265,3 +265,29 @@ def test_batched_ingest_builds_the_scripts_ids_and_payloads(client, tmp_path):
                              "class_name": "cup", "is_delegate": False, "delegate_type": None,
                              "img_path": r.payload["img_path"]} and r.payload["img_path"].endswith(".png") for r in recs)
     assert np.allclose(np.linalg.norm(np.array([r.vector for r in recs]), axis=1), 1.0, atol=1e-6)
+
+
+def test_filter_mask_compiles_equalities_like_the_general_evaluator(client):
+    """§8 f1: the vectorised column compile and the set-based evaluator give the same row bitmask."""
+    m = _models()
+    _fill(client, n=200)
+    col = client._root.get("thesis")
+    F, C, V = m.Filter, m.FieldCondition, m.MatchValue
+    filters = [
+        F(must=[C(key="class_name", match=V(value="dog"))]),
+        F(must=[C(key="class_name", match=V(value="dog")), C(key="is_segmented", match=V(value=True))]),
+        F(must=[C(key="is_cropped", match=V(value=1))]),                     # 1 is not True
+        F(must=[C(key="delegate_type", match=V(value=None))]),               # None never matches
+        F(must=[C(key="missing_key", match=V(value="x"))]),
+        F(must=[C(key="class_name", match=V(value="unknown"))]),
+        F(must=[C(key="class_name", match=m.MatchAny(any=["dog", "cup"]))]),  # general path
+        F(must_not=[C(key="class_name", match=V(value="dog"))]),             # general path
+    ]
+    for flt in filters:
+        got = col.filter_mask(flt)
+        want = col.row_mask(col.filter_slots(flt))
+        assert np.array_equal(got, want), flt
+    assert col.filter_mask(None) is None
+    client.upsert("thesis", points=[m.PointStruct(id=5, vector=np.ones(512).tolist(), payload={"class_name": "dog"})])
+    got = col.filter_mask(filters[0])                                       # column cache follows mutations
+    assert np.array_equal(got, col.row_mask(col.filter_slots(filters[0]))) and O.unpack_row_mask(got, len(col))[-1]
