@@ -58,8 +58,40 @@ __device__ __forceinline__ void finish_row_stats(float s16, float sy, float sd, 
   wmax_dev = fmaxf(wmax_dev, dev);
 }
 
-template <int NV>
-__global__ void __launch_bounds__(K1_WARPS * 32)
+// Error-free fp32 building blocks: the per-element work stays on the fp32 pipe (no f32<->f64 conversions, no
+// 64-bit registers), fp64 is touched a handful of times per ROW.
+//   acc_sq:  (s, c) += x*x exactly.  p + e == x*x (FMA residual), Knuth's TwoSum adds p to s without loss.
+//   scale :  fp32(x * (rh + rl)) with one rounding up to ~2^-47 relative.
+__device__ __forceinline__ void acc_sq(float& s, float& c, float x) {
+  const float p = __fmul_rn(x, x);
+  const float e = __fmaf_rn(x, x, -p);
+  const float t = __fadd_rn(s, p);
+  const float bp = __fsub_rn(t, s);
+  const float err = __fadd_rn(__fsub_rn(s, __fsub_rn(t, bp)), __fsub_rn(p, bp));
+  s = t;
+  c = __fadd_rn(c, __fadd_rn(err, e));
+}
+__device__ __forceinline__ float scale_ff(float x, float rh, float rl) {
+  const float p = __fmul_rn(x, rh);
+  const float e = __fmaf_rn(x, rh, -p);
+  return __fadd_rn(p, __fmaf_rn(x, rl, e));
+}
+// 1/sqrt(ss) in fp64: MUFU.RSQ seed + two Newton steps (relative error ~1e-16, a few DFMA per row instead of
+// the ~60-instruction fp64 sqrt + divide); values outside the fp32 range take the long way.
+__device__ __forceinline__ double rsqrt_f64(double ss) {
+  if (!(ss > 0.0)) return 0.0;
+  if (ss < 1e-30 || ss > 1e30) return 1.0 / sqrt(ss);
+  double y = (double)rsqrtf((float)ss);
+  const double h = 0.5 * ss;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+
+// HAS32: the collection keeps an fp32 master row (then the 16-bit row is a shadow and its distance to the
+// master is tracked); otherwise the 16-bit row IS the stored vector and only its norm matters.
+template <int NV, int HAS32>
+__global__ void __launch_bounds__(K1_WARPS * 32, NV <= 6 ? 4 : 2)
 l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const int64_t* __restrict__ slots,
                        int64_t slot0, int normalize, int cosine, float* __restrict__ master32, int64_t ld32,
                        uint16_t* __restrict__ out16, int64_t ld16, int kind16, uint16_t* __restrict__ shadow16,
@@ -72,8 +104,7 @@ l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const i
   for (int64_t row = warp0; row < n; row += nwarps) {
     const float4* src = reinterpret_cast<const float4*>(in + row * dim);
     // pull the row this warp handles two iterations from now into L2 (one 128-byte line per lane): the
-    // demand loads below then see L2 latency instead of HBM latency, which is what the 2 resident CTAs
-    // per SM (100 registers per thread) cannot hide on their own
+    // demand loads below then see L2 latency instead of HBM latency
     {
       const int64_t ahead = row + K1_PREFETCH_ROWS * nwarps;
       if (ahead < n && lane < NV * 4) prefetch_l2(in + ahead * dim + lane * 32);
@@ -82,31 +113,35 @@ l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const i
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = __ldcs(src + lane + 32 * i);
 
-    double ss = 0.0;
+    // sum of squares: four independent error-free chains per lane, combined in fp64 once per row
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      ss = fma((double)v[i].x, (double)v[i].x, ss);
-      ss = fma((double)v[i].y, (double)v[i].y, ss);
-      ss = fma((double)v[i].z, (double)v[i].z, ss);
-      ss = fma((double)v[i].w, (double)v[i].w, ss);
+      acc_sq(s0, c0, v[i].x);
+      acc_sq(s1, c1, v[i].y);
+      acc_sq(s2, c2, v[i].z);
+      acc_sq(s3, c3, v[i].w);
     }
+    double ss = ((double)s0 + (double)s1) + ((double)s2 + (double)s3) + (((double)c0 + (double)c1) + ((double)c2 + (double)c3));
     ss = warp_sum_f64(ss);
-    if (lane == 0 && out_norms) out_norms[row] = (float)sqrt(ss);
+    if (out_norms != nullptr && lane == 0) out_norms[row] = (float)sqrt(ss);
 
     if (normalize) {
-      const double r = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+      const double r = rsqrt_f64(ss);
+      const float rh = (float)r;
+      const float rl = (float)(r - (double)rh);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        v[i].x = (float)((double)v[i].x * r);
-        v[i].y = (float)((double)v[i].y * r);
-        v[i].z = (float)((double)v[i].z * r);
-        v[i].w = (float)((double)v[i].w * r);
+        v[i].x = scale_ff(v[i].x, rh, rl);
+        v[i].y = scale_ff(v[i].y, rh, rl);
+        v[i].z = scale_ff(v[i].z, rh, rl);
+        v[i].w = scale_ff(v[i].w, rh, rl);
       }
     }
 
     const int64_t slot = slots ? slots[row] : slot0 + row;
     float s16 = 0.f, sy = 0.f, sd = 0.f;
-    if (master32) {
+    if (HAS32) {
       float4* dst = reinterpret_cast<float4*>(master32 + slot * ld32);
 #pragma unroll
       for (int i = 0; i < NV; ++i) dst[lane + 32 * i] = v[i];
@@ -121,25 +156,27 @@ l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const i
       const float f0 = h16_to_f32(h0, kind16), f1 = h16_to_f32(h1, kind16);
       const float f2 = h16_to_f32(h2, kind16), f3 = h16_to_f32(h3, kind16);
       if (dsts) {
-        const uint16_t s0 = f32_to_h16(f0, 2), s1 = f32_to_h16(f1, 2), s2 = f32_to_h16(f2, 2), s3 = f32_to_h16(f3, 2);
-        const float g0 = h16_to_f32(s0, 2), g1 = h16_to_f32(s1, 2), g2 = h16_to_f32(s2, 2), g3 = h16_to_f32(s3, 2);
+        const uint16_t t0 = f32_to_h16(f0, 2), t1 = f32_to_h16(f1, 2), t2 = f32_to_h16(f2, 2), t3 = f32_to_h16(f3, 2);
+        const float g0 = h16_to_f32(t0, 2), g1 = h16_to_f32(t1, 2), g2 = h16_to_f32(t2, 2), g3 = h16_to_f32(t3, 2);
         ssn += g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3;
         ssd += (g0 - f0) * (g0 - f0) + (g1 - f1) * (g1 - f1) + (g2 - f2) * (g2 - f2) + (g3 - f3) * (g3 - f3);
         uint2 ps;
-        ps.x = static_cast<uint32_t>(s0) | (static_cast<uint32_t>(s1) << 16);
-        ps.y = static_cast<uint32_t>(s2) | (static_cast<uint32_t>(s3) << 16);
+        ps.x = static_cast<uint32_t>(t0) | (static_cast<uint32_t>(t1) << 16);
+        ps.y = static_cast<uint32_t>(t2) | (static_cast<uint32_t>(t3) << 16);
         dsts[lane + 32 * i] = ps;
       }
       s16 += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
-      sy += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-      const float d0 = f0 - v[i].x, d1 = f1 - v[i].y, d2 = f2 - v[i].z, d3 = f3 - v[i].w;
-      sd += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      if (HAS32) {
+        sy += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        const float d0 = f0 - v[i].x, d1 = f1 - v[i].y, d2 = f2 - v[i].z, d3 = f3 - v[i].w;
+        sd += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      }
       uint2 p;
       p.x = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
       p.y = static_cast<uint32_t>(h2) | (static_cast<uint32_t>(h3) << 16);
       if (out16) dst16[lane + 32 * i] = p;
     }
-    finish_row_stats(s16, sy, sd, master32 != nullptr, cosine != 0, wmax_norm, wmax_dev);
+    finish_row_stats(s16, sy, sd, HAS32 != 0, cosine != 0, wmax_norm, wmax_dev);
     if (dsts) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -252,16 +289,21 @@ int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots
                           cudaStream_t st) {
   if (n <= 0) return RBOD_OK;
   const int64_t want = (n + K1_WARPS - 1) / K1_WARPS;
-  const int grid = (int)(want < (int64_t)num_sms * 8 ? want : (int64_t)num_sms * 8);
+  int grid = (int)(want < (int64_t)num_sms * 8 ? want : (int64_t)num_sms * 8);
   const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) &&
                        (master32 == nullptr || (reinterpret_cast<uintptr_t>(master32) % 16 == 0 && ld32 % 4 == 0)) &&
                        (out16 == nullptr || (reinterpret_cast<uintptr_t>(out16) % 8 == 0 && ld16 % 4 == 0));
-#define RBOD_K1_CASE(NV)                                                                                   \
-  case NV:                                                                                                 \
-    l2norm_pack_vec_kernel<NV><<<grid, K1_WARPS * 32, 0, st>>>(in, n, dim, slots_dev, slot0, normalize,     \
-                                                               cosine, master32, ld32, out16, ld16, kind16, \
-                                                               shadow16, out_norms, stats);                \
-    break;
+  // persistent grid: exactly the CTAs that are resident at once (no second wave with a ragged tail)
+#define RBOD_K1_CASE(NV)                                                                                     \
+  case NV: {                                                                                                 \
+    auto kern = master32 ? l2norm_pack_vec_kernel<NV, 1> : l2norm_pack_vec_kernel<NV, 0>;                    \
+    int per_sm = 0;                                                                                          \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1_WARPS * 32, 0) == cudaSuccess &&     \
+        per_sm > 0)                                                                                          \
+      grid = (int)(want < (int64_t)num_sms * per_sm ? want : (int64_t)num_sms * per_sm);                     \
+    kern<<<grid, K1_WARPS * 32, 0, st>>>(in, n, dim, slots_dev, slot0, normalize, cosine, master32, ld32,     \
+                                         out16, ld16, kind16, shadow16, out_norms, stats);                   \
+  } break;
   if (aligned && dim % 128 == 0 && dim / 128 >= 1 && dim / 128 <= 8) {
     switch (dim / 128) {
       RBOD_K1_CASE(1)

@@ -19,6 +19,9 @@
 #include "rbod_common.cuh"
 #include "rbod_internal.h"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace rbod {
 
 namespace {
@@ -79,6 +82,37 @@ __global__ void seg_plan_kernel(const int64_t* __restrict__ offsets, int64_t C, 
 // partial slots (node (level, i) is stored in the slot of its leftmost leaf): a warp stores its sum, sets the
 // parent's bit in that slot's flag word, and the second of two siblings to arrive adds left + right and climbs.
 // The shape of the tree depends only on the chunk count, so the sum is deterministic, and no warp ever waits.
+// Column accumulators of one lane.  FF = 0: fp64 registers (one F2F + DADD per element).  FF = 1: unevaluated
+// fp32 pairs (hi, lo) updated with Knuth's TwoSum -- the element work stays on the fp32 pipe and the pair
+// carries ~48 bits, so fp32(sum / len) is the same value the fp64 accumulator gives (both are far below
+// half an fp32 ulp from the exact sum).
+template <int N, int FF>
+struct K2Acc {
+  double a[N];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i] = 0.0;
+  }
+  __device__ __forceinline__ void add(int i, float x) { a[i] += (double)x; }
+  __device__ __forceinline__ double get(int i) const { return a[i]; }
+};
+template <int N>
+struct K2Acc<N, 1> {
+  float h[N], l[N];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < N; ++i) { h[i] = 0.f; l[i] = 0.f; }
+  }
+  __device__ __forceinline__ void add(int i, float x) {
+    const float t = __fadd_rn(h[i], x);
+    const float bp = __fsub_rn(t, h[i]);
+    const float err = __fadd_rn(__fsub_rn(h[i], __fsub_rn(t, bp)), __fsub_rn(x, bp));
+    h[i] = t;
+    l[i] = __fadd_rn(l[i], err);
+  }
+  __device__ __forceinline__ double get(int i) const { return (double)h[i] + (double)l[i]; }
+};
+
 template <int IS16, int NG>
 struct K2Row {
   uint2 v[NG];
@@ -90,13 +124,14 @@ struct K2Row {
 #pragma unroll
     for (int g = 0; g < NG; ++g) v[g] = make_uint2(0u, 0u);
   }
-  __device__ __forceinline__ void add_to(double* acc, int kind16) const {
+  template <class ACC>
+  __device__ __forceinline__ void add_to(ACC& acc, int kind16) const {
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      acc[4 * g + 0] += (double)h16_to_f32((uint16_t)(v[g].x & 0xffffu), kind16);
-      acc[4 * g + 1] += (double)h16_to_f32((uint16_t)(v[g].x >> 16), kind16);
-      acc[4 * g + 2] += (double)h16_to_f32((uint16_t)(v[g].y & 0xffffu), kind16);
-      acc[4 * g + 3] += (double)h16_to_f32((uint16_t)(v[g].y >> 16), kind16);
+      acc.add(4 * g + 0, h16_to_f32((uint16_t)(v[g].x & 0xffffu), kind16));
+      acc.add(4 * g + 1, h16_to_f32((uint16_t)(v[g].x >> 16), kind16));
+      acc.add(4 * g + 2, h16_to_f32((uint16_t)(v[g].y & 0xffffu), kind16));
+      acc.add(4 * g + 3, h16_to_f32((uint16_t)(v[g].y >> 16), kind16));
     }
   }
 };
@@ -111,18 +146,19 @@ struct K2Row<0, NG> {
 #pragma unroll
     for (int g = 0; g < NG; ++g) v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  __device__ __forceinline__ void add_to(double* acc, int) const {
+  template <class ACC>
+  __device__ __forceinline__ void add_to(ACC& acc, int) const {
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      acc[4 * g + 0] += (double)v[g].x;
-      acc[4 * g + 1] += (double)v[g].y;
-      acc[4 * g + 2] += (double)v[g].z;
-      acc[4 * g + 3] += (double)v[g].w;
+      acc.add(4 * g + 0, v[g].x);
+      acc.add(4 * g + 1, v[g].y);
+      acc.add(4 * g + 2, v[g].z);
+      acc.add(4 * g + 3, v[g].w);
     }
   }
 };
 
-template <int VEC, int NG, int IS16>
+template <int VEC, int NG, int IS16, int FF>
 __global__ void __launch_bounds__(SEG_THREADS)
 seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__ rows16, int kind16, int dim,
                 int64_t ld32, int64_t ld16, int64_t n_valid, const int64_t* __restrict__ row_idx,
@@ -146,9 +182,8 @@ seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__
   const int64_t r1 = (r0 + SEG_CHUNK < seg1) ? r0 + SEG_CHUNK : seg1;
 
   constexpr int NACC = VEC * NG;
-  double acc[NACC];
-#pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+  K2Acc<NACC, FF> run;
+  run.clear();
 
   auto row_of = [&](int64_t i) -> int64_t {
     const int64_t r = row_idx ? row_idx[i] : i;
@@ -188,7 +223,7 @@ seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__
         }
       }
 #pragma unroll
-      for (int u = 0; u < UN; ++u) row[u].add_to(acc, kind16);
+      for (int u = 0; u < UN; ++u) row[u].add_to(run, kind16);
     }
     for (; i < r1; ++i) {
       const int64_t r = row_of(i);
@@ -196,7 +231,7 @@ seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__
       K2Row<IS16, NG> row;
       if constexpr (IS16) row.load(rows16, r, ld16, lane);
       else row.load(master32, r, ld32, lane);
-      row.add_to(acc, kind16);
+      row.add_to(run, kind16);
     }
   } else {
     for (int64_t i = r0; i < r1; ++i) {
@@ -207,11 +242,15 @@ seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__
         const int col = lane + 32 * g;
         if (col < dim) {
           const float x = IS16 ? h16_to_f32(rows16[r * ld16 + col], kind16) : master32[r * ld32 + col];
-          acc[g] += (double)x;
+          run.add(g, x);
         }
       }
     }
   }
+
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = run.get(i);
 
   // column index of accumulator a of this lane
   auto col_of = [&](int a) -> int { return VEC == 4 ? (lane + 32 * (a >> 2)) * 4 + (a & 3) : lane + 32 * a; };
@@ -294,21 +333,25 @@ int launch_segment_mean(const float* master32, const uint16_t* rows16, int kind1
   seg_plan_kernel<<<1, 1024, 0, st>>>(offsets, n_classes, chunk_prefix);
   RBOD_CUDA(cudaGetLastError());
   const int grid = (int)((n_items_upper + SEG_WARPS - 1) / SEG_WARPS);
+  static const int acc_ff = [] {   // probe switch (RBOD_K2_ACC=f64 selects the fp64 accumulators)
+    const char* e = getenv("RBOD_K2_ACC");
+    return (e && !strcmp(e, "f64")) ? 0 : 1;
+  }();
   const bool vec_ok = dim % 128 == 0 && dim / 128 <= 8 &&
                       (master32 ? (reinterpret_cast<uintptr_t>(master32) % 16 == 0 && ld32 % 4 == 0)
                                 : (reinterpret_cast<uintptr_t>(rows16) % 8 == 0 && ld16 % 4 == 0));
+#define RBOD_K2_ARGS                                                                                         \
+  master32, rows16, kind16, dim, ld32, ld16, n_valid, row_idx, offsets, n_classes, chunk_prefix, partials,   \
+      arrive_cnt, out, err_flag
 #define RBOD_K2_LAUNCH(VEC, NG)                                                                              \
   do {                                                                                                       \
-    if (master32)                                                                                            \
-      seg_mean_kernel<VEC, NG, 0><<<grid, SEG_THREADS, 0, st>>>(master32, rows16, kind16, dim, ld32, ld16,    \
-                                                                n_valid, row_idx, offsets, n_classes,        \
-                                                                chunk_prefix, partials, arrive_cnt, out,     \
-                                                                err_flag);                                   \
-    else                                                                                                     \
-      seg_mean_kernel<VEC, NG, 1><<<grid, SEG_THREADS, 0, st>>>(master32, rows16, kind16, dim, ld32, ld16,    \
-                                                                n_valid, row_idx, offsets, n_classes,        \
-                                                                chunk_prefix, partials, arrive_cnt, out,     \
-                                                                err_flag);                                   \
+    if (master32) {                                                                                          \
+      if (acc_ff) seg_mean_kernel<VEC, NG, 0, 1><<<grid, SEG_THREADS, 0, st>>>(RBOD_K2_ARGS);                \
+      else seg_mean_kernel<VEC, NG, 0, 0><<<grid, SEG_THREADS, 0, st>>>(RBOD_K2_ARGS);                       \
+    } else {                                                                                                 \
+      if (acc_ff) seg_mean_kernel<VEC, NG, 1, 1><<<grid, SEG_THREADS, 0, st>>>(RBOD_K2_ARGS);                \
+      else seg_mean_kernel<VEC, NG, 1, 0><<<grid, SEG_THREADS, 0, st>>>(RBOD_K2_ARGS);                       \
+    }                                                                                                        \
   } while (0)
   if (vec_ok) {
     switch (dim / 128) {
@@ -329,6 +372,7 @@ int launch_segment_mean(const float* master32, const uint16_t* rows16, int kind1
     return set_error(RBOD_E_UNSUPPORTED, "segment_mean: dim %d > 1024 must be a multiple of 128", dim);
   }
 #undef RBOD_K2_LAUNCH
+#undef RBOD_K2_ARGS
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }
