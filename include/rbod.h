@@ -68,6 +68,8 @@ extern "C" {
 /* distance of the collection (Distance enum, util/qdrant_manager.py:61-66) */
 #define RBOD_COSINE 0
 #define RBOD_DOT 1
+#define RBOD_EUCLID 2    /* score = L2 distance, smaller is closer; exact fp64 sweep on CUDA cores (kernel K5) */
+#define RBOD_MANHATTAN 3 /* score = L1 distance, smaller is closer; exact fp64 sweep on CUDA cores (kernel K5) */
 
 /* rbod_upsert flags */
 #define RBOD_UPSERT_RAW 1 /* rows are already in stored form: do not normalise (used on reload) */
@@ -78,7 +80,7 @@ typedef struct rbod_gallery_info {
   int32_t dim;            /* logical vector size                                   */
   int32_t dim_padded;     /* row stride (elements) of the 16-bit search operand    */
   int32_t dtype;          /* RBOD_F32 / RBOD_BF16 / RBOD_F16                       */
-  int32_t metric;         /* RBOD_COSINE / RBOD_DOT                                */
+  int32_t metric;         /* RBOD_COSINE / RBOD_DOT / RBOD_EUCLID / RBOD_MANHATTAN */
   int32_t device;         /* CUDA device ordinal                                   */
   int32_t reserved;
   int64_t rows;           /* number of row slots in use (max slot + 1)             */
@@ -144,11 +146,22 @@ int rbod_l2norm_pack(const float* in, int64_t n, int32_t dim, int32_t out_dtype,
 
 /* --- K2: delegate ("average") vectors ---------------------------------------------------
  * Class c owns gallery rows row_idx[offsets[c] .. offsets[c+1]) (row_idx == NULL: the rows
- * themselves are label-sorted, i.e. row_idx[i] = i).  out_centroids[c, :] is the fp32
- * L2-normalised mean of those stored rows; an empty class or a zero mean gives zeros.
+ * themselves are label-sorted, i.e. row_idx[i] = i).  out_centroids[c, :] is the fp32 mean of those
+ * stored rows, L2-normalised for COSINE collections (the stored form an upsert of the mean would
+ * leave); an empty class or a zero mean gives zeros.
  * row_idx / offsets / out_centroids: host or device.                                      */
 int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* offsets, int64_t n_classes,
                       float* out_centroids, void* stream);
+
+/* Sharded build of the same delegates (SURVEY.md 8(e), K2 row "per-rank partial sums + all-reduce"): every rank
+ * calls rbod_segment_sums on its own rows with the same class list, the [n_classes, dim] fp64 sums and the
+ * per-class row counts are summed over the ranks (ncclAllReduce, issued by the caller), and rbod_segment_finish
+ * turns them into the stored form: fp32(sum / count), L2-normalised when `normalize` is non-zero.  A class with
+ * count 0 gives zeros.  out_sums / sums / counts / out_vectors: device pointers.                              */
+int rbod_segment_sums(rbod_gallery* g, const int64_t* row_idx, const int64_t* offsets, int64_t n_classes,
+                      double* out_sums, void* stream);
+int rbod_segment_finish(const double* sums, const int64_t* counts, int64_t n_classes, int32_t dim, int32_t normalize,
+                        float* out_vectors, void* stream);
 
 /* Other delegate types of 32_create_delegate_vector.py, one vector per class, float64 arithmetic on the
  * stored rows like the reference, output in stored form (fp32, L2-normalised for COSINE collections):
@@ -166,14 +179,18 @@ int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx
                            int64_t n_classes, double alpha, float* out_vectors, int64_t* out_member_rows,
                            void* stream);
 
-/* --- K3: cosine top-k -------------------------------------------------------------------
+/* --- K3: cosine top-k (K5 for EUCLID / MANHATTAN collections) ---------------------------
  * queries:      [Q, dim] fp32 (any norm), host or device.
  * row_mask:     optional bitmask over row slots (bit r%32 of word r/32 set = row allowed),
  *               ceil(rows/32) words, host or device; NULL = all rows.
  * out_scores:   [Q, k] fp32 cosine, descending; ties broken by smaller row slot.
  * out_rows:     [Q, k] int64 row slots; -1 (score -inf) where fewer than k rows qualify.
  * out_scores64: optional [Q, k] fp64 scores (what the multi-GPU merge consumes), or NULL.
- * stats:        optional.                                                                 */
+ * stats:        optional.
+ * EUCLID / MANHATTAN collections: out_scores holds the DISTANCE (sqrt of the squared sum / sum of absolute
+ * differences), ascending, +inf where fewer than k rows qualify; ties broken by smaller row slot;
+ * out_scores64 holds the ordering key (-squared distance / -L1 distance, larger = closer), which is what
+ * rbod_merge_topk orders by.  k <= 1024, dim <= 1024 for these two distances.             */
 int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, const uint32_t* row_mask,
                 float* out_scores, int64_t* out_rows, double* out_scores64, rbod_search_stats* stats,
                 void* stream);

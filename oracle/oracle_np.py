@@ -107,12 +107,14 @@ def compute_medoid(vectors):
     return vectors[np.argmin(total_distances)]
 
 
-def segment_mean_renorm(stored: np.ndarray, row_idx, offsets, average_fn=compute_average) -> np.ndarray:
+def segment_mean_renorm(stored: np.ndarray, row_idx, offsets, average_fn=compute_average,
+                        normalize: bool = True) -> np.ndarray:
     """K2: per class c, the stored form of compute_average(rows of class c).
 
     Exactly what the reference does per class: scroll the class's stored vectors into a float64
     array (32:137), compute_average (32:9-10), upsert the mean (32:41-42) -- which the COSINE
-    collection stores L2-normalised (float32).  Empty classes give zero rows.
+    collection stores L2-normalised (float32).  Empty classes give zero rows.  ``normalize=False``: the
+    collection is not COSINE, the mean is stored as float32 as given.
     """
     stored = np.asarray(stored, dtype=np.float32)
     offsets = np.asarray(offsets, dtype=np.int64)
@@ -125,7 +127,8 @@ def segment_mean_renorm(stored: np.ndarray, row_idx, offsets, average_fn=compute
         rows = np.arange(a, b) if row_idx is None else np.asarray(row_idx[a:b], dtype=np.int64)
         vectors_np = stored[rows].astype(np.float64)          # np.array([r.vector ...]) is float64
         mean = average_fn(vectors_np)
-        out[c] = l2_normalize_store(mean.astype(np.float32)[None, :], "f32")[0][0]
+        m32 = mean.astype(np.float32)
+        out[c] = l2_normalize_store(m32[None, :], "f32")[0][0] if normalize else m32
     return out
 
 
@@ -196,6 +199,31 @@ def cosine_topk(queries, stored, k: int, row_mask=None, rowwise: bool = False, c
         sc = cosine_matrix(queries[a : a + chunk], stored, rowwise=rowwise, _g64=g64)
         out_s[a : a + chunk], out_i[a : a + chunk] = topk_from_scores(sc, k, row_mask=row_mask)
     return out_s, out_i
+
+
+def distance_topk(queries, stored, k: int, metric: str, row_mask=None):
+    """Exact float64 brute force for the two distances of the collection menu that are not inner products
+    (util/qdrant_manager.py:61-66): metric "euclid" -> sqrt(sum (q-g)^2), "manhattan" -> sum |q-g|, on the
+    stored values (these collections store vectors as given).  Ordered by (ordering key desc, row asc) with
+    key = -(squared L2) / -(L1), i.e. distance ascending, ties to the smaller row.  Qdrant-side semantics
+    (score = distance, smaller is closer) are third-party behaviour: parity unpinned, see the module header.
+    Returns (distances f64 [Q,k] padded with +inf, rows i64 [Q,k] padded with -1, keys f64 [Q,k])."""
+    if metric not in ("euclid", "manhattan"):
+        raise ValueError(metric)
+    q = np.atleast_2d(np.asarray(queries, dtype=np.float32)).astype(np.float64)
+    g = np.atleast_2d(np.asarray(stored, dtype=np.float32)).astype(np.float64)
+    Q = q.shape[0]
+    dist = np.full((Q, k), np.inf)
+    rows = np.full((Q, k), -1, dtype=np.int64)
+    keys = np.full((Q, k), -np.inf)
+    for i in range(Q):
+        d = g - q[i][None, :]
+        key = -(d * d).sum(axis=1) if metric == "euclid" else -np.abs(d).sum(axis=1)
+        s, r = topk_from_scores(key[None, :], k, row_mask=row_mask)
+        keys[i], rows[i] = s[0], r[0]
+        ok = r[0] >= 0
+        dist[i, ok] = np.sqrt(-s[0][ok]) if metric == "euclid" else -s[0][ok]
+    return dist, rows, keys
 
 
 def unpack_row_mask(words: np.ndarray, n_rows: int) -> np.ndarray:

@@ -207,8 +207,11 @@ class QdrantClient:
 
     # ------------------------------------------------------------------ search
     def _scored(self, col: Collection, scores, slots, with_payload, with_vectors, score_threshold) -> List[ScoredPoint]:
+        # EUCLID / MANHATTAN scores are distances (ascending, smaller = closer): the threshold is an upper bound
+        is_distance = col.distance in ("Euclid", "Manhattan")
         keep = [(float(sc), int(s)) for sc, s in zip(scores, slots)
-                if s >= 0 and (score_threshold is None or sc >= score_threshold)]
+                if s >= 0 and (score_threshold is None
+                               or (sc <= score_threshold if is_distance else sc >= score_threshold))]
         vecs = col.stored_vectors([s for _, s in keep]) if with_vectors and keep else None
         return [ScoredPoint(id=col.ids[s], version=0, score=sc,
                             payload=dict(col.payloads[s]) if with_payload else None,

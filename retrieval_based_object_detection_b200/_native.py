@@ -21,13 +21,15 @@ RBOD_E_OVERFLOW = -75
 RBOD_E_UNSUPPORTED = -95
 
 RBOD_F32, RBOD_BF16, RBOD_F16 = 0, 1, 2
-RBOD_COSINE, RBOD_DOT = 0, 1
+RBOD_COSINE, RBOD_DOT, RBOD_EUCLID, RBOD_MANHATTAN = 0, 1, 2, 3
 RBOD_UPSERT_RAW = 1
 DELEGATE_KINDS = {"average": 0, "centroid": 1, "weighted": 2, "medoid": 3}
 
 DTYPES = {"f32": RBOD_F32, "fp32": RBOD_F32, "float32": RBOD_F32, "bf16": RBOD_BF16, "bfloat16": RBOD_BF16,
           "f16": RBOD_F16, "fp16": RBOD_F16, "float16": RBOD_F16}
-METRICS = {"cosine": RBOD_COSINE, "dot": RBOD_DOT}
+METRICS = {"cosine": RBOD_COSINE, "dot": RBOD_DOT, "euclid": RBOD_EUCLID, "manhattan": RBOD_MANHATTAN}
+# distances (smaller = closer): search scores ascend, out_scores64 carries the ordering key (-d^2 / -d)
+DISTANCE_METRICS = ("euclid", "manhattan")
 
 
 class GalleryInfo(ctypes.Structure):
@@ -68,6 +70,8 @@ SIGNATURES = {
     "rbod_get_rows": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "rbod_l2norm_pack": (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _P]),
     "rbod_segment_mean": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P]),
+    "rbod_segment_sums": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P]),
+    "rbod_segment_finish": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
     "rbod_segment_delegates": (ctypes.c_int, [_P, _I32, _P, _P, _I64, ctypes.c_double, _P, _P, _P]),
     "rbod_search": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, ctypes.POINTER(SearchStats), _P]),
     "rbod_merge_topk": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),

@@ -164,7 +164,7 @@ seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__
                 int64_t ld32, int64_t ld16, int64_t n_valid, const int64_t* __restrict__ row_idx,
                 const int64_t* __restrict__ offsets, int64_t C, const int* __restrict__ prefix,
                 double* __restrict__ partials, unsigned int* __restrict__ node_bits, float* __restrict__ out,
-                int* __restrict__ err_flag) {
+                double* __restrict__ sums_out, int normalize, int* __restrict__ err_flag) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * SEG_WARPS + warp;
   if (item >= prefix[C]) return;
@@ -298,6 +298,15 @@ seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__
     }
   }
 
+  // shard mode: hand the raw fp64 column sums to the caller (they are all-reduced over the ranks that hold
+  // the other rows of this class and finished by seg_finish_kernel)
+  if (sums_out != nullptr) {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+      if (col_of(a) < dim) sums_out[c * dim + col_of(a)] = acc[a];
+    return;
+  }
+
   // finish: m = fp32(sum / len); out = K1 normalisation of m
   const int64_t len = seg1 - seg0;
   double ss = 0.0;
@@ -308,7 +317,8 @@ seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__
     ss = fma((double)m, (double)m, ss);
   }
   ss = warp_sum_f64(ss);
-  const double r = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+  // COSINE collections store the mean renormalised (what the upsert at 32_…py:41-42 leaves); the others keep it
+  const double r = normalize ? (ss > 0.0 ? 1.0 / sqrt(ss) : 0.0) : 1.0;
   float* o = out + c * dim;
   if constexpr (VEC == 4) {
 #pragma unroll
@@ -323,26 +333,62 @@ seg_mean_kernel(const float* __restrict__ master32, const uint16_t* __restrict__
   }
 }
 
+// Second half of the sharded delegate build: sums [C, dim] fp64 (already reduced over the shards) and counts
+// [C] -> out[c] = K1 normalisation of fp32(sum / count); one warp per class, same arithmetic as the tail above.
+__global__ void __launch_bounds__(256)
+seg_finish_kernel(const double* __restrict__ sums, const int64_t* __restrict__ counts, int64_t C, int dim,
+                  int normalize, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const int64_t len = counts[c];
+  const double* s = sums + c * dim;
+  double ss = 0.0;
+  for (int i = lane; i < dim; i += 32) {
+    const float m = len > 0 ? (float)(s[i] / (double)len) : 0.0f;
+    ss = fma((double)m, (double)m, ss);
+  }
+  ss = warp_sum_f64(ss);
+  const double r = normalize ? (ss > 0.0 ? 1.0 / sqrt(ss) : 0.0) : 1.0;
+  for (int i = lane; i < dim; i += 32) {
+    const float m = len > 0 ? (float)(s[i] / (double)len) : 0.0f;
+    out[c * dim + i] = (float)((double)m * r);
+  }
+}
+
 }  // namespace
+
+int launch_segment_finish(const double* sums, const int64_t* counts, int64_t n_classes, int dim, int normalize,
+                          float* out, cudaStream_t st) {
+  if (n_classes <= 0) return RBOD_OK;
+  seg_finish_kernel<<<(unsigned)((n_classes + 7) / 8), 256, 0, st>>>(sums, counts, n_classes, dim, normalize, out);
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
 
 int launch_segment_mean(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32,
                         int64_t ld16, int64_t n_valid, const int64_t* row_idx, const int64_t* offsets,
                         int64_t n_classes, int64_t n_items_upper, double* partials, int* chunk_prefix,
-                        unsigned int* arrive_cnt, float* out, int* err_flag, cudaStream_t st) {
+                        unsigned int* arrive_cnt, float* out, double* sums_out, int normalize, int* err_flag,
+                        cudaStream_t st) {
   if (n_classes <= 0) return RBOD_OK;
   seg_plan_kernel<<<1, 1024, 0, st>>>(offsets, n_classes, chunk_prefix);
   RBOD_CUDA(cudaGetLastError());
   const int grid = (int)((n_items_upper + SEG_WARPS - 1) / SEG_WARPS);
-  static const int acc_ff = [] {   // probe switch (RBOD_K2_ACC=f64 selects the fp64 accumulators)
+  // Accumulators: fp32 rows add up as TwoSum pairs on the fp32 pipe, 16-bit rows in fp64 registers (measured on
+  // B200: 1M x 768 fp32 Zipf classes 75% -> 83% of the HBM peak with pairs; 4M x 768 bf16 79% with fp64 vs 59%
+  // with pairs, whose 7 fp32 ops per element outweigh the element's 2 bytes).  RBOD_K2_ACC=f64|ff overrides.
+  static const int acc_env = [] {
     const char* e = getenv("RBOD_K2_ACC");
-    return (e && !strcmp(e, "f64")) ? 0 : 1;
+    return !e ? -1 : (!strcmp(e, "f64") ? 0 : 1);
   }();
+  const int acc_ff = acc_env >= 0 ? acc_env : (master32 != nullptr ? 1 : 0);
   const bool vec_ok = dim % 128 == 0 && dim / 128 <= 8 &&
                       (master32 ? (reinterpret_cast<uintptr_t>(master32) % 16 == 0 && ld32 % 4 == 0)
                                 : (reinterpret_cast<uintptr_t>(rows16) % 8 == 0 && ld16 % 4 == 0));
 #define RBOD_K2_ARGS                                                                                         \
   master32, rows16, kind16, dim, ld32, ld16, n_valid, row_idx, offsets, n_classes, chunk_prefix, partials,   \
-      arrive_cnt, out, err_flag
+      arrive_cnt, out, sums_out, normalize, err_flag
 #define RBOD_K2_LAUNCH(VEC, NG)                                                                              \
   do {                                                                                                       \
     if (master32) {                                                                                          \

@@ -77,6 +77,7 @@ struct alignas(64) K3Params {
   int num_acc;     // accumulator buffers (1 or 2)
   int acc_col0;    // first accumulator column in TMEM
   int debug_epi;   // bring-up only: 1 = epilogue loads the tile but selects nothing, 2 = does not even load it
+  int l2_prefetch; // > 0: the producer prefetches the gallery tile this many tiles ahead into L2
   uint32_t idesc;
 };
 
@@ -275,6 +276,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         for (int ch = 0; ch < num_chunks; ++ch) {
           const int kb0 = ch * G::KBS;
           const int nkb = min(G::KBS, P.num_kb - kb0);
+          if (P.l2_prefetch > 0 && ti + P.l2_prefetch < tr.n && elect_one()) {
+            // keep more HBM requests in flight than the smem stages hold: the same boxes, l2_prefetch tiles ahead
+            const int tp = t + P.l2_prefetch * tr.step;
+            for (int j = 0; j < nkb; ++j)
+              tma_prefetch_l2_2d(&P.tmap_b, (kb0 + j) * K3_KBLOCK, tp * K3_TILE_N + (PAIR ? (int)rank * G::BOX_N : 0));
+          }
           mbar_wait(&bars->empty[stage], phase ^ 1u, 1);
           if (elect_one()) {
             uint8_t* sb = stage_base + (size_t)stage * G::STAGE_BYTES;
@@ -747,6 +754,7 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.sync_windows = L.sync_windows;
   P.a_tmem_kb = L.a_tmem_kb;
   P.debug_epi = L.debug_epi;
+  P.l2_prefetch = L.l2_prefetch;
   P.num_acc = (L.variant == 1 || L.a_tmem_kb * 32 + 2 * K3_TILE_N <= TMEM_COLS) ? 2 : 1;
   P.acc_col0 = TMEM_COLS - P.num_acc * K3_TILE_N;
   P.idesc = make_idesc_f16(L.a_fmt, L.b_fmt, L.variant == 2 ? 2 * K3_TILE_M : K3_TILE_M, K3_TILE_N);

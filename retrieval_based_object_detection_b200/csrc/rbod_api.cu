@@ -214,7 +214,7 @@ int rbod_create(int32_t dim, int32_t dtype, int32_t metric, int64_t capacity_hin
   if (dim < 1 || dim > 65536) return set_error(RBOD_E_INVAL, "rbod_create: dim %d out of range", dim);
   if (dtype != RBOD_F32 && dtype != RBOD_BF16 && dtype != RBOD_F16)
     return set_error(RBOD_E_INVAL, "rbod_create: unknown dtype %d", dtype);
-  if (metric != RBOD_COSINE && metric != RBOD_DOT)
+  if (metric != RBOD_COSINE && metric != RBOD_DOT && metric != RBOD_EUCLID && metric != RBOD_MANHATTAN)
     return set_error(RBOD_E_INVAL, "rbod_create: unknown metric %d", metric);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -271,7 +271,7 @@ int rbod_destroy(rbod_gallery* g) {
                     &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->flag_lo, &g->fq16, &g->groupmax, &g->tau_init, &g->coll_score,
                     &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->sync_counters, &g->seg_idx, &g->seg_off, &g->seg_out,
                     &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->seg_scratch, &g->seg_member, &g->gather_idx,
-                    &g->gather_out};
+                    &g->gather_out, &g->dist_q64, &g->dist_thr, &g->dist_ctl};
   for (DevBuf* b : bufs) b->release();
   g->pin_a.release();
   g->pin_b.release();
@@ -359,6 +359,9 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
   } else if (!strcmp(key, "sync_window")) {
     if (value < 1 || value > 4096) return set_error(RBOD_E_INVAL, "sync_window must be in [1, 4096]");
     g->sync_window = (int)value;
+  } else if (!strcmp(key, "l2_prefetch")) {
+    if (value < 0 || value > 64) return set_error(RBOD_E_INVAL, "l2_prefetch must be in [0, 64]");
+    g->l2_prefetch = (int)value;
   } else if (!strcmp(key, "sync_lead")) {
     if (value < 1 || value > 64) return set_error(RBOD_E_INVAL, "sync_lead must be in [1, 64]");
     g->sync_lead = (int)value;
@@ -480,11 +483,15 @@ int rbod_l2norm_pack(const float* in, int64_t n, int32_t dim, int32_t out_dtype,
 }
 
 // ---------------------------------------------------------------------------------------------
-int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* offsets, int64_t n_classes,
-                      float* out_centroids, void* stream) {
+// K2 front end.  out_centroids != NULL: finished delegate vectors [C, dim] fp32 (host or device);
+// out_sums != NULL: raw fp64 column sums [C, dim] (device only) for the sharded build.
+static int segment_mean_impl(rbod_gallery* g, const int64_t* row_idx, const int64_t* offsets, int64_t n_classes,
+                             float* out_centroids, double* out_sums, void* stream) {
   if (!g) return set_error(RBOD_E_INVAL, "rbod_segment_mean: NULL handle");
-  if (n_classes < 0 || (n_classes > 0 && (!offsets || !out_centroids)))
+  if (n_classes < 0 || (n_classes > 0 && (!offsets || (!out_centroids && !out_sums))))
     return set_error(RBOD_E_INVAL, "rbod_segment_mean: bad arguments");
+  if (out_sums && !is_device_ptr(out_sums))
+    return set_error(RBOD_E_INVAL, "rbod_segment_sums: out_sums must be a device pointer");
   if (n_classes == 0) return RBOD_OK;
   if (n_classes > (1ll << 30)) return set_error(RBOD_E_INVAL, "rbod_segment_mean: too many classes");
   RBOD_CUDA(cudaSetDevice(g->device));
@@ -505,7 +512,7 @@ int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* of
   const void *idx_dev = nullptr, *off_dev = nullptr;
   if (row_idx) RBOD_TRY(to_device(row_idx, (size_t)total * 8, g->seg_idx, st, &idx_dev));
   RBOD_TRY(to_device(offsets, (size_t)(n_classes + 1) * 8, g->seg_off, st, &off_dev));
-  const bool out_dev = is_device_ptr(out_centroids);
+  const bool out_dev = out_sums != nullptr || is_device_ptr(out_centroids);
   float* dst = out_centroids;
   if (!out_dev) {
     RBOD_TRY(g->seg_out.ensure((size_t)n_classes * g->dim * 4));
@@ -523,7 +530,8 @@ int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* of
   RBOD_TRY(launch_segment_mean(g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp, g->rows,
                                static_cast<const int64_t*>(idx_dev), static_cast<const int64_t*>(off_dev), n_classes,
                                items_upper, g->seg_partials.as<double>(), g->seg_prefix.as<int>(),
-                               g->seg_arrive.as<unsigned int>(), dst, g->flags.as<int>() + 2, st));
+                               g->seg_arrive.as<unsigned int>(), dst, out_sums, g->metric == RBOD_COSINE,
+                               g->flags.as<int>() + 2, st));
   if (!out_dev)
     RBOD_CUDA(cudaMemcpyAsync(out_centroids, dst, (size_t)n_classes * g->dim * 4, cudaMemcpyDeviceToHost, st));
   int err = 0;
@@ -531,6 +539,28 @@ int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* of
   RBOD_CUDA(cudaStreamSynchronize(st));
   if (err) return set_error(RBOD_E_RANGE, "rbod_segment_mean: row index outside [0, %lld)", (long long)g->rows);
   return RBOD_OK;
+}
+
+int rbod_segment_mean(rbod_gallery* g, const int64_t* row_idx, const int64_t* offsets, int64_t n_classes,
+                      float* out_centroids, void* stream) {
+  if (n_classes > 0 && !out_centroids) return set_error(RBOD_E_INVAL, "rbod_segment_mean: out_centroids is NULL");
+  return segment_mean_impl(g, row_idx, offsets, n_classes, out_centroids, nullptr, stream);
+}
+
+int rbod_segment_sums(rbod_gallery* g, const int64_t* row_idx, const int64_t* offsets, int64_t n_classes,
+                      double* out_sums, void* stream) {
+  if (n_classes > 0 && !out_sums) return set_error(RBOD_E_INVAL, "rbod_segment_sums: out_sums is NULL");
+  return segment_mean_impl(g, row_idx, offsets, n_classes, nullptr, out_sums, stream);
+}
+
+int rbod_segment_finish(const double* sums, const int64_t* counts, int64_t n_classes, int32_t dim, int32_t normalize,
+                        float* out_vectors, void* stream) {
+  if (n_classes < 0 || dim < 1 || (n_classes > 0 && (!sums || !counts || !out_vectors)))
+    return set_error(RBOD_E_INVAL, "rbod_segment_finish: bad arguments");
+  if (n_classes == 0) return RBOD_OK;
+  if (!is_device_ptr(sums) || !is_device_ptr(counts) || !is_device_ptr(out_vectors))
+    return set_error(RBOD_E_INVAL, "rbod_segment_finish: device pointers only");
+  return launch_segment_finish(sums, counts, n_classes, dim, normalize, out_vectors, static_cast<cudaStream_t>(stream));
 }
 
 int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx, const int64_t* offsets,
@@ -649,6 +679,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.a_tmem_kb = P.a_tmem_kb;
   L.variant = g->k3_variant;
   L.debug_epi = g->debug_epi;
+  L.l2_prefetch = sample ? 0 : g->l2_prefetch;
   L.a_fmt = query_kind(g) == 1 ? 1 : 0;
   L.b_fmt = query_kind(g) == 1 ? 1 : 0;
   L.part_score = g->part_score.as<float>();
@@ -694,6 +725,73 @@ static int prepare_queries(rbod_gallery* g, const float* queries, int64_t Q, con
                              g->q_dq.as<float>(), g->q_qq.as<double>(), g->tau_shared.as<uint32_t>(), st);
 }
 
+// EUCLID / MANHATTAN: exact fp64 sweep (kernel K5), 32 queries per pass over the gallery.
+static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int k, const uint32_t* mask_dev,
+                           float* d_scores, int64_t* d_rows, double* d_keys, int64_t* launches, int64_t* resweeps,
+                           cudaStream_t st) {
+  const int cap = 4096, batch = 32, max_iter = 12;
+  if (k > cap / 4)
+    return set_error(RBOD_E_UNSUPPORTED, "rbod_search: k=%d > %d for EUCLID / MANHATTAN collections", k, cap / 4);
+  if (g->dim > 1024) return set_error(RBOD_E_UNSUPPORTED, "rbod_search: EUCLID / MANHATTAN support dim <= 1024");
+  const void* qd = nullptr;
+  RBOD_TRY(to_device(queries, (size_t)Q * g->dim * 4, g->q32, st, &qd));
+  const float* q_dev = static_cast<const float*>(qd);
+  RBOD_TRY(g->dist_q64.ensure((size_t)batch * g->dim * 8));
+  RBOD_TRY(g->dist_thr.ensure((size_t)batch * 8));
+  RBOD_TRY(g->dist_ctl.ensure((size_t)(2 * batch + 1) * 4));
+  RBOD_TRY(g->coll_score.ensure((size_t)batch * cap * 8));
+  RBOD_TRY(g->coll_idx.ensure((size_t)batch * cap * 4));
+  RBOD_TRY(g->coll_cnt.ensure((size_t)batch * 4));
+  int* d_qsel = g->dist_ctl.as<int>();
+  int* d_active = d_qsel + batch;
+  int* d_nactive = d_qsel + 2 * batch;
+  double* d_thr = g->dist_thr.as<double>();
+  std::vector<double> h_thr(batch, -INFINITY);
+  std::vector<int> h_ctl(2 * batch + 1);
+  const int64_t sample_stride = (g->rows + cap - 1) / cap;   // > 1 iff the gallery holds more than `cap` rows
+  for (int64_t q0 = 0; q0 < Q; q0 += batch) {
+    const int nf = (int)std::min<int64_t>(batch, Q - q0);
+    for (int f = 0; f < batch; ++f) {
+      h_ctl[f] = (int)(q0 + std::min(f, nf - 1));
+      h_ctl[batch + f] = f < nf ? 1 : 0;
+    }
+    h_ctl[2 * batch] = 0;
+    RBOD_CUDA(cudaMemcpyAsync(d_qsel, h_ctl.data(), h_ctl.size() * 4, cudaMemcpyHostToDevice, st));
+    RBOD_CUDA(cudaMemcpyAsync(d_thr, h_thr.data(), (size_t)batch * 8, cudaMemcpyHostToDevice, st));
+    RBOD_CUDA(cudaMemsetAsync(g->coll_cnt.p, 0, (size_t)batch * 4, st));
+    RBOD_TRY(launch_dist_widen_queries(q_dev, d_qsel, nf, g->dim, g->dist_q64.as<double>(), st));
+    ++*launches;
+    if (sample_stride > 1) {
+      RBOD_TRY(launch_dist_collect(g->metric, g->dist_q64.as<double>(), g->master32, g->rows16, g->kind16, g->dim,
+                                   g->dim, g->dp, g->rows, 0, sample_stride, mask_dev, d_thr, d_active, nf, cap,
+                                   g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
+                                   g->num_sms, st));
+      RBOD_TRY(launch_dist_select(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
+                                  d_qsel, nf, cap, k, 1, g->metric, d_thr, d_active, d_nactive, d_scores, d_rows,
+                                  d_keys, st));
+      *launches += 2;
+    }
+    int iter = 0, left = nf;
+    for (; iter < max_iter && left > 0; ++iter) {
+      RBOD_CUDA(cudaMemsetAsync(d_nactive, 0, 4, st));
+      RBOD_TRY(launch_dist_collect(g->metric, g->dist_q64.as<double>(), g->master32, g->rows16, g->kind16, g->dim,
+                                   g->dim, g->dp, g->rows, 0, 1, mask_dev, d_thr, d_active, nf, cap,
+                                   g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
+                                   g->num_sms, st));
+      RBOD_TRY(launch_dist_select(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
+                                  d_qsel, nf, cap, k, 0, g->metric, d_thr, d_active, d_nactive, d_scores, d_rows,
+                                  d_keys, st));
+      *launches += 2;
+      RBOD_CUDA(cudaMemcpyAsync(&left, d_nactive, 4, cudaMemcpyDeviceToHost, st));
+      RBOD_CUDA(cudaStreamSynchronize(st));
+      if (iter > 0) ++*resweeps;
+    }
+    if (left > 0)
+      return set_error(RBOD_E_OVERFLOW, "rbod_search: more than %d rows tie around the k-th distance of a query", cap);
+  }
+  return RBOD_OK;
+}
+
 int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, const uint32_t* row_mask,
                 float* out_scores, int64_t* out_rows, double* out_scores64, rbod_search_stats* stats,
                 void* stream) {
@@ -702,13 +800,50 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     return set_error(RBOD_E_INVAL, "rbod_search: bad arguments");
   if (stats) memset(stats, 0, sizeof(*stats));
   if (Q == 0) return RBOD_OK;
-  if (g->dp > K3_MAX_DP)
+  const bool distance_metric = g->metric == RBOD_EUCLID || g->metric == RBOD_MANHATTAN;
+  if (!distance_metric && g->dp > K3_MAX_DP)
     return set_error(RBOD_E_UNSUPPORTED, "rbod_search: dim %d > %d not supported by the tcgen05 pass", g->dim,
                      K3_MAX_DP);
   if (Q > (1ll << 24)) return set_error(RBOD_E_INVAL, "rbod_search: Q too large");
   if (g->rows >= 0xffffffffll) return set_error(RBOD_E_UNSUPPORTED, "rbod_search: more than 2^32-2 rows per shard");
   RBOD_CUDA(cudaSetDevice(g->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  if (distance_metric) {
+    const size_t n_out = (size_t)Q * k;
+    RBOD_TRY(g->out_scores.ensure(n_out * 4));
+    RBOD_TRY(g->out_rows.ensure(n_out * 8));
+    RBOD_TRY(g->out_scores64.ensure(n_out * 8));
+    float* ds = is_device_ptr(out_scores) ? out_scores : g->out_scores.as<float>();
+    int64_t* dr = is_device_ptr(out_rows) ? out_rows : g->out_rows.as<int64_t>();
+    double* dk = (out_scores64 && is_device_ptr(out_scores64)) ? out_scores64 : g->out_scores64.as<double>();
+    if (g->rows == 0) {
+      std::vector<float> hs(n_out, INFINITY);
+      std::vector<int64_t> hr(n_out, -1);
+      std::vector<double> hd(n_out, -INFINITY);
+      RBOD_CUDA(cudaMemcpyAsync(out_scores, hs.data(), n_out * 4, cudaMemcpyDefault, st));
+      RBOD_CUDA(cudaMemcpyAsync(out_rows, hr.data(), n_out * 8, cudaMemcpyDefault, st));
+      if (out_scores64) RBOD_CUDA(cudaMemcpyAsync(out_scores64, hd.data(), n_out * 8, cudaMemcpyDefault, st));
+      RBOD_CUDA(cudaStreamSynchronize(st));
+      return RBOD_OK;
+    }
+    const void* md = nullptr;
+    if (row_mask) RBOD_TRY(to_device(row_mask, (size_t)((g->rows + 31) / 32) * 4, g->mask_dev, st, &md));
+    int64_t n_launch = 0, resweeps = 0;
+    RBOD_TRY(search_distance(g, queries, Q, k, static_cast<const uint32_t*>(md), ds, dr, dk, &n_launch, &resweeps, st));
+    RBOD_TRY(copy_out(out_scores, ds, n_out * 4, st));
+    RBOD_TRY(copy_out(out_rows, dr, n_out * 8, st));
+    if (out_scores64) RBOD_TRY(copy_out(out_scores64, dk, n_out * 8, st));
+    RBOD_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+      stats->queries = Q;
+      stats->total_launches = n_launch;
+      stats->sweep_queries = Q;        // every query is answered by the exact fp64 sweep
+      stats->fallback_queries = resweeps;
+    }
+    return RBOD_OK;
+  }
+
   const int smem_optin = k3_configure(g->device);
   if (smem_optin < 0) return smem_optin;
 

@@ -89,6 +89,7 @@ struct K3Launch {
   int* sync_counters;     // zeroed [slices * sync_span * sync_windows] ints, or nullptr
   int sync_window, sync_lead, sync_span, sync_windows;
   int debug_epi;          // bring-up: 1 = epilogue selects nothing, 2 = epilogue does not read the tile
+  int l2_prefetch;        // gallery tiles the producer prefetches ahead into L2 (0 = off)
   int grid;
   size_t smem_bytes;
 };
@@ -105,7 +106,10 @@ int launch_gather_rows(const float* master32, const uint16_t* rows16, int kind16
 int launch_segment_mean(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32,
                         int64_t ld16, int64_t n_valid, const int64_t* row_idx, const int64_t* offsets,
                         int64_t n_classes, int64_t n_items_upper, double* partials, int* chunk_prefix,
-                        unsigned int* arrive_cnt, float* out, int* err_flag, cudaStream_t st);
+                        unsigned int* arrive_cnt, float* out, double* sums_out, int normalize, int* err_flag,
+                        cudaStream_t st);
+int launch_segment_finish(const double* sums, const int64_t* counts, int64_t n_classes, int dim, int normalize,
+                          float* out, cudaStream_t st);
 int launch_segment_delegates(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32,
                              int64_t ld16, int64_t n_valid, const int64_t* row_idx, const int64_t* offsets,
                              int64_t n_classes, int kind, double alpha, int cosine, double* scratch, float* out,
@@ -146,6 +150,15 @@ int launch_exact_collect(const float* q, const double* q_qq, const float* master
 int launch_select_collected(const double* coll_score, const uint32_t* coll_idx, const int* coll_cnt,
                             const int* flag_q, int f0, int nf, int cap, int k, float* out_scores,
                             int64_t* out_rows, double* out_scores64, int* overflow, cudaStream_t st);
+// K5 (EUCLID / MANHATTAN)
+int launch_dist_widen_queries(const float* q, const int* qsel, int nf, int dim, double* q64, cudaStream_t st);
+int launch_dist_collect(int metric, const double* q64, const float* master32, const uint16_t* rows16, int kind16,
+                        int dim, int64_t ld32, int64_t ld16, int64_t n_rows, int64_t row0, int64_t stride,
+                        const uint32_t* row_mask, const double* thr, const int* active, int nf, int cap,
+                        double* coll_key, uint32_t* coll_idx, int* coll_cnt, int num_sms, cudaStream_t st);
+int launch_dist_select(const double* coll_key, const uint32_t* coll_idx, int* coll_cnt, const int* qsel, int nf,
+                       int cap, int k, int sample, int metric, double* thr, int* active, int* n_active,
+                       float* out_scores, int64_t* out_rows, double* out_keys, cudaStream_t st);
 int launch_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t Q, int k, float* out_scores,
                       int64_t* out_ids, double* out_scores64, cudaStream_t st);
 
@@ -173,6 +186,7 @@ struct rbod_gallery {
   int hybrid = 1;         // allow the query tile to be split between TMEM and resident smem
   int l2_sync = 1;        // producer throttle that keeps slice-mates within an L2 window
   int sync_window = 16, sync_lead = 4;
+  int l2_prefetch = 0;    // producer L2 prefetch distance in tiles (0 = off)
   // workspaces
   rbod::DevBuf stage_rows, stage_slots, stage_norms;          // upsert staging
   rbod::DevBuf q32, q16, q_dq, q_qq, tau_shared;              // query prep
@@ -184,6 +198,7 @@ struct rbod_gallery {
   rbod::DevBuf mask_dev, dump, sync_counters;
   rbod::DevBuf seg_idx, seg_off, seg_out, seg_partials, seg_prefix, seg_arrive, seg_scratch, seg_member;
   rbod::DevBuf gather_idx, gather_out;
+  rbod::DevBuf dist_q64, dist_thr, dist_ctl;   // K5: widened query batch, thresholds, {qsel, active, n_active}
   rbod::PinBuf pin_a, pin_b;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };

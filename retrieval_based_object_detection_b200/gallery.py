@@ -146,6 +146,21 @@ class Gallery:
         N.check(self._lib.rbod_segment_mean(self._h, p_idx, p_off, C, p_out, _current_stream()))
         return out
 
+    def segment_sums(self, offsets, row_idx=None):
+        """Raw per-class float64 column sums [C, dim] of this shard's stored rows as a torch CUDA tensor -- the
+        local half of the sharded delegate build (``ShardedGallery.segment_mean`` all-reduces and finishes them)."""
+        torch = sys.modules.get("torch")
+        if torch is None:
+            import torch
+        k_off, p_off = self._in(offsets, np.int64, "int64")
+        k_idx, p_idx = self._in(row_idx, np.int64, "int64")
+        C = int(k_off.shape[0]) - 1
+        if C < 0:
+            raise ValueError("segment_sums: offsets must have at least one entry")
+        out = torch.empty((C, self.dim), dtype=torch.float64, device=torch.device("cuda", self.device))
+        N.check(self._lib.rbod_segment_sums(self._h, p_idx, p_off, C, out.data_ptr(), _current_stream()))
+        return out
+
     def segment_delegates(self, kind: str, offsets, row_idx=None, alpha: float = 2.0):
         """Per-class delegate of ``kind`` in {"average", "centroid", "weighted", "medoid"}
         (32_create_delegate_vector.py:9-26) in stored form -> (vectors [C, dim] float32, member rows [C] int64,
@@ -213,6 +228,22 @@ def merge_topk(scores64, ids, k: int, stream=None):
     N.check(lib.rbod_merge_topk(scores64.data_ptr(), ids.data_ptr(), G, Q, k, out_s.data_ptr(), out_i.data_ptr(),
                                 out_d.data_ptr(), stream if stream is not None else _current_stream()))
     return out_s, out_i, out_d
+
+
+def segment_finish(sums, counts, normalize: bool = True, stream=None):
+    """sums [C, dim] float64 and counts [C] int64 (torch CUDA tensors, already reduced over the shards) ->
+    delegate vectors [C, dim] float32: fp32(sum / count), L2-normalised for COSINE collections."""
+    torch = sys.modules["torch"]
+    lib = N.load()
+    sums = sums.to(torch.float64).contiguous()
+    counts = counts.to(torch.int64).contiguous()
+    C, dim = sums.shape
+    if counts.shape != (C,):
+        raise ValueError("segment_finish: counts must have one entry per class")
+    out = torch.empty((C, dim), dtype=torch.float32, device=sums.device)
+    N.check(lib.rbod_segment_finish(sums.data_ptr(), counts.data_ptr(), C, dim, 1 if normalize else 0, out.data_ptr(),
+                                    stream if stream is not None else _current_stream()))
+    return out
 
 
 def l2norm_pack(x, out_dtype: str = "bf16", want_norms: bool = False):

@@ -48,7 +48,8 @@ class ShardedGallery:
 
     def __init__(self, dim: int, n_rows_total: int, dtype: str = "bf16", metric: str = "cosine", group=None,
                  device: Optional[int] = None, local_search: Optional[Callable] = None,
-                 merge: Optional[Callable] = None, create_local: bool = True):
+                 merge: Optional[Callable] = None, create_local: bool = True,
+                 local_sums: Optional[Callable] = None, finish: Optional[Callable] = None):
         import torch.distributed as dist
 
         self.group = group
@@ -59,6 +60,9 @@ class ShardedGallery:
         self.row_start, self.row_end = shard_range(self.n_rows_total, self.rank, self.world)
         self._local_search = local_search
         self._merge = merge
+        self._local_sums = local_sums
+        self._finish = finish
+        self.metric = metric
         self.local = None
         if create_local:
             from .gallery import Gallery
@@ -92,7 +96,41 @@ class ShardedGallery:
             g_s = all_gather_stack(s64, self.group)
             g_i = all_gather_stack(ids, self.group)
         if self._merge is not None:
-            return self._merge(g_s, g_i, k)
-        from .gallery import merge_topk
+            out = self._merge(g_s, g_i, k)
+        else:
+            from .gallery import merge_topk
 
-        return merge_topk(g_s, g_i, k)
+            out = merge_topk(g_s, g_i, k)
+        if self.metric in ("euclid", "manhattan"):
+            # the lists travel and merge as ordering keys (-d^2 / -d, larger = closer); hand back distances
+            s32, ids, keys = out
+            dist = torch.sqrt(-keys) if self.metric == "euclid" else -keys
+            dist = torch.where(ids >= 0, dist, torch.full_like(dist, float("inf")))
+            return dist.to(torch.float32), ids, keys
+        return out
+
+    def segment_mean(self, offsets, row_idx=None):
+        """"average" delegates of classes whose rows are spread over the shards.
+
+        Every rank passes the SAME class list: ``offsets`` [C+1] is the CSR over this rank's own rows
+        (``row_idx`` = local slots, or None when the local rows are stored in class order); a class with no
+        local rows is an empty range.  Local K2 launch -> float64 column sums [C, dim]; ONE all-reduce of the
+        sums and one of the counts; the finish kernel divides, rounds to fp32 and renormalises, so every rank
+        ends with the same [C, dim] float32 delegates a single GPU holding all the rows would produce."""
+        import torch
+        import torch.distributed as dist
+
+        if self._local_sums is not None:
+            sums = self._local_sums(offsets, row_idx)
+        else:
+            sums = self.local.segment_sums(offsets, row_idx)
+        off = torch.as_tensor(offsets).to(torch.int64)
+        counts = (off[1:] - off[:-1]).to(sums.device)
+        if self.world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+        if self._finish is not None:
+            return self._finish(sums, counts, self.metric == "cosine")
+        from .gallery import segment_finish
+
+        return segment_finish(sums, counts, normalize=self.metric == "cosine")

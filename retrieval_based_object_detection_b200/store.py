@@ -274,7 +274,7 @@ class Collection:
         if self.gallery is None:
             from .gallery import Gallery
 
-            metric = "cosine" if self.distance == "Cosine" else "dot"
+            metric = {"Cosine": "cosine", "Dot": "dot", "Euclid": "euclid", "Manhattan": "manhattan"}[self.distance]
             self.gallery = Gallery(self.dim, dtype=self.dtype, metric=metric, capacity=max(len(self.ids), 1024),
                                    device=self.device)
             if self.dtype in ("bf16", "bfloat16") and os.environ.get("RBOD_BF16_SHADOW", "0") == "1":

@@ -63,14 +63,15 @@ class FakeGallery:
         offsets = np.asarray(offsets, dtype=np.int64)
         row_idx = np.arange(offsets[-1]) if row_idx is None else np.asarray(row_idx, dtype=np.int64)
         self.calls.append(("segment_mean", len(offsets) - 1))
-        return O.segment_mean_renorm(self._rows, row_idx, offsets)
+        return O.segment_mean_renorm(self._rows, row_idx, offsets, normalize=self.metric == "cosine")
 
     def segment_delegates(self, kind, offsets, row_idx=None, alpha=2.0):
         fn = {"average": O.compute_average, "centroid": O.compute_centroid, "medoid": O.compute_medoid,
               "weighted": lambda v: O.compute_weighted_average(v, alpha)}[kind]
         offsets = np.asarray(offsets, dtype=np.int64)
         row_idx = np.arange(offsets[-1]) if row_idx is None else np.asarray(row_idx, dtype=np.int64)
-        return O.segment_mean_renorm(self._rows, row_idx, offsets, average_fn=fn), np.full(len(offsets) - 1, -1)
+        return (O.segment_mean_renorm(self._rows, row_idx, offsets, average_fn=fn, normalize=self.metric == "cosine"),
+                np.full(len(offsets) - 1, -1))
 
     def search(self, queries, k, row_mask=None, want_scores64=False, out=None, stream=None):
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
@@ -79,6 +80,9 @@ class FakeGallery:
         if len(self._rows) == 0:
             s = np.full((len(q), k), -np.inf)
             i = np.full((len(q), k), -1, dtype=np.int64)
+        elif self.metric in ("euclid", "manhattan"):
+            d, i, keys = O.distance_topk(q, self._rows, k, self.metric, row_mask=allowed)
+            return SimpleNamespace(scores=d.astype(np.float32), rows=i, scores64=keys, stats={})
         else:
             s, i = O.cosine_topk(q, self._rows, k, row_mask=allowed)
         return SimpleNamespace(scores=s.astype(np.float32), rows=i, scores64=s, stats={})

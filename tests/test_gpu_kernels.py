@@ -137,6 +137,49 @@ def test_k2_matches_reference_golden(G, golden_dir):
         g.close()
 
 
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_k2_shard_sums_then_finish_equals_one_gallery(G, dtype):
+    """The sharded delegate build on one device: two galleries hold the two halves of the rows, each gives its
+    fp64 column sums (rbod_segment_sums), the sums and counts are added (what the NCCL all-reduce does) and
+    rbod_segment_finish produces the delegates -- same vectors as K2 on a single gallery holding every row."""
+    import torch
+    from retrieval_based_object_detection_b200.gallery import segment_finish
+
+    n, dim, ncls = 6001, 768, 37
+    x, labels, _ = O.synthetic_clustered(n, dim, ncls, seed=11)
+    labels = labels.copy()
+    labels[labels == 4] = 3                                   # class 4 has no rows anywhere
+    labels[:3000][labels[:3000] == 9] = 8                     # class 9 lives on the second shard only
+    whole = G(dim, dtype=dtype, capacity=n)
+    whole.upsert(x)
+    stored = whole.get_rows(np.arange(n))
+    order = np.argsort(labels, kind="stable").astype(np.int64)
+    offsets = np.zeros(ncls + 1, np.int64)
+    np.cumsum(np.bincount(labels, minlength=ncls), out=offsets[1:])
+    want_k2 = whole.segment_mean(offsets, row_idx=order)
+    want = O.segment_mean_renorm(stored, order, offsets)
+    sums, counts = None, None
+    for a, b in ((0, 3000), (3000, n)):
+        g = G(dim, dtype=dtype, capacity=b - a)
+        g.upsert(x[a:b])
+        lo = np.argsort(labels[a:b], kind="stable").astype(np.int64)
+        off = np.zeros(ncls + 1, np.int64)
+        np.cumsum(np.bincount(labels[a:b], minlength=ncls), out=off[1:])
+        s = g.segment_sums(off, row_idx=lo)
+        assert s.is_cuda and s.dtype == torch.float64 and tuple(s.shape) == (ncls, dim)
+        ref = np.stack([stored[a:b][lo[off[c]:off[c + 1]]].astype(np.float64).sum(axis=0) for c in range(ncls)])
+        assert np.allclose(s.cpu().numpy(), ref, rtol=0, atol=1e-12)
+        c = torch.from_numpy(off[1:] - off[:-1]).cuda()
+        sums = s.clone() if sums is None else sums + s
+        counts = c if counts is None else counts + c
+        g.close()
+    got = segment_finish(sums, counts, normalize=True).cpu().numpy()
+    assert np.all(got[4] == 0) and _ulp(got, want) <= 2 and _ulp(got, want_k2) <= 1
+    raw = segment_finish(sums, counts, normalize=False).cpu().numpy()
+    assert np.allclose(raw[8], (sums[8].cpu().numpy() / float(counts[8])).astype(np.float32), rtol=0, atol=0)
+    whole.close()
+
+
 # ------------------------------------------------------------------ K2b: centroid / weighted / medoid
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 @pytest.mark.parametrize("n,dim,ncls", [(1200, 512, 12), (900, 768, 5), (300, 100, 7)])

@@ -380,3 +380,64 @@ def test_dot_collection_search(G, dtype):
     assert np.array_equal(res.rows, wi), int((res.rows != wi).any(axis=1).sum())
     assert np.allclose(res.scores64, ws, rtol=1e-9, atol=1e-9)
     g.close()
+
+
+# ------------------------------------------------------------------ K5: EUCLID / MANHATTAN
+@pytest.mark.parametrize("metric", ["euclid", "manhattan"])
+@pytest.mark.parametrize("dtype,n,dim", [("f32", 20000, 512), ("bf16", 9000, 768), ("f32", 3000, 100)])
+def test_distance_collections_exact_topk(G, metric, dtype, n, dim):
+    """Distance.EUCLID / Distance.MANHATTAN (util/qdrant_manager.py:61-66): vectors stored as given, distances in
+    fp64 on the stored values, ascending, ties to the smaller row -- against the float64 oracle, including a
+    duplicate cluster wider than k, a row mask, k larger than the gallery's allowed rows, and a gallery larger
+    than the kernel's record buffer (sample pass + sweep).  (Third-party semantics: parity unpinned.)"""
+    Q, k = 70, 10
+    rng = np.random.default_rng(n + dim)
+    x = (rng.standard_normal((n, dim)) * rng.uniform(0.5, 2.0, (n, 1))).astype(np.float32)
+    x[100:130] = x[7]                                                    # 31 identical rows
+    g = G(dim, dtype=dtype, metric=metric, capacity=n)
+    g.upsert(x)
+    stored = g.get_rows(np.arange(n))
+    assert np.array_equal(stored, O.round_store(x, dtype))
+    q = (rng.standard_normal((Q, dim)) * 1.3).astype(np.float32)
+    q[0] = stored[7]                                                     # distance 0 to the duplicate cluster
+    q[1] = stored[500] + np.float32(1e-3)
+    res = g.search(q, k, want_scores64=True)
+    wd, wi, wk = O.distance_topk(q, stored, k, metric)
+    assert np.array_equal(res.rows, wi), int((res.rows != wi).any(axis=1).sum())
+    assert list(res.rows[0]) == [7] + list(range(100, 109)) and np.all(res.scores[0] == 0)
+    assert np.allclose(res.scores64, wk, rtol=1e-12, atol=1e-300)
+    assert np.allclose(res.scores, wd.astype(np.float32), rtol=1e-6)
+    assert np.all(np.diff(res.scores, axis=1) >= 0)                      # distances ascend
+    # row mask: every 3rd row allowed; k beyond what is allowed pads with (+inf, -1)
+    allowed = np.zeros(n, dtype=bool)
+    allowed[::3] = True
+    res_m = g.search(q[:9], 25, row_mask=O.pack_row_mask(allowed), want_scores64=True)
+    _, wi_m, wk_m = O.distance_topk(q[:9], stored, 25, metric, row_mask=allowed)
+    assert np.array_equal(res_m.rows, wi_m) and np.allclose(res_m.scores64, wk_m, rtol=1e-12, atol=1e-300)
+    few = np.zeros(n, dtype=bool)
+    few[[3, 11, 4000 % n]] = True
+    res_f = g.search(q[:2], 5, row_mask=O.pack_row_mask(few))
+    assert np.all(res_f.rows[:, 3:] == -1) and np.all(np.isinf(res_f.scores[:, 3:])) and np.all(res_f.rows[:, :3] >= 0)
+    # delegate means of such a collection are not renormalised
+    off = np.array([0, 50, 50, 300], np.int64)
+    cent = g.segment_mean(off)
+    want_c = O.segment_mean_renorm(stored, None, off, normalize=False)
+    assert np.all(cent[1] == 0) and np.allclose(cent, want_c, rtol=1e-6, atol=1e-7)
+    g.close()
+
+
+def test_distance_collection_device_io_and_empty(G):
+    import torch
+
+    g = G(64, dtype="f32", metric="euclid", capacity=16)
+    r0 = g.search(np.zeros((2, 64), np.float32), 3)
+    assert np.all(r0.rows == -1) and np.all(np.isinf(r0.scores))
+    x = torch.randn(5000, 64, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    g.upsert(x)
+    q = torch.randn(33, 64, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    r = g.search(q, 4, want_scores64=True)
+    assert r.rows.is_cuda
+    d = torch.cdist(q.double(), x.double())
+    top = torch.topk(d, 4, dim=1, largest=False)
+    assert torch.equal(top.indices, r.rows) and torch.allclose(top.values, r.scores.double(), rtol=1e-6)
+    g.close()

@@ -76,3 +76,65 @@ def test_two_rank_search_equals_single_brute_force(tmp_path, n, k):
         fin = np.isfinite(ws)
         assert np.allclose(s64[fin], ws[fin], rtol=0, atol=1e-15)
     assert list(wi[0][:2]) == [5, n // 2 + 3]                 # the cross-shard tie resolves to the smaller global id
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 over row shards: per-rank fp64 column sums -> all-reduce -> finish
+# ---------------------------------------------------------------------------------------------
+def _k2_inputs(n, dim, n_cls):
+    x, labels, _ = O.synthetic_clustered(n, dim, n_cls, seed=3)
+    labels = labels.copy()
+    labels[labels == 2] = 1                                   # class 2 is empty on every rank
+    stored = O.l2_normalize_store(x, "f32")[0]
+    return stored, labels
+
+
+def _worker_k2(rank, world, port, n, dim, n_cls, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        stored, labels = _k2_inputs(n, dim, n_cls)
+        a, b = shard_range(n, rank, world)
+        loc_labels = labels[a:b]
+        order = np.argsort(loc_labels, kind="stable")          # local slots in class order
+        offsets = np.zeros(n_cls + 1, dtype=np.int64)
+        np.cumsum(np.bincount(loc_labels, minlength=n_cls), out=offsets[1:])
+
+        def local_sums(off, idx):                             # what Gallery.segment_sums returns for this shard
+            s = np.zeros((n_cls, dim), dtype=np.float64)
+            for c in range(n_cls):
+                rows = np.asarray(idx[off[c]:off[c + 1]], dtype=np.int64)
+                if len(rows):
+                    s[c] = stored[a:b][rows].astype(np.float64).sum(axis=0)
+            return torch.from_numpy(s)
+
+        def finish(sums, counts, normalize):                  # what rbod_segment_finish does
+            sums, counts = sums.numpy(), counts.numpy()
+            out = np.zeros((n_cls, dim), dtype=np.float32)
+            for c in range(n_cls):
+                if counts[c] > 0:
+                    m = (sums[c] / float(counts[c])).astype(np.float32)
+                    out[c] = O.l2_normalize_store(m[None, :], "f32")[0][0] if normalize else m
+            return torch.from_numpy(out)
+
+        sg = ShardedGallery(dim, n, dtype="f32", create_local=False, local_sums=local_sums, finish=finish)
+        cent = sg.segment_mean(offsets, order)
+        np.save(os.path.join(out_dir, f"cent_{rank}.npy"), cent.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_delegate_means_equal_single_gallery(tmp_path):
+    n, dim, n_cls, world = 403, 64, 7, 2
+    port = _free_port()
+    mp.spawn(_worker_k2, args=(world, port, n, dim, n_cls, str(tmp_path)), nprocs=world, join=True)
+    stored, labels = _k2_inputs(n, dim, n_cls)
+    order = np.argsort(labels, kind="stable")
+    offsets = np.zeros(n_cls + 1, dtype=np.int64)
+    np.cumsum(np.bincount(labels, minlength=n_cls), out=offsets[1:])
+    want = O.segment_mean_renorm(stored, order, offsets)
+    assert np.all(want[2] == 0)
+    for r in range(world):
+        got = np.load(tmp_path / f"cent_{r}.npy")
+        ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64)).max()
+        assert ulp <= 1, ulp                                  # fp64 sums added in a different order: <= 1 fp32 ulp

@@ -291,3 +291,33 @@ def test_filter_mask_compiles_equalities_like_the_general_evaluator(client):
     client.upsert("thesis", points=[m.PointStruct(id=5, vector=np.ones(512).tolist(), payload={"class_name": "dog"})])
     got = col.filter_mask(filters[0])                                       # column cache follows mutations
     assert np.array_equal(got, col.row_mask(col.filter_slots(filters[0]))) and O.unpack_row_mask(got, len(col))[-1]
+
+
+@pytest.mark.parametrize("distance,metric", [("EUCLID", "euclid"), ("MANHATTAN", "manhattan")])
+def test_distance_menu_collections_rank_ascending_and_store_vectors_as_given(client, distance, metric):
+    """util/qdrant_manager.py:61-79 lets the operator pick EUCLID or MANHATTAN: such a collection stores vectors as
+    given, search scores are distances (ascending) and score_threshold is an upper bound."""
+    m = _models()
+    dim, n = 32, 40
+    client.recreate_collection(collection_name="dist", vectors_config=m.VectorParams(size=dim,
+                                                                                    distance=getattr(m.Distance, distance)))
+    rng = np.random.default_rng(2)
+    vecs = (rng.standard_normal((n, dim)) * 2.5).astype(np.float32)
+    client.upsert("dist", points=[m.PointStruct(id=i, vector=vecs[i].tolist(), payload={"class_name": "a" if i % 2 else "b"})
+                                  for i in range(n)])
+    assert client.get_collection("dist").config.params.vectors.distance == getattr(m.Distance, distance)
+    rec = client.retrieve("dist", ids=[7], with_vectors=True)[0]
+    assert np.array_equal(np.asarray(rec.vector, dtype=np.float32), vecs[7])         # not normalised
+    hits = client.search("dist", query_vector=vecs[7].tolist(), limit=5)
+    want_d, want_i, _ = O.distance_topk(vecs[7:8], vecs, 5, metric)
+    assert [h.id for h in hits] == list(want_i[0]) and hits[0].id == 7 and hits[0].score == 0.0
+    assert [h.score for h in hits] == sorted(h.score for h in hits)
+    assert np.allclose([h.score for h in hits], want_d[0], rtol=1e-6)
+    near = client.search("dist", query_vector=vecs[7].tolist(), limit=40, score_threshold=float(want_d[0][2]) * 1.0000001)
+    assert [h.id for h in near] == list(want_i[0][:3])
+    flt = m.Filter(must=[m.FieldCondition(key="class_name", match=m.MatchValue(value="b"))])
+    only_b = client.query_points("dist", query=vecs[7].tolist(), query_filter=flt, limit=3).points
+    assert all(h.payload["class_name"] == "b" for h in only_b) and 7 not in [h.id for h in only_b]
+    names, means = client.build_delegates("dist", group_key="class_name")
+    assert names == ["a", "b"]
+    assert np.allclose(means[0], vecs[1::2].astype(np.float64).mean(axis=0), rtol=1e-6, atol=1e-7)   # not renormalised

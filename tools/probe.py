@@ -58,7 +58,7 @@ def build_gallery(a, dev):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("op", choices=["search", "k1", "k2", "merge"])
+    ap.add_argument("op", choices=["search", "k1", "k2", "merge", "copy", "dist"])
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--dtype", default="bf16")
@@ -82,6 +82,39 @@ def main():
     if os.path.exists(peaks):
         hbm = json.load(open(peaks)).get("hbm_gbs", hbm)
 
+    if a.op == "copy":
+        # this box's copy bandwidth, measured the way MEASURED_PEAKS.json was (read + write bytes of b.copy_(a)):
+        # boxes differ by several percent, so kernel bandwidths are best compared with this number
+        n = 1 << 30
+        src = torch.empty(n, dtype=torch.bfloat16, device=dev).normal_()
+        dst = torch.empty_like(src)
+        best = min(time_ms(lambda: dst.copy_(src), 3, warmup=1) for _ in range(5))
+        rd = min(time_ms(lambda: src.sum(), 3, warmup=1) for _ in range(3))
+        emit(op="copy", bytes=4 * n, ms=round(best, 4), copy_gbs=round(4 * n / best / 1e6, 1),
+             read_only_gbs=round(2 * n / rd / 1e6, 1), measured_peaks_gbs=hbm)
+        return
+    if a.op == "dist":
+        from retrieval_based_object_detection_b200 import Gallery
+
+        for metric in ("euclid", "manhattan"):
+            g = Gallery(a.dim, dtype=a.dtype, metric=metric, capacity=a.rows, device=0)
+            gen = torch.Generator(dev).manual_seed(3)
+            for s0 in range(0, a.rows, 500_000):
+                g.upsert(torch.randn(min(500_000, a.rows - s0), a.dim, device=dev, generator=gen))
+            for Q in [int(x) for x in a.queries.split(",")]:
+                q = torch.randn(Q, a.dim, device=dev, generator=torch.Generator(dev).manual_seed(7))
+                stats = {}
+
+                def run():
+                    stats.update(g.search(q, a.k).stats)
+
+                ms = time_ms(run, max(1, a.iters // 2), warmup=1)
+                pair_elems = float(Q) * a.rows * a.dim
+                emit(op="dist", metric=metric, rows=a.rows, dim=a.dim, dtype=a.dtype, Q=Q, k=a.k, ms=round(ms, 3),
+                     qps=round(Q / ms * 1e3, 1), fp64_tflops=round(2 * pair_elems / ms / 1e9, 2),
+                     launches=stats.get("total_launches"), resweeps=stats.get("fallback_queries"))
+            g.close()
+        return
     if a.op == "search":
         g = build_gallery(a, dev)
         g.set_option("time_k3", 1)
