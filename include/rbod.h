@@ -190,7 +190,7 @@ int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx
  * EUCLID / MANHATTAN collections: out_scores holds the DISTANCE (sqrt of the squared sum / sum of absolute
  * differences), ascending, +inf where fewer than k rows qualify; ties broken by smaller row slot;
  * out_scores64 holds the ordering key (-squared distance / -L1 distance, larger = closer), which is what
- * rbod_merge_topk orders by.  k <= 1024, dim <= 1024 for these two distances.             */
+ * rbod_merge_topk orders by.  k <= 1024 for these two distances.                          */
 int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, const uint32_t* row_mask,
                 float* out_scores, int64_t* out_rows, double* out_scores64, rbod_search_stats* stats,
                 void* stream);

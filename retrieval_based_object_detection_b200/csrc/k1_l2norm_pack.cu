@@ -27,7 +27,6 @@
 #include "rbod_internal.h"
 
 #include <cstdlib>
-#include <cstring>
 
 namespace rbod {
 
@@ -61,45 +60,14 @@ __device__ __forceinline__ void finish_row_stats(float s16, float sy, float sd, 
   wmax_dev = fmaxf(wmax_dev, dev);
 }
 
-// Error-free fp32 building blocks: the per-element work stays on the fp32 pipe (no f32<->f64 conversions, no
-// 64-bit registers), fp64 is touched a handful of times per ROW.
-//   acc_sq:  (s, c) += x*x exactly.  p + e == x*x (FMA residual), Knuth's TwoSum adds p to s without loss.
-//   scale :  fp32(x * (rh + rl)) with one rounding up to ~2^-47 relative.
-__device__ __forceinline__ void acc_sq(float& s, float& c, float x) {
-  const float p = __fmul_rn(x, x);
-  const float e = __fmaf_rn(x, x, -p);
-  const float t = __fadd_rn(s, p);
-  const float bp = __fsub_rn(t, s);
-  const float err = __fadd_rn(__fsub_rn(s, __fsub_rn(t, bp)), __fsub_rn(p, bp));
-  s = t;
-  c = __fadd_rn(c, __fadd_rn(err, e));
-}
-__device__ __forceinline__ float scale_ff(float x, float rh, float rl) {
-  const float p = __fmul_rn(x, rh);
-  const float e = __fmaf_rn(x, rh, -p);
-  const float w = __fmaf_rn(x, rl, e);
-  return w == 0.0f ? p : __fadd_rn(p, w);   // keeps the sign of a zero input (-0 * r = -0, but -0 + +0 = +0)
-}
-// 1/sqrt(ss) in fp64: MUFU.RSQ seed + two Newton steps (relative error ~1e-16, a few DFMA per row instead of
-// the ~60-instruction fp64 sqrt + divide); values outside the fp32 range take the long way.
-__device__ __forceinline__ double rsqrt_f64(double ss) {
-  if (!(ss > 0.0)) return 0.0;
-  if (ss < 1e-30 || ss > 1e30) return 1.0 / sqrt(ss);
-  double y = (double)rsqrtf((float)ss);
-  const double h = 0.5 * ss;
-#pragma unroll
-  for (int it = 0; it < 2; ++it) y = y * fma(-h * y, y, 1.5);
-  return y;
-}
-
 // HAS32: the collection keeps an fp32 master row (then the 16-bit row is a shadow and its distance to the
 // master is tracked); otherwise the 16-bit row IS the stored vector and only its norm matters.
 template <int NV, int HAS32>
-__global__ void __launch_bounds__(K1_WARPS * 32, NV <= 6 ? 4 : 2)
+__global__ void __launch_bounds__(K1_WARPS * 32)
 l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const int64_t* __restrict__ slots,
                        int64_t slot0, int normalize, int cosine, float* __restrict__ master32, int64_t ld32,
                        uint16_t* __restrict__ out16, int64_t ld16, int kind16, uint16_t* __restrict__ shadow16,
-                       float* __restrict__ out_norms, float* __restrict__ stats, int pf_rows, int st_cs) {
+                       float* __restrict__ out_norms, float* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * K1_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * K1_WARPS;
@@ -107,39 +75,35 @@ l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const i
 
   for (int64_t row = warp0; row < n; row += nwarps) {
     const float4* src = reinterpret_cast<const float4*>(in + row * dim);
-    // pull the row this warp handles pf_rows iterations from now into L2 (one 128-byte line per lane): the
+    // pull the row this warp handles two iterations from now into L2 (one 128-byte line per lane): the
     // demand loads below then see L2 latency instead of HBM latency
-    if (pf_rows > 0) {
-      const int64_t ahead = row + pf_rows * nwarps;
+    {
+      const int64_t ahead = row + K1_PREFETCH_ROWS * nwarps;
       if (ahead < n && lane < NV * 4) prefetch_l2(in + ahead * dim + lane * 32);
     }
     float4 v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = __ldcs(src + lane + 32 * i);
 
-    // sum of squares: four independent error-free chains per lane, combined in fp64 once per row
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    double ss = 0.0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      acc_sq(s0, c0, v[i].x);
-      acc_sq(s1, c1, v[i].y);
-      acc_sq(s2, c2, v[i].z);
-      acc_sq(s3, c3, v[i].w);
+      ss = fma((double)v[i].x, (double)v[i].x, ss);
+      ss = fma((double)v[i].y, (double)v[i].y, ss);
+      ss = fma((double)v[i].z, (double)v[i].z, ss);
+      ss = fma((double)v[i].w, (double)v[i].w, ss);
     }
-    double ss = ((double)s0 + (double)s1) + ((double)s2 + (double)s3) + (((double)c0 + (double)c1) + ((double)c2 + (double)c3));
     ss = warp_sum_f64(ss);
     if (out_norms != nullptr && lane == 0) out_norms[row] = (float)sqrt(ss);
 
     if (normalize) {
-      const double r = rsqrt_f64(ss);
-      const float rh = (float)r;
-      const float rl = (float)(r - (double)rh);
+      const double r = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        v[i].x = scale_ff(v[i].x, rh, rl);
-        v[i].y = scale_ff(v[i].y, rh, rl);
-        v[i].z = scale_ff(v[i].z, rh, rl);
-        v[i].w = scale_ff(v[i].w, rh, rl);
+        v[i].x = (float)((double)v[i].x * r);
+        v[i].y = (float)((double)v[i].y * r);
+        v[i].z = (float)((double)v[i].z * r);
+        v[i].w = (float)((double)v[i].w * r);
       }
     }
 
@@ -148,10 +112,7 @@ l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const i
     if (HAS32) {
       float4* dst = reinterpret_cast<float4*>(master32 + slot * ld32);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        if (st_cs) __stcs(dst + lane + 32 * i, v[i]);
-        else dst[lane + 32 * i] = v[i];
-      }
+      for (int i = 0; i < NV; ++i) dst[lane + 32 * i] = v[i];
     }
     uint2* dst16 = reinterpret_cast<uint2*>(out16 + slot * ld16);
     uint2* dsts = shadow16 ? reinterpret_cast<uint2*>(shadow16 + slot * ld16) : nullptr;
@@ -181,115 +142,9 @@ l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const i
       uint2 p;
       p.x = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
       p.y = static_cast<uint32_t>(h2) | (static_cast<uint32_t>(h3) << 16);
-      if (out16) {
-        if (st_cs) __stcs(dst16 + lane + 32 * i, p);
-        else dst16[lane + 32 * i] = p;
-      }
-    }
-    finish_row_stats(s16, sy, sd, HAS32 != 0, cosine != 0, wmax_norm, wmax_dev);
-    if (dsts) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        ssn += __shfl_xor_sync(FULL_MASK, ssn, o);
-        ssd += __shfl_xor_sync(FULL_MASK, ssd, o);
-      }
-      wmax_snorm = fmaxf(wmax_snorm, sqrtf(ssn));
-      wmax_sdev = fmaxf(wmax_sdev, sqrtf(ssd));
-    }
-  }
-  if (lane == 0 && stats) {
-    atomic_max_nonneg(stats + 0, wmax_norm);
-    atomic_max_nonneg(stats + 1, wmax_dev);
-    if (shadow16) {
-      atomic_max_nonneg(stats + 2, wmax_snorm);
-      atomic_max_nonneg(stats + 3, wmax_sdev);
-    }
-  }
-}
-
-// PROBE ONLY (RBOD_K1_IMPL=f64): the previous fp64-per-element kernel, kept for same-box A/B timing.
-template <int NV>
-__global__ void __launch_bounds__(K1_WARPS * 32)
-l2norm_pack_vec_f64_kernel(const float* __restrict__ in, int64_t n, int dim, const int64_t* __restrict__ slots,
-                       int64_t slot0, int normalize, int cosine, float* __restrict__ master32, int64_t ld32,
-                       uint16_t* __restrict__ out16, int64_t ld16, int kind16, uint16_t* __restrict__ shadow16,
-                       float* __restrict__ out_norms, float* __restrict__ stats) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * K1_WARPS + (threadIdx.x >> 5);
-  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * K1_WARPS;
-  float wmax_norm = 0.f, wmax_dev = 0.f, wmax_snorm = 0.f, wmax_sdev = 0.f;
-
-  for (int64_t row = warp0; row < n; row += nwarps) {
-    const float4* src = reinterpret_cast<const float4*>(in + row * dim);
-    // pull the row this warp handles two iterations from now into L2 (one 128-byte line per lane): the
-    // demand loads below then see L2 latency instead of HBM latency, which is what the 2 resident CTAs
-    // per SM (100 registers per thread) cannot hide on their own
-    {
-      const int64_t ahead = row + K1_PREFETCH_ROWS * nwarps;
-      if (ahead < n && lane < NV * 4) prefetch_l2(in + ahead * dim + lane * 32);
-    }
-    float4 v[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = __ldcs(src + lane + 32 * i);
-
-    double ss = 0.0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      ss = fma((double)v[i].x, (double)v[i].x, ss);
-      ss = fma((double)v[i].y, (double)v[i].y, ss);
-      ss = fma((double)v[i].z, (double)v[i].z, ss);
-      ss = fma((double)v[i].w, (double)v[i].w, ss);
-    }
-    ss = warp_sum_f64(ss);
-    if (lane == 0 && out_norms) out_norms[row] = (float)sqrt(ss);
-
-    if (normalize) {
-      const double r = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        v[i].x = (float)((double)v[i].x * r);
-        v[i].y = (float)((double)v[i].y * r);
-        v[i].z = (float)((double)v[i].z * r);
-        v[i].w = (float)((double)v[i].w * r);
-      }
-    }
-
-    const int64_t slot = slots ? slots[row] : slot0 + row;
-    float s16 = 0.f, sy = 0.f, sd = 0.f;
-    if (master32) {
-      float4* dst = reinterpret_cast<float4*>(master32 + slot * ld32);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) dst[lane + 32 * i] = v[i];
-    }
-    uint2* dst16 = reinterpret_cast<uint2*>(out16 + slot * ld16);
-    uint2* dsts = shadow16 ? reinterpret_cast<uint2*>(shadow16 + slot * ld16) : nullptr;
-    float ssn = 0.f, ssd = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const uint16_t h0 = f32_to_h16(v[i].x, kind16), h1 = f32_to_h16(v[i].y, kind16);
-      const uint16_t h2 = f32_to_h16(v[i].z, kind16), h3 = f32_to_h16(v[i].w, kind16);
-      const float f0 = h16_to_f32(h0, kind16), f1 = h16_to_f32(h1, kind16);
-      const float f2 = h16_to_f32(h2, kind16), f3 = h16_to_f32(h3, kind16);
-      if (dsts) {
-        const uint16_t s0 = f32_to_h16(f0, 2), s1 = f32_to_h16(f1, 2), s2 = f32_to_h16(f2, 2), s3 = f32_to_h16(f3, 2);
-        const float g0 = h16_to_f32(s0, 2), g1 = h16_to_f32(s1, 2), g2 = h16_to_f32(s2, 2), g3 = h16_to_f32(s3, 2);
-        ssn += g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3;
-        ssd += (g0 - f0) * (g0 - f0) + (g1 - f1) * (g1 - f1) + (g2 - f2) * (g2 - f2) + (g3 - f3) * (g3 - f3);
-        uint2 ps;
-        ps.x = static_cast<uint32_t>(s0) | (static_cast<uint32_t>(s1) << 16);
-        ps.y = static_cast<uint32_t>(s2) | (static_cast<uint32_t>(s3) << 16);
-        dsts[lane + 32 * i] = ps;
-      }
-      s16 += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
-      sy += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-      const float d0 = f0 - v[i].x, d1 = f1 - v[i].y, d2 = f2 - v[i].z, d3 = f3 - v[i].w;
-      sd += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-      uint2 p;
-      p.x = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
-      p.y = static_cast<uint32_t>(h2) | (static_cast<uint32_t>(h3) << 16);
       if (out16) dst16[lane + 32 * i] = p;
     }
-    finish_row_stats(s16, sy, sd, master32 != nullptr, cosine != 0, wmax_norm, wmax_dev);
+    finish_row_stats(s16, sy, sd, HAS32 != 0, cosine != 0, wmax_norm, wmax_dev);
     if (dsts) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -406,31 +261,23 @@ int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots
   const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) &&
                        (master32 == nullptr || (reinterpret_cast<uintptr_t>(master32) % 16 == 0 && ld32 % 4 == 0)) &&
                        (out16 == nullptr || (reinterpret_cast<uintptr_t>(out16) % 8 == 0 && ld16 % 4 == 0));
-  // probe knobs (environment, read once): CTAs per SM, L2 prefetch distance in rows per warp, streaming stores
-  static const int tune_ctas = getenv("RBOD_K1_CTAS") ? atoi(getenv("RBOD_K1_CTAS")) : 0;
-  static const int tune_pf = getenv("RBOD_K1_PF") ? atoi(getenv("RBOD_K1_PF")) : K1_PREFETCH_ROWS;
-  static const int tune_f64 = getenv("RBOD_K1_IMPL") && !strcmp(getenv("RBOD_K1_IMPL"), "f64");
-  static const int tune_cs = getenv("RBOD_K1_CS") ? atoi(getenv("RBOD_K1_CS")) : 0;
-  // persistent grid: exactly the CTAs that are resident at once (no second wave with a ragged tail)
+  // Grid: 64 CTAs per SM of row-strided warps, i.e. many short waves instead of one persistent one.  Measured on one
+  // B200 (copy bandwidth of that box 6602 GB/s), 8M x 768 -> bf16 / 4M x 512 -> fp32: 2 CTAs per SM (= the resident
+  // set) 86% / 93% of the copy bandwidth, 8: 86% / 92%, 16: 88% / 97%, 64: 88% / 101%, one row per warp: 67% / 85%.
+  // RBOD_K1_CTAS overrides for probing.
+  static const int tune_ctas = getenv("RBOD_K1_CTAS") ? atoi(getenv("RBOD_K1_CTAS")) : 64;
+  grid = (int)(want < (int64_t)num_sms * tune_ctas ? want : (int64_t)num_sms * tune_ctas);
 #define RBOD_K1_CASE(NV)                                                                                     \
-  case NV: {                                                                                                 \
-    if (tune_f64) {                                                                                          \
-      const int g2 = (int)(want < (int64_t)num_sms * 8 ? want : (int64_t)num_sms * 8);                       \
-      l2norm_pack_vec_f64_kernel<NV><<<g2, K1_WARPS * 32, 0, st>>>(in, n, dim, slots_dev, slot0, normalize,   \
-                                                                   cosine, master32, ld32, out16, ld16,      \
-                                                                   kind16, shadow16, out_norms, stats);      \
-      break;                                                                                                 \
-    }                                                                                                        \
-    auto kern = master32 ? l2norm_pack_vec_kernel<NV, 1> : l2norm_pack_vec_kernel<NV, 0>;                    \
-    int per_sm = 0;                                                                                          \
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1_WARPS * 32, 0) == cudaSuccess &&     \
-        per_sm > 0) {                                                                                        \
-      if (tune_ctas > 0) per_sm = tune_ctas;                                                                 \
-      grid = (int)(want < (int64_t)num_sms * per_sm ? want : (int64_t)num_sms * per_sm);                     \
-    }                                                                                                        \
-    kern<<<grid, K1_WARPS * 32, 0, st>>>(in, n, dim, slots_dev, slot0, normalize, cosine, master32, ld32,     \
-                                         out16, ld16, kind16, shadow16, out_norms, stats, tune_pf, tune_cs);  \
-  } break;
+  case NV:                                                                                                   \
+    if (master32)                                                                                            \
+      l2norm_pack_vec_kernel<NV, 1><<<grid, K1_WARPS * 32, 0, st>>>(in, n, dim, slots_dev, slot0, normalize,  \
+                                                                    cosine, master32, ld32, out16, ld16,     \
+                                                                    kind16, shadow16, out_norms, stats);     \
+    else                                                                                                     \
+      l2norm_pack_vec_kernel<NV, 0><<<grid, K1_WARPS * 32, 0, st>>>(in, n, dim, slots_dev, slot0, normalize,  \
+                                                                    cosine, master32, ld32, out16, ld16,     \
+                                                                    kind16, shadow16, out_norms, stats);     \
+    break;
   if (aligned && dim % 128 == 0 && dim / 128 >= 1 && dim / 128 <= 8) {
     switch (dim / 128) {
       RBOD_K1_CASE(1)

@@ -14,8 +14,8 @@
 //      rows); a list that overflows `cap` tightens its threshold to the k-th best key it did record --
 //      still a lower bound of the true k-th key -- and only those queries are swept again;
 //   3. select: rank by counting, emit (distance, row) ascending by distance.
-// One warp owns one gallery row (kept in fp64 registers) and scores it against a batch of queries whose
-// fp64 copies sit in L1/L2, so the gallery is read once per batch of 32 queries.
+// A warp scores two gallery rows at a time against a batch of 32 queries whose fp64 copies sit in L1/L2 (64
+// independent DFMA chains per lane), so the gallery is read once per batch of 32 queries.
 #include "rbod_common.cuh"
 #include "rbod_internal.h"
 
@@ -40,52 +40,122 @@ dist_widen_queries_kernel(const float* __restrict__ q, const int* __restrict__ q
   }
 }
 
-// Rows r = row0, row0 + stride, ... < n_rows; every (row, query f) with key >= thr[f] is appended to list f.
-template <int METRIC, int NMAX>
-__global__ void __launch_bounds__(256)
+// Lane l ends up with the sum over all lanes of acc[l] (a 32 x 32 transpose-reduce: 31 shuffle-adds instead of
+// 32 five-step butterflies).
+__device__ __forceinline__ double warp_transpose_sum(double (&acc)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const double send = up ? acc[i] : acc[i + o];
+      const double keep = up ? acc[i + o] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(FULL_MASK, send, o);
+    }
+  }
+  return acc[0];
+}
+
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// Rows r = row0, row0 + stride, ... < n_rows.  A warp takes R rows at a time: it copies them into its own
+// shared-memory buffer with cp.async (all of a row group's loads in flight at once, the next group's copy
+// overlapping this group's arithmetic), then lane l walks columns l, l + 32, ... keeping one fp64 accumulator
+// per (row, query) -- 32 queries x R rows of independent DFMA chains, each query element loaded once per R
+// rows -- and the transpose-reduce leaves query f's key in lane f, which owns that query's threshold and
+// appends to its list.  q64 is [32, dim], zero rows beyond the batch.  `words` = 4-byte words per stored row.
+template <int METRIC, int R>
+__global__ void __launch_bounds__(256, 1)
 dist_collect_kernel(const double* __restrict__ q64, const float* __restrict__ master32,
-                    const uint16_t* __restrict__ rows16, int kind16, int dim, int64_t ld32, int64_t ld16,
+                    const uint16_t* __restrict__ rows16, int kind16, int dim, int64_t ld32, int64_t ld16, int words,
                     int64_t n_rows, int64_t row0, int64_t stride, const uint32_t* __restrict__ row_mask,
                     const double* __restrict__ thr, const int* __restrict__ active, int nf, int cap,
                     double* __restrict__ coll_key, uint32_t* __restrict__ coll_idx, int* __restrict__ coll_cnt) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  extern __shared__ uint32_t k5_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + warp;
   const int64_t nw = (int64_t)gridDim.x * 8;
-  for (int64_t r = row0 + w0 * stride; r < n_rows; r += nw * stride) {
-    if (row_mask && !((row_mask[r >> 5] >> (r & 31)) & 1u)) continue;
-    double g[NMAX];
+  const bool mine = lane < nf && active[lane] != 0;
+  const double my_thr = mine ? thr[lane] : INFINITY;
+  const int64_t n_visit = n_rows > row0 ? (n_rows - row0 + stride - 1) / stride : 0;   // rows of this pass
+  uint32_t* wbuf = k5_smem + (size_t)warp * 2 * R * words;
+
+  auto row_ok = [&](int64_t v) -> bool {
+    if (v >= n_visit) return false;
+    const int64_t r = row0 + v * stride;
+    return row_mask == nullptr || ((row_mask[r >> 5] >> (r & 31)) & 1u);
+  };
+  auto issue = [&](int64_t v0, int b) {
 #pragma unroll
-    for (int i = 0; i < NMAX; ++i) {
-      const int c = lane + 32 * i;
-      double x = 0.0;
-      if (c < dim) x = master32 ? (double)master32[r * ld32 + c] : (double)h16_to_f32(rows16[r * ld16 + c], kind16);
-      g[i] = x;
+    for (int j = 0; j < R; ++j) {
+      if (!row_ok(v0 + j)) continue;
+      const int64_t r = row0 + (v0 + j) * stride;
+      const uint32_t* src = master32 ? reinterpret_cast<const uint32_t*>(master32 + r * ld32)
+                                     : reinterpret_cast<const uint32_t*>(rows16 + r * ld16);
+      uint32_t* dst = wbuf + (size_t)(b * R + j) * words;
+      for (int w = lane; w < words; w += 32) cp_async_4(dst + w, src + w);
     }
-    for (int f = 0; f < nf; ++f) {
-      if (!active[f]) continue;
-      const double* qv = q64 + (int64_t)f * dim;
-      double acc = 0.0;
+    cp_async_commit();
+  };
+
+  int b = 0;
+  int64_t v0 = w0 * R;
+  if (v0 < n_visit) issue(v0, 0);
+  for (; v0 < n_visit; v0 += nw * R, b ^= 1) {
+    const int64_t vn = v0 + nw * R;
+    if (vn < n_visit) issue(vn, b ^ 1); else cp_async_commit();
+    cp_async_wait_1();
+    __syncwarp();
+    bool ok[R];
 #pragma unroll
-      for (int i = 0; i < NMAX; ++i) {
-        const int c = lane + 32 * i;
-        if (c < dim) {
-          const double d = qv[c] - g[i];
-          if (METRIC == RBOD_EUCLID) acc = fma(d, d, acc);
-          else acc += fabs(d);
-        }
-      }
-      acc = warp_sum_f64(acc);
-      if (lane == 0) {
-        const double key = -acc;
-        if (key >= thr[f]) {
-          const int slot = atomicAdd(coll_cnt + f, 1);
-          if (slot < cap) {
-            coll_key[(size_t)f * cap + slot] = key;
-            coll_idx[(size_t)f * cap + slot] = (uint32_t)r;
+    for (int j = 0; j < R; ++j) ok[j] = row_ok(v0 + j);
+    double acc[R][32];
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+      for (int f = 0; f < 32; ++f) acc[j][f] = 0.0;
+    const uint32_t* rows_s = wbuf + (size_t)b * R * words;
+    for (int c = lane; c < dim; c += 32) {
+      double x[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        x[j] = 0.0;
+        if (ok[j]) {
+          if (master32) {
+            x[j] = (double)__uint_as_float(rows_s[(size_t)j * words + c]);
+          } else {
+            const uint32_t w = rows_s[(size_t)j * words + (c >> 1)];
+            x[j] = (double)h16_to_f32((uint16_t)((c & 1) ? (w >> 16) : (w & 0xffffu)), kind16);
           }
         }
       }
+#pragma unroll
+      for (int f = 0; f < 32; ++f) {
+        const double qf = q64[(int64_t)f * dim + c];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const double d = qf - x[j];
+          if (METRIC == RBOD_EUCLID) acc[j][f] = fma(d, d, acc[j][f]);
+          else acc[j][f] += fabs(d);
+        }
+      }
     }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const double key = -warp_transpose_sum(acc[j], lane);
+      if (ok[j] && mine && key >= my_thr) {
+        const int slot = atomicAdd(coll_cnt + lane, 1);
+        if (slot < cap) {
+          coll_key[(size_t)lane * cap + slot] = key;
+          coll_idx[(size_t)lane * cap + slot] = (uint32_t)(row0 + (v0 + j) * stride);
+        }
+      }
+    }
+    __syncwarp();   // every lane is done with buffer b before the next iteration's copy lands in it
   }
 }
 
@@ -139,23 +209,6 @@ dist_select_kernel(const double* __restrict__ coll_key, const uint32_t* __restri
   }
 }
 
-template <int METRIC>
-void launch_collect_t(int nmax, int grid, cudaStream_t st, const double* q64, const float* master32,
-                      const uint16_t* rows16, int kind16, int dim, int64_t ld32, int64_t ld16, int64_t n_rows,
-                      int64_t row0, int64_t stride, const uint32_t* row_mask, const double* thr, const int* active,
-                      int nf, int cap, double* coll_key, uint32_t* coll_idx, int* coll_cnt) {
-#define RBOD_K5_GO(NM)                                                                                          \
-  dist_collect_kernel<METRIC, NM><<<grid, 256, 0, st>>>(q64, master32, rows16, kind16, dim, ld32, ld16, n_rows,   \
-                                                        row0, stride, row_mask, thr, active, nf, cap, coll_key,  \
-                                                        coll_idx, coll_cnt)
-  if (nmax <= 4) RBOD_K5_GO(4);
-  else if (nmax <= 8) RBOD_K5_GO(8);
-  else if (nmax <= 16) RBOD_K5_GO(16);
-  else if (nmax <= 24) RBOD_K5_GO(24);
-  else RBOD_K5_GO(32);
-#undef RBOD_K5_GO
-}
-
 }  // namespace
 
 int launch_dist_widen_queries(const float* q, const int* qsel, int nf, int dim, double* q64, cudaStream_t st) {
@@ -171,17 +224,29 @@ int launch_dist_collect(int metric, const double* q64, const float* master32, co
                         const uint32_t* row_mask, const double* thr, const int* active, int nf, int cap,
                         double* coll_key, uint32_t* coll_idx, int* coll_cnt, int num_sms, cudaStream_t st) {
   if (nf <= 0 || n_rows <= 0) return RBOD_OK;
-  if (dim > 1024) return set_error(RBOD_E_UNSUPPORTED, "EUCLID / MANHATTAN search supports dim <= 1024");
+  if (nf > 32) return set_error(RBOD_E_INVAL, "dist_collect: at most 32 queries per pass");
+  constexpr int R = 2;
+  // a row is staged as 4-byte words (16-bit rows are stored padded to a multiple of 64 elements)
+  const int words = master32 ? dim : (int)(ld16 / 2);
+  const size_t smem = (size_t)8 * 2 * R * words * 4;
+  if (smem > 200 * 1024)
+    return set_error(RBOD_E_UNSUPPORTED, "EUCLID / MANHATTAN search: dim %d needs %zu bytes of staging per SM", dim, smem);
   const int64_t rows_visited = (n_rows - row0 + stride - 1) / stride;
-  const int64_t want = (rows_visited + 7) / 8;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms * 4));
-  const int nmax = (dim + 31) / 32;
-  if (metric == RBOD_EUCLID)
-    launch_collect_t<RBOD_EUCLID>(nmax, grid, st, q64, master32, rows16, kind16, dim, ld32, ld16, n_rows, row0,
-                                  stride, row_mask, thr, active, nf, cap, coll_key, coll_idx, coll_cnt);
-  else
-    launch_collect_t<RBOD_MANHATTAN>(nmax, grid, st, q64, master32, rows16, kind16, dim, ld32, ld16, n_rows, row0,
-                                     stride, row_mask, thr, active, nf, cap, coll_key, coll_idx, coll_cnt);
+  const int64_t want = (rows_visited + 8 * R - 1) / (8 * R);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms));
+  if (metric == RBOD_EUCLID) {
+    RBOD_CUDA(cudaFuncSetAttribute(dist_collect_kernel<RBOD_EUCLID, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    dist_collect_kernel<RBOD_EUCLID, R><<<grid, 256, smem, st>>>(q64, master32, rows16, kind16, dim, ld32, ld16,
+                                                                 words, n_rows, row0, stride, row_mask, thr, active,
+                                                                 nf, cap, coll_key, coll_idx, coll_cnt);
+  } else {
+    RBOD_CUDA(cudaFuncSetAttribute(dist_collect_kernel<RBOD_MANHATTAN, R>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dist_collect_kernel<RBOD_MANHATTAN, R><<<grid, 256, smem, st>>>(q64, master32, rows16, kind16, dim, ld32, ld16,
+                                                                    words, n_rows, row0, stride, row_mask, thr,
+                                                                    active, nf, cap, coll_key, coll_idx, coll_cnt);
+  }
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

@@ -359,9 +359,9 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
   } else if (!strcmp(key, "sync_window")) {
     if (value < 1 || value > 4096) return set_error(RBOD_E_INVAL, "sync_window must be in [1, 4096]");
     g->sync_window = (int)value;
-  } else if (!strcmp(key, "l2_prefetch")) {
-    if (value < 0 || value > 64) return set_error(RBOD_E_INVAL, "l2_prefetch must be in [0, 64]");
-    g->l2_prefetch = (int)value;
+  } else if (!strcmp(key, "stagger")) {
+    if (value < 0 || value > 1024) return set_error(RBOD_E_INVAL, "stagger must be in [0, 1024]");
+    g->stagger = (int)value;
   } else if (!strcmp(key, "sync_lead")) {
     if (value < 1 || value > 64) return set_error(RBOD_E_INVAL, "sync_lead must be in [1, 64]");
     g->sync_lead = (int)value;
@@ -679,7 +679,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.a_tmem_kb = P.a_tmem_kb;
   L.variant = g->k3_variant;
   L.debug_epi = g->debug_epi;
-  L.l2_prefetch = sample ? 0 : g->l2_prefetch;
+  L.stagger = g->stagger;
   L.a_fmt = query_kind(g) == 1 ? 1 : 0;
   L.b_fmt = query_kind(g) == 1 ? 1 : 0;
   L.part_score = g->part_score.as<float>();
@@ -729,10 +729,11 @@ static int prepare_queries(rbod_gallery* g, const float* queries, int64_t Q, con
 static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int k, const uint32_t* mask_dev,
                            float* d_scores, int64_t* d_rows, double* d_keys, int64_t* launches, int64_t* resweeps,
                            cudaStream_t st) {
-  const int cap = 4096, batch = 32, max_iter = 12;
-  if (k > cap / 4)
-    return set_error(RBOD_E_UNSUPPORTED, "rbod_search: k=%d > %d for EUCLID / MANHATTAN collections", k, cap / 4);
-  if (g->dim > 1024) return set_error(RBOD_E_UNSUPPORTED, "rbod_search: EUCLID / MANHATTAN support dim <= 1024");
+  // lists hold 8192 rows; the sample is sized so that ~k * stride rows pass the threshold it yields (about a
+  // quarter of a list for k <= 8), which keeps second sweeps rare
+  const int cap = 8192, sample_cap = 4096, batch = 32, max_iter = 12;
+  if (k > 1024)
+    return set_error(RBOD_E_UNSUPPORTED, "rbod_search: k=%d > 1024 for EUCLID / MANHATTAN collections", k);
   const void* qd = nullptr;
   RBOD_TRY(to_device(queries, (size_t)Q * g->dim * 4, g->q32, st, &qd));
   const float* q_dev = static_cast<const float*>(qd);
@@ -748,7 +749,7 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
   double* d_thr = g->dist_thr.as<double>();
   std::vector<double> h_thr(batch, -INFINITY);
   std::vector<int> h_ctl(2 * batch + 1);
-  const int64_t sample_stride = (g->rows + cap - 1) / cap;   // > 1 iff the gallery holds more than `cap` rows
+  const int64_t sample_stride = (g->rows + sample_cap - 1) / sample_cap;   // > 1 iff more than `sample_cap` rows
   for (int64_t q0 = 0; q0 < Q; q0 += batch) {
     const int nf = (int)std::min<int64_t>(batch, Q - q0);
     for (int f = 0; f < batch; ++f) {
@@ -759,6 +760,7 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
     RBOD_CUDA(cudaMemcpyAsync(d_qsel, h_ctl.data(), h_ctl.size() * 4, cudaMemcpyHostToDevice, st));
     RBOD_CUDA(cudaMemcpyAsync(d_thr, h_thr.data(), (size_t)batch * 8, cudaMemcpyHostToDevice, st));
     RBOD_CUDA(cudaMemsetAsync(g->coll_cnt.p, 0, (size_t)batch * 4, st));
+    if (nf < batch) RBOD_CUDA(cudaMemsetAsync(g->dist_q64.p, 0, (size_t)batch * g->dim * 8, st));   // zero rows pad the batch
     RBOD_TRY(launch_dist_widen_queries(q_dev, d_qsel, nf, g->dim, g->dist_q64.as<double>(), st));
     ++*launches;
     if (sample_stride > 1) {

@@ -143,13 +143,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
-// 2D tiled prefetch of one box into L2 (no shared memory, no barrier): raises the number of HBM requests
-// in flight beyond what the smem pipeline holds.
-__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int x, int y) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(x), "r"(y)
-               : "memory");
-}
-
 // ------------------------------------------------------------------------------------
 // thread-block clusters (CTA pairs)
 // ------------------------------------------------------------------------------------

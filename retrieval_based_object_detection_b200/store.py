@@ -121,12 +121,12 @@ class Collection:
         if os.path.exists(ppath) and os.path.exists(vpath):
             with open(ppath, encoding="utf-8") as f:
                 pts = json.load(f)
-            vec = np.load(vpath)
+            vec = np.load(vpath, mmap_mode="r")      # paged in chunk by chunk when the gallery is materialised
             if vec.shape != (len(pts), col.dim):
                 raise RuntimeError(f"collection {col.name!r}: snapshot shape {vec.shape} != ({len(pts)}, {col.dim})")
             for pid, payload in pts:
                 col._add_point(pid if isinstance(pid, int) else str(pid), payload)
-            col.snapshot_vectors = np.ascontiguousarray(vec, dtype=np.float32)
+            col.snapshot_vectors = vec
         wal = os.path.join(directory, "wal.jsonl")
         if os.path.exists(wal):
             with open(wal, encoding="utf-8") as f:
@@ -280,7 +280,11 @@ class Collection:
             if self.dtype in ("bf16", "bfloat16") and os.environ.get("RBOD_BF16_SHADOW", "0") == "1":
                 self.gallery.set_option("shadow16", 1)    # fp16 search operand: tighter certification, 2x memory
             if self.snapshot_vectors is not None and len(self.snapshot_vectors):
-                self.gallery.upsert(self.snapshot_vectors, raw=True)
+                # the snapshot file is memory-mapped: stream it to the device in 256 MB pieces (stored form, no K1
+                # normalisation), so reopening a large collection never holds a second copy in host memory
+                step = max(1, (256 << 20) // (4 * self.dim))
+                for a in range(0, len(self.snapshot_vectors), step):
+                    self.gallery.upsert(np.ascontiguousarray(self.snapshot_vectors[a:a + step], dtype=np.float32), raw=True)
             self.snapshot_vectors = None
         return self.gallery
 
