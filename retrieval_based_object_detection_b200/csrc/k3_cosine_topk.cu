@@ -77,7 +77,6 @@ struct alignas(64) K3Params {
   int num_acc;     // accumulator buffers (1 or 2)
   int acc_col0;    // first accumulator column in TMEM
   int debug_epi;   // bring-up only: 1 = epilogue loads the tile but selects nothing, 2 = does not even load it
-  int stagger;     // tiles between the starting points of the query tiles that share a slice (0 = all start at 0)
   uint32_t idesc;
 };
 
@@ -134,18 +133,6 @@ __device__ __forceinline__ K3TileRange k3_unit_tiles(const K3Params& P, int slic
     r.step = 1;
   }
   return r;
-}
-
-// Tile visited at step ti of a unit.  With a stagger, the query tiles that share a gallery slice walk it in the same
-// cyclic order but rot tiles apart, so the CTAs that follow find the leader's tiles already resident in L2
-// instead of joining its in-flight misses.
-__device__ __forceinline__ int k3_tile_at(const K3TileRange& tr, int ti, int rot) {
-  int i = ti + rot;
-  if (i >= tr.n) i -= tr.n;
-  return tr.t0 + i * tr.step;
-}
-__device__ __forceinline__ int k3_unit_rot(const K3Params& P, const K3TileRange& tr, int qt) {
-  return (P.stagger > 0 && P.group_stride == 0 && tr.n > 0) ? (int)(((int64_t)qt * P.stagger) % tr.n) : 0;
 }
 
 // Geometry of one kernel flavour.
@@ -245,7 +232,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
     for (int u = worker; u < num_units; u += num_workers) {
       const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
       const K3TileRange tr = k3_unit_tiles(P, slice);
-      const int rot = k3_unit_rot(P, tr, qt);
       // L2 sharing throttle: the CTAs that stream this slice in this round form a group; nobody
       // issues window w before every member has issued window w - lead.  That keeps the group's
       // working set (lead + 1 windows) hot in L2, so each gallery tile is fetched from HBM once per
@@ -261,7 +247,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         cnt = P.sync_counters + ((size_t)slice * P.sync_span + (round - first_round)) * P.sync_windows;
       }
       for (int ti = 0; ti < tr.n; ++ti) {
-        const int t = k3_tile_at(tr, ti, rot);
+        const int t = tr.t0 + ti * tr.step;
         if (cnt != nullptr && gsize > 1 && ti % P.sync_window == 0) {
           const int w = ti / P.sync_window;
           if (elect_one()) {
@@ -411,7 +397,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
     for (int u = worker; u < num_units; u += num_workers) {
       const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
       const K3TileRange tr = k3_unit_tiles(P, slice);
-      const int rot = k3_unit_rot(P, tr, qt);
       const int64_t q_unit0 = (int64_t)qt * G::Q_PER_UNIT + (int64_t)rank * K3_TILE_M;   // first query row of this CTA
       const int64_t qg = q_unit0 + row;
 
@@ -464,7 +449,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
       const bool groupmax = P.groupmax_out != nullptr;
       float gmax_run = -INFINITY;
       for (int ti = 0; ti < tr.n; ++ti) {
-        const int t = k3_tile_at(tr, ti, rot);
+        const int t = tr.t0 + ti * tr.step;
         if (tau_cell != nullptr && (ti & (K3_TAU_REFRESH - 1)) == K3_TAU_REFRESH - 1) {
           const float root = my_sc[0];
           if (root > tau_published) {
@@ -762,7 +747,6 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.sync_windows = L.sync_windows;
   P.a_tmem_kb = L.a_tmem_kb;
   P.debug_epi = L.debug_epi;
-  P.stagger = L.stagger;
   P.num_acc = (L.variant == 1 || L.a_tmem_kb * 32 + 2 * K3_TILE_N <= TMEM_COLS) ? 2 : 1;
   P.acc_col0 = TMEM_COLS - P.num_acc * K3_TILE_N;
   P.idesc = make_idesc_f16(L.a_fmt, L.b_fmt, L.variant == 2 ? 2 * K3_TILE_M : K3_TILE_M, K3_TILE_N);

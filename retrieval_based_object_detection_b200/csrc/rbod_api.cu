@@ -345,7 +345,8 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
       }
     }
   } else if (!strcmp(key, "presample")) {
-    g->presample = value != 0;
+    if (value < 0 || value > 2) return set_error(RBOD_E_INVAL, "presample must be 0 (off), 1 (when it pays) or 2 (always)");
+    g->presample = (int)value;
   } else if (!strcmp(key, "collect_pass")) {
     g->collect_pass = value != 0;
   } else if (!strcmp(key, "tau_share")) {
@@ -359,9 +360,6 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
   } else if (!strcmp(key, "sync_window")) {
     if (value < 1 || value > 4096) return set_error(RBOD_E_INVAL, "sync_window must be in [1, 4096]");
     g->sync_window = (int)value;
-  } else if (!strcmp(key, "stagger")) {
-    if (value < 0 || value > 1024) return set_error(RBOD_E_INVAL, "stagger must be in [0, 1024]");
-    g->stagger = (int)value;
   } else if (!strcmp(key, "sync_lead")) {
     if (value < 1 || value > 64) return set_error(RBOD_E_INVAL, "sync_lead must be in [1, 64]");
     g->sync_lead = (int)value;
@@ -679,7 +677,6 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.a_tmem_kb = P.a_tmem_kb;
   L.variant = g->k3_variant;
   L.debug_epi = g->debug_epi;
-  L.stagger = g->stagger;
   L.a_fmt = query_kind(g) == 1 ? 1 : 0;
   L.b_fmt = query_kind(g) == 1 ? 1 : 0;
   L.part_score = g->part_score.as<float>();
@@ -902,9 +899,15 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev0, st));
   // Threshold pre-pass: row maxima over K3_SAMPLE_GROUPS strided samples of the gallery give every query a
   // starting threshold, so the candidate heaps of the main pass skip their cold start (see tau_init_kernel).
+  // It pays only when it can spread over the chip: it runs K3_SAMPLE_GROUPS units per query tile, so a small batch
+  // would stream the sample on a handful of SMs (measured at Q <= 256 on 12.5M x 768: 0.48 ms next to a 2.9 ms main
+  // pass that is HBM-bound anyway).  Small candidate lists (k <= 10) need it least, so they skip it until the
+  // pre-pass fills the chip; larger lists, whose cold start costs ~10 %, skip it only for one or two query tiles.
   const float* tau_init = nullptr;
   const int sample_tiles = std::max(1, P.tiles_total / (K3_SAMPLE_RATIO * P.kc));
-  if (g->tau_share && g->presample && P.tiles_total >= 10 * P.kc &&
+  const int sample_units = P.num_qt * K3_SAMPLE_GROUPS * (g->k3_variant == 2 ? 2 : 1);
+  const bool sample_pays = g->presample >= 2 || (P.kc <= 32 ? sample_units >= g->num_sms : P.num_qt > 2);
+  if (g->tau_share && g->presample && sample_pays && P.tiles_total >= 10 * P.kc &&
       P.tiles_total / sample_tiles >= K3_SAMPLE_GROUPS) {
     SearchPlan PA = P;
     PA.slices = K3_SAMPLE_GROUPS;

@@ -89,7 +89,6 @@ struct K3Launch {
   int* sync_counters;     // zeroed [slices * sync_span * sync_windows] ints, or nullptr
   int sync_window, sync_lead, sync_span, sync_windows;
   int debug_epi;          // bring-up: 1 = epilogue selects nothing, 2 = epilogue does not read the tile
-  int stagger;            // tiles between the starting points of query tiles sharing a slice (0 = off)
   int grid;
   size_t smem_bytes;
 };
@@ -186,7 +185,6 @@ struct rbod_gallery {
   int hybrid = 1;         // allow the query tile to be split between TMEM and resident smem
   int l2_sync = 1;        // producer throttle that keeps slice-mates within an L2 window
   int sync_window = 16, sync_lead = 4;
-  int stagger = 0;        // K3: cyclic offset (tiles) between the query tiles that stream the same slice
   // workspaces
   rbod::DevBuf stage_rows, stage_slots, stage_norms;          // upsert staging
   rbod::DevBuf q32, q16, q_dq, q_qq, tau_shared;              // query prep

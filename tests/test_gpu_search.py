@@ -180,7 +180,7 @@ def test_threshold_prepass_keeps_the_answer_exact(G, dtype, ordered):
     mask = rng.random(n) < 0.5
     ws, wi = O.cosine_topk(q, stored, k)
     wms, wmi = O.cosine_topk(q, stored, k, row_mask=mask)
-    for presample in (1, 0):
+    for presample in (2, 0):                                    # 2 = forced (a 300-query batch would skip it)
         g.set_option("presample", presample)
         res = g.search(q, k, want_scores64=True)
         assert np.array_equal(res.rows, wi), (presample, (res.rows != wi).any(axis=1).sum())
@@ -203,8 +203,11 @@ def test_prepass_threshold_too_high_is_retried(G):
     g.upsert(x)
     stored = g.get_rows(np.arange(n))
     q = np.stack([x[77], x[1234]]).astype(np.float32)
-    res = g.search(q, k, want_scores64=True)
     ws, wi = OC.cosine_topk(q, stored, k)
+    res = g.search(q, k, want_scores64=True)                 # a 2-query batch skips the pre-pass on its own
+    assert np.array_equal(res.rows, wi) and res.stats["presample_retries"] == 0
+    g.set_option("presample", 2)
+    res = g.search(q, k, want_scores64=True)
     assert np.array_equal(res.rows, wi)
     assert res.stats["presample_retries"] >= 1
     g.close()
