@@ -123,7 +123,7 @@ int rbod_truncate(rbod_gallery* g, int64_t rows);
  * 2 = TMEM-resident + CTA pairs / cta_group::2), "slack" (extra candidates kept per query),
  * "time_k3" (1 = fill stats.k3_ms), "tau_share" (slices of a query share their threshold),
  * "collect_pass" (tensor-core second pass for uncertified queries), "presample" (sampled
- * starting thresholds: 0 = never, 1 = when the pre-pass can fill the chip, 2 = always), "l2_sync" / "sync_window" /
+ * starting thresholds: 0 = never, 1 = for batches of more than 8 queries, 2 = always), "l2_sync" / "sync_window" /
  * "sync_lead" (L2-sharing producer throttle), "hybrid" (query tile split TMEM / smem). */
 int rbod_set_option(rbod_gallery* g, const char* key, int64_t value);
 

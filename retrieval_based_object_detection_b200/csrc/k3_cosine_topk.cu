@@ -55,6 +55,7 @@ struct alignas(64) K3Params {
   float* groupmax_out;        // sample mode: [slices][q_pad] row maxima over the unit's tiles (no candidate lists)
   int group_stride;           // > 0: unit `slice` visits tiles slice, slice + stride, ... (at most group_tiles of them)
   int group_tiles;
+  int group_splits;           // sample mode: each group's comb is dealt round-robin to this many units (>= 1)
   float* dump;
   int64_t dump_ld;
   int64_t n_rows;
@@ -122,11 +123,17 @@ struct K3TileRange { int t0, n, step; };
 __device__ __forceinline__ K3TileRange k3_unit_tiles(const K3Params& P, int slice) {
   K3TileRange r;
   if (P.group_stride > 0) {
-    // group g starts g/slices of a stride in, so even one-tile groups are spread over the whole gallery
-    r.t0 = (int)(((int64_t)slice * P.group_stride) / P.slices);
-    r.step = P.group_stride;
-    const int avail = r.t0 < P.tiles_total ? (P.tiles_total - r.t0 + r.step - 1) / r.step : 0;
-    r.n = min(P.group_tiles, avail);
+    // unit = (group g, split s).  Group g starts g/groups of a stride in, so even one-tile groups are spread over
+    // the whole gallery; its comb of group_tiles tiles is dealt round-robin to the group's splits, so a small
+    // batch still spreads the sample over the whole chip.
+    const int S = P.group_splits, groups = P.slices / S;
+    const int g = slice / S, s = slice - g * S;
+    const int t0g = (int)(((int64_t)g * P.group_stride) / groups);
+    const int avail = t0g < P.tiles_total ? (P.tiles_total - t0g + P.group_stride - 1) / P.group_stride : 0;
+    const int ng = min(P.group_tiles, avail);
+    r.t0 = t0g + s * P.group_stride;
+    r.step = P.group_stride * S;
+    r.n = ng > s ? (ng - s + S - 1) / S : 0;
   } else {
     r.t0 = (int)(((int64_t)slice * P.tiles_total) / P.slices);
     r.n = (int)(((int64_t)(slice + 1) * P.tiles_total) / P.slices) - r.t0;
@@ -727,6 +734,7 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.groupmax_out = L.groupmax_out;
   P.group_stride = L.group_stride;
   P.group_tiles = L.group_tiles;
+  P.group_splits = L.group_splits > 0 ? L.group_splits : 1;
   P.dump = L.dump;
   P.dump_ld = L.dump_ld;
   P.n_rows = L.n_rows;

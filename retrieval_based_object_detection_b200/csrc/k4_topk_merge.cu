@@ -84,12 +84,17 @@ merge_partials_kernel(const float* __restrict__ part_score, const uint32_t* __re
 // per query (8 groups: < 1e-9 even at k = 100, kc = 128); the host then redoes the call without it.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-tau_init_kernel(const float* __restrict__ groupmax, int groups, int64_t q_pad, uint32_t* __restrict__ tau_shared,
-                float* __restrict__ tau_init) {
+tau_init_kernel(const float* __restrict__ groupmax, int groups, int splits, int64_t q_pad,
+                uint32_t* __restrict__ tau_shared, float* __restrict__ tau_init) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= q_pad) return;
-  float t = groupmax[q];
-  for (int g = 1; g < groups; ++g) t = fminf(t, groupmax[(size_t)g * q_pad + q]);
+  // a group's maximum = the largest of its splits' maxima (each split visited part of the group's comb)
+  float t = INFINITY;
+  for (int g = 0; g < groups; ++g) {
+    float m = -INFINITY;
+    for (int s = 0; s < splits; ++s) m = fmaxf(m, groupmax[((size_t)g * splits + s) * q_pad + q]);
+    t = fminf(t, m);
+  }
   if (!(t > -INFINITY)) t = -INFINITY;   // an empty (or fully masked) group: no starting threshold
   tau_init[q] = t;
   tau_shared[q] = f32_to_ordered(t);
@@ -441,10 +446,11 @@ int launch_merge_partials(const float* part_score, const uint32_t* part_idx, int
   return RBOD_OK;
 }
 
-int launch_tau_init(const float* groupmax, int groups, int64_t q_pad, uint32_t* tau_shared, float* tau_init,
-                    cudaStream_t st) {
+int launch_tau_init(const float* groupmax, int groups, int splits, int64_t q_pad, uint32_t* tau_shared,
+                    float* tau_init, cudaStream_t st) {
   if (q_pad <= 0) return RBOD_OK;
-  tau_init_kernel<<<(unsigned)((q_pad + 255) / 256), 256, 0, st>>>(groupmax, groups, q_pad, tau_shared, tau_init);
+  tau_init_kernel<<<(unsigned)((q_pad + 255) / 256), 256, 0, st>>>(groupmax, groups, splits, q_pad, tau_shared,
+                                                                   tau_init);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

@@ -647,8 +647,8 @@ struct K3Collect {
 };
 
 struct K3Sample {
-  float* groupmax;   // [groups][q_pad]
-  int stride, tiles;
+  float* groupmax;   // [groups * splits][q_pad]
+  int stride, tiles, splits;
 };
 
 static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_t* q16, const uint32_t* mask_dev,
@@ -688,6 +688,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
     L.groupmax_out = sample->groupmax;
     L.group_stride = sample->stride;
     L.group_tiles = sample->tiles;
+    L.group_splits = sample->splits;
   }
   L.dump = dump;
   L.dump_ld = dump_ld;
@@ -899,30 +900,31 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev0, st));
   // Threshold pre-pass: row maxima over K3_SAMPLE_GROUPS strided samples of the gallery give every query a
   // starting threshold, so the candidate heaps of the main pass skip their cold start (see tau_init_kernel).
-  // It pays only when it can spread over the chip: it runs K3_SAMPLE_GROUPS units per query tile, so a small batch
-  // would stream the sample on a handful of SMs (measured at Q <= 256 on 12.5M x 768: 0.48 ms next to a 2.9 ms main
-  // pass that is HBM-bound anyway).  Small candidate lists (k <= 10) need it least, so they skip it until the
-  // pre-pass fills the chip; larger lists, whose cold start costs ~10 %, skip it only for one or two query tiles.
+  // Each group's comb is split over enough units to fill the chip, so a small batch does not stream the sample on
+  // eight SMs (Q <= 128 on 12.5M x 768: 0.48 ms before the split, next to a 2.9 ms main pass).  Batches of at most
+  // 8 queries skip it: their epilogue has almost nothing to insert (measured: Q = 1 is 0.47 ms faster without,
+  // Q = 16 already 0.17 ms slower).  presample = 2 forces it.
   const float* tau_init = nullptr;
   const int sample_tiles = std::max(1, P.tiles_total / (K3_SAMPLE_RATIO * P.kc));
-  const int sample_units = P.num_qt * K3_SAMPLE_GROUPS * (g->k3_variant == 2 ? 2 : 1);
-  const bool sample_pays = g->presample >= 2 || (P.kc <= 32 ? sample_units >= g->num_sms : P.num_qt > 2);
+  const bool sample_pays = g->presample >= 2 || Q > 8;
   if (g->tau_share && g->presample && sample_pays && P.tiles_total >= 10 * P.kc &&
       P.tiles_total / sample_tiles >= K3_SAMPLE_GROUPS) {
     SearchPlan PA = P;
-    PA.slices = K3_SAMPLE_GROUPS;
     const int workers = g->k3_variant == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
+    const int splits = std::max(1, std::min({16, sample_tiles, workers / (K3_SAMPLE_GROUPS * std::max(1, PA.num_qt))}));
+    PA.slices = K3_SAMPLE_GROUPS * splits;
     PA.grid = (int)std::min<int64_t>((int64_t)PA.slices * PA.num_qt, workers) * (g->k3_variant == 2 ? 2 : 1);
-    RBOD_TRY(g->groupmax.ensure((size_t)K3_SAMPLE_GROUPS * P.q_pad * 4));
+    RBOD_TRY(g->groupmax.ensure((size_t)PA.slices * P.q_pad * 4));
     RBOD_TRY(g->tau_init.ensure((size_t)P.q_pad * 4));
     K3Sample S;
     S.groupmax = g->groupmax.as<float>();
     S.tiles = sample_tiles;
     S.stride = P.tiles_total / sample_tiles;
+    S.splits = splits;
     RBOD_TRY(run_k3(g, PA, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st,
                     &S));
-    RBOD_TRY(launch_tau_init(g->groupmax.as<float>(), K3_SAMPLE_GROUPS, P.q_pad, g->tau_shared.as<uint32_t>(),
-                             g->tau_init.as<float>(), st));
+    RBOD_TRY(launch_tau_init(g->groupmax.as<float>(), K3_SAMPLE_GROUPS, splits, P.q_pad,
+                             g->tau_shared.as<uint32_t>(), g->tau_init.as<float>(), st));
     tau_init = g->tau_init.as<float>();
     launches += 2;
   }

@@ -83,7 +83,7 @@ struct K3Launch {
   int* coll_cnt;
   int coll_cap;
   float* groupmax_out;        // sample mode: [slices][q_pad] row maxima (threshold pre-pass)
-  int group_stride, group_tiles;
+  int group_stride, group_tiles, group_splits;
   float* dump;            // optional raw scores [q_pad][dump_ld]
   int64_t dump_ld;
   int* sync_counters;     // zeroed [slices * sync_span * sync_windows] ints, or nullptr
@@ -126,8 +126,8 @@ int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int d
 int launch_merge_partials(const float* part_score, const uint32_t* part_idx, int slices, int64_t q_pad,
                           int64_t Q, int kc, const float* tau_init, uint32_t* cand_idx, float* cand_tau,
                           cudaStream_t st);
-int launch_tau_init(const float* groupmax, int groups, int64_t q_pad, uint32_t* tau_shared, float* tau_init,
-                    cudaStream_t st);
+int launch_tau_init(const float* groupmax, int groups, int splits, int64_t q_pad, uint32_t* tau_shared,
+                    float* tau_init, cudaStream_t st);
 int launch_rescore(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16, int kind16,
                    int dim, int64_t ld32, int64_t ld16, int metric, const uint32_t* cand_idx, int64_t Q, int kc,
                    double* cand_score, cudaStream_t st);
