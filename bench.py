@@ -324,6 +324,40 @@ def run_b200(a):
 
     for _ in range(max(a.warmup, 3)):
         step_device()
+
+    # ---- parity check outside the timed region: the first queries of the batch against a float64 brute force over
+    # the rows as stored (torch on the device, row chunks; checker only).  This is the north star's "exact top-k
+    # parity" and stands in for recall against the reference's Qdrant path, which is not installable offline.
+    def parity_check(n_check=64):
+        nq = min(n_check, a.queries)
+        result, _ = step_device()
+        got_ids, got_s = result[1][:nq].clone(), result[2][:nq].clone()
+        qd = q_dev[:nq].double()
+        qd = qd / qd.norm(dim=1, keepdim=True)
+        best_s = torch.full((nq, 0), 0.0, dtype=torch.float64, device=dev)
+        best_i = torch.zeros((nq, 0), dtype=torch.int64, device=dev)
+        step = 250_000
+        for s0 in range(0, n_local, step):
+            idx = torch.arange(s0, min(s0 + step, n_local), device=dev)
+            rows = g.get_rows(idx).double()
+            sc = (qd @ rows.T) / rows.norm(dim=1)[None, :]
+            cs, ci = torch.cat([best_s, sc], 1), torch.cat([best_i, (idx + r0)[None, :].expand(nq, -1)], 1)
+            top = torch.topk(cs, min(a.k, cs.shape[1]), dim=1)
+            best_s, best_i = top.values, torch.gather(ci, 1, top.indices)
+            del rows, sc, cs, ci
+        if world > 1:                                    # merge the per-shard exact lists the same way
+            gs, gi = all_gather_stack(best_s, None), all_gather_stack(best_i, None)
+            cs, ci = gs.permute(1, 0, 2).reshape(nq, -1), gi.permute(1, 0, 2).reshape(nq, -1)
+            top = torch.topk(cs, a.k, dim=1)
+            best_s, best_i = top.values, torch.gather(ci, 1, top.indices)
+        same = (best_i == got_ids)
+        recall = sum(len(set(best_i[i].tolist()) & set(got_ids[i].tolist())) for i in range(nq)) / float(nq * a.k)
+        return {"queries_checked": nq, "ids_identical": bool(same.all().item()), "recall_at_k": recall,
+                "max_rel_score_err": float(((best_s - got_s).abs() / best_s.abs().clamp_min(1e-30)).max().item()),
+                "against": "float64 brute force over the stored rows (torch, on device); the reference's Qdrant "
+                           "path is not installable offline"}
+
+    parity = parity_check()
     last_stats = None
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -396,6 +430,7 @@ def run_b200(a):
                 "d2h_bytes_per_step": a.queries * a.k * (4 + 8 + 8), "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": n_launch_timed,
         "roofline": roofline,
+        "parity": parity,
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
