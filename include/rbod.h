@@ -120,7 +120,8 @@ int rbod_info(const rbod_gallery* g, rbod_gallery_info* out);
 /* Shrinks the number of used row slots (rows beyond `rows` are forgotten). */
 int rbod_truncate(rbod_gallery* g, int64_t rows);
 /* Tunables: "k3_variant" (0 = query tile resident in TMEM, 1 = query tile streamed through smem,
- * 2 = TMEM-resident + CTA pairs / cta_group::2), "slack" (extra candidates kept per query),
+ * 2 = TMEM-resident + CTA pairs / cta_group::2), "k3_kbs" (64-element k-blocks per pipeline stage of variant 0:
+ * 0 = chosen by batch size, 2, 4), "slack" (extra candidates kept per query),
  * "time_k3" (1 = fill stats.k3_ms), "tau_share" (slices of a query share their threshold),
  * "collect_pass" (tensor-core second pass for uncertified queries), "presample" (sampled
  * starting thresholds: 0 = never, 1 = for batches of more than 8 queries, 2 = always), "l2_sync" / "sync_window" /

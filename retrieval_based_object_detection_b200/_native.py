@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librbod.so")
+LIB_PATH = os.environ.get("RBOD_LIBRARY") or os.path.join(_HERE, "librbod.so")   # override: another build of the same ABI
 
 RBOD_OK = 0
 RBOD_E_IO = -5

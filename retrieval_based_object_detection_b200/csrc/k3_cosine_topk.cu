@@ -147,12 +147,15 @@ __device__ __forceinline__ K3TileRange k3_unit_tiles(const K3Params& P, int slic
 //   PAIR = 1: a 2-CTA cluster (tcgen05 cta_group::2) owns 256 queries; each CTA holds its own 128 query
 //             rows in TMEM and streams only HALF of every gallery tile (64 rows); the leader CTA issues
 //             M=256 MMAs that read both halves.  L2 -> SM operand traffic per flop is halved.
-template <int VARIANT, int PAIR>
+//   KBS     : k-blocks (64 elements of K) per pipeline stage.  Coarser stages mean fewer barrier round trips per
+//             tile -- measured on the headline shape, same box: 1 -> 1019 TF/s, 2 -> 1209-1218, 4 -> 1264 -- but a
+//             later first MMA and half as many stages in flight, which costs small, HBM-bound batches 5-10 %.
+template <int VARIANT, int PAIR, int KBS_>
 struct K3Geom {
   static constexpr int BOX_N = PAIR ? K3_TILE_N / 2 : K3_TILE_N;   // gallery rows this CTA loads per tile
   static constexpr int B_KB_BYTES = BOX_N * 128;
   static constexpr int A_KB_BYTES = VARIANT == 1 ? A_TILE_KB_BYTES : 0;   // streamed A (variant 1 only)
-  static constexpr int KBS = PAIR ? 4 : 2;                         // k-blocks per pipeline stage
+  static constexpr int KBS = KBS_;                                 // k-blocks per pipeline stage
   static constexpr int STAGE_BYTES = KBS * (B_KB_BYTES + A_KB_BYTES);
   static constexpr int Q_PER_UNIT = PAIR ? 2 * K3_TILE_M : K3_TILE_M;
   static constexpr uint32_t EPI_ARRIVALS = PAIR ? 8 : 4;   // one arrival per epilogue warp
@@ -161,10 +164,10 @@ struct K3Geom {
 // Issues the MMAs of one full pipeline stage as straight-line code: per MMA one uniform add for the
 // A address / descriptor and one for the B descriptor.  A_SMEM: the A operand of this stage comes from
 // shared memory (streamed tile in variant 1, resident tail of the query tile otherwise).
-template <int VARIANT, int PAIR, int A_SMEM>
+template <int VARIANT, int PAIR, int KBS, int A_SMEM>
 __device__ __forceinline__ void issue_full_stage(uint32_t d_tmem, uint32_t a_tmem0, uint64_t adesc, uint64_t bdesc,
                                                  uint32_t idesc, uint32_t first_accumulate) {
-  using G = K3Geom<VARIANT, PAIR>;
+  using G = K3Geom<VARIANT, PAIR, KBS>;
 #pragma unroll
   for (int j = 0; j < G::KBS; ++j) {
 #pragma unroll
@@ -184,9 +187,9 @@ __device__ __forceinline__ void issue_full_stage(uint32_t d_tmem, uint32_t a_tme
   }
 }
 
-template <int VARIANT, int PAIR>
+template <int VARIANT, int PAIR, int KBS>
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __grid_constant__ K3Params P) {
-  using G = K3Geom<VARIANT, PAIR>;
+  using G = K3Geom<VARIANT, PAIR, KBS>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled operand tiles
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -352,8 +355,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
               const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3fffu);
               const uint32_t a_tmem0 = tmem_b + (uint32_t)kb0 * 32u;   // 4 K=16 steps x 8 columns per k-block
               if (nkb == G::KBS) {
-                if (a_smem) issue_full_stage<VARIANT, PAIR, 1>(d_tmem, a_tmem0, adesc, bdesc, P.idesc, first);
-                else issue_full_stage<VARIANT, PAIR, 0>(d_tmem, a_tmem0, adesc, bdesc, P.idesc, first);
+                if (a_smem) issue_full_stage<VARIANT, PAIR, KBS, 1>(d_tmem, a_tmem0, adesc, bdesc, P.idesc, first);
+                else issue_full_stage<VARIANT, PAIR, KBS, 0>(d_tmem, a_tmem0, adesc, bdesc, P.idesc, first);
               } else {
                 for (int j = 0; j < nkb; ++j) {
                   const bool js = VARIANT == 1 || (kb0 + j) >= P.a_tmem_kb;
@@ -668,13 +671,14 @@ int make_tmap_2d_sw128(CUtensorMap* out, const void* base, int64_t rows, int dp,
   return RBOD_OK;
 }
 
-static size_t k3_stage_bytes(int variant) {
-  return variant == 1 ? (size_t)K3Geom<1, 0>::STAGE_BYTES
-                      : (variant == 2 ? (size_t)K3Geom<0, 1>::STAGE_BYTES : (size_t)K3Geom<0, 0>::STAGE_BYTES);
+static size_t k3_stage_bytes(int variant, int kbs) {
+  if (variant == 1) return (size_t)K3Geom<1, 0, 2>::STAGE_BYTES;
+  if (variant == 2) return (size_t)K3Geom<0, 1, 4>::STAGE_BYTES;
+  return kbs == 4 ? (size_t)K3Geom<0, 0, 4>::STAGE_BYTES : (size_t)K3Geom<0, 0, 2>::STAGE_BYTES;
 }
 
-size_t k3_smem_bytes(int variant, int kc, int num_stages, int tail_kb) {
-  return 1024 + (size_t)num_stages * k3_stage_bytes(variant) + (size_t)tail_kb * A_TILE_KB_BYTES +
+size_t k3_smem_bytes(int variant, int kbs, int kc, int num_stages, int tail_kb) {
+  return 1024 + (size_t)num_stages * k3_stage_bytes(variant, kbs) + (size_t)tail_kb * A_TILE_KB_BYTES +
          (size_t)K3_TILE_M * kc * 8 + sizeof(K3Barriers);
 }
 
@@ -682,38 +686,60 @@ size_t k3_smem_bytes(int variant, int kc, int num_stages, int tail_kb) {
 //   dp <= 512            : whole tile in TMEM (<= 256 columns), two accumulator buffers.
 //   dp  > 512, room left : first 8 k-blocks in TMEM, the tail resident in shared memory, two buffers.
 //   dp  > 512, smem short: whole tile in TMEM (384 columns), one accumulator buffer.
-int k3_plan(int variant, int kc, int dp, int smem_optin, int allow_hybrid, int* num_stages, int* a_tmem_kb,
-            size_t* smem_bytes) {
+// `want_kbs` = 4 asks for the coarse 4-k-block stages of the single-CTA kernel; they are used when two of them fit
+// next to the candidate heaps (k <= 40), otherwise the 2-k-block stages are.
+int k3_plan(int variant, int want_kbs, int kc, int dp, int smem_optin, int allow_hybrid, int* num_stages,
+            int* a_tmem_kb, int* kbs_out, size_t* smem_bytes) {
   const int num_kb = dp / K3_KBLOCK;
-  auto fit = [&](int tail_kb) {
-    int st = MAX_STAGES;
-    while (st > 0 && k3_smem_bytes(variant, kc, st, tail_kb) > (size_t)smem_optin) --st;
-    return st;
+  auto attempt = [&](int kbs, int min_stages_hybrid, int* st_out, int* tmem_out, int* tail_out) -> bool {
+    auto fit = [&](int tail_kb) {
+      int st = MAX_STAGES;
+      while (st > 0 && k3_smem_bytes(variant, kbs, kc, st, tail_kb) > (size_t)smem_optin) --st;
+      return st;
+    };
+    int tmem_kb = num_kb, tail = 0;
+    if (variant == 1) {
+      tmem_kb = 0;
+    } else if (num_kb > 8 && allow_hybrid) {
+      if (fit(num_kb - 8) >= min_stages_hybrid) { tmem_kb = 8; tail = num_kb - 8; }
+    }
+    const int st = fit(tail);
+    *st_out = st;
+    *tmem_out = tmem_kb;
+    *tail_out = tail;
+    return !(st < 1 || (variant != 1 && st < 2));
   };
-  int tmem_kb = num_kb, tail = 0;
-  if (variant == 1) {
-    tmem_kb = 0;
-  } else if (num_kb > 8 && allow_hybrid) {
-    if (fit(num_kb - 8) >= 3) { tmem_kb = 8; tail = num_kb - 8; }
+  int st = 0, tmem_kb = 0, tail = 0, kbs = variant == 2 ? 4 : 2;
+  bool ok = false;
+  if (variant == 0 && want_kbs == 4) {
+    ok = attempt(4, 2, &st, &tmem_kb, &tail);
+    // two accumulator buffers matter more than coarse stages: never trade the hybrid layout for them
+    if (ok && num_kb > 8 && allow_hybrid && tail == 0) ok = false;
+    if (ok) kbs = 4;
   }
-  const int st = fit(tail);
-  if (st < 1 || (variant != 1 && st < 2))
+  if (!ok) {
+    kbs = variant == 2 ? 4 : 2;
+    ok = attempt(kbs, variant == 2 ? 2 : 3, &st, &tmem_kb, &tail);
+  }
+  if (!ok)
     return set_error(RBOD_E_UNSUPPORTED, "search: variant %d with %d candidates per query does not fit shared memory",
                      variant, kc);
   *num_stages = st;
   *a_tmem_kb = tmem_kb;
-  *smem_bytes = k3_smem_bytes(variant, kc, st, tail);
+  *kbs_out = kbs;
+  *smem_bytes = k3_smem_bytes(variant, kbs, kc, st, tail);
   return RBOD_OK;
 }
 
-int k3_box_rows(int variant) { return variant == 2 ? K3Geom<0, 1>::BOX_N : K3_TILE_N; }
+int k3_box_rows(int variant) { return variant == 2 ? K3Geom<0, 1, 4>::BOX_N : K3_TILE_N; }
 
 int k3_configure(int device) {
   int optin = 0;
   RBOD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   return optin;
 }
 
@@ -785,9 +811,10 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (L.variant == 2) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1>, P));
-  else if (L.variant == 0) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0>, P));
-  else RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<1, 0>, P));
+  if (L.variant == 2) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 4>, P));
+  else if (L.variant == 0 && L.kbs == 4) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 4>, P));
+  else if (L.variant == 0) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 2>, P));
+  else RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<1, 0, 2>, P));
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

@@ -73,6 +73,7 @@ struct K3Launch {
   int num_stages;
   int a_tmem_kb;          // k-blocks of the query tile kept in TMEM (rest resident in smem)
   int variant;            // 0 = A in TMEM, 1 = A streamed through smem, 2 = A in TMEM + CTA pairs (cta_group::2)
+  int kbs;                // k-blocks per pipeline stage of the variant-0 kernel (2 or 4)
   int a_fmt, b_fmt;       // 0 = f16, 1 = bf16
   float* part_score;      // [slices][q_pad][kc]
   uint32_t* part_idx;     // [slices][q_pad][kc]
@@ -115,8 +116,8 @@ int launch_segment_delegates(const float* master32, const uint16_t* rows16, int 
                              int64_t* out_member, int* err_flag, cudaStream_t st);
 // K3
 int k3_configure(int device);
-int k3_plan(int variant, int kc, int dp, int smem_optin, int allow_hybrid, int* num_stages, int* a_tmem_kb,
-            size_t* smem_bytes);
+int k3_plan(int variant, int want_kbs, int kc, int dp, int smem_optin, int allow_hybrid, int* num_stages,
+            int* a_tmem_kb, int* kbs_out, size_t* smem_bytes);
 int k3_box_rows(int variant);   // gallery rows per TMA box (64 for the CTA-pair kernel)
 int launch_k3(const K3Launch& L, cudaStream_t st);
 // query preparation: normalise, round to 16 bit, per-query error radius and |q|^2
@@ -176,6 +177,7 @@ struct rbod_gallery {
   int num_sms = 148;
   // options
   int k3_variant = 0;
+  int k3_kbs = 0;         // k-blocks per stage of the single-CTA kernel: 0 = by batch size, 2, 4
   int slack = -1;  // -1 = automatic
   int time_k3 = 0;
   int debug_epi = 0;
