@@ -201,8 +201,10 @@ def run_b200(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line of the contract
+        # keep stdout to the one JSON line of the contract: NCCL prints its version banner there at the VERSION level,
+        # which an nccl.conf on the box can select even when the variable is unset
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- build the resident gallery: synthetic unit-norm rows, generated on device, stored by K1

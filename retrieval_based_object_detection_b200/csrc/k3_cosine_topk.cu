@@ -734,12 +734,16 @@ int k3_plan(int variant, int want_kbs, int kc, int dp, int smem_optin, int allow
 int k3_box_rows(int variant) { return variant == 2 ? K3Geom<0, 1, 4>::BOX_N : K3_TILE_N; }
 
 int k3_configure(int device) {
+  // once per device and process: the four attribute calls cost ~40 us, which a sharded search pays on every call
+  static int cached_optin[64] = {0};
+  if (device >= 0 && device < 64 && cached_optin[device] > 0) return cached_optin[device];
   int optin = 0;
   RBOD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  if (device >= 0 && device < 64) cached_optin[device] = optin;
   return optin;
 }
 
