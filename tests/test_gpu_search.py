@@ -444,3 +444,33 @@ def test_distance_collection_device_io_and_empty(G):
     top = torch.topk(d, 4, dim=1, largest=False)
     assert torch.equal(top.indices, r.rows) and torch.allclose(top.values, r.scores.double(), rtol=1e-6)
     g.close()
+
+
+@pytest.mark.parametrize("dtype,dim", [("bf16", 768), ("f16", 512), ("bf16", 320)])
+def test_stage_width_and_split_prepass_do_not_change_the_answer(G, dtype, dim):
+    """The planner's choices are invisible in the result: 2 or 4 k-blocks per pipeline stage (k3_kbs), the threshold
+    pre-pass with its combs split over many CTAs (a gallery of >= 1024 tiles gives every sample group >= 2 tiles),
+    forced on, off, or left to the batch-size rule -- always the ids of the float64 brute force."""
+    n, Q, k = 140_000, 130, 10
+    x = O.synthetic_unit_rows(n, dim, seed=31)
+    g = G(dim, dtype=dtype, capacity=n)
+    g.upsert(x)
+    stored = g.get_rows(np.arange(n))
+    q = O.synthetic_unit_rows(Q, dim, seed=32)
+    q[:20] = x[1000:1020] + 0.05 * O.synthetic_unit_rows(20, dim, seed=33)
+    ws, wi = O.cosine_topk(q, stored, k)
+    seen = set()
+    for kbs in (2, 4, 0):
+        for presample in (2, 0, 1):
+            g.set_option("k3_kbs", kbs)
+            g.set_option("presample", presample)
+            res = g.search(q, k, want_scores64=True)
+            assert np.array_equal(res.rows, wi), (kbs, presample, int((res.rows != wi).any(axis=1).sum()))
+            assert np.allclose(res.scores64, ws, rtol=1e-5, atol=1e-9)
+            seen.add(res.stats["total_launches"])
+    assert len(seen) >= 2                                   # with and without the two pre-pass launches
+    res8 = g.search(q[:8], k)                               # <= 8 queries: the rule skips the pre-pass
+    res9 = g.search(q[:9], k)
+    assert res9.stats["total_launches"] == res8.stats["total_launches"] + 2
+    assert np.array_equal(res8.rows, wi[:8]) and np.array_equal(res9.rows, wi[:9])
+    g.close()
