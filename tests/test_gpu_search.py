@@ -474,3 +474,47 @@ def test_stage_width_and_split_prepass_do_not_change_the_answer(G, dtype, dim):
     assert res9.stats["total_launches"] == res8.stats["total_launches"] + 2
     assert np.array_equal(res8.rows, wi[:8]) and np.array_equal(res9.rows, wi[:9])
     g.close()
+
+
+def _torch_topk_fp64_from_gallery(g, n, q, k, chunk=500_000):
+    """Like _torch_topk_fp64, but pulls the stored rows out of the gallery chunk by chunk (a 10M x 768 gallery
+    widened to float32 would not be worth holding twice)."""
+    import torch
+
+    qq = q.double()
+    qq = qq / qq.norm(dim=1, keepdim=True)
+    best_s = torch.zeros((q.shape[0], 0), dtype=torch.float64, device=q.device)
+    best_i = torch.zeros((q.shape[0], 0), dtype=torch.int64, device=q.device)
+    for a in range(0, n, chunk):
+        rows = g.get_rows(torch.arange(a, min(a + chunk, n), device=q.device)).double()
+        sc = (qq @ rows.T) / rows.norm(dim=1)[None, :]
+        top = torch.topk(sc, min(k, sc.shape[1]), dim=1)
+        s_all, i_all = torch.cat([best_s, top.values], 1), torch.cat([best_i, top.indices + a], 1)
+        o = torch.topk(s_all, min(k, s_all.shape[1]), dim=1).indices
+        best_s, best_i = torch.gather(s_all, 1, o), torch.gather(i_all, 1, o)
+        del rows, sc
+    return best_s, best_i
+
+
+@pytest.mark.parametrize("dtype,n,Q,k", [("bf16", 10_000_000, 1024, 100),      # BASELINE config C4, one GPU's view
+                                         ("f16", 12_500_000, 48, 10)])         # config C5: one GPU's 12.5M-row shard
+def test_configs_c4_c5_full_size_exact(G, dtype, n, Q, k):
+    """The 768-wide BASELINE configs at their full per-GPU size: every query against a torch float64 brute force
+    over the stored rows (ids identical, scores within 1e-5 relative), plus the single-query latency path."""
+    import torch
+
+    dim = 768
+    g = G(dim, dtype=dtype, capacity=n)
+    gen = torch.Generator("cuda").manual_seed(17)
+    for a in range(0, n, 500_000):
+        g.upsert(torch.randn(min(500_000, n - a), dim, device="cuda", generator=gen))
+    assert len(g) == n
+    q = torch.randn(Q, dim, device="cuda", generator=gen)
+    r = g.search(q, k, want_scores64=True)
+    ws, wi = _torch_topk_fp64_from_gallery(g, n, q, k)
+    assert torch.equal(r.rows, wi), int((r.rows != wi).any(dim=1).sum())
+    assert torch.allclose(r.scores64, ws, rtol=1e-5, atol=1e-9)
+    assert r.stats["sweep_queries"] == 0
+    r1 = g.search(q[:1], k, want_scores64=True)               # Q = 1: the HBM-bound end of the C5 sweep
+    assert torch.equal(r1.rows, wi[:1])
+    g.close()
