@@ -13,9 +13,9 @@
 //   2. sweep: one pass over the gallery records every row whose key >= threshold (expected k * stride
 //      rows); a list that overflows `cap` tightens its threshold to the k-th best key it did record --
 //      still a lower bound of the true k-th key -- and only those queries are swept again;
-//   3. select: rank by counting, emit (distance, row) ascending by distance.
-// A warp scores two gallery rows at a time against a batch of 32 queries whose fp64 copies sit in L1/L2 (64
-// independent DFMA chains per lane), so the gallery is read once per batch of 32 queries.
+//   3. select: sort each list in shared memory, emit (distance, row) ascending by distance.
+// Every lane owns one gallery row and scores it against a batch of up to 32 queries staged in shared memory (32
+// independent DFMA chains per lane, no cross-lane reduction), so the gallery is read once per batch of 32 queries.
 #include "rbod_common.cuh"
 #include "rbod_internal.h"
 
@@ -24,10 +24,6 @@
 namespace rbod {
 
 namespace {
-
-__device__ __forceinline__ bool key_beats(double sa, uint32_t ia, double sb, uint32_t ib) {
-  return sa > sb || (sa == sb && ia < ib);
-}
 
 // fp32 queries of one batch -> fp64 (done once, so the sweep's inner loop has no conversions)
 __global__ void __launch_bounds__(256)
@@ -40,166 +36,210 @@ dist_widen_queries_kernel(const float* __restrict__ q, const int* __restrict__ q
   }
 }
 
-// Lane l ends up with the sum over all lanes of acc[l] (a 32 x 32 transpose-reduce: 31 shuffle-adds instead of
-// 32 five-step butterflies).
-__device__ __forceinline__ double warp_transpose_sum(double (&acc)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const double send = up ? acc[i] : acc[i + o];
-      const double keep = up ? acc[i + o] : acc[i];
-      acc[i] = keep + __shfl_xor_sync(FULL_MASK, send, o);
-    }
-  }
-  return acc[0];
-}
-
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-// Rows r = row0, row0 + stride, ... < n_rows.  A warp takes R rows at a time: it copies them into its own
-// shared-memory buffer with cp.async (all of a row group's loads in flight at once, the next group's copy
-// overlapping this group's arithmetic), then lane l walks columns l, l + 32, ... keeping one fp64 accumulator
-// per (row, query) -- 32 queries x R rows of independent DFMA chains, each query element loaded once per R
-// rows -- and the transpose-reduce leaves query f's key in lane f, which owns that query's threshold and
-// appends to its list.  q64 is [32, dim], zero rows beyond the batch.  `words` = 4-byte words per stored row.
-template <int METRIC, int R>
+constexpr int K5_CH = 64;        // columns per staged chunk
+constexpr int K5_ROWS = 256;     // gallery rows per CTA step: 8 warps x 32 lanes, one row per lane
+
+// Rows r = row0, row0 + stride, ... < n_rows.  A CTA takes 256 of them at a time and every LANE owns one row, so a
+// row's distance to a query is a private fp64 accumulator: no reduction across lanes, NQ independent DFMA chains
+// per lane.  The work is staged through shared memory in chunks of 64 columns, double-buffered with cp.async: each
+// warp copies its 32 rows' chunk (coalesced, a row at a time, pitch odd so lane-strided reads are conflict-free),
+// the CTA copies the chunk of the NQ fp64 queries once for all 8 warps, and the inner loop is one broadcast
+// LDS.128 (two query elements) per four fp64 operations.  q64 is [32, dim], zero rows beyond the batch; `wpr` =
+// 4-byte words per chunk row (64 for fp32 rows, 32 for 16-bit rows), `pitch` = wpr + 1.
+template <int METRIC, int NQ>
 __global__ void __launch_bounds__(256, 1)
 dist_collect_kernel(const double* __restrict__ q64, const float* __restrict__ master32,
-                    const uint16_t* __restrict__ rows16, int kind16, int dim, int64_t ld32, int64_t ld16, int words,
+                    const uint16_t* __restrict__ rows16, int kind16, int dim, int64_t ld32, int64_t ld16,
                     int64_t n_rows, int64_t row0, int64_t stride, const uint32_t* __restrict__ row_mask,
                     const double* __restrict__ thr, const int* __restrict__ active, int nf, int cap,
                     double* __restrict__ coll_key, uint32_t* __restrict__ coll_idx, int* __restrict__ coll_cnt) {
-  extern __shared__ uint32_t k5_smem[];
+  extern __shared__ __align__(16) uint8_t k5_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t w0 = (int64_t)blockIdx.x * 8 + warp;
-  const int64_t nw = (int64_t)gridDim.x * 8;
-  const bool mine = lane < nf && active[lane] != 0;
-  const double my_thr = mine ? thr[lane] : INFINITY;
-  const int64_t n_visit = n_rows > row0 ? (n_rows - row0 + stride - 1) / stride : 0;   // rows of this pass
-  uint32_t* wbuf = k5_smem + (size_t)warp * 2 * R * words;
+  const bool f32rows = master32 != nullptr;
+  const int wpr = f32rows ? K5_CH : K5_CH / 2, pitch = wpr + 1;
+  double* qs = reinterpret_cast<double*>(k5_smem);                                   // [2][NQ][K5_CH]
+  uint32_t* xs = reinterpret_cast<uint32_t*>(k5_smem + (size_t)2 * NQ * K5_CH * 8);  // [2][8][32][pitch]
+  __shared__ double thr_s[32];
+  if (threadIdx.x < 32) thr_s[threadIdx.x] = (threadIdx.x < nf && active[threadIdx.x]) ? thr[threadIdx.x] : INFINITY;
+  __syncthreads();
 
-  auto row_ok = [&](int64_t v) -> bool {
-    if (v >= n_visit) return false;
+  const int64_t n_visit = n_rows > row0 ? (n_rows - row0 + stride - 1) / stride : 0;   // rows of this pass
+  const int n_chunks = (dim + K5_CH - 1) / K5_CH;
+  const int64_t n_groups = (n_visit + K5_ROWS - 1) / K5_ROWS;
+  const int64_t my_groups = n_groups > blockIdx.x ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_steps = my_groups * n_chunks;     // (group, chunk) pairs this CTA walks, in order
+
+  auto row_of = [&](int64_t g, int l) -> int64_t {  // gallery row of lane l of this warp in group g, or -1
+    const int64_t v = (blockIdx.x + g * gridDim.x) * K5_ROWS + warp * 32 + l;
+    if (v >= n_visit) return -1;
     const int64_t r = row0 + v * stride;
-    return row_mask == nullptr || ((row_mask[r >> 5] >> (r & 31)) & 1u);
+    if (row_mask != nullptr && !((row_mask[r >> 5] >> (r & 31)) & 1u)) return -1;
+    return r;
   };
-  auto issue = [&](int64_t v0, int b) {
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      if (!row_ok(v0 + j)) continue;
-      const int64_t r = row0 + (v0 + j) * stride;
-      const uint32_t* src = master32 ? reinterpret_cast<const uint32_t*>(master32 + r * ld32)
-                                     : reinterpret_cast<const uint32_t*>(rows16 + r * ld16);
-      uint32_t* dst = wbuf + (size_t)(b * R + j) * words;
-      for (int w = lane; w < words; w += 32) cp_async_4(dst + w, src + w);
+  auto issue = [&](int64_t step, int b) {
+    const int64_t g = step / n_chunks;
+    const int c0 = (int)(step - g * n_chunks) * K5_CH;
+    const int cw = min(K5_CH, dim - c0);
+    // this warp's 32 rows, one row per iteration, lanes across the chunk's words
+    uint32_t* xb = xs + ((size_t)b * 8 + warp) * 32 * pitch;
+    for (int j = 0; j < 32; ++j) {
+      const int64_t r = row_of(g, j);
+      if (r < 0) continue;
+      if (f32rows) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(master32 + r * ld32 + c0);
+        for (int w = lane; w < cw; w += 32) cp_async_4(xb + j * pitch + w, src + w);
+      } else {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(rows16 + r * ld16 + c0);   // padded to 64 elements
+        cp_async_4(xb + j * pitch + lane, src + lane);
+      }
+    }
+    // the CTA's query chunk
+    double* qb = qs + (size_t)b * NQ * K5_CH;
+    for (int i = threadIdx.x; i < NQ * K5_CH; i += 256) {
+      const int f = i / K5_CH, c = i - f * K5_CH;
+      if (c < cw) cp_async_8(qb + i, q64 + (int64_t)f * dim + c0 + c);
     }
     cp_async_commit();
   };
 
-  int b = 0;
-  int64_t v0 = w0 * R;
-  if (v0 < n_visit) issue(v0, 0);
-  for (; v0 < n_visit; v0 += nw * R, b ^= 1) {
-    const int64_t vn = v0 + nw * R;
-    if (vn < n_visit) issue(vn, b ^ 1); else cp_async_commit();
+  double acc[NQ];
+  if (n_steps > 0) issue(0, 0);
+  for (int64_t step = 0; step < n_steps; ++step) {
+    const int b = (int)(step & 1);
+    const int64_t g = step / n_chunks;
+    const int ci = (int)(step - g * n_chunks);
+    if (step + 1 < n_steps) issue(step + 1, b ^ 1); else cp_async_commit();
     cp_async_wait_1();
-    __syncwarp();
-    bool ok[R];
+    __syncthreads();
+    if (ci == 0) {
 #pragma unroll
-    for (int j = 0; j < R; ++j) ok[j] = row_ok(v0 + j);
-    double acc[R][32];
+      for (int f = 0; f < NQ; ++f) acc[f] = 0.0;
+    }
+    const int cw = min(K5_CH, dim - ci * K5_CH);
+    const uint32_t* xr = xs + (((size_t)b * 8 + warp) * 32 + lane) * pitch;
+    const double* qb = qs + (size_t)b * NQ * K5_CH;
+    auto elem = [&](int c) -> double {
+      if (f32rows) return (double)__uint_as_float(xr[c]);
+      const uint32_t w = xr[c >> 1];
+      return (double)h16_to_f32((uint16_t)((c & 1) ? (w >> 16) : (w & 0xffffu)), kind16);
+    };
+    int c = 0;
+    for (; c + 1 < cw; c += 2) {
+      const double x0 = elem(c), x1 = elem(c + 1);
 #pragma unroll
-    for (int j = 0; j < R; ++j)
+      for (int f = 0; f < NQ; ++f) {
+        const double2 qq = *reinterpret_cast<const double2*>(qb + f * K5_CH + c);
+        const double d0 = qq.x - x0, d1 = qq.y - x1;
+        if (METRIC == RBOD_EUCLID) acc[f] = fma(d1, d1, fma(d0, d0, acc[f]));
+        else acc[f] += fabs(d0) + fabs(d1);
+      }
+    }
+    if (c < cw) {
+      const double x0 = elem(c);
 #pragma unroll
-      for (int f = 0; f < 32; ++f) acc[j][f] = 0.0;
-    const uint32_t* rows_s = wbuf + (size_t)b * R * words;
-    for (int c = lane; c < dim; c += 32) {
-      double x[R];
+      for (int f = 0; f < NQ; ++f) {
+        const double d0 = qb[f * K5_CH + c] - x0;
+        if (METRIC == RBOD_EUCLID) acc[f] = fma(d0, d0, acc[f]);
+        else acc[f] += fabs(d0);
+      }
+    }
+    if (ci == n_chunks - 1) {
+      const int64_t r = row_of(g, lane);
+      if (r >= 0) {
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        x[j] = 0.0;
-        if (ok[j]) {
-          if (master32) {
-            x[j] = (double)__uint_as_float(rows_s[(size_t)j * words + c]);
-          } else {
-            const uint32_t w = rows_s[(size_t)j * words + (c >> 1)];
-            x[j] = (double)h16_to_f32((uint16_t)((c & 1) ? (w >> 16) : (w & 0xffffu)), kind16);
+        for (int f = 0; f < NQ; ++f) {
+          const double key = -acc[f];
+          if (key >= thr_s[f]) {             // thr_s is +inf for slots beyond the batch and for finished queries
+            const int slot = atomicAdd(coll_cnt + f, 1);
+            if (slot < cap) {
+              coll_key[(size_t)f * cap + slot] = key;
+              coll_idx[(size_t)f * cap + slot] = (uint32_t)r;
+            }
           }
         }
       }
-#pragma unroll
-      for (int f = 0; f < 32; ++f) {
-        const double qf = q64[(int64_t)f * dim + c];
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const double d = qf - x[j];
-          if (METRIC == RBOD_EUCLID) acc[j][f] = fma(d, d, acc[j][f]);
-          else acc[j][f] += fabs(d);
-        }
-      }
     }
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const double key = -warp_transpose_sum(acc[j], lane);
-      if (ok[j] && mine && key >= my_thr) {
-        const int slot = atomicAdd(coll_cnt + lane, 1);
-        if (slot < cap) {
-          coll_key[(size_t)lane * cap + slot] = key;
-          coll_idx[(size_t)lane * cap + slot] = (uint32_t)(row0 + (v0 + j) * stride);
-        }
-      }
-    }
-    __syncwarp();   // every lane is done with buffer b before the next iteration's copy lands in it
+    __syncthreads();   // everyone is done with buffer b before the copy of step + 2 lands in it
   }
 }
 
-// One CTA per query of the batch.
+// Monotone map double -> uint64 (larger double <=> larger key).
+__device__ __forceinline__ unsigned long long f64_to_ordered(double d) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// One CTA per query of the batch: the recorded (key, row) pairs are sorted in shared memory (bitonic, key
+// descending then row ascending), then
 //   sample != 0         : thr[f] = k-th best recorded key (-inf if fewer than k were recorded); no output.
-//   list fits (<= cap)  : rank by counting, write the top k, active[f] = 0.
+//   list fits (<= cap)  : the first k entries are the answer, active[f] = 0.
 //   list overflowed     : thr[f] = k-th best key among the `cap` rows that were recorded, active[f] stays 1.
+// Shared memory: p2 * 12 bytes, p2 = capacity rounded up to a power of two.
 __global__ void __launch_bounds__(256)
 dist_select_kernel(const double* __restrict__ coll_key, const uint32_t* __restrict__ coll_idx,
-                   int* __restrict__ coll_cnt, const int* __restrict__ qsel, int cap, int k, int sample, int metric,
-                   double* __restrict__ thr, int* __restrict__ active, int* __restrict__ n_active,
+                   int* __restrict__ coll_cnt, const int* __restrict__ qsel, int cap, int p2_max, int k, int sample,
+                   int metric, double* __restrict__ thr, int* __restrict__ active, int* __restrict__ n_active,
                    float* __restrict__ out_scores, int64_t* __restrict__ out_rows, double* __restrict__ out_keys) {
+  extern __shared__ __align__(16) uint8_t k5_sel_smem[];
+  unsigned long long* sk = reinterpret_cast<unsigned long long*>(k5_sel_smem);       // [p2_max] ordered keys
+  uint32_t* si = reinterpret_cast<uint32_t*>(k5_sel_smem + (size_t)p2_max * 8);      // [p2_max] rows
   const int f = blockIdx.x;
   if (!active[f]) return;
   const int total = coll_cnt[f];
   const int cnt = total < cap ? total : cap;
   const bool overflow = total > cap;
-  const double* sc = coll_key + (size_t)f * cap;
-  const uint32_t* ix = coll_idx + (size_t)f * cap;
   const int64_t q = qsel[f];
   const bool emit = !sample && !overflow;
+  int p2 = 1;
+  while (p2 < cnt) p2 <<= 1;
+  for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+    const bool have = i < cnt;
+    sk[i] = have ? f64_to_ordered(coll_key[(size_t)f * cap + i]) : 0ull;   // 0 sorts below every real key
+    si[i] = have ? coll_idx[(size_t)f * cap + i] : 0xffffffffu;
+  }
+  __syncthreads();
+  for (int size = 2; size <= p2; size <<= 1) {
+    for (int strd = size >> 1; strd > 0; strd >>= 1) {
+      for (int i = threadIdx.x; i < (p2 >> 1); i += blockDim.x) {
+        const int lo = 2 * i - (i & (strd - 1));
+        const int hi = lo + strd;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long ka = sk[lo], kb = sk[hi];
+        const uint32_t ia = si[lo], ib = si[hi];
+        const bool a_first = ka > kb || (ka == kb && ia < ib);   // a belongs before b in the final order
+        if (desc ? !a_first : a_first) {
+          sk[lo] = kb; sk[hi] = ka;
+          si[lo] = ib; si[hi] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
   if (emit) {
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
-      out_scores[q * k + j] = INFINITY;       // "no result": infinitely far
-      out_rows[q * k + j] = -1;
-      if (out_keys) out_keys[q * k + j] = -INFINITY;
+      const bool have = j < cnt;
+      // recover the key from the row's recorded value order: re-read by position is not possible after the sort,
+      // so invert the ordered map
+      const unsigned long long o = have ? sk[j] : 0ull;
+      const unsigned long long bits = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+      const double key = have ? __longlong_as_double((long long)bits) : -INFINITY;
+      out_scores[q * k + j] = have ? (float)(metric == RBOD_EUCLID ? sqrt(-key) : -key) : INFINITY;
+      out_rows[q * k + j] = have ? (int64_t)si[j] : -1;
+      if (out_keys) out_keys[q * k + j] = key;
     }
-    __syncthreads();
-  }
-  for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
-    const double s = sc[j];
-    const uint32_t id = ix[j];
-    int rank = 0;
-    for (int i = 0; i < cnt; ++i)
-      if (key_beats(sc[i], ix[i], s, id)) ++rank;
-    if (emit) {
-      if (rank < k) {
-        out_scores[q * k + rank] = (float)(metric == RBOD_EUCLID ? sqrt(-s) : -s);
-        out_rows[q * k + rank] = (int64_t)id;
-        if (out_keys) out_keys[q * k + rank] = s;
-      }
-    } else if (rank == k - 1) {
-      thr[f] = s;
-    }
+  } else if (threadIdx.x == 0 && cnt >= k) {
+    const unsigned long long o = sk[k - 1];
+    const unsigned long long bits = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+    thr[f] = __longlong_as_double((long long)bits);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -225,28 +265,26 @@ int launch_dist_collect(int metric, const double* q64, const float* master32, co
                         double* coll_key, uint32_t* coll_idx, int* coll_cnt, int num_sms, cudaStream_t st) {
   if (nf <= 0 || n_rows <= 0) return RBOD_OK;
   if (nf > 32) return set_error(RBOD_E_INVAL, "dist_collect: at most 32 queries per pass");
-  constexpr int R = 2;
-  // a row is staged as 4-byte words (16-bit rows are stored padded to a multiple of 64 elements)
-  const int words = master32 ? dim : (int)(ld16 / 2);
-  const size_t smem = (size_t)8 * 2 * R * words * 4;
-  if (smem > 200 * 1024)
-    return set_error(RBOD_E_UNSUPPORTED, "EUCLID / MANHATTAN search: dim %d needs %zu bytes of staging per SM", dim, smem);
   const int64_t rows_visited = (n_rows - row0 + stride - 1) / stride;
-  const int64_t want = (rows_visited + 8 * R - 1) / (8 * R);
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms));
+  const int64_t groups = (rows_visited + K5_ROWS - 1) / K5_ROWS;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)num_sms));
+  const int pitch = (master32 ? K5_CH : K5_CH / 2) + 1;
+#define RBOD_K5_GO(METRIC, NQ)                                                                                 \
+  do {                                                                                                         \
+    const size_t smem = (size_t)2 * NQ * K5_CH * 8 + (size_t)2 * 8 * 32 * pitch * 4;                           \
+    RBOD_CUDA(cudaFuncSetAttribute(dist_collect_kernel<METRIC, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)smem));                                                                \
+    dist_collect_kernel<METRIC, NQ><<<grid, 256, smem, st>>>(q64, master32, rows16, kind16, dim, ld32, ld16,    \
+                                                             n_rows, row0, stride, row_mask, thr, active, nf,  \
+                                                             cap, coll_key, coll_idx, coll_cnt);               \
+  } while (0)
+  // 8 accumulators per lane for batches of up to 8 queries (single-query searches of the scripts), 32 otherwise
   if (metric == RBOD_EUCLID) {
-    RBOD_CUDA(cudaFuncSetAttribute(dist_collect_kernel<RBOD_EUCLID, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-    dist_collect_kernel<RBOD_EUCLID, R><<<grid, 256, smem, st>>>(q64, master32, rows16, kind16, dim, ld32, ld16,
-                                                                 words, n_rows, row0, stride, row_mask, thr, active,
-                                                                 nf, cap, coll_key, coll_idx, coll_cnt);
+    if (nf <= 8) RBOD_K5_GO(RBOD_EUCLID, 8); else RBOD_K5_GO(RBOD_EUCLID, 32);
   } else {
-    RBOD_CUDA(cudaFuncSetAttribute(dist_collect_kernel<RBOD_MANHATTAN, R>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dist_collect_kernel<RBOD_MANHATTAN, R><<<grid, 256, smem, st>>>(q64, master32, rows16, kind16, dim, ld32, ld16,
-                                                                    words, n_rows, row0, stride, row_mask, thr,
-                                                                    active, nf, cap, coll_key, coll_idx, coll_cnt);
+    if (nf <= 8) RBOD_K5_GO(RBOD_MANHATTAN, 8); else RBOD_K5_GO(RBOD_MANHATTAN, 32);
   }
+#undef RBOD_K5_GO
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }
@@ -255,8 +293,13 @@ int launch_dist_select(const double* coll_key, const uint32_t* coll_idx, int* co
                        int cap, int k, int sample, int metric, double* thr, int* active, int* n_active,
                        float* out_scores, int64_t* out_rows, double* out_keys, cudaStream_t st) {
   if (nf <= 0) return RBOD_OK;
-  dist_select_kernel<<<nf, 256, 0, st>>>(coll_key, coll_idx, coll_cnt, qsel, cap, k, sample, metric, thr, active,
-                                         n_active, out_scores, out_rows, out_keys);
+  int p2 = 1;
+  while (p2 < cap) p2 <<= 1;
+  const size_t smem = (size_t)p2 * 12;
+  if (smem > 200 * 1024) return set_error(RBOD_E_INVAL, "dist_select: list capacity %d too large", cap);
+  RBOD_CUDA(cudaFuncSetAttribute(dist_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dist_select_kernel<<<nf, 256, smem, st>>>(coll_key, coll_idx, coll_cnt, qsel, cap, p2, k, sample, metric, thr, active,
+                                            n_active, out_scores, out_rows, out_keys);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

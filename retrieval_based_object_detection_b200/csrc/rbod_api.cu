@@ -737,9 +737,10 @@ static int prepare_queries(rbod_gallery* g, const float* queries, int64_t Q, con
 static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int k, const uint32_t* mask_dev,
                            float* d_scores, int64_t* d_rows, double* d_keys, int64_t* launches, int64_t* resweeps,
                            cudaStream_t st) {
-  // lists hold 8192 rows; the sample is sized so that ~k * stride rows pass the threshold it yields (about a
-  // quarter of a list for k <= 8), which keeps second sweeps rare
-  const int cap = 8192, sample_cap = 4096, batch = 32, max_iter = 12;
+  // lists hold 8192 rows and so does the sample: ~k * stride rows pass the threshold it yields (1M rows, k = 10:
+  // ~1200), so one sweep is enough unless k * rows / 8192 exceeds a list (then a second sweep with the tightened
+  // threshold finishes it)
+  const int cap = 8192, sample_cap = 8192, batch = 32, max_iter = 12;
   if (k > 1024)
     return set_error(RBOD_E_UNSUPPORTED, "rbod_search: k=%d > 1024 for EUCLID / MANHATTAN collections", k);
   const void* qd = nullptr;
