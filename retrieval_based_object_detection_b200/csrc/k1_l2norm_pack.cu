@@ -63,14 +63,15 @@ __device__ __forceinline__ void finish_row_stats(float s16, float sy, float sd, 
 // HAS32: the collection keeps an fp32 master row (then the 16-bit row is a shadow and its distance to the
 // master is tracked); otherwise the 16-bit row IS the stored vector and only its norm matters.
 template <int NV, int HAS32>
-__global__ void __launch_bounds__(K1_WARPS * 32)
+__global__ void __launch_bounds__(256)
 l2norm_pack_vec_kernel(const float* __restrict__ in, int64_t n, int dim, const int64_t* __restrict__ slots,
                        int64_t slot0, int normalize, int cosine, float* __restrict__ master32, int64_t ld32,
                        uint16_t* __restrict__ out16, int64_t ld16, int kind16, uint16_t* __restrict__ shadow16,
                        float* __restrict__ out_norms, float* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * K1_WARPS + (threadIdx.x >> 5);
-  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * K1_WARPS;
+  const int wpb = blockDim.x >> 5;   // warps per block
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5);
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * wpb;
   float wmax_norm = 0.f, wmax_dev = 0.f, wmax_snorm = 0.f, wmax_sdev = 0.f;
 
   for (int64_t row = warp0; row < n; row += nwarps) {
@@ -261,22 +262,23 @@ int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots
   const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) &&
                        (master32 == nullptr || (reinterpret_cast<uintptr_t>(master32) % 16 == 0 && ld32 % 4 == 0)) &&
                        (out16 == nullptr || (reinterpret_cast<uintptr_t>(out16) % 8 == 0 && ld16 % 4 == 0));
-  // Grid: 64 CTAs per SM of row-strided warps, i.e. many short waves instead of one persistent one.  Measured on one
-  // B200 (copy bandwidth of that box 6602 GB/s), 8M x 768 -> bf16 / 4M x 512 -> fp32: 2 CTAs per SM (= the resident
-  // set) 86% / 93% of the copy bandwidth, 8: 86% / 92%, 16: 88% / 97%, 64: 88% / 101%, one row per warp: 67% / 85%.
-  // RBOD_K1_CTAS overrides for probing.
-  static const int tune_ctas = getenv("RBOD_K1_CTAS") ? atoi(getenv("RBOD_K1_CTAS")) : 64;
-  grid = (int)(want < (int64_t)num_sms * tune_ctas ? want : (int64_t)num_sms * tune_ctas);
+  // Launch shape of the vector kernel: blocks of 4 warps, 128 blocks per SM in the grid (many short waves of
+  // row-strided warps).  Same-box A/B on B200s whose b.copy_(a) bandwidth measured 6594-6602 GB/s, 8M x 768 -> bf16 /
+  // 4M x 512 -> fp32, % of that copy bandwidth: grid = exactly the resident set 86 / 93; 8 warps x 64 blocks per
+  // SM 88-92 / 93-101; 4 warps x 128 per SM 94 / 101; one row per warp (no grid-stride) 67 / 85.  Also tried and
+  // dropped (slower or equal): error-free fp32 arithmetic instead of fp64 (77 / 90), four fp64 chains + Newton rsqrt
+  // (89 / 92), streaming stores, L2 prefetch distances 0 / 1 / 3 / 4 rows instead of 2.
+  // RBOD_K1_CTAS / RBOD_K1_WARPS override for probing.
+  static const int tune_ctas = getenv("RBOD_K1_CTAS") ? atoi(getenv("RBOD_K1_CTAS")) : 128;
+  static const int tune_warps = getenv("RBOD_K1_WARPS") ? atoi(getenv("RBOD_K1_WARPS")) : 4;
+  const int64_t vwant = (n + tune_warps - 1) / tune_warps;
+  const int64_t vcap = (int64_t)num_sms * tune_ctas;
+  const int vgrid = (int)(vwant < vcap ? vwant : vcap);
+#define RBOD_K1_ARGS in, n, dim, slots_dev, slot0, normalize, cosine, master32, ld32, out16, ld16, kind16, shadow16, out_norms, stats
 #define RBOD_K1_CASE(NV)                                                                                     \
   case NV:                                                                                                   \
-    if (master32)                                                                                            \
-      l2norm_pack_vec_kernel<NV, 1><<<grid, K1_WARPS * 32, 0, st>>>(in, n, dim, slots_dev, slot0, normalize,  \
-                                                                    cosine, master32, ld32, out16, ld16,     \
-                                                                    kind16, shadow16, out_norms, stats);     \
-    else                                                                                                     \
-      l2norm_pack_vec_kernel<NV, 0><<<grid, K1_WARPS * 32, 0, st>>>(in, n, dim, slots_dev, slot0, normalize,  \
-                                                                    cosine, master32, ld32, out16, ld16,     \
-                                                                    kind16, shadow16, out_norms, stats);     \
+    if (master32) l2norm_pack_vec_kernel<NV, 1><<<vgrid, tune_warps * 32, 0, st>>>(RBOD_K1_ARGS);            \
+    else l2norm_pack_vec_kernel<NV, 0><<<vgrid, tune_warps * 32, 0, st>>>(RBOD_K1_ARGS);                     \
     break;
   if (aligned && dim % 128 == 0 && dim / 128 >= 1 && dim / 128 <= 8) {
     switch (dim / 128) {
@@ -295,6 +297,7 @@ int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots
                                                                out_norms, stats);
   }
 #undef RBOD_K1_CASE
+#undef RBOD_K1_ARGS
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

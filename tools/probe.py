@@ -90,8 +90,14 @@ def main():
         dst = torch.empty_like(src)
         best = min(time_ms(lambda: dst.copy_(src), 3, warmup=1) for _ in range(5))
         rd = min(time_ms(lambda: src.sum(), 3, warmup=1) for _ in range(3))
+        # same traffic mix as K1 with a 16-bit gallery: read fp32, write 16 bit (torch's own elementwise cast)
+        m = 1 << 29
+        s32 = torch.empty(m, dtype=torch.float32, device=dev).normal_()
+        d16 = torch.empty(m, dtype=torch.bfloat16, device=dev)
+        cast = min(time_ms(lambda: d16.copy_(s32), 3, warmup=1) for _ in range(5))
         emit(op="copy", bytes=4 * n, ms=round(best, 4), copy_gbs=round(4 * n / best / 1e6, 1),
-             read_only_gbs=round(2 * n / rd / 1e6, 1), measured_peaks_gbs=hbm)
+             read_only_gbs=round(2 * n / rd / 1e6, 1), cast_f32_to_bf16_gbs=round(6 * m / cast / 1e6, 1),
+             measured_peaks_gbs=hbm)
         return
     if a.op == "dist":
         from retrieval_based_object_detection_b200 import Gallery
