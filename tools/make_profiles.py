@@ -38,11 +38,13 @@ def launches(tag):
         a = tot.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += v
-    ours = {k: v for k, v in tot.items() if "at::" not in k}
+    mine = ("k3_cosine", "rescore", "merge_partials", "prep_queries", "select_", "tau_init", "l2norm", "seg_", "gather_",
+            "merge_topk", "dist_", "exact_collect")
+    ours = {k: v for k, v in tot.items() if any(m in k for m in mine)}
     total, total_search = sum(v for _, v in tot.values()), sum(v for k, (_, v) in ours.items() if "l2norm" not in k)
     with open(os.path.join(PROF, f"{tag}_launches_bench_summary.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, command: python bench.py --steps 2 --warmup 3 "
-                "--no-cpu-baseline\n# cold-cache, serialised launches: compare SHARES, not absolutes\n")
+                "--no-cpu-baseline --no-parity\n# cold-cache, serialised launches: compare SHARES, not absolutes\n")
         f.write(f"# total {total:.3f} ms over {sum(n for n, _ in tot.values())} launches; search kernels only "
                 f"{total_search:.3f} ms\n")
         for k, (n, v) in sorted(tot.items(), key=lambda x: -x[1][1]):
