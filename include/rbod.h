@@ -68,7 +68,8 @@ extern "C" {
 /* distance of the collection (Distance enum, util/qdrant_manager.py:61-66) */
 #define RBOD_COSINE 0
 #define RBOD_DOT 1
-#define RBOD_EUCLID 2    /* score = L2 distance, smaller is closer; exact fp64 sweep on CUDA cores (kernel K5) */
+#define RBOD_EUCLID 2    /* score = L2 distance, smaller is closer; tensor-core pass with a row-bias epilogue (K3) up to
+                            768 columns, exact fp64 sweep on CUDA cores (K5) beyond */
 #define RBOD_MANHATTAN 3 /* score = L1 distance, smaller is closer; exact fp64 sweep on CUDA cores (kernel K5) */
 
 /* rbod_upsert flags */
@@ -191,7 +192,7 @@ int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx
  * EUCLID / MANHATTAN collections: out_scores holds the DISTANCE (sqrt of the squared sum / sum of absolute
  * differences), ascending, +inf where fewer than k rows qualify; ties broken by smaller row slot;
  * out_scores64 holds the ordering key (-squared distance / -L1 distance, larger = closer), which is what
- * rbod_merge_topk orders by.  k <= 1024 for these two distances.                          */
+ * rbod_merge_topk orders by.  MANHATTAN (and EUCLID wider than 768 columns): k <= 1024.   */
 int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, const uint32_t* row_mask,
                 float* out_scores, int64_t* out_rows, double* out_scores64, rbod_search_stats* stats,
                 void* stream);

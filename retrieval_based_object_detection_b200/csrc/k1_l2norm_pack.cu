@@ -228,6 +228,28 @@ l2norm_pack_generic_kernel(const float* __restrict__ in, int64_t n, int dim, con
   }
 }
 
+// EUCLID collections: row_bias[slot] = fp32(-|stored row|^2 / 2), the per-row term the K3 epilogue adds so that the
+// tensor-core score q . g - |g|^2 / 2 orders rows by Euclidean distance.  Sum in fp64 over the row AS STORED (after
+// K1), one warp per row; slots = slots_dev[i] or slot0 + i.
+__global__ void __launch_bounds__(256)
+row_bias_kernel(const float* __restrict__ master32, const uint16_t* __restrict__ rows16, int kind16, int dim,
+                int64_t ld32, int64_t ld16, const int64_t* __restrict__ slots, int64_t slot0, int64_t n,
+                float* __restrict__ row_bias) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t nw = static_cast<int64_t>(gridDim.x) * 8;
+  for (int64_t i = w0; i < n; i += nw) {
+    const int64_t slot = slots ? slots[i] : slot0 + i;
+    double ss = 0.0;
+    for (int c = lane; c < dim; c += 32) {
+      const double x = master32 ? (double)master32[slot * ld32 + c] : (double)h16_to_f32(rows16[slot * ld16 + c], kind16);
+      ss = fma(x, x, ss);
+    }
+    ss = warp_sum_f64(ss);
+    if (lane == 0) row_bias[slot] = (float)(-0.5 * ss);
+  }
+}
+
 // out[i, :] = widen(stored row rows[i])
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ master32, const uint16_t* __restrict__ rows16, int kind16, int dim,
@@ -298,6 +320,16 @@ int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots
   }
 #undef RBOD_K1_CASE
 #undef RBOD_K1_ARGS
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+int launch_row_bias(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32, int64_t ld16,
+                    const int64_t* slots_dev, int64_t slot0, int64_t n, float* row_bias, cudaStream_t st) {
+  if (n <= 0) return RBOD_OK;
+  const int64_t want = (n + 7) / 8;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  row_bias_kernel<<<grid, 256, 0, st>>>(master32, rows16, kind16, dim, ld32, ld16, slots_dev, slot0, n, row_bias);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

@@ -47,6 +47,7 @@ struct alignas(64) K3Params {
   float* part_score;
   uint32_t* part_idx;
   const uint32_t* row_mask;
+  const float* row_bias;  // BIAS kernels (EUCLID collections): score = q . g + row_bias[row], row_bias = -|g|^2 / 2
   uint32_t* tau_shared;   // [q_pad] per-query lower bound on the kc-th best score, as ordered keys (nullptr = off)
   const float* collect_thr;   // collect mode: [q_pad] fixed per-query thresholds; every row scoring above is recorded
   uint32_t* coll_idx;         //   [q_pad][coll_cap] recorded row indices
@@ -187,7 +188,10 @@ __device__ __forceinline__ void issue_full_stage(uint32_t d_tmem, uint32_t a_tme
   }
 }
 
-template <int VARIANT, int PAIR, int KBS>
+// BIAS = 1 (EUCLID collections): the epilogue adds a per-gallery-row term to every score before anything looks at
+// it, so thresholds, candidate lists, the collecting pass and the sampled pre-pass all work on
+// q . g - |g|^2 / 2 = (|q|^2 - |q - g|^2) / 2, which orders rows by Euclidean distance.
+template <int VARIANT, int PAIR, int KBS, int BIAS>
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __grid_constant__ K3Params P) {
   using G = K3Geom<VARIANT, PAIR, KBS>;
   extern __shared__ uint8_t smem_raw[];
@@ -501,6 +505,19 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         }
         if (++acc == P.num_acc) { acc = 0; acc_phase ^= 1u; }
         const int64_t col0 = (int64_t)t * K3_TILE_N;
+        if (BIAS) {
+          // the same 512 bytes for all four epilogue warps: L1-resident after the first touch (the array is
+          // allocated in whole tiles, rows beyond n_rows are masked below)
+          const float4* bp = reinterpret_cast<const float4*>(P.row_bias + col0);
+#pragma unroll
+          for (int c4 = 0; c4 < K3_TILE_N / 4; ++c4) {
+            const float4 b4 = __ldg(bp + c4);
+            v[4 * c4 + 0] += b4.x;
+            v[4 * c4 + 1] += b4.y;
+            v[4 * c4 + 2] += b4.z;
+            v[4 * c4 + 3] += b4.w;
+          }
+        }
 
         if (P.dump != nullptr && qg < P.q_valid) {
 #pragma unroll
@@ -739,10 +756,12 @@ int k3_configure(int device) {
   if (device >= 0 && device < 64 && cached_optin[device] > 0) return cached_optin[device];
   int optin = 0;
   RBOD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<1, 0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   if (device >= 0 && device < 64) cached_optin[device] = optin;
   return optin;
 }
@@ -756,6 +775,7 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.part_score = L.part_score;
   P.part_idx = L.part_idx;
   P.row_mask = L.row_mask;
+  P.row_bias = L.row_bias;
   P.tau_shared = L.tau_shared;
   P.collect_thr = L.collect_thr;
   P.coll_idx = L.coll_idx;
@@ -815,10 +835,16 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (L.variant == 2) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 4>, P));
-  else if (L.variant == 0 && L.kbs == 4) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 4>, P));
-  else if (L.variant == 0) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 2>, P));
-  else RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<1, 0, 2>, P));
+  if (L.row_bias != nullptr && L.variant != 0)
+    return set_error(RBOD_E_UNSUPPORTED, "k3: the row-bias (EUCLID) epilogue exists for variant 0 only");
+  if (L.variant == 2) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 4, 0>, P));
+  else if (L.variant == 0 && L.row_bias != nullptr && L.kbs == 4)
+    RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 4, 1>, P));
+  else if (L.variant == 0 && L.row_bias != nullptr)
+    RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 2, 1>, P));
+  else if (L.variant == 0 && L.kbs == 4) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 4, 0>, P));
+  else if (L.variant == 0) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 2, 0>, P));
+  else RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<1, 0, 2, 0>, P));
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

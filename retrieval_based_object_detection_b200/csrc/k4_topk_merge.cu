@@ -27,6 +27,40 @@ __device__ __forceinline__ bool beats(double sa, uint32_t ia, double sb, uint32_
   return sa > sb || (sa == sb && ia < ib);
 }
 
+// Exact score of one (query, stored row) pair, one warp per pair, fp64 on the stored values; every lane returns it.
+//   COSINE : dot / (|q| |g|)  -- cosine_similarity, 33_run_all_experiments.py:76-77
+//   DOT    : dot
+//   EUCLID : the ordering key -sum (q_i - g_i)^2, accumulated directly (no |q|^2 - 2 q.g + |g|^2 cancellation)
+__device__ __forceinline__ double exact_pair_score(const float* __restrict__ qv, double qq,
+                                                   const float* __restrict__ g32, const uint16_t* __restrict__ g16,
+                                                   int kind16, int dim, int metric, int lane) {
+  double a = 0.0, b = 0.0;
+  for (int c = lane; c < dim; c += 32) {
+    const double x = g32 ? (double)g32[c] : (double)h16_to_f32(g16[c], kind16);
+    const double qc = (double)qv[c];
+    if (metric == RBOD_EUCLID) {
+      const double d = qc - x;
+      a = fma(d, d, a);
+    } else {
+      a = fma(qc, x, a);
+      b = fma(x, x, b);
+    }
+  }
+  a = warp_sum_f64(a);
+  if (metric == RBOD_EUCLID) return -a;
+  if (metric == RBOD_DOT) return a;
+  b = warp_sum_f64(b);
+  const double den = sqrt(qq) * sqrt(b);
+  return den > 0.0 ? a / den : 0.0;
+}
+
+// What the caller sees for an internal score: EUCLID keys (-d^2) come out as the distance d (fp32) and keep the
+// key in the fp64 output (the order the multi-GPU merge uses); "no result" is an infinite distance.
+__device__ __forceinline__ float user_score(double s, int metric) {
+  return metric == RBOD_EUCLID ? (float)sqrt(-s) : (float)s;
+}
+__device__ __forceinline__ float user_no_result(int metric) { return metric == RBOD_EUCLID ? INFINITY : -INFINITY; }
+
 // ---------------------------------------------------------------------------------------------
 // merge_partials: one CTA per query, bitonic sort (descending) of packed keys in shared memory.
 // key = ordered(score) << 32 | ~idx   (ties: smaller row index first); 0 = padding.
@@ -117,29 +151,9 @@ rescore_kernel(const float* __restrict__ q, const double* __restrict__ q_qq, con
       continue;
     }
     const int64_t qi = p / kc;
-    const float* qv = q + qi * dim;
-    double dot = 0.0, gg = 0.0;
-    if (master32) {
-      const float* g = master32 + (int64_t)idx * ld32;
-      for (int c = lane; c < dim; c += 32) {
-        const double x = (double)g[c];
-        dot = fma((double)qv[c], x, dot);
-        gg = fma(x, x, gg);
-      }
-    } else {
-      const uint16_t* g = rows16 + (int64_t)idx * ld16;
-      for (int c = lane; c < dim; c += 32) {
-        const double x = (double)h16_to_f32(g[c], kind16);
-        dot = fma((double)qv[c], x, dot);
-        gg = fma(x, x, gg);
-      }
-    }
-    dot = warp_sum_f64(dot);
-    gg = warp_sum_f64(gg);
-    if (lane == 0) {
-      const double den = sqrt(q_qq[qi]) * sqrt(gg);
-      cand_score[p] = metric == RBOD_DOT ? dot : (den > 0.0 ? dot / den : 0.0);
-    }
+    const double sc = exact_pair_score(q + qi * dim, q_qq[qi], master32 ? master32 + (int64_t)idx * ld32 : nullptr,
+                                       master32 ? nullptr : rows16 + (int64_t)idx * ld16, kind16, dim, metric, lane);
+    if (lane == 0) cand_score[p] = sc;
   }
 }
 
@@ -163,7 +177,7 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
     s_ix[w][j] = cand_idx[q * kc + j];
   }
   for (int j = lane; j < k; j += 32) {
-    out_scores[q * k + j] = -INFINITY;
+    out_scores[q * k + j] = user_no_result(metric);
     out_rows[q * k + j] = -1;
     if (out_scores64) out_scores64[q * k + j] = -INFINITY;
   }
@@ -180,7 +194,7 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
       if (oi != 0xffffffffu && beats(s_sc[w][i], oi, s, ix)) ++rank;
     }
     if (rank < k) {
-      out_scores[q * k + rank] = (float)s;
+      out_scores[q * k + rank] = user_score(s, metric);
       out_rows[q * k + rank] = (int64_t)ix;
       if (out_scores64) out_scores64[q * k + rank] = s;
       if (rank == k - 1) { kth = s; have_kth = 1; }
@@ -202,16 +216,25 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
   const float gmax = (shadow ? stats[2] : stats[0]) * 1.000001f, gdev = stats[1] * 1.000001f;
   // DOT collections: nothing is normalised, so every term scales with the query norm |q| and the row term is
   // |q| * ||g16 - g|| (zero for 16-bit masters, whose operand is the stored row).
-  const float qn = metric == RBOD_DOT ? (float)sqrt(q_qq[q]) * 1.000001f + q_dq[q] : 1.0f;
+  // EUCLID collections: the tensor-core pass scores a = q16 . g16 + bias32 with bias32 = fp32(-|g|^2 / 2), an
+  // approximation of (key + |q|^2) / 2 for the exact key = -|q - g|^2.  Nothing is normalised, so the dot-product
+  // terms are those of DOT, plus the rounding of the bias and of its addition: 2^-23 (|q| G + G^2), G = max |g|.
+  const bool unnorm = metric != RBOD_COSINE;
+  const float qn = unnorm ? (float)sqrt(q_qq[q]) * 1.000001f + q_dq[q] : 1.0f;
   const float e = q_dq[q] * gmax + (float)dp * 1.2e-7f * gmax * qn + (shadow ? stats[3] * 1.000001f * qn : 0.0f);
-  const float row_term = metric == RBOD_DOT ? (master16 ? 0.0f : qn * gdev)
-                                            : (master16 ? (fabsf(tau) + e) * gdev / (1.0f - gdev) : gdev);
-  const float eps = e + row_term + fabsf(tau) * 1e-6f + 1e-7f;
+  const float row_term = unnorm ? (master16 ? 0.0f : qn * gdev)
+                                : (master16 ? (fabsf(tau) + e) * gdev / (1.0f - gdev) : gdev);
+  const float gbig = gmax + (master16 ? 0.0f : gdev);
+  const float bias_term = metric == RBOD_EUCLID ? 1.2e-7f * (qn * gbig + gbig * gbig) : 0.0f;
+  const float eps = e + row_term + bias_term + fabsf(tau) * 1e-6f + 1e-7f;
+  const double qq_half = metric == RBOD_EUCLID ? 0.5 * q_qq[q] : 0.0;
   bool flagged = true;
   if (who) {
     const int src = __ffs(who) - 1;
     const double kth_b = __shfl_sync(FULL_MASK, kth, src);
-    flagged = !((double)tau + (double)eps < kth_b);
+    // the k-th exact score in the domain the tensor-core pass works in
+    const double kth_a = metric == RBOD_EUCLID ? 0.5 * kth_b + qq_half : kth_b;
+    flagged = !((double)tau + (double)eps < kth_a);
     kth = kth_b;
   } else {
     // Fewer than k candidates although rows were dropped: the pre-sampled starting threshold sat above this
@@ -228,8 +251,9 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
       flag_thr[slot] = kth;
       // Threshold for the collecting second pass: every row whose exact score reaches kth has an
       // approximate score above lo (same error model, applied from the exact side).
-      const float kf = (float)kth;
-      const float lo = metric == RBOD_DOT ? kf - e - row_term : (master16 ? kf - fabsf(kf) * gdev - e : kf - e - gdev);
+      const float kf = (float)(metric == RBOD_EUCLID ? 0.5 * kth + qq_half : kth);
+      const float lo = unnorm ? kf - e - row_term - bias_term
+                              : (master16 ? kf - fabsf(kf) * gdev - e : kf - e - gdev);
       flag_lo[slot] = kth == -INFINITY ? -INFINITY : lo - fabsf(kf) * 2e-6f - 2e-7f;
     }
   }
@@ -266,16 +290,23 @@ exact_collect_kernel(const float* __restrict__ q, const double* __restrict__ q_q
     for (int f = 0; f < nf; ++f) {
       const int qi = flag_q[f0 + f];
       const float* qv = q + (int64_t)qi * dim;
-      double dot = 0.0;
+      double acc = 0.0;
 #pragma unroll
       for (int i = 0; i < EX_NMAX; ++i) {
         const int c = lane + 32 * i;
-        if (c < dim) dot = fma((double)qv[c], g[i], dot);
+        if (c < dim) {
+          if (metric == RBOD_EUCLID) {
+            const double d = (double)qv[c] - g[i];
+            acc = fma(d, d, acc);
+          } else {
+            acc = fma((double)qv[c], g[i], acc);
+          }
+        }
       }
-      dot = warp_sum_f64(dot);
+      acc = warp_sum_f64(acc);
       if (lane == 0) {
         const double den = sqrt(q_qq[qi]) * gn;
-        const double s = metric == RBOD_DOT ? dot : (den > 0.0 ? dot / den : 0.0);
+        const double s = metric == RBOD_EUCLID ? -acc : (metric == RBOD_DOT ? acc : (den > 0.0 ? acc / den : 0.0));
         if (s >= flag_thr[f0 + f]) {
           const int slot = atomicAdd(coll_cnt + f, 1);
           if (slot < cap) {
@@ -291,7 +322,7 @@ exact_collect_kernel(const float* __restrict__ q, const double* __restrict__ q_q
 __global__ void __launch_bounds__(256)
 select_collected_kernel(const double* __restrict__ coll_score, const uint32_t* __restrict__ coll_idx,
                         const int* __restrict__ coll_cnt, const int* __restrict__ flag_q, int f0, int cap, int k,
-                        float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+                        int metric, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
                         double* __restrict__ out_scores64, int* __restrict__ overflow) {
   const int f = blockIdx.x;
   const int q = flag_q[f0 + f];
@@ -304,7 +335,7 @@ select_collected_kernel(const double* __restrict__ coll_score, const uint32_t* _
   const double* sc = coll_score + (size_t)f * cap;
   const uint32_t* ix = coll_idx + (size_t)f * cap;
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    out_scores[(int64_t)q * k + j] = -INFINITY;
+    out_scores[(int64_t)q * k + j] = user_no_result(metric);
     out_rows[(int64_t)q * k + j] = -1;
     if (out_scores64) out_scores64[(int64_t)q * k + j] = -INFINITY;
   }
@@ -316,7 +347,7 @@ select_collected_kernel(const double* __restrict__ coll_score, const uint32_t* _
     for (int i = 0; i < cnt; ++i)
       if (beats(sc[i], ix[i], s, id)) ++rank;
     if (rank < k) {
-      out_scores[(int64_t)q * k + rank] = (float)s;
+      out_scores[(int64_t)q * k + rank] = user_score(s, metric);
       out_rows[(int64_t)q * k + rank] = (int64_t)id;
       if (out_scores64) out_scores64[(int64_t)q * k + rank] = s;
     }
@@ -357,31 +388,11 @@ rescore_collected_kernel(const float* __restrict__ q, const double* __restrict__
   const int cnt = min(coll_cnt[f], cap);
   const int qi = flag_q[f0 + f];
   const float* qv = q + (int64_t)qi * dim;
-  const double qn = sqrt(q_qq[qi]);
   for (int j = blockIdx.x * 8 + (threadIdx.x >> 5); j < cnt; j += gridDim.x * 8) {
     const uint32_t idx = coll_idx[(size_t)f * cap + j];
-    double dot = 0.0, gg = 0.0;
-    if (master32) {
-      const float* g = master32 + (int64_t)idx * ld32;
-      for (int c = lane; c < dim; c += 32) {
-        const double x = (double)g[c];
-        dot = fma((double)qv[c], x, dot);
-        gg = fma(x, x, gg);
-      }
-    } else {
-      const uint16_t* g = rows16 + (int64_t)idx * ld16;
-      for (int c = lane; c < dim; c += 32) {
-        const double x = (double)h16_to_f32(g[c], kind16);
-        dot = fma((double)qv[c], x, dot);
-        gg = fma(x, x, gg);
-      }
-    }
-    dot = warp_sum_f64(dot);
-    gg = warp_sum_f64(gg);
-    if (lane == 0) {
-      const double den = qn * sqrt(gg);
-      coll_score[(size_t)f * cap + j] = metric == RBOD_DOT ? dot : (den > 0.0 ? dot / den : 0.0);
-    }
+    const double sc = exact_pair_score(qv, q_qq[qi], master32 ? master32 + (int64_t)idx * ld32 : nullptr,
+                                       master32 ? nullptr : rows16 + (int64_t)idx * ld16, kind16, dim, metric, lane);
+    if (lane == 0) coll_score[(size_t)f * cap + j] = sc;
   }
 }
 
@@ -497,10 +508,10 @@ int launch_exact_collect(const float* q, const double* q_qq, const float* master
 }
 
 int launch_select_collected(const double* coll_score, const uint32_t* coll_idx, const int* coll_cnt,
-                            const int* flag_q, int f0, int nf, int cap, int k, float* out_scores,
+                            const int* flag_q, int f0, int nf, int cap, int k, int metric, float* out_scores,
                             int64_t* out_rows, double* out_scores64, int* overflow, cudaStream_t st) {
   if (nf <= 0) return RBOD_OK;
-  select_collected_kernel<<<nf, 256, 0, st>>>(coll_score, coll_idx, coll_cnt, flag_q, f0, cap, k, out_scores,
+  select_collected_kernel<<<nf, 256, 0, st>>>(coll_score, coll_idx, coll_cnt, flag_q, f0, cap, k, metric, out_scores,
                                               out_rows, out_scores64, overflow);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;

@@ -137,6 +137,20 @@ static int grow(rbod_gallery* g, int64_t need, cudaStream_t st) {
       return set_error(RBOD_E_NOMEM, "gallery: cudaMalloc of %zu bytes failed", (size_t)cap * g->dim * 4);
     }
   }
+  float* nbias = nullptr;
+  if (g->metric == RBOD_EUCLID) {
+    e = cudaMalloc(&nbias, (size_t)(cap + K3_TILE_N) * 4);   // whole tiles: the K3 epilogue reads 128 entries at a time
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(n16);
+      if (nsh) cudaFree(nsh);
+      if (n32) cudaFree(n32);
+      return set_error(RBOD_E_NOMEM, "gallery: cudaMalloc of %zu bytes (row bias) failed", (size_t)(cap + K3_TILE_N) * 4);
+    }
+    RBOD_CUDA(cudaMemsetAsync(nbias, 0, (size_t)(cap + K3_TILE_N) * 4, st));
+    if (g->rows > 0 && g->row_bias)
+      RBOD_CUDA(cudaMemcpyAsync(nbias, g->row_bias, (size_t)g->rows * 4, cudaMemcpyDeviceToDevice, st));
+  }
   // zero the new tail (keeps the dim..dp padding columns zero), then carry the old rows over
   const size_t old16 = (size_t)g->rows * g->dp * 2;
   RBOD_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(n16) + old16, 0, (size_t)cap * g->dp * 2 - old16, st));
@@ -151,9 +165,11 @@ static int grow(rbod_gallery* g, int64_t need, cudaStream_t st) {
   if (g->rows16) cudaFree(g->rows16);
   if (g->master32) cudaFree(g->master32);
   if (g->shadow16) cudaFree(g->shadow16);
+  if (g->row_bias) cudaFree(g->row_bias);
   g->rows16 = n16;
   g->master32 = n32;
   g->shadow16 = nsh;
+  g->row_bias = nbias;
   g->capacity = cap;
   return RBOD_OK;
 }
@@ -277,6 +293,7 @@ int rbod_destroy(rbod_gallery* g) {
   if (g->rows16) cudaFree(g->rows16);
   if (g->master32) cudaFree(g->master32);
   if (g->shadow16) cudaFree(g->shadow16);
+  if (g->row_bias) cudaFree(g->row_bias);
   if (g->stats) cudaFree(g->stats);
   DevBuf* bufs[] = {&g->stage_rows, &g->stage_slots, &g->stage_norms, &g->q32, &g->q16, &g->q_dq, &g->q_qq, &g->tau_shared,
                     &g->part_score, &g->part_idx, &g->cand_idx, &g->cand_tau, &g->cand_score, &g->out_scores,
@@ -337,6 +354,8 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
   if (!g || !key) return set_error(RBOD_E_INVAL, "rbod_set_option: NULL argument");
   if (!strcmp(key, "k3_variant")) {
     if (value < 0 || value > 2) return set_error(RBOD_E_INVAL, "k3_variant must be 0, 1 or 2");
+    if (value != 0 && g->metric == RBOD_EUCLID)
+      return set_error(RBOD_E_UNSUPPORTED, "k3_variant: EUCLID collections use variant 0 (the row-bias epilogue)");
     g->k3_variant = (int)value;
   } else if (!strcmp(key, "k3_kbs")) {
     if (value != 0 && value != 2 && value != 4) return set_error(RBOD_E_INVAL, "k3_kbs must be 0 (auto), 2 or 4");
@@ -440,6 +459,9 @@ int rbod_upsert(rbod_gallery* g, const float* rows, int64_t n, const int64_t* ro
     }
     RBOD_TRY(launch_l2norm_pack(src, m, g->dim, slots_dev, g->rows + r0, normalize, cosine, g->master32, g->dim,
                                 g->rows16, g->dp, g->kind16, g->shadow16, norms_dst, g->stats, g->num_sms, st));
+    if (g->row_bias)
+      RBOD_TRY(launch_row_bias(g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp, slots_dev, g->rows + r0, m,
+                               g->row_bias, st));
     if (out_norms && !norms_dev)
       RBOD_CUDA(cudaMemcpyAsync(out_norms + r0, norms_dst, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     if (!rows_dev || row_slots) RBOD_CUDA(cudaStreamSynchronize(st));  // staging buffers are reused
@@ -698,6 +720,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.part_score = g->part_score.as<float>();
   L.part_idx = g->part_idx.as<uint32_t>();
   L.row_mask = mask_dev;
+  L.row_bias = g->metric == RBOD_EUCLID ? g->row_bias : nullptr;
   L.tau_shared = (g->tau_share && dump == nullptr && collect == nullptr && sample == nullptr)
                      ? g->tau_shared.as<uint32_t>() : nullptr;
   if (sample) {
@@ -817,7 +840,9 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     return set_error(RBOD_E_INVAL, "rbod_search: bad arguments");
   if (stats) memset(stats, 0, sizeof(*stats));
   if (Q == 0) return RBOD_OK;
-  const bool distance_metric = g->metric == RBOD_EUCLID || g->metric == RBOD_MANHATTAN;
+  // MANHATTAN always, EUCLID only when the vectors are too wide for the tensor-core pass: exact fp64 sweep (K5).
+  // EUCLID up to K3_MAX_DP columns runs on the tensor cores with the row-bias epilogue.
+  const bool distance_metric = g->metric == RBOD_MANHATTAN || (g->metric == RBOD_EUCLID && g->dp > K3_MAX_DP);
   if (!distance_metric && g->dp > K3_MAX_DP)
     return set_error(RBOD_E_UNSUPPORTED, "rbod_search: dim %d > %d not supported by the tcgen05 pass", g->dim,
                      K3_MAX_DP);
@@ -887,7 +912,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
 
   if (g->rows == 0) {
     // empty collection: every slot is "no result"
-    std::vector<float> hs(nout, -INFINITY);
+    std::vector<float> hs(nout, g->metric == RBOD_EUCLID ? INFINITY : -INFINITY);
     std::vector<int64_t> hr(nout, -1);
     std::vector<double> hd(nout, -INFINITY);
     RBOD_CUDA(cudaMemcpyAsync(out_scores, hs.data(), nout * 4, cudaMemcpyDefault, st));
@@ -1001,8 +1026,8 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
                                       g->dp, g->metric, g->flag_q.as<int>(), 0, n_flag, cap, g->coll_idx.as<uint32_t>(),
                                       g->coll_cnt.as<int>(), g->coll_score.as<double>(), st));
     RBOD_TRY(launch_select_collected(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
-                                     g->flag_q.as<int>(), 0, n_flag, cap, k, d_scores, d_rows, d_scores64, nullptr,
-                                     st));
+                                     g->flag_q.as<int>(), 0, n_flag, cap, k, g->metric, d_scores, d_rows, d_scores64,
+                                     nullptr, st));
     launches += 4;
     ++k3_launches;
     // queries whose list overflowed (a tie cluster wider than `cap`) keep going to the exact sweep
@@ -1039,8 +1064,8 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
                                     g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
                                     g->num_sms, st));
       RBOD_TRY(launch_select_collected(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(),
-                                       g->coll_cnt.as<int>(), g->flag_q.as<int>(), f0, nf, cap, k, d_scores, d_rows,
-                                       d_scores64, d_flags + 1, st));
+                                       g->coll_cnt.as<int>(), g->flag_q.as<int>(), f0, nf, cap, k, g->metric, d_scores,
+                                       d_rows, d_scores64, d_flags + 1, st));
       launches += 2;
     }
     RBOD_CUDA(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));

@@ -78,6 +78,7 @@ struct K3Launch {
   float* part_score;      // [slices][q_pad][kc]
   uint32_t* part_idx;     // [slices][q_pad][kc]
   const uint32_t* row_mask;
+  const float* row_bias;  // EUCLID collections: [capacity rounded up to whole tiles] -|g|^2 / 2 per stored row
   uint32_t* tau_shared;   // [q_pad] ordered-key thresholds shared across slices, preset to key(-inf); or nullptr
   const float* collect_thr;   // collect mode (second pass for uncertified queries), see k3_cosine_topk.cu
   uint32_t* coll_idx;
@@ -99,6 +100,8 @@ struct K3Launch {
 int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots_dev, int64_t slot0,
                        int normalize, int cosine, float* master32, int64_t ld32, uint16_t* out16, int64_t ld16,
                        int kind16, uint16_t* shadow16, float* out_norms, float* stats, int num_sms, cudaStream_t st);
+int launch_row_bias(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32, int64_t ld16,
+                    const int64_t* slots_dev, int64_t slot0, int64_t n, float* row_bias, cudaStream_t st);
 int launch_gather_rows(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32,
                        int64_t ld16, const int64_t* rows, int64_t n, int64_t n_valid, float* out, int* err_flag,
                        cudaStream_t st);
@@ -148,7 +151,7 @@ int launch_exact_collect(const float* q, const double* q_qq, const float* master
                          int cap, double* coll_score, uint32_t* coll_idx, int* coll_cnt, int num_sms,
                          cudaStream_t st);
 int launch_select_collected(const double* coll_score, const uint32_t* coll_idx, const int* coll_cnt,
-                            const int* flag_q, int f0, int nf, int cap, int k, float* out_scores,
+                            const int* flag_q, int f0, int nf, int cap, int k, int metric, float* out_scores,
                             int64_t* out_rows, double* out_scores64, int* overflow, cudaStream_t st);
 // K5 (EUCLID / MANHATTAN)
 int launch_dist_widen_queries(const float* q, const int* qsel, int nf, int dim, double* q64, cudaStream_t st);
@@ -171,6 +174,7 @@ struct rbod_gallery {
   float* master32 = nullptr;    // [capacity, dim]  (dtype == RBOD_F32 only)
   uint16_t* rows16 = nullptr;   // [capacity, dp]
   uint16_t* shadow16 = nullptr; // [capacity, dp] fp16 copy of a bf16 gallery used as the search operand (option)
+  float* row_bias = nullptr;    // [capacity + 128] EUCLID collections: -|stored row|^2 / 2 (the K3 epilogue adds it)
   int use_shadow = 0;
   float* stats = nullptr;       // device [4]: max ||row16||, max ||row16 - unit(master)||, max ||shadow||,
                                 // max ||shadow - row16||

@@ -518,3 +518,35 @@ def test_configs_c4_c5_full_size_exact(G, dtype, n, Q, k):
     r1 = g.search(q[:1], k, want_scores64=True)               # Q = 1: the HBM-bound end of the C5 sweep
     assert torch.equal(r1.rows, wi[:1])
     g.close()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+def test_euclid_collection_on_the_tensor_core_path(G, dtype):
+    """EUCLID collections up to 768 columns run on the tcgen05 pass with the row-bias epilogue (score = q.g - |g|^2/2),
+    exact rescoring of -|q-g|^2 in fp64 and the usual certification: a mid-size gallery of rows with very different
+    norms, every query against torch.cdist in float64 (ids identical, distances within 1e-6 relative)."""
+    import torch
+
+    n, dim, Q, k = 300_000, 512, 1500, 10
+    gen = torch.Generator("cuda").manual_seed(41)
+    x = torch.randn(n, dim, device="cuda", generator=gen) * (0.05 + 2.0 * torch.rand(n, 1, device="cuda", generator=gen))
+    if dtype == "f16":
+        x = x * 0.25
+    g = G(dim, dtype=dtype, metric="euclid", capacity=1000)          # grows several times: the bias array follows
+    for a in range(0, n, 100_000):
+        g.upsert(x[a:a + 100_000])
+    stored = g.get_rows(torch.arange(n, device="cuda"))
+    q = torch.randn(Q, dim, device="cuda", generator=gen) * (0.1 + torch.rand(Q, 1, device="cuda", generator=gen))
+    q[:50] = stored[1000:1050] + 0.01 * torch.randn(50, dim, device="cuda", generator=gen)   # near neighbours exist
+    r = g.search(q, k, want_scores64=True)
+    assert r.stats["k3_launches"] >= 1 and r.stats["sweep_queries"] < Q           # tensor-core path, not the K5 sweep
+    d = torch.cdist(q.double(), stored.double())
+    top = torch.topk(d, k, dim=1, largest=False)
+    assert torch.equal(top.indices, r.rows), int((top.indices != r.rows).any(dim=1).sum())
+    assert torch.allclose(top.values, r.scores.double(), rtol=1e-6, atol=1e-9)
+    assert torch.allclose(-top.values ** 2, r.scores64, rtol=1e-9, atol=1e-12)
+    # overwrite a row: its bias follows
+    g.upsert(q[7:8], slots=np.array([123], dtype=np.int64))
+    r2 = g.search(q[7:8], 3)
+    assert int(r2.rows[0, 0]) == 123 and float(r2.scores[0, 0]) <= (0.0 if dtype == "f32" else 1e-1)
+    g.close()
