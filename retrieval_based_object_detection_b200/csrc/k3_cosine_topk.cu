@@ -10,11 +10,12 @@
 //     (128 x dp) is parked in TMEM columns [0, dp/2) for the life of a work unit and used as the
 //     A operand straight from tensor memory (tcgen05.mma with A in TMEM), so the only operand
 //     that streams is the gallery: HBM -> L2 -> shared memory by TMA (128-byte swizzle, boxes of
-//     64 rows x 64 elements), 4 k-blocks per pipeline stage.
+//     64 rows x 64 elements), 2 or 4 k-blocks per pipeline stage (chosen by the planner).
 //   * Accumulators: 128x128 fp32 tiles (one N=128 MMA shape: measured 90% of peak per clock and
-//     ~23% less energy per flop than N=64) at the top of TMEM.  dim <= 512 leaves room for two
-//     buffers (MMA of tile j+1 overlaps the epilogue of tile j); dim 768 has room for one, so the
-//     epilogue copies the tile to registers and releases TMEM before it starts selecting.
+//     ~23% less energy per flop than N=64) at the top of TMEM, two buffers, so the MMA of tile j+1
+//     overlaps the epilogue of tile j.  For dim > 512 the last k-blocks of the query tile live in
+//     shared memory instead of TMEM to leave room for both buffers (hybrid layout); the epilogue
+//     copies a tile to registers and releases its TMEM buffer before it starts selecting.
 //   * Epilogue (4 warps, one thread per query row): tcgen05.ld the 128 scores of the row, compare
 //     against the row's running threshold (one FMNMX per score on the fast path); survivors replace
 //     the root of the row's min-heap of candidates in shared memory (transposed, conflict-free).
@@ -22,6 +23,8 @@
 //     running at the same time stream the same gallery slice and share it through L2.
 // Output: per (slice, query) the `kc` best approximate scores and their row indices.  The K4
 // kernels merge slices, rescore exactly in fp64 and certify the result.
+// The same kernel serves DOT collections (nothing normalised) and, in its BIAS instantiation,
+// EUCLID collections (a per-row -|g|^2/2 added to the scores; util/qdrant_manager.py:61-66).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).

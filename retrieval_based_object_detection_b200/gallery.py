@@ -22,7 +22,7 @@ from . import _native as N
 
 @dataclass
 class SearchResult:
-    scores: object      # [Q, k] float32 cosine, descending
+    scores: object      # [Q, k] float32: cosine / dot descending, or distance ascending (euclid, manhattan)
     rows: object        # [Q, k] int64 row slots, -1 = no result
     scores64: object    # [Q, k] float64 (None unless requested)
     stats: dict
@@ -180,7 +180,8 @@ class Gallery:
 
     # -- K3 ---------------------------------------------------------------------------------
     def search(self, queries, k: int, row_mask=None, want_scores64: bool = False, out=None, stream=None) -> SearchResult:
-        """Exact cosine top-k of ``queries`` [Q, dim] against the stored rows."""
+        """Exact top-k of ``queries`` [Q, dim] against the stored rows under the collection's distance (cosine by
+        default; ``scores64`` carries the ordering key -d^2 / -d for euclid / manhattan collections)."""
         keep, p_q = self._in(queries, np.float32, "float32")
         if keep.ndim == 1:
             keep = keep.reshape(1, -1)
