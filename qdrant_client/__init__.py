@@ -248,7 +248,8 @@ class QdrantClient:
         if queries is None or k is None:
             raise ValueError("search_batch needs either requests= or queries= and k=")
         scores, slots = col.search(np.asarray(queries, dtype=np.float32), int(k), row_filter)
-        ids = [[col.ids[s] if s >= 0 else None for s in row] for row in slots]
+        id_of = np.asarray(col.ids + [None], dtype=object)          # slot -1 -> None through the last entry
+        ids = id_of[np.asarray(slots)].tolist()
         return scores, ids
 
     # ------------------------------------------------------------------ delegates (K2)
@@ -261,18 +262,7 @@ class QdrantClient:
         (:23-26); the result is the stored (renormalised) form the script's upsert would leave.
         -> (group values, [G, dim] float32)."""
         col = self._root.get(collection_name)
-        allowed = col.filter_slots(scroll_filter)
-        groups: Dict[Any, List[int]] = {}
-        for s in col.ordered_slots():
-            if allowed is not None and s not in allowed:
-                continue
-            v = col.payloads[s].get(group_key)
-            if v is not None:
-                groups.setdefault(v, []).append(s)
-        names = sorted(groups, key=lambda x: (type(x).__name__, x))
-        row_idx = np.fromiter((s for n in names for s in groups[n]), dtype=np.int64)
-        offsets = np.zeros(len(names) + 1, dtype=np.int64)
-        np.cumsum([len(groups[n]) for n in names], out=offsets[1:])
+        names, row_idx, offsets = col.group_rows(group_key, scroll_filter)
         col.flush()
         if kind == "average":
             return names, col.gallery.segment_mean(offsets, row_idx=row_idx)

@@ -486,6 +486,31 @@ class Collection:
             self._columns[key] = col
         return col
 
+    def group_rows(self, key: str, flt=None):
+        """Rows grouped by the scalar payload value under ``key`` (the per-class loop of 32_…py:119-156 as one CSR):
+        -> (group values sorted by (type name, value), row slots [n] grouped in that order and in id order inside a
+        group, offsets [G+1]).  Rows whose value is None / missing / not a scalar belong to no group.  Vectorised over
+        the dictionary-encoded column, so a million labelled rows group in milliseconds."""
+        n = len(self.ids)
+        codes, table = self._column(key)
+        allowed = np.ones(n, dtype=bool)
+        if flt is not None:
+            words = self.filter_mask(flt)
+            allowed = np.unpackbits(words.view(np.uint8), bitorder="little")[:n].astype(bool)
+        order = np.fromiter(self.ordered_slots(), dtype=np.int64, count=n)
+        sel = order[(codes[order] >= 0) & allowed[order]]
+        present = np.unique(codes[sel])
+        by_code = {code: vk for vk, code in table.items()}
+        names_vk = sorted((by_code[int(c)] for c in present), key=lambda vk: (vk[0], vk[1]))
+        rank = np.full(len(table) + 1, -1, dtype=np.int64)
+        for r, vk in enumerate(names_vk):
+            rank[table[vk]] = r
+        r_sel = rank[codes[sel]]
+        o = np.argsort(r_sel, kind="stable")
+        offsets = np.zeros(len(names_vk) + 1, dtype=np.int64)
+        np.cumsum(np.bincount(r_sel, minlength=len(names_vk)), out=offsets[1:])
+        return [vk[1] for vk in names_vk], sel[o], offsets
+
     def filter_mask(self, flt) -> Optional[np.ndarray]:
         """Filter -> uint32 row bitmask for the device search.  The filters the reference issues
         (AND of payload equalities, 32:125-129, 33:98-103,117-137) compile to vectorised compares over

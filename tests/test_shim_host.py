@@ -321,3 +321,42 @@ def test_distance_menu_collections_rank_ascending_and_store_vectors_as_given(cli
     names, means = client.build_delegates("dist", group_key="class_name")
     assert names == ["a", "b"]
     assert np.allclose(means[0], vecs[1::2].astype(np.float64).mean(axis=0), rtol=1e-6, atol=1e-7)   # not renormalised
+
+
+def test_group_rows_matches_the_per_class_loop(client):
+    """Collection.group_rows (vectorised CSR for build_delegates) against the obvious loop over payloads, with a
+    filter, missing / None values and mixed value types."""
+    m = _models()
+    client.recreate_collection(collection_name="grp", vectors_config=m.VectorParams(size=8, distance=m.Distance.COSINE))
+    rng = np.random.default_rng(9)
+    values = ["cup", "dog", "tree", None, 3, 7, True]
+    pts, labels = [], []
+    for i in range(400):
+        v = values[int(rng.integers(0, len(values)))]
+        pl = {"class_name": v, "is_augmented": bool(i % 3 == 0)}
+        if i % 17 == 0:
+            pl.pop("class_name")
+            v = None
+        labels.append(v)
+        pid = int(rng.integers(0, 1 << 40)) if i % 2 else hashlib.md5(str(i).encode()).hexdigest()
+        pts.append(m.PointStruct(id=pid, vector=rng.standard_normal(8).tolist(), payload=pl))
+    client.upsert("grp", points=pts)
+    col = client._root.get("grp")
+    for flt in (None, m.Filter(must=[m.FieldCondition(key="is_augmented", match=m.MatchValue(value=False))])):
+        names, row_idx, offsets = col.group_rows("class_name", flt)
+        allowed = col.filter_slots(flt)
+        groups = {}
+        for s in col.ordered_slots():
+            if allowed is not None and s not in allowed:
+                continue
+            v = col.payloads[s].get("class_name")
+            if v is not None:
+                groups.setdefault((type(v).__name__, v), []).append(s)
+        want_names = sorted(groups)
+        assert [(type(x).__name__, x) for x in names] == want_names
+        assert list(row_idx) == [s for n in want_names for s in groups[n]]
+        assert list(np.diff(offsets)) == [len(groups[n]) for n in want_names]
+    names, means = client.build_delegates("grp", group_key="class_name")
+    assert len(names) == means.shape[0] == 6 and means.shape[1] == 8
+    scores, ids = client.search_batch("grp", queries=rng.standard_normal((3, 8)).astype(np.float32), k=500)
+    assert len(ids) == 3 and len(ids[0]) == 500 and ids[0][399] is not None and ids[0][400] is None
