@@ -189,6 +189,7 @@ int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx
  * out_rows:     [Q, k] int64 row slots; -1 (score -inf) where fewer than k rows qualify.
  * out_scores64: optional [Q, k] fp64 scores (what the multi-GPU merge consumes), or NULL.
  * stats:        optional.
+ * k <= 128 on the tensor-core pass (COSINE, DOT, EUCLID up to 768 columns); RBOD_E_UNSUPPORTED beyond.
  * EUCLID / MANHATTAN collections: out_scores holds the DISTANCE (sqrt of the squared sum / sum of absolute
  * differences), ascending, +inf where fewer than k rows qualify; ties broken by smaller row slot;
  * out_scores64 holds the ordering key (-squared distance / -L1 distance, larger = closer), which is what

@@ -190,7 +190,7 @@ static int plan_search(const rbod_gallery* g, int64_t Q, int k, int variant, int
   const int tiles = (int)((g->rows + K3_TILE_N - 1) / K3_TILE_N);
   int kc;
   if (g->slack >= 0) kc = round_up(k + g->slack, 8);
-  else if (tiles < 320) kc = std::max(8, round_up(k + 3, 8));
+  else if (tiles < 320) kc = std::min(K3_MAX_KC, std::max(8, round_up(k + 3, 8)));
   else kc = k <= 10 ? 32 : (k <= 40 ? 64 : 128);
   if (kc > K3_MAX_KC || kc < k)
     return set_error(RBOD_E_UNSUPPORTED, "search: k=%d (+slack) needs %d candidates per query, max is %d", k, kc,
