@@ -222,11 +222,51 @@ def run_b200(a):
     gen = torch.Generator(dev).manual_seed(1234 + rank)
     t_build0 = time.perf_counter()
     chunk = 500_000
+    k1_events = []
     for s in range(0, n_local, chunk):
         m = min(chunk, n_local - s)
-        g.upsert(torch.randn(m, a.dim, device=dev, generator=gen))
+        x = torch.randn(m, a.dim, device=dev, generator=gen)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.upsert(x)                                       # K1 l2norm_pack: fp32 in, stored rows out
+        e1.record()
+        k1_events.append((e0, e1, m))
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build0
+
+    # ---- the two HBM-bound kernels of the path, measured on the side (not part of the timed step):
+    # K1 during the build above (the first chunk is the warm-up), K2 over classes of 100 consecutive rows (4M rows)
+    def side_kernels():
+        sus, burst, hbm, src = load_peaks()
+        out = []
+        esz = 4 if a.dtype in ("f32", "fp32") else 2
+        timed = k1_events[1:] or k1_events
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in timed)
+        rows = sum(m for _, _, m in timed)
+        out_bytes = 2 + (4 if esz == 4 else 0)            # 16-bit operand (+ fp32 master for fp32 collections)
+        gbs = rows * a.dim * (4 + out_bytes) / ms / 1e6
+        out.append({"kernel": "l2norm_pack (K1, rbod_upsert)", "bound": "hbm", "achieved": gbs, "peak": hbm,
+                    "unit": "GB/s", "frac": gbs / hbm, "algorithmic": f"dim*(4+{out_bytes}) bytes per row, {rows} rows"})
+        n2 = min(n_local, 4_000_000)
+        C = n2 // 100
+        if C >= 1:
+            off = torch.arange(0, C * 100 + 1, 100, device=dev, dtype=torch.int64)
+            for _ in range(2):
+                g.segment_mean(off)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                g.segment_mean(off)
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / 5
+            b2 = C * 100 * a.dim * esz + C * a.dim * 4
+            out.append({"kernel": f"segment_mean_renorm (K2, rbod_segment_mean, whole call, {a.dtype} rows)", "bound": "hbm",
+                        "achieved": b2 / ms2 / 1e6, "peak": hbm, "unit": "GB/s", "frac": b2 / ms2 / 1e6 / hbm,
+                        "algorithmic": f"{C} classes x 100 rows x dim*{esz} bytes + {C}*dim*4 bytes out"})
+        return out
+
+    other_kernels = side_kernels() if rank == 0 else []
 
     qgen = torch.Generator(dev).manual_seed(99)          # same queries on every rank
     q_dev = torch.randn(a.queries, a.dim, device=dev, generator=qgen)
@@ -434,6 +474,7 @@ def run_b200(a):
                 "d2h_bytes_per_step": a.queries * a.k * (4 + 8 + 8), "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": n_launch_timed,
         "roofline": roofline,
+        "other_kernels": other_kernels,
         "parity": parity,
         "cpu_baseline": cpu,
         "clocks": clocks,
