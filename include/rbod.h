@@ -26,6 +26,8 @@
  *   rbod_search                                    (kernel K3 cosine_topk + exact rescoring)
  *       cosine_similarity(a, b)  33_run_all_experiments.py:76-77, used at :151, generalised
  *       from one pair to Q x N with top-k selection (client.search / query_points semantics).
+ *       Distance.MANHATTAN collections (util/qdrant_manager.py:61-66), vectors wider than 768 columns and
+ *       k > 128 are answered by kernel K5 distance_topk (exact fp64 sweep) behind the same entry point.
  *   rbod_merge_topk                                (kernel K4 topk_merge)
  *       no reference call site; merges per-GPU top-k lists after the NCCL all-gather.
  *
@@ -189,7 +191,8 @@ int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx
  * out_rows:     [Q, k] int64 row slots; -1 (score -inf) where fewer than k rows qualify.
  * out_scores64: optional [Q, k] fp64 scores (what the multi-GPU merge consumes), or NULL.
  * stats:        optional.
- * k <= 128 on the tensor-core pass (COSINE, DOT, EUCLID up to 768 columns); RBOD_E_UNSUPPORTED beyond.
+ * COSINE, DOT and EUCLID collections up to 768 columns with k <= 128 run on the tensor-core pass; MANHATTAN, wider
+ * vectors and larger k (up to 1024) take the exact fp64 sweep on the CUDA cores (kernel K5) -- same results.
  * EUCLID / MANHATTAN collections: out_scores holds the DISTANCE (sqrt of the squared sum / sum of absolute
  * differences), ascending, +inf where fewer than k rows qualify; ties broken by smaller row slot;
  * out_scores64 holds the ordering key (-squared distance / -L1 distance, larger = closer), which is what

@@ -26,13 +26,21 @@ namespace rbod {
 namespace {
 
 // fp32 queries of one batch -> fp64 (done once, so the sweep's inner loop has no conversions)
+// One warp per query; also |q| (fp64), which the COSINE key divides by.
 __global__ void __launch_bounds__(256)
 dist_widen_queries_kernel(const float* __restrict__ q, const int* __restrict__ qsel, int nf, int dim,
-                          double* __restrict__ q64) {
-  const int64_t n = (int64_t)nf * dim;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int f = (int)(i / dim), c = (int)(i - (int64_t)f * dim);
-    q64[i] = (double)q[(int64_t)qsel[f] * dim + c];
+                          double* __restrict__ q64, double* __restrict__ qnorm) {
+  const int lane = threadIdx.x & 31;
+  for (int f = blockIdx.x * 8 + (threadIdx.x >> 5); f < nf; f += gridDim.x * 8) {
+    const float* src = q + (int64_t)qsel[f] * dim;
+    double ss = 0.0;
+    for (int c = lane; c < dim; c += 32) {
+      const double x = (double)src[c];
+      q64[(int64_t)f * dim + c] = x;
+      ss = fma(x, x, ss);
+    }
+    ss = warp_sum_f64(ss);
+    if (lane == 0) qnorm[f] = sqrt(ss);
   }
 }
 
@@ -60,17 +68,23 @@ __global__ void __launch_bounds__(256, 1)
 dist_collect_kernel(const double* __restrict__ q64, const float* __restrict__ master32,
                     const uint16_t* __restrict__ rows16, int kind16, int dim, int64_t ld32, int64_t ld16,
                     int64_t n_rows, int64_t row0, int64_t stride, const uint32_t* __restrict__ row_mask,
-                    const double* __restrict__ thr, const int* __restrict__ active, int nf, int cap,
-                    double* __restrict__ coll_key, uint32_t* __restrict__ coll_idx, int* __restrict__ coll_cnt) {
+                    const double* __restrict__ thr, const int* __restrict__ active, const double* __restrict__ qnorm,
+                    int nf, int cap, double* __restrict__ coll_key, uint32_t* __restrict__ coll_idx,
+                    int* __restrict__ coll_cnt) {
   extern __shared__ __align__(16) uint8_t k5_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool f32rows = master32 != nullptr;
   const int wpr = f32rows ? K5_CH : K5_CH / 2, pitch = wpr + 1;
   double* qs = reinterpret_cast<double*>(k5_smem);                                   // [2][NQ][K5_CH]
   uint32_t* xs = reinterpret_cast<uint32_t*>(k5_smem + (size_t)2 * NQ * K5_CH * 8);  // [2][8][32][pitch]
-  __shared__ double thr_s[32];
-  if (threadIdx.x < 32) thr_s[threadIdx.x] = (threadIdx.x < nf && active[threadIdx.x]) ? thr[threadIdx.x] : INFINITY;
+  __shared__ double thr_s[32], qn_s[32];
+  if (threadIdx.x < 32) {
+    thr_s[threadIdx.x] = (threadIdx.x < nf && active[threadIdx.x]) ? thr[threadIdx.x] : INFINITY;
+    qn_s[threadIdx.x] = threadIdx.x < nf ? qnorm[threadIdx.x] : 0.0;
+  }
   __syncthreads();
+  constexpr bool kInner = METRIC == RBOD_COSINE || METRIC == RBOD_DOT;   // keys built from q . g
+  double gg = 0.0;                                                        // |row|^2 of this lane's row (COSINE)
 
   const int64_t n_visit = n_rows > row0 ? (n_rows - row0 + stride - 1) / stride : 0;   // rows of this pass
   const int n_chunks = (dim + K5_CH - 1) / K5_CH;
@@ -123,6 +137,7 @@ dist_collect_kernel(const double* __restrict__ q64, const float* __restrict__ ma
     if (ci == 0) {
 #pragma unroll
       for (int f = 0; f < NQ; ++f) acc[f] = 0.0;
+      gg = 0.0;
     }
     const int cw = min(K5_CH, dim - ci * K5_CH);
     const uint32_t* xr = xs + (((size_t)b * 8 + warp) * 32 + lane) * pitch;
@@ -135,21 +150,31 @@ dist_collect_kernel(const double* __restrict__ q64, const float* __restrict__ ma
     int c = 0;
     for (; c + 1 < cw; c += 2) {
       const double x0 = elem(c), x1 = elem(c + 1);
+      if (METRIC == RBOD_COSINE) gg = fma(x1, x1, fma(x0, x0, gg));
 #pragma unroll
       for (int f = 0; f < NQ; ++f) {
         const double2 qq = *reinterpret_cast<const double2*>(qb + f * K5_CH + c);
-        const double d0 = qq.x - x0, d1 = qq.y - x1;
-        if (METRIC == RBOD_EUCLID) acc[f] = fma(d1, d1, fma(d0, d0, acc[f]));
-        else acc[f] += fabs(d0) + fabs(d1);
+        if (kInner) {
+          acc[f] = fma(qq.y, x1, fma(qq.x, x0, acc[f]));
+        } else {
+          const double d0 = qq.x - x0, d1 = qq.y - x1;
+          if (METRIC == RBOD_EUCLID) acc[f] = fma(d1, d1, fma(d0, d0, acc[f]));
+          else acc[f] += fabs(d0) + fabs(d1);
+        }
       }
     }
     if (c < cw) {
       const double x0 = elem(c);
+      if (METRIC == RBOD_COSINE) gg = fma(x0, x0, gg);
 #pragma unroll
       for (int f = 0; f < NQ; ++f) {
-        const double d0 = qb[f * K5_CH + c] - x0;
-        if (METRIC == RBOD_EUCLID) acc[f] = fma(d0, d0, acc[f]);
-        else acc[f] += fabs(d0);
+        if (kInner) {
+          acc[f] = fma(qb[f * K5_CH + c], x0, acc[f]);
+        } else {
+          const double d0 = qb[f * K5_CH + c] - x0;
+          if (METRIC == RBOD_EUCLID) acc[f] = fma(d0, d0, acc[f]);
+          else acc[f] += fabs(d0);
+        }
       }
     }
     if (ci == n_chunks - 1) {
@@ -157,7 +182,15 @@ dist_collect_kernel(const double* __restrict__ q64, const float* __restrict__ ma
       if (r >= 0) {
 #pragma unroll
         for (int f = 0; f < NQ; ++f) {
-          const double key = -acc[f];
+          double key;
+          if (METRIC == RBOD_COSINE) {
+            const double den = qn_s[f] * sqrt(gg);
+            key = den > 0.0 ? acc[f] / den : 0.0;        // the formula of cosine_similarity, 33_…py:76-77
+          } else if (METRIC == RBOD_DOT) {
+            key = acc[f];
+          } else {
+            key = -acc[f];
+          }
           if (key >= thr_s[f]) {             // thr_s is +inf for slots beyond the batch and for finished queries
             const int slot = atomicAdd(coll_cnt + f, 1);
             if (slot < cap) {
@@ -232,7 +265,9 @@ dist_select_kernel(const double* __restrict__ coll_key, const uint32_t* __restri
       const unsigned long long o = have ? sk[j] : 0ull;
       const unsigned long long bits = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
       const double key = have ? __longlong_as_double((long long)bits) : -INFINITY;
-      out_scores[q * k + j] = have ? (float)(metric == RBOD_EUCLID ? sqrt(-key) : -key) : INFINITY;
+      const bool dist = metric == RBOD_EUCLID || metric == RBOD_MANHATTAN;
+      out_scores[q * k + j] = !have ? (dist ? INFINITY : -INFINITY)
+                                    : (float)(metric == RBOD_EUCLID ? sqrt(-key) : (metric == RBOD_MANHATTAN ? -key : key));
       out_rows[q * k + j] = have ? (int64_t)si[j] : -1;
       if (out_keys) out_keys[q * k + j] = key;
     }
@@ -251,18 +286,18 @@ dist_select_kernel(const double* __restrict__ coll_key, const uint32_t* __restri
 
 }  // namespace
 
-int launch_dist_widen_queries(const float* q, const int* qsel, int nf, int dim, double* q64, cudaStream_t st) {
+int launch_dist_widen_queries(const float* q, const int* qsel, int nf, int dim, double* q64, double* qnorm,
+                              cudaStream_t st) {
   if (nf <= 0) return RBOD_OK;
-  const int64_t n = (int64_t)nf * dim;
-  dist_widen_queries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, qsel, nf, dim, q64);
+  dist_widen_queries_kernel<<<(unsigned)((nf + 7) / 8), 256, 0, st>>>(q, qsel, nf, dim, q64, qnorm);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }
 
 int launch_dist_collect(int metric, const double* q64, const float* master32, const uint16_t* rows16, int kind16,
                         int dim, int64_t ld32, int64_t ld16, int64_t n_rows, int64_t row0, int64_t stride,
-                        const uint32_t* row_mask, const double* thr, const int* active, int nf, int cap,
-                        double* coll_key, uint32_t* coll_idx, int* coll_cnt, int num_sms, cudaStream_t st) {
+                        const uint32_t* row_mask, const double* thr, const int* active, const double* qnorm, int nf,
+                        int cap, double* coll_key, uint32_t* coll_idx, int* coll_cnt, int num_sms, cudaStream_t st) {
   if (nf <= 0 || n_rows <= 0) return RBOD_OK;
   if (nf > 32) return set_error(RBOD_E_INVAL, "dist_collect: at most 32 queries per pass");
   const int64_t rows_visited = (n_rows - row0 + stride - 1) / stride;
@@ -275,14 +310,18 @@ int launch_dist_collect(int metric, const double* q64, const float* master32, co
     RBOD_CUDA(cudaFuncSetAttribute(dist_collect_kernel<METRIC, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)smem));                                                                \
     dist_collect_kernel<METRIC, NQ><<<grid, 256, smem, st>>>(q64, master32, rows16, kind16, dim, ld32, ld16,    \
-                                                             n_rows, row0, stride, row_mask, thr, active, nf,  \
-                                                             cap, coll_key, coll_idx, coll_cnt);               \
+                                                             n_rows, row0, stride, row_mask, thr, active,      \
+                                                             qnorm, nf, cap, coll_key, coll_idx, coll_cnt);    \
   } while (0)
   // 8 accumulators per lane for batches of up to 8 queries (single-query searches of the scripts), 32 otherwise
   if (metric == RBOD_EUCLID) {
     if (nf <= 8) RBOD_K5_GO(RBOD_EUCLID, 8); else RBOD_K5_GO(RBOD_EUCLID, 32);
-  } else {
+  } else if (metric == RBOD_MANHATTAN) {
     if (nf <= 8) RBOD_K5_GO(RBOD_MANHATTAN, 8); else RBOD_K5_GO(RBOD_MANHATTAN, 32);
+  } else if (metric == RBOD_DOT) {
+    if (nf <= 8) RBOD_K5_GO(RBOD_DOT, 8); else RBOD_K5_GO(RBOD_DOT, 32);
+  } else {
+    if (nf <= 8) RBOD_K5_GO(RBOD_COSINE, 8); else RBOD_K5_GO(RBOD_COSINE, 32);
   }
 #undef RBOD_K5_GO
   RBOD_CUDA(cudaGetLastError());

@@ -771,12 +771,12 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
   // threshold finishes it)
   const int cap = 8192, sample_cap = 8192, batch = 32, max_iter = 12;
   if (k > 1024)
-    return set_error(RBOD_E_UNSUPPORTED, "rbod_search: k=%d > 1024 for EUCLID / MANHATTAN collections", k);
+    return set_error(RBOD_E_UNSUPPORTED, "rbod_search: k=%d > 1024", k);
   const void* qd = nullptr;
   RBOD_TRY(to_device(queries, (size_t)Q * g->dim * 4, g->q32, st, &qd));
   const float* q_dev = static_cast<const float*>(qd);
   RBOD_TRY(g->dist_q64.ensure((size_t)batch * g->dim * 8));
-  RBOD_TRY(g->dist_thr.ensure((size_t)batch * 8));
+  RBOD_TRY(g->dist_thr.ensure((size_t)2 * batch * 8));       // thresholds, then the batch's query norms
   RBOD_TRY(g->dist_ctl.ensure((size_t)(2 * batch + 1) * 4));
   RBOD_TRY(g->coll_score.ensure((size_t)batch * cap * 8));
   RBOD_TRY(g->coll_idx.ensure((size_t)batch * cap * 4));
@@ -785,6 +785,7 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
   int* d_active = d_qsel + batch;
   int* d_nactive = d_qsel + 2 * batch;
   double* d_thr = g->dist_thr.as<double>();
+  double* d_qnorm = d_thr + batch;
   std::vector<double> h_thr(batch, -INFINITY);
   std::vector<int> h_ctl(2 * batch + 1);
   const int64_t sample_stride = (g->rows + sample_cap - 1) / sample_cap;   // > 1 iff more than `sample_cap` rows
@@ -799,11 +800,11 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
     RBOD_CUDA(cudaMemcpyAsync(d_thr, h_thr.data(), (size_t)batch * 8, cudaMemcpyHostToDevice, st));
     RBOD_CUDA(cudaMemsetAsync(g->coll_cnt.p, 0, (size_t)batch * 4, st));
     if (nf < batch) RBOD_CUDA(cudaMemsetAsync(g->dist_q64.p, 0, (size_t)batch * g->dim * 8, st));   // zero rows pad the batch
-    RBOD_TRY(launch_dist_widen_queries(q_dev, d_qsel, nf, g->dim, g->dist_q64.as<double>(), st));
+    RBOD_TRY(launch_dist_widen_queries(q_dev, d_qsel, nf, g->dim, g->dist_q64.as<double>(), d_qnorm, st));
     ++*launches;
     if (sample_stride > 1) {
       RBOD_TRY(launch_dist_collect(g->metric, g->dist_q64.as<double>(), g->master32, g->rows16, g->kind16, g->dim,
-                                   g->dim, g->dp, g->rows, 0, sample_stride, mask_dev, d_thr, d_active, nf, cap,
+                                   g->dim, g->dp, g->rows, 0, sample_stride, mask_dev, d_thr, d_active, d_qnorm, nf, cap,
                                    g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
                                    g->num_sms, st));
       RBOD_TRY(launch_dist_select(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
@@ -815,7 +816,7 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
     for (; iter < max_iter && left > 0; ++iter) {
       RBOD_CUDA(cudaMemsetAsync(d_nactive, 0, 4, st));
       RBOD_TRY(launch_dist_collect(g->metric, g->dist_q64.as<double>(), g->master32, g->rows16, g->kind16, g->dim,
-                                   g->dim, g->dp, g->rows, 0, 1, mask_dev, d_thr, d_active, nf, cap,
+                                   g->dim, g->dp, g->rows, 0, 1, mask_dev, d_thr, d_active, d_qnorm, nf, cap,
                                    g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
                                    g->num_sms, st));
       RBOD_TRY(launch_dist_select(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
@@ -840,12 +841,10 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     return set_error(RBOD_E_INVAL, "rbod_search: bad arguments");
   if (stats) memset(stats, 0, sizeof(*stats));
   if (Q == 0) return RBOD_OK;
-  // MANHATTAN always, EUCLID only when the vectors are too wide for the tensor-core pass: exact fp64 sweep (K5).
-  // EUCLID up to K3_MAX_DP columns runs on the tensor cores with the row-bias epilogue.
-  const bool distance_metric = g->metric == RBOD_MANHATTAN || (g->metric == RBOD_EUCLID && g->dp > K3_MAX_DP);
-  if (!distance_metric && g->dp > K3_MAX_DP)
-    return set_error(RBOD_E_UNSUPPORTED, "rbod_search: dim %d > %d not supported by the tcgen05 pass", g->dim,
-                     K3_MAX_DP);
+  // What the tensor-core pass does not cover takes the exact fp64 sweep (K5): MANHATTAN (not a contraction), vectors
+  // wider than K3_MAX_DP columns, and k beyond the K3 candidate lists.  Everything else -- COSINE, DOT and EUCLID
+  // (row-bias epilogue) up to 768 columns, k <= 128 -- runs on the tensor cores.
+  const bool distance_metric = g->metric == RBOD_MANHATTAN || g->dp > K3_MAX_DP || k > K3_MAX_KC;
   if (Q > (1ll << 24)) return set_error(RBOD_E_INVAL, "rbod_search: Q too large");
   if (g->rows >= 0xffffffffll) return set_error(RBOD_E_UNSUPPORTED, "rbod_search: more than 2^32-2 rows per shard");
   RBOD_CUDA(cudaSetDevice(g->device));
@@ -860,7 +859,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     int64_t* dr = is_device_ptr(out_rows) ? out_rows : g->out_rows.as<int64_t>();
     double* dk = (out_scores64 && is_device_ptr(out_scores64)) ? out_scores64 : g->out_scores64.as<double>();
     if (g->rows == 0) {
-      std::vector<float> hs(n_out, INFINITY);
+      std::vector<float> hs(n_out, (g->metric == RBOD_EUCLID || g->metric == RBOD_MANHATTAN) ? INFINITY : -INFINITY);
       std::vector<int64_t> hr(n_out, -1);
       std::vector<double> hd(n_out, -INFINITY);
       RBOD_CUDA(cudaMemcpyAsync(out_scores, hs.data(), n_out * 4, cudaMemcpyDefault, st));

@@ -154,11 +154,12 @@ int launch_select_collected(const double* coll_score, const uint32_t* coll_idx, 
                             const int* flag_q, int f0, int nf, int cap, int k, int metric, float* out_scores,
                             int64_t* out_rows, double* out_scores64, int* overflow, cudaStream_t st);
 // K5 (EUCLID / MANHATTAN)
-int launch_dist_widen_queries(const float* q, const int* qsel, int nf, int dim, double* q64, cudaStream_t st);
+int launch_dist_widen_queries(const float* q, const int* qsel, int nf, int dim, double* q64, double* qnorm,
+                              cudaStream_t st);
 int launch_dist_collect(int metric, const double* q64, const float* master32, const uint16_t* rows16, int kind16,
                         int dim, int64_t ld32, int64_t ld16, int64_t n_rows, int64_t row0, int64_t stride,
-                        const uint32_t* row_mask, const double* thr, const int* active, int nf, int cap,
-                        double* coll_key, uint32_t* coll_idx, int* coll_cnt, int num_sms, cudaStream_t st);
+                        const uint32_t* row_mask, const double* thr, const int* active, const double* qnorm, int nf,
+                        int cap, double* coll_key, uint32_t* coll_idx, int* coll_cnt, int num_sms, cudaStream_t st);
 int launch_dist_select(const double* coll_key, const uint32_t* coll_idx, int* coll_cnt, const int* qsel, int nf,
                        int cap, int k, int sample, int metric, double* thr, int* active, int* n_active,
                        float* out_scores, int64_t* out_rows, double* out_keys, cudaStream_t st);

@@ -32,6 +32,15 @@ for metric, dtype in itertools.product(("cosine", "dot", "euclid", "manhattan"),
                       int(_rng.choice([1, 5, 33])), bool(_rng.integers(0, 2)), int(_rng.integers(0, 1 << 30))))
 
 
+# beyond the tensor-core pass: vectors wider than 768 columns and k above its candidate lists take the exact fp64
+# sweep (K5) for every distance
+for metric in ("cosine", "dot", "euclid", "manhattan"):
+    CASES.append((metric, "f32", 3000, 1024, 9, 5, False, 77))
+    CASES.append((metric, "bf16", 2500, 1280, 40, 10, True, 78))
+    CASES.append((metric, "f16", 6000, 256, 3, 300, False, 79))
+    CASES.append((metric, "f32", 9000, 768, 33, 129, True, 80))
+
+
 @pytest.mark.parametrize("metric,dtype,n,dim,Q,k,masked,seed", CASES)
 def test_small_shapes_all_distances(metric, dtype, n, dim, Q, k, masked, seed):
     from retrieval_based_object_detection_b200 import Gallery
