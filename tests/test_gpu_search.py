@@ -241,11 +241,15 @@ def test_empty_gallery_bad_args_and_device_io(G):
     g.upsert(x)
     with pytest.raises(RbodError):
         g.search(x[:2], 0)
+    stored = g.get_rows(np.arange(3000))
+    r500 = g.search(x[:2], 500, want_scores64=True)          # beyond the tensor-core candidate lists: exact fp64 sweep
+    ws5, wi5 = O.cosine_topk(x[:2], stored, 500, rowwise=True)
+    assert np.array_equal(r500.rows, wi5) and np.allclose(r500.scores64, ws5, rtol=1e-9, atol=1e-12)
+    assert r500.stats["sweep_queries"] == 2
     with pytest.raises(RbodError):
-        g.search(x[:2], 500)                 # more candidates than the kernel keeps
+        g.search(x[:2], 2000)                # more than any path keeps
     with pytest.raises(ValueError):
         g.search(np.ones((2, 100), np.float32), 3)
-    stored = g.get_rows(np.arange(3000))
     qd = torch.from_numpy(x[:50]).cuda()
     r = g.search(qd, 10, want_scores64=True)  # device in -> device out
     assert r.rows.is_cuda and r.scores.is_cuda
