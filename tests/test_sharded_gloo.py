@@ -138,3 +138,44 @@ def test_two_rank_delegate_means_equal_single_gallery(tmp_path):
         got = np.load(tmp_path / f"cent_{r}.npy")
         ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64)).max()
         assert ulp <= 1, ulp                                  # fp64 sums added in a different order: <= 1 fp32 ulp
+
+
+# ---------------------------------------------------------------------------------------------
+# EUCLID collection over row shards: the lists travel and merge as ordering keys (-d^2), distances come back
+# ---------------------------------------------------------------------------------------------
+def _worker_euclid(rank, world, port, n, dim, Q, k, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = O.synthetic_unit_rows(n, dim, seed=5) * np.float32(1.7)
+        q = O.synthetic_unit_rows(Q, dim, seed=6)
+        a, b = shard_range(n, rank, world)
+
+        def local_search(queries, kk):                        # what Gallery.search gives for an EUCLID shard
+            _, rows, keys = O.distance_topk(np.asarray(queries), x[a:b], kk, "euclid")
+            return torch.from_numpy(keys), torch.from_numpy(rows)
+
+        def merge(g_s, g_i, kk):
+            s, i = O.merge_topk(g_s.numpy(), g_i.numpy(), kk)
+            return torch.from_numpy(s.astype(np.float32)), torch.from_numpy(i), torch.from_numpy(s)
+
+        sg = ShardedGallery(dim, n, dtype="f32", metric="euclid", local_search=local_search, merge=merge,
+                            create_local=False)
+        d32, ids, keys = sg.search(q, k)
+        np.save(os.path.join(out_dir, f"e_ids_{rank}.npy"), ids.numpy())
+        np.save(os.path.join(out_dir, f"e_d_{rank}.npy"), d32.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_euclid_search_returns_distances(tmp_path):
+    n, dim, Q, k, world = 205, 32, 6, 7, 2
+    port = _free_port()
+    mp.spawn(_worker_euclid, args=(world, port, n, dim, Q, k, str(tmp_path)), nprocs=world, join=True)
+    x = O.synthetic_unit_rows(n, dim, seed=5) * np.float32(1.7)
+    q = O.synthetic_unit_rows(Q, dim, seed=6)
+    wd, wi, _ = O.distance_topk(q, x, k, "euclid")
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"e_ids_{r}.npy"), wi)
+        d = np.load(tmp_path / f"e_d_{r}.npy")
+        assert np.allclose(d, wd, rtol=1e-6) and np.all(np.diff(d, axis=1) >= 0)
