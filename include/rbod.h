@@ -35,7 +35,8 @@
  *   - Every function returns 0 (RBOD_OK) or a negative errno-style code; rbod_last_error()
  *     returns a thread-local, human-readable message for the last failure.  Nothing aborts.
  *   - Pointers marked "host or device" are classified with cudaPointerGetAttributes; host
- *     buffers are staged through pinned memory inside the call.
+ *     buffers are copied to / from device workspaces inside the call (pass pinned memory to
+ *     keep those copies at full PCIe speed).
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls that
  *     write host outputs synchronise the stream before returning; rbod_search always does
  *     (it reports certification statistics).

@@ -50,25 +50,6 @@ void DevBuf::release() {
   p = nullptr;
   cap = 0;
 }
-int PinBuf::ensure(size_t bytes) {
-  if (bytes <= cap) return RBOD_OK;
-  if (p) cudaFreeHost(p);
-  p = nullptr;
-  cap = 0;
-  cudaError_t e = cudaMallocHost(&p, bytes);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    p = nullptr;
-    return set_error(RBOD_E_NOMEM, "cudaMallocHost of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-  }
-  cap = bytes;
-  return RBOD_OK;
-}
-void PinBuf::release() {
-  if (p) cudaFreeHost(p);
-  p = nullptr;
-  cap = 0;
-}
 
 static bool is_device_ptr(const void* p) {
   if (!p) return false;
@@ -302,8 +283,6 @@ int rbod_destroy(rbod_gallery* g) {
                     &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->seg_scratch, &g->seg_member, &g->gather_idx,
                     &g->gather_out, &g->dist_q64, &g->dist_thr, &g->dist_ctl};
   for (DevBuf* b : bufs) b->release();
-  g->pin_a.release();
-  g->pin_b.release();
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
   cudaGetLastError();

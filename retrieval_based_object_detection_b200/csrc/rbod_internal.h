@@ -26,19 +26,11 @@ int set_error(int code, const char* fmt, ...);
     if (_rc != RBOD_OK) return _rc; \
   } while (0)
 
-// ---- growable device / pinned buffers ---------------------------------------------------
+// ---- growable device buffers ------------------------------------------------------------
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   int ensure(size_t bytes);  // contents are NOT preserved on growth
-  void release();
-  template <class T>
-  T* as() const { return static_cast<T*>(p); }
-};
-struct PinBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  int ensure(size_t bytes);
   void release();
   template <class T>
   T* as() const { return static_cast<T*>(p); }
@@ -204,6 +196,5 @@ struct rbod_gallery {
   rbod::DevBuf seg_idx, seg_off, seg_out, seg_partials, seg_prefix, seg_arrive, seg_scratch, seg_member;
   rbod::DevBuf gather_idx, gather_out;
   rbod::DevBuf dist_q64, dist_thr, dist_ctl;   // K5: widened query batch, thresholds, {qsel, active, n_active}
-  rbod::PinBuf pin_a, pin_b;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
