@@ -9,6 +9,9 @@
  *   oracle_l2_normalize    normalise-on-upsert of a COSINE collection (third party, parity unpinned)
  *   oracle_segment_mean    compute_average per class     32_create_delegate_vector.py:9-10
  *                          + the stored (normalised, float32) form of the mean  :41-42
+ *   oracle_distance_topk   the other distances of the collection menu (util/qdrant_manager.py:61-66): DOT, EUCLID,
+ *                          MANHATTAN on the stored values, ordered by (key desc, id asc), key = q.g / -d^2 / -d
+ *                          (third-party scoring semantics, parity unpinned)
  * Pinned against tests/golden/ (vectors produced by the reference's own functions).
  */
 #include <math.h>
@@ -94,4 +97,26 @@ void oracle_cosine_topk(const float* q, int64_t Q, const float* g, int64_t N, in
     }
   }
   free(gn);
+}
+
+/* metric: 1 = DOT (key = q.g), 2 = EUCLID (key = -sum (q-g)^2), 3 = MANHATTAN (key = -sum |q-g|).
+ * out_keys: the ordering keys, descending; out_ids: rows, -1 where fewer than k rows are allowed. */
+void oracle_distance_topk(const float* q, int64_t Q, const float* g, int64_t N, int64_t dim, int64_t k, int metric,
+                          const uint8_t* row_allowed, double* out_keys, int64_t* out_ids) {
+  for (int64_t i = 0; i < Q; ++i) {
+    double* s = out_keys + i * k;
+    int64_t* ids = out_ids + i * k;
+    for (int64_t j = 0; j < k; ++j) { s[j] = -INFINITY; ids[j] = -1; }
+    for (int64_t r = 0; r < N; ++r) {
+      if (row_allowed && !row_allowed[r]) continue;
+      double acc = 0.0;
+      for (int64_t d = 0; d < dim; ++d) {
+        const double a = (double)q[i * dim + d], b = (double)g[r * dim + d];
+        if (metric == 1) acc += a * b;
+        else if (metric == 2) acc += (a - b) * (a - b);
+        else acc += fabs(a - b);
+      }
+      topk_insert(s, ids, k, metric == 1 ? acc : -acc, r);
+    }
+  }
 }

@@ -37,6 +37,8 @@ def lib():
         L.oracle_segment_mean.argtypes = [P, I, P, P, I, P]
         L.oracle_cosine_topk.restype = None
         L.oracle_cosine_topk.argtypes = [P, I, P, I, I, I, P, P, P]
+        L.oracle_distance_topk.restype = None
+        L.oracle_distance_topk.argtypes = [P, I, P, I, I, I, ctypes.c_int, P, P, P]
         _lib = L
     return _lib
 
@@ -76,4 +78,16 @@ def cosine_topk(queries, stored, k, row_allowed=None):
     out_s = np.empty((q.shape[0], k), dtype=np.float64)
     out_i = np.empty((q.shape[0], k), dtype=np.int64)
     lib().oracle_cosine_topk(_p(q), q.shape[0], _p(g), g.shape[0], g.shape[1], k, _p(allowed), _p(out_s), _p(out_i))
+    return out_s, out_i
+
+
+def distance_topk(queries, stored, k, metric, row_allowed=None):
+    """(keys f64 [Q,k] descending, rows i64 [Q,k]); metric in {"dot", "euclid", "manhattan"}; key = q.g / -d^2 / -d."""
+    q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+    g = np.ascontiguousarray(stored, dtype=np.float32)
+    allowed = None if row_allowed is None else np.ascontiguousarray(row_allowed, dtype=np.uint8)
+    out_s = np.empty((q.shape[0], k), dtype=np.float64)
+    out_i = np.empty((q.shape[0], k), dtype=np.int64)
+    lib().oracle_distance_topk(_p(q), q.shape[0], _p(g), g.shape[0], g.shape[1], k,
+                               {"dot": 1, "euclid": 2, "manhattan": 3}[metric], _p(allowed), _p(out_s), _p(out_i))
     return out_s, out_i

@@ -149,3 +149,30 @@ def test_merge_topk_oracle():
     ms, mi = O.merge_topk(np.stack(per_s), np.stack(per_i), k)
     ws, wi = O.topk_from_scores(full, k)
     assert np.array_equal(mi, wi) and np.array_equal(ms, ws)
+
+
+@pytest.mark.parametrize("metric", ["euclid", "manhattan"])
+def test_numpy_and_c_restatements_of_the_distance_topk_agree(metric):
+    """Two independent restatements (vectorised numpy, strictly sequential C) of the distance top-k give the same
+    rows and keys, with duplicates (ties to the smaller row), a row mask and k beyond the allowed rows."""
+    from oracle import oracle_c as OC
+
+    rng = np.random.default_rng(12)
+    n, dim, Q, k = 700, 48, 9, 12
+    g = (rng.standard_normal((n, dim)) * 1.3).astype(np.float32)
+    g[300:305] = g[17]
+    q = rng.standard_normal((Q, dim)).astype(np.float32)
+    q[0] = g[17]
+    allowed = rng.random(n) < 0.5
+    allowed[[17, 300, 301]] = True
+    for mask in (None, allowed):
+        d, rows, keys = O.distance_topk(q, g, k, metric, row_mask=mask)
+        ck, crows = OC.distance_topk(q, g, k, metric, row_allowed=mask)
+        assert np.array_equal(rows, crows)
+        assert np.allclose(keys, ck, rtol=1e-12, atol=0)
+        assert np.all(np.diff(d, axis=1) >= 0) and d[0, 0] == 0.0 and rows[0, 0] == 17
+    few = np.zeros(n, dtype=bool)
+    few[[5, 9]] = True
+    d, rows, keys = O.distance_topk(q[:2], g, 4, metric, row_mask=few)
+    ck, crows = OC.distance_topk(q[:2], g, 4, metric, row_allowed=few)
+    assert np.array_equal(rows, crows) and np.all(rows[:, 2:] == -1) and np.all(np.isinf(d[:, 2:]))
