@@ -59,3 +59,29 @@ def test_product_never_imports_oracle():
                     if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "liboracle" in src:
                         bad.append(os.path.join(dirpath, fn))
     assert not bad, f"product code references the oracle: {bad}"
+
+
+def test_header_constants_match_the_binding():
+    """Every #define RBOD_* value in include/rbod.h that the ctypes layer mirrors has the same value there, and the
+    metric / dtype / delegate tables of the Python layer cover exactly the codes the header defines."""
+    text = open(os.path.join(ROOT, "include", "rbod.h"), encoding="utf-8").read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"^#define\s+(RBOD_[A-Z0-9_]+)\s+\(?(-?\d+)\)?", text, flags=re.M)}
+    for name in ("RBOD_OK", "RBOD_E_IO", "RBOD_E_NOMEM", "RBOD_E_INVAL", "RBOD_E_RANGE", "RBOD_E_OVERFLOW",
+                 "RBOD_E_UNSUPPORTED", "RBOD_F32", "RBOD_BF16", "RBOD_F16", "RBOD_COSINE", "RBOD_DOT", "RBOD_EUCLID",
+                 "RBOD_MANHATTAN", "RBOD_UPSERT_RAW"):
+        assert defs[name] == getattr(_native, name), name
+    assert defs["RBOD_ABI_VERSION"] == 1
+    assert set(_native.METRICS.values()) == {defs[n] for n in ("RBOD_COSINE", "RBOD_DOT", "RBOD_EUCLID", "RBOD_MANHATTAN")}
+    assert set(_native.DTYPES.values()) == {defs[n] for n in ("RBOD_F32", "RBOD_BF16", "RBOD_F16")}
+    assert _native.DELEGATE_KINDS == {"average": defs["RBOD_DELEGATE_AVERAGE"], "centroid": defs["RBOD_DELEGATE_CENTROID"],
+                                      "weighted": defs["RBOD_DELEGATE_WEIGHTED"], "medoid": defs["RBOD_DELEGATE_MEDOID"]}
+    # struct sizes the ctypes mirrors must agree with (checked through a round trip of rbod_info's error path only:
+    # no GPU here) -- field counts guard against silent drift
+    assert len(_native.GalleryInfo._fields_) == 11 and len(_native.SearchStats._fields_) == 10
+    # every distance of the reference's menu (util/qdrant_manager.py:61-66) maps to a metric of the library
+    from qdrant_client.models import Distance
+    from retrieval_based_object_detection_b200 import store
+
+    src = open(store.__file__, encoding="utf-8").read()
+    for d in Distance:
+        assert f'"{d.value}"' in src, d
