@@ -360,3 +360,33 @@ def test_group_rows_matches_the_per_class_loop(client):
     assert len(names) == means.shape[0] == 6 and means.shape[1] == 8
     scores, ids = client.search_batch("grp", queries=rng.standard_normal((3, 8)).astype(np.float32), k=500)
     assert len(ids) == 3 and len(ids[0]) == 500 and ids[0][399] is not None and ids[0][400] is None
+
+
+def test_distance_of_a_collection_survives_reopening(client, store_dir):
+    """A collection created from the distance menu keeps its distance across processes: after a snapshot and a reopen
+    (memory-mapped vectors.npy streamed back in raw form) an EUCLID collection still stores vectors as given, ranks
+    by ascending distance and pages its scroll by id."""
+    import os
+
+    import qdrant_client as qc
+
+    m = _models()
+    dim, n = 24, 30
+    client.recreate_collection(collection_name="eu", vectors_config=m.VectorParams(size=dim, distance=m.Distance.EUCLID))
+    rng = np.random.default_rng(4)
+    vecs = (rng.standard_normal((n, dim)) * 3.0).astype(np.float32)
+    client.upsert("eu", points=[m.PointStruct(id=100 + i, vector=vecs[i].tolist(), payload={"i": i}) for i in range(n)])
+    assert client.search("eu", vecs[4].tolist(), limit=1)[0].id == 104            # materialises the device copy
+    qc._close_all()                                                               # snapshot: vectors.npy + points.json
+    assert os.path.exists(os.path.join(store_dir, "localhost_6333", "eu", "vectors.npy"))
+    c2 = qc.QdrantClient(host="localhost", port=6333)
+    assert c2.get_collection("eu").config.params.vectors.distance == m.Distance.EUCLID
+    hits = c2.search("eu", vecs[4].tolist(), limit=4, with_vectors=True)
+    wd, wi, _ = O.distance_topk(vecs[4:5], vecs, 4, "euclid")
+    assert [h.id for h in hits] == [100 + int(i) for i in wi[0]] and hits[0].score == 0.0
+    assert np.allclose([h.score for h in hits], wd[0], rtol=1e-6)
+    assert np.array_equal(np.asarray(hits[0].vector, dtype=np.float32), vecs[4])  # still not normalised
+    page1, nxt = c2.scroll("eu", limit=7)
+    page2, nxt2 = c2.scroll("eu", limit=7, offset=nxt)
+    assert [r.id for r in page1] == list(range(100, 107)) and nxt == 107
+    assert [r.id for r in page2] == list(range(107, 114)) and nxt2 == 114
