@@ -266,7 +266,7 @@ def run_b200(a):
                         "algorithmic": f"{C} classes x 100 rows x dim*{esz} bytes + {C}*dim*4 bytes out"})
         return out
 
-    other_kernels = side_kernels() if rank == 0 else []
+    other_kernels = side_kernels()          # every rank (keeps the ranks in step); rank 0's numbers are reported
 
     qgen = torch.Generator(dev).manual_seed(99)          # same queries on every rank
     q_dev = torch.randn(a.queries, a.dim, device=dev, generator=qgen)
