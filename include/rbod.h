@@ -214,6 +214,14 @@ int rbod_merge_topk(const double* scores64, const int64_t* ids, int32_t G, int64
  * fp32, device or host.  Small problems only (Q * rows <= 2^28).                          */
 int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* out, void* stream);
 
+/* Host-only: the work decomposition rbod_search would choose for a tensor-core search of Q queries, top k, over a
+ * gallery of `rows` vectors of `dim` columns on a device with `num_sms` SMs and `smem_optin` bytes of opt-in shared
+ * memory per CTA (B200: 148, 232448).  Needs no GPU.  out[0..8] = candidates per query, slices, grid, query tiles,
+ * gallery tiles, pipeline stages, k-blocks per stage, query-tile k-blocks kept in TMEM, dynamic shared memory bytes.
+ * Returns RBOD_E_UNSUPPORTED when the shape must take the fp64 sweep instead (k > 128 or more than 768 columns). */
+int rbod_debug_plan(int32_t dim, int64_t rows, int64_t Q, int32_t k, int32_t variant, int32_t num_sms,
+                    int32_t smem_optin, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

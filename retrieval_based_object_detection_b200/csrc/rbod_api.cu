@@ -1102,6 +1102,32 @@ int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* o
   return RBOD_OK;
 }
 
+int rbod_debug_plan(int32_t dim, int64_t rows, int64_t Q, int32_t k, int32_t variant, int32_t num_sms,
+                    int32_t smem_optin, int64_t* out) {
+  if (!out || dim < 1 || rows < 1 || Q < 1 || k < 1 || variant < 0 || variant > 2 || num_sms < 2)
+    return set_error(RBOD_E_INVAL, "rbod_debug_plan: bad arguments");
+  rbod_gallery g;                 // host fields only: nothing is allocated, nothing touches a device
+  g.dim = dim;
+  g.dp = round_up(dim, K3_KBLOCK);
+  g.rows = rows;
+  g.num_sms = num_sms;
+  if (g.dp > K3_MAX_DP || k > K3_MAX_KC)
+    return set_error(RBOD_E_UNSUPPORTED, "rbod_debug_plan: dim %d / k %d take the fp64 sweep, not the tensor-core pass",
+                     dim, k);
+  SearchPlan P;
+  RBOD_TRY(plan_search(&g, Q, k, variant, smem_optin, &P));
+  out[0] = P.kc;
+  out[1] = P.slices;
+  out[2] = P.grid;
+  out[3] = P.num_qt;
+  out[4] = P.tiles_total;
+  out[5] = P.num_stages;
+  out[6] = P.kbs;
+  out[7] = P.a_tmem_kb;
+  out[8] = (int64_t)P.smem;
+  return RBOD_OK;
+}
+
 int rbod_merge_topk(const double* scores64, const int64_t* ids, int32_t G, int64_t Q, int32_t k,
                     float* out_scores, int64_t* out_ids, double* out_scores64, void* stream) {
   if (!scores64 || !ids || !out_scores || !out_ids || Q < 0 || k < 1)

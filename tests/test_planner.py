@@ -1,0 +1,68 @@
+"""The search planner (host code of librbod.so, no GPU needed): for every shape the tensor-core pass accepts, the work
+decomposition it chooses respects the kernel's hard limits -- shared memory, candidate-list and merge capacities,
+pipeline depth, the one-CTA-per-SM cooperative grid -- and covers the whole problem."""
+import ctypes
+import itertools
+
+import pytest
+
+from retrieval_based_object_detection_b200 import _native
+
+SMS, SMEM_OPTIN = 148, 232448          # B200
+
+
+def _plan(dim, rows, Q, k, variant=0):
+    lib = _native.load()
+    out = (ctypes.c_int64 * 9)()
+    rc = lib.rbod_debug_plan(dim, rows, Q, k, variant, SMS, SMEM_OPTIN, out)
+    return rc, dict(zip(("kc", "slices", "grid", "num_qt", "tiles", "stages", "kbs", "a_tmem_kb", "smem"), list(out)))
+
+
+DIMS = (3, 64, 100, 128, 320, 512, 640, 768)
+ROWS = (1, 127, 128, 129, 4_000, 40_960, 41_000, 1_000_000, 12_500_000, 100_000_000)
+QS = (1, 8, 9, 128, 129, 1_000, 10_000, 65_536)
+KS = (1, 5, 10, 11, 40, 41, 100, 125, 128)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_every_accepted_shape_gets_a_plan_within_the_kernel_limits(variant):
+    seen_kbs = set()
+    for dim, rows, Q, k in itertools.product(DIMS, ROWS, QS, KS):
+        rc, p = _plan(dim, rows, Q, k, variant)
+        assert rc == 0, (dim, rows, Q, k, variant, _native.load().rbod_last_error())
+        per_unit = 256 if variant == 2 else 128
+        assert p["kc"] >= k and p["kc"] <= 128 and p["kc"] % 8 == 0
+        assert p["tiles"] == (rows + 127) // 128 and p["num_qt"] == (Q + per_unit - 1) // per_unit
+        assert 1 <= p["slices"] <= p["tiles"] and p["slices"] * p["kc"] <= 8192         # merge_partials sorts <= 8192 keys
+        assert 1 <= p["grid"] <= SMS and (variant != 2 or p["grid"] % 2 == 0)            # cooperative launch: <= 1 CTA / SM
+        assert p["grid"] <= p["slices"] * p["num_qt"] * (2 if variant == 2 else 1)
+        assert p["smem"] <= SMEM_OPTIN
+        assert p["stages"] >= (1 if variant == 1 else 2) and p["stages"] <= 8
+        assert p["kbs"] in (2, 4) and (variant != 2 or p["kbs"] == 4) and (variant != 1 or p["kbs"] == 2)
+        num_kb = (dim + 63) // 64
+        assert 0 <= p["a_tmem_kb"] <= num_kb and (variant == 1) == (p["a_tmem_kb"] == 0)
+        if variant != 1:                                   # query tile in TMEM next to >= 1 accumulator of 128 columns
+            assert p["a_tmem_kb"] * 32 + 128 <= 512
+        seen_kbs.add(p["kbs"])
+    assert seen_kbs == ({2, 4} if variant == 0 else ({4} if variant == 2 else {2}))
+
+
+def test_planner_policies():
+    # tiny galleries keep k + 3 candidates (rounded to 8), larger ones the fixed lists
+    assert _plan(768, 10_000, 10_000, 5)[1]["kc"] == 8
+    assert _plan(768, 10_000, 10_000, 10)[1]["kc"] == 16
+    assert _plan(768, 10_000, 10_000, 128)[1]["kc"] == 128
+    assert _plan(768, 10_000_000, 10_000, 10)[1]["kc"] == 32
+    assert _plan(768, 10_000_000, 10_000, 100)[1]["kc"] == 128
+    # coarse stages only for long tensor-bound units, and never at the price of the hybrid layout
+    head = _plan(768, 10_000_000, 10_000, 10)[1]
+    assert head["kbs"] == 4 and head["stages"] == 2 and head["a_tmem_kb"] == 8 and head["slices"] == 11
+    assert _plan(768, 10_000_000, 256, 10)[1]["kbs"] == 2            # small batch
+    assert _plan(512, 1_000_000, 10_000, 10)[1]["kbs"] == 2          # short units
+    k100 = _plan(768, 10_000_000, 10_000, 100)[1]
+    assert k100["kbs"] == 2 and k100["stages"] >= 2
+    # small batches spread one query tile over (almost) every SM
+    assert _plan(768, 12_500_000, 1, 10)[1]["slices"] >= 140
+    # what the tensor-core pass does not take is refused here (rbod_search routes it to the fp64 sweep)
+    assert _plan(1024, 1000, 1, 1)[0] == _native.RBOD_E_UNSUPPORTED
+    assert _plan(512, 1000, 1, 129)[0] == _native.RBOD_E_UNSUPPORTED
