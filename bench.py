@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the float64 exactness check (profiling runs: keeps "
                     "the checker's torch kernels out of the launch list)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the side configurations (k=100, sharded K2, "
+                    "the 100M-row sweep at 8 GPUs): profiling runs")
     ap.add_argument("--variant", type=int, default=-1, help="override the K3 kernel variant (debug)")
     ap.add_argument("--opt", action="append", default=[], help="library tunable key=value (debug), repeatable")
     ap.add_argument("--sweep", default="", help="comma list of batch sizes: per-size p50 latency and q/s on the "

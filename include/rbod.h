@@ -216,8 +216,9 @@ int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* o
 
 /* Host-only: the work decomposition rbod_search would choose for a tensor-core search of Q queries, top k, over a
  * gallery of `rows` vectors of `dim` columns on a device with `num_sms` SMs and `smem_optin` bytes of opt-in shared
- * memory per CTA (B200: 148, 232448).  Needs no GPU.  out[0..8] = candidates per query, slices, grid, query tiles,
- * gallery tiles, pipeline stages, k-blocks per stage, query-tile k-blocks kept in TMEM, dynamic shared memory bytes.
+ * memory per CTA (B200: 148, 232448).  Needs no GPU.  out[0..12] = candidates per query, slices, grid, query tiles,
+ * gallery tiles, pipeline stages, k-blocks per stage, query-tile k-blocks kept in TMEM, dynamic shared memory bytes,
+ * candidate-list prune trigger, list stride, longest list handed to the merge, keys the merge holds per query.
  * Returns RBOD_E_UNSUPPORTED when the shape must take the fp64 sweep instead (k > 128 or more than 768 columns). */
 int rbod_debug_plan(int32_t dim, int64_t rows, int64_t Q, int32_t k, int32_t variant, int32_t num_sms,
                     int32_t smem_optin, int64_t* out);

@@ -17,12 +17,18 @@
 //     shared memory instead of TMEM to leave room for both buffers (hybrid layout); the epilogue
 //     copies a tile to registers and releases its TMEM buffer before it starts selecting.
 //   * Epilogue (4 warps, one thread per query row): tcgen05.ld the 128 scores of the row, compare
-//     against the row's running threshold (one FMNMX per score on the fast path); survivors replace
-//     the root of the row's min-heap of candidates in shared memory (transposed, conflict-free).
+//     against the row's running threshold (one FMNMX per score on the fast path); survivors are
+//     APPENDED to the row's candidate list in global memory (one 8-byte store, L2-resident).  When a
+//     list reaches its capacity the warp prunes it cooperatively: a radix descent over the 32 lanes'
+//     registers finds the kc-th best score, the list is compacted to the rows at or above it and that
+//     score becomes the row's new threshold.  No shared memory is spent on candidates, so the gallery
+//     pipeline keeps all of it whatever k is (round 1 kept a kc-deep heap per row in shared memory:
+//     128 KB at k = 100, which cost the second accumulator buffer and ~500 cycles per insert).
 //   * Work unit = (gallery slice, query tile).  Units are ordered slice-major so that CTAs
 //     running at the same time stream the same gallery slice and share it through L2.
-// Output: per (slice, query) the `kc` best approximate scores and their row indices.  The K4
-// kernels merge slices, rescore exactly in fp64 and certify the result.
+// Output: per (slice, query) a list of at least the `kc` best approximate scores of the slice with
+// their row indices (unsorted, plus whatever else passed the threshold since the last prune).  The
+// finish kernel (k4_topk_merge.cu) merges the slices, rescores exactly in fp64 and certifies.
 // The same kernel serves DOT collections (nothing normalised) and, in its BIAS instantiation,
 // EUCLID collections (a per-row -|g|^2/2 added to the scores; util/qdrant_manager.py:61-66).
 //
@@ -47,8 +53,11 @@ struct alignas(64) K3Params {
   CUtensorMap tmap_b;
   CUtensorMap tmap_a;
   const uint16_t* q16;
-  float* part_score;
-  uint32_t* part_idx;
+  uint2* lists;           // [slices][q_pad][list_stride] candidate lists: {score bits, row index}
+  int* list_cnt;          // [slices][q_pad] entries in each list when its unit is done
+  int list_cap;           // a list is pruned back to ~kc entries once it holds this many (64, 128 or 256)
+  int list_stride;        // list_cap + 128: a tile can append 128 entries before the capacity check
+  int final_cap;          // lists longer than this get a last exact prune to kc entries (keeps the merge within 8192)
   const uint32_t* row_mask;
   const float* row_bias;  // BIAS kernels (EUCLID collections): score = q . g + row_bias[row], row_bias = -|g|^2 / 2
   uint32_t* tau_shared;   // [q_pad] per-query lower bound on the kc-th best score, as ordered keys (nullptr = off)
@@ -95,29 +104,96 @@ struct K3Barriers {
   uint32_t pad;
 };
 
-// Per-row candidate list = a min-heap of `kc` (score, row index) pairs kept by the row's own thread.
-// Storage is transposed -- entry j of row r lives at [j * 128 + r] -- so whatever heap positions the
-// 32 lanes of a warp touch, they always hit 32 different banks.  Replacing the root with a better
-// candidate and sifting it down keeps the kc best scores seen so far; the root is the threshold.
-// Unused slots hold -inf, so the threshold stays -inf until the list is full.
-__device__ __noinline__ float k3_heap_replace_root(float* sc, uint32_t* ix, int kc, float s, uint32_t id) {
-  int j = 0;
-  while (true) {
-    const int l = 2 * j + 1;
-    if (l >= kc) break;
-    const int r = l + 1;
-    const float sl = sc[l * K3_TILE_M];
-    const float sr = r < kc ? sc[r * K3_TILE_M] : INFINITY;
-    const int m = sr < sl ? r : l;
-    const float sm = fminf(sl, sr);
-    if (!(sm < s)) break;
-    sc[j * K3_TILE_M] = sm;
-    ix[j * K3_TILE_M] = ix[m * K3_TILE_M];
-    j = m;
+// Per-row candidate list = an append-only array of {score bits, row index} in global memory, owned by the row's
+// epilogue thread for the life of a work unit.  Appending costs one 8-byte store; nothing is ordered.  When a list
+// holds `list_cap` entries the whole warp prunes it: each lane takes the entries j = lane, lane + 32, ... into
+// registers as order-preserving integer keys, a most-significant-bit-first radix descent (one warp-wide count per
+// bit, starting at the first bit in which the keys differ at all) finds the keep-th largest key, and the entries
+// at or above it are compacted to the front of the list with a ballot scan.  The descent stops as soon as at most
+// keep + 16 entries survive (the threshold is then the decided prefix with zeros below, a slightly lower but still
+// valid bound); `exact` runs it to the last bit and resolves score ties by the smaller row index, leaving exactly
+// `keep` entries.  Returns (entries kept << 32) | threshold key: `keep` rows of this unit score at least that much.
+template <int MAXCH>
+__device__ __noinline__ unsigned long long k3_prune_list(uint2* lst, int n, int keep, int exact) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();   // the entries were written by other lanes of this warp
+  uint32_t key[MAXCH], idx[MAXCH];
+  uint32_t kmax = 0u, kmin = 0xffffffffu;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int j = 32 * i + lane;
+    key[i] = 0u;             // 0 is below every real key (even -inf maps to 0x007fffff)
+    idx[i] = 0xffffffffu;
+    if (j < n) {
+      const uint2 e = __ldcg(lst + j);
+      key[i] = f32_to_ordered(__uint_as_float(e.x));
+      idx[i] = e.y;
+      kmax = max(kmax, key[i]);
+      kmin = min(kmin, key[i]);
+    }
   }
-  sc[j * K3_TILE_M] = s;
-  ix[j * K3_TILE_M] = id;
-  return sc[0];
+  if (n <= keep) return (static_cast<unsigned long long>(static_cast<uint32_t>(n)) << 32) | f32_to_ordered(-INFINITY);
+  kmax = __reduce_max_sync(FULL_MASK, kmax);
+  kmin = __reduce_min_sync(FULL_MASK, kmin);
+  const uint32_t diff = kmax ^ kmin;
+  int b = diff ? 31 - __clz(diff) : -1;
+  uint32_t prefix = diff ? (kmax & ~((2u << b) - 1u)) : kmax;   // the bits all keys share
+  // invariant: the keep-th largest key is the `remaining`-th largest of the `share` keys that carry `prefix`
+  int remaining = keep, share = n;
+  const int slack = exact ? 0 : 16;
+  while (b >= 0 && share - remaining > slack) {
+    const uint32_t want = (prefix >> b) | 1u;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) c += ((key[i] >> b) == want) ? 1 : 0;
+    c = __reduce_add_sync(FULL_MASK, c);
+    if (c >= remaining) {
+      prefix |= 1u << b;
+      share = c;
+    } else {
+      remaining -= c;
+      share -= c;
+    }
+    --b;
+  }
+  uint32_t istar = 0u;   // entries equal to `prefix` survive when ~idx >= istar
+  if (share - remaining > slack) {
+    // every bit is decided and more rows tie with the keep-th score than may stay: keep the `remaining` of them
+    // with the smallest row index (the order the exact selection uses), found by the same descent over ~idx
+    int rem2 = remaining, sh2 = share;
+    for (int bb = 31; bb >= 0 && sh2 > rem2; --bb) {
+      const uint32_t want = (istar >> bb) | 1u;
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < MAXCH; ++i) c += (key[i] == prefix && ((~idx[i]) >> bb) == want) ? 1 : 0;
+      c = __reduce_add_sync(FULL_MASK, c);
+      if (c >= rem2) {
+        istar |= 1u << bb;
+        sh2 = c;
+      } else {
+        rem2 -= c;
+        sh2 -= c;
+      }
+    }
+  }
+  int base = 0;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const bool kp = key[i] > prefix || (key[i] == prefix && (~idx[i]) >= istar);   // prefix > 0, so padding never passes
+    const unsigned bal = __ballot_sync(FULL_MASK, kp);
+    if (kp)
+      __stcg(lst + base + __popc(bal & ((1u << lane) - 1u)),
+             make_uint2(__float_as_uint(ordered_to_f32(key[i])), idx[i]));
+    base += __popc(bal);
+  }
+  __syncwarp();
+  return (static_cast<unsigned long long>(static_cast<uint32_t>(base)) << 32) | prefix;
+}
+
+__device__ __forceinline__ unsigned long long k3_prune(uint2* lst, int n, int keep, int exact, int list_cap) {
+  if (list_cap <= 64) return k3_prune_list<6>(lst, n, keep, exact);
+  if (list_cap <= 128) return k3_prune_list<8>(lst, n, keep, exact);
+  return k3_prune_list<12>(lst, n, keep, exact);
 }
 
 // Tiles a work unit visits: t0, t0 + step, ... (n of them).  Normal launches cut the gallery into `slices`
@@ -211,9 +287,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
   uint8_t* stage_base = smem;
   uint8_t* a_tail = smem + (size_t)P.num_stages * G::STAGE_BYTES;       // resident query-tile tail (k-blocks >= a_tmem_kb)
   const int tail_kb = VARIANT == 1 ? 0 : (P.num_kb - P.a_tmem_kb);
-  float* sc = reinterpret_cast<float*>(a_tail + (size_t)tail_kb * A_TILE_KB_BYTES);
-  uint32_t* ix = reinterpret_cast<uint32_t*>(sc + K3_TILE_M * P.kc);
-  K3Barriers* bars = reinterpret_cast<K3Barriers*>(ix + K3_TILE_M * P.kc);
+  K3Barriers* bars = reinterpret_cast<K3Barriers*>(a_tail + (size_t)tail_kb * A_TILE_KB_BYTES);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.tmap_b);
@@ -445,36 +519,27 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
           if (PAIR) mbar_arrive_cluster(a_ready_leader); else mbar_arrive(&bars->a_ready);
         }
       }
-      // reset this row's candidate heap
-      float* my_sc = sc + row;
-      uint32_t* my_ix = ix + row;
-      for (int j = 0; j < kc; ++j) {
-        my_sc[j * K3_TILE_M] = -INFINITY;
-        my_ix[j * K3_TILE_M] = 0xffffffffu;
-      }
-      // Threshold shared between the units (gallery slices) of one query.  A unit publishes the root of its
-      // heap once the heap is full: kc rows score at least that much, so no row below it can be among the
-      // kc best of the whole gallery, whichever slice it sits in.  Other units start from, and
-      // periodically re-read, the best published bound, which removes almost all heap traffic after the
-      // first slice of a query has warmed up.
+      // Threshold shared between the units (gallery slices) of one query.  A unit publishes the threshold a prune
+      // of its list leaves behind: kc rows of the unit score at least that much, so no row below it can be among
+      // the kc best of the whole gallery, whichever slice it sits in.  Other units start from, and periodically
+      // re-read, the best published bound, which removes almost all list traffic after the first slice of a query
+      // has warmed up.  Rows that only pad the query tile never append anything.
       uint32_t* tau_cell = P.tau_shared != nullptr ? P.tau_shared + qg : nullptr;
       float tau = tau_cell != nullptr ? ordered_to_f32(ld_relaxed_u32(tau_cell)) : -INFINITY;
       float tau_published = tau;
       const bool collect = P.collect_thr != nullptr;
       if (collect) tau = qg < P.q_valid ? P.collect_thr[qg] : INFINITY;
+      else if (qg >= P.q_valid) tau = INFINITY;
+      // this row's candidate list (select mode only): `wp` is where the next survivor goes
+      uint2* const my_list = P.lists + ((size_t)slice * P.q_pad + qg) * P.list_stride;
+      uint2* wp = my_list;
 
       const bool groupmax = P.groupmax_out != nullptr;
       float gmax_run = -INFINITY;
       for (int ti = 0; ti < tr.n; ++ti) {
         const int t = tr.t0 + ti * tr.step;
-        if (tau_cell != nullptr && (ti & (K3_TAU_REFRESH - 1)) == K3_TAU_REFRESH - 1) {
-          const float root = my_sc[0];
-          if (root > tau_published) {
-            atomicMax(tau_cell, f32_to_ordered(root));
-            tau_published = root;
-          }
+        if (tau_cell != nullptr && (ti & (K3_TAU_REFRESH - 1)) == K3_TAU_REFRESH - 1)
           tau = fmaxf(tau, ordered_to_f32(ld_relaxed_u32(tau_cell)));
-        }
         mbar_wait(&bars->tfull[acc], acc_phase, 5);
         tc_fence_after();
         if (P.debug_epi == 2) {
@@ -570,34 +635,75 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
           gmax_run = fmaxf(gmax_run, m);
           continue;
         }
-        if (m > tau) {
+        if (collect) {
+          // second pass over uncertified queries: record every row above the query's fixed threshold
+          if (m > tau) {
 #pragma unroll
-          for (int gi = 0; gi < K3_TILE_N / 16; ++gi) {
-            if (gm[gi] > tau) {
+            for (int gi = 0; gi < K3_TILE_N / 16; ++gi) {
+              if (gm[gi] > tau) {
 #pragma unroll
-              for (int c = 0; c < 16; ++c)
-                if (v[16 * gi + c] > tau) {
-                  if (collect) {
+                for (int c = 0; c < 16; ++c)
+                  if (v[16 * gi + c] > tau) {
                     const int slot = atomicAdd(P.coll_cnt + qg, 1);
                     if (slot < P.coll_cap) P.coll_idx[(size_t)qg * P.coll_cap + slot] = (uint32_t)(col0 + 16 * gi + c);
-                  } else {
-                    tau = fmaxf(tau, k3_heap_replace_root(my_sc, my_ix, kc, v[16 * gi + c], (uint32_t)(col0 + 16 * gi + c)));
                   }
+              }
+            }
+          }
+          continue;
+        }
+        // Select mode.  The branches are warp-uniform (votes), the appends inside are predicated stores: what a
+        // tile costs depends on how many 16-column groups hold a survivor in ANY of the warp's 32 rows, not on the
+        // number of survivors.
+        if (__any_sync(FULL_MASK, m > tau)) {
+#pragma unroll
+          for (int gi = 0; gi < K3_TILE_N / 16; ++gi) {
+            if (__any_sync(FULL_MASK, gm[gi] > tau)) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float s = v[16 * gi + c];
+                if (s > tau) {
+                  __stcg(wp, make_uint2(__float_as_uint(s), (uint32_t)(col0 + 16 * gi + c)));
+                  ++wp;
                 }
+              }
+            }
+          }
+          const int cnt = (int)(wp - my_list);
+          unsigned need = __ballot_sync(FULL_MASK, cnt >= P.list_cap);
+          while (need) {
+            const int L = __ffs(need) - 1;
+            need &= need - 1;
+            const int n = __shfl_sync(FULL_MASK, cnt, L);
+            uint2* lst = P.lists + ((size_t)slice * P.q_pad + (q_unit0 + wrow0 + L)) * P.list_stride;
+            const unsigned long long r = k3_prune(lst, n, kc, 0, P.list_cap);
+            if (lane == L) {
+              wp = my_list + (int)(r >> 32);
+              tau = fmaxf(tau, ordered_to_f32((uint32_t)r));
+              if (tau_cell != nullptr && tau > tau_published) {
+                atomicMax(tau_cell, f32_to_ordered(tau));
+                tau_published = tau;
+              }
             }
           }
         }
       }
 
-      // unit done: publish this row's candidates (heap order; the merge kernel sorts)
-      if (tau_cell != nullptr && my_sc[0] > tau_published) atomicMax(tau_cell, f32_to_ordered(my_sc[0]));
+      // unit done
       if (groupmax) P.groupmax_out[(size_t)slice * P.q_pad + qg] = gmax_run;
-      if (qg < P.q_valid && !collect && !groupmax) {
-        const size_t base = ((size_t)slice * P.q_pad + qg) * kc;
-        for (int j = 0; j < kc; ++j) {
-          P.part_score[base + j] = my_sc[j * K3_TILE_M];
-          P.part_idx[base + j] = my_ix[j * K3_TILE_M];
+      if (!collect && !groupmax) {
+        // lists the merge could not hold get a last, exact prune to kc entries; the others stay as they are
+        int cnt = (int)(wp - my_list);
+        unsigned need = __ballot_sync(FULL_MASK, cnt > P.final_cap);
+        while (need) {
+          const int L = __ffs(need) - 1;
+          need &= need - 1;
+          const int n = __shfl_sync(FULL_MASK, cnt, L);
+          uint2* lst = P.lists + ((size_t)slice * P.q_pad + (q_unit0 + wrow0 + L)) * P.list_stride;
+          const unsigned long long r = k3_prune(lst, n, kc, 1, P.list_cap);
+          if (lane == L) cnt = (int)(r >> 32);
         }
+        if (qg < P.q_valid) P.list_cnt[(size_t)slice * P.q_pad + qg] = cnt;
       }
     }
   }
@@ -697,24 +803,24 @@ static size_t k3_stage_bytes(int variant, int kbs) {
   return kbs == 4 ? (size_t)K3Geom<0, 0, 4>::STAGE_BYTES : (size_t)K3Geom<0, 0, 2>::STAGE_BYTES;
 }
 
-size_t k3_smem_bytes(int variant, int kbs, int kc, int num_stages, int tail_kb) {
+size_t k3_smem_bytes(int variant, int kbs, int num_stages, int tail_kb) {
   return 1024 + (size_t)num_stages * k3_stage_bytes(variant, kbs) + (size_t)tail_kb * A_TILE_KB_BYTES +
-         (size_t)K3_TILE_M * kc * 8 + sizeof(K3Barriers);
+         sizeof(K3Barriers);
 }
 
 // Chooses where the query tile lives and how deep the gallery pipeline is.
 //   dp <= 512            : whole tile in TMEM (<= 256 columns), two accumulator buffers.
 //   dp  > 512, room left : first 8 k-blocks in TMEM, the tail resident in shared memory, two buffers.
 //   dp  > 512, smem short: whole tile in TMEM (384 columns), one accumulator buffer.
-// `want_kbs` = 4 asks for the coarse 4-k-block stages of the single-CTA kernel; they are used when two of them fit
-// next to the candidate heaps (k <= 40), otherwise the 2-k-block stages are.
-int k3_plan(int variant, int want_kbs, int kc, int dp, int smem_optin, int allow_hybrid, int* num_stages,
+// `want_kbs` = 4 asks for the coarse 4-k-block stages of the single-CTA kernel.  Candidate lists live in global
+// memory, so the plan does not depend on k.
+int k3_plan(int variant, int want_kbs, int dp, int smem_optin, int allow_hybrid, int* num_stages,
             int* a_tmem_kb, int* kbs_out, size_t* smem_bytes) {
   const int num_kb = dp / K3_KBLOCK;
   auto attempt = [&](int kbs, int min_stages_hybrid, int* st_out, int* tmem_out, int* tail_out) -> bool {
     auto fit = [&](int tail_kb) {
       int st = MAX_STAGES;
-      while (st > 0 && k3_smem_bytes(variant, kbs, kc, st, tail_kb) > (size_t)smem_optin) --st;
+      while (st > 0 && k3_smem_bytes(variant, kbs, st, tail_kb) > (size_t)smem_optin) --st;
       return st;
     };
     int tmem_kb = num_kb, tail = 0;
@@ -742,12 +848,11 @@ int k3_plan(int variant, int want_kbs, int kc, int dp, int smem_optin, int allow
     ok = attempt(kbs, variant == 2 ? 2 : 3, &st, &tmem_kb, &tail);
   }
   if (!ok)
-    return set_error(RBOD_E_UNSUPPORTED, "search: variant %d with %d candidates per query does not fit shared memory",
-                     variant, kc);
+    return set_error(RBOD_E_UNSUPPORTED, "search: variant %d with %d columns does not fit shared memory", variant, dp);
   *num_stages = st;
   *a_tmem_kb = tmem_kb;
   *kbs_out = kbs;
-  *smem_bytes = k3_smem_bytes(variant, kbs, kc, st, tail);
+  *smem_bytes = k3_smem_bytes(variant, kbs, st, tail);
   return RBOD_OK;
 }
 
@@ -775,8 +880,11 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.tmap_b = L.tmap_b;
   P.tmap_a = L.tmap_a;
   P.q16 = L.q16;
-  P.part_score = L.part_score;
-  P.part_idx = L.part_idx;
+  P.lists = L.lists;
+  P.list_cnt = L.list_cnt;
+  P.list_cap = L.list_cap;
+  P.list_stride = L.list_stride;
+  P.final_cap = L.final_cap;
   P.row_mask = L.row_mask;
   P.row_bias = L.row_bias;
   P.tau_shared = L.tau_shared;
@@ -813,6 +921,12 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.idesc = make_idesc_f16(L.a_fmt, L.b_fmt, L.variant == 2 ? 2 * K3_TILE_M : K3_TILE_M, K3_TILE_N);
   if (L.num_stages < 1 || L.num_stages > MAX_STAGES)
     return set_error(RBOD_E_INVAL, "k3: bad stage count %d", L.num_stages);
+  const bool select_mode = L.collect_thr == nullptr && L.groupmax_out == nullptr;
+  if (select_mode && (L.lists == nullptr || L.list_cnt == nullptr || L.kc < 1 || L.kc > K3_MAX_KC ||
+                      (L.list_cap != 64 && L.list_cap != 128 && L.list_cap != 256) || L.list_cap < 2 * L.kc ||
+                      L.list_stride != L.list_cap + K3_TILE_N || L.final_cap < L.kc))
+    return set_error(RBOD_E_INVAL, "k3: bad candidate-list geometry (kc %d, cap %d, stride %d, final %d)", L.kc,
+                     L.list_cap, L.list_stride, L.final_cap);
   if (L.variant == 2 && L.grid % 2) return set_error(RBOD_E_INVAL, "k3: pair kernel needs an even grid");
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

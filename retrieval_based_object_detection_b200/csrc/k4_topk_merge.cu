@@ -1,14 +1,17 @@
 // K4 family -- everything between the tensor-core pass and the answer:
 //
-//   merge_partials   per query, the per-slice candidate lists of K3 -> the kc best approximate
-//                    candidates and tau = the kc-th best approximate score (every row K3 dropped
-//                    scores <= tau).
-//   rescore          exact cosine of every (query, candidate) pair in fp64 on the stored values:
-//                    dot / (|q| * |g|), the formula of cosine_similarity
-//                    (33_run_all_experiments.py:76-77).
-//   select           per query: order candidates by (score desc, row asc), emit the top k, and
-//                    certify them: if tau + eps < (k-th exact score) no dropped row can belong to
-//                    the top k.  Uncertified queries are appended to a flag list.
+//   finish           one CTA per query, everything between the tensor-core pass and the answer:
+//                    (1) gather the query's per-slice candidate lists (K3's append lists) as packed
+//                        64-bit keys, (2) radix-select the kc best approximate candidates (tau = the
+//                        kc-th best approximate score: every row K3 or this step dropped scores <= tau),
+//                        (3) rescore them exactly in fp64 on the stored values -- dot / (|q| * |g|),
+//                        the formula of cosine_similarity (33_run_all_experiments.py:76-77) --
+//                        (4) order by (score desc, row asc), emit the top k, and (5) certify them: if
+//                        tau + eps < (k-th exact score) no dropped row can belong to the top k.
+//                        Uncertified queries are appended to a flag list.  (Round 1 ran this as three
+//                        kernels -- bitonic merge, rescore, select -- with the candidates round-tripping
+//                        through global memory; the bitonic sort of up to 8192 keys per query was the
+//                        largest fixed cost of a sharded search.)
 //   exact_collect /  exact fp64 sweep over the whole gallery for flagged queries only: collect
 //   select_collected every row whose exact score >= the query's provisional k-th score, then
 //                    select among those.  This is the guarantee behind "identical ids".
@@ -35,9 +38,7 @@ __device__ __forceinline__ double exact_pair_score(const float* __restrict__ qv,
                                                    const float* __restrict__ g32, const uint16_t* __restrict__ g16,
                                                    int kind16, int dim, int metric, int lane) {
   double a = 0.0, b = 0.0;
-  for (int c = lane; c < dim; c += 32) {
-    const double x = g32 ? (double)g32[c] : (double)h16_to_f32(g16[c], kind16);
-    const double qc = (double)qv[c];
+  auto acc = [&](double qc, double x) {
     if (metric == RBOD_EUCLID) {
       const double d = qc - x;
       a = fma(d, d, a);
@@ -45,6 +46,41 @@ __device__ __forceinline__ double exact_pair_score(const float* __restrict__ qv,
       a = fma(qc, x, a);
       b = fma(x, x, b);
     }
+  };
+  const bool vec = (dim & 7) == 0 && (reinterpret_cast<uintptr_t>(qv) & 15) == 0 &&
+                   (g32 ? (reinterpret_cast<uintptr_t>(g32) & 15) == 0 : (reinterpret_cast<uintptr_t>(g16) & 15) == 0);
+  if (vec) {
+    // 8 elements per lane and step: 16-byte loads of the stored row, two float4 of the query
+    for (int c0 = lane * 8; c0 < dim; c0 += 256) {
+      const float4 q0 = *reinterpret_cast<const float4*>(qv + c0);
+      const float4 q1 = *reinterpret_cast<const float4*>(qv + c0 + 4);
+      float x[8];
+      if (g32) {
+        const float4 g0 = *reinterpret_cast<const float4*>(g32 + c0);
+        const float4 g1 = *reinterpret_cast<const float4*>(g32 + c0 + 4);
+        x[0] = g0.x; x[1] = g0.y; x[2] = g0.z; x[3] = g0.w;
+        x[4] = g1.x; x[5] = g1.y; x[6] = g1.z; x[7] = g1.w;
+      } else {
+        const uint4 h = *reinterpret_cast<const uint4*>(g16 + c0);
+        const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          x[2 * i] = h16_to_f32(static_cast<uint16_t>(w[i] & 0xffffu), kind16);
+          x[2 * i + 1] = h16_to_f32(static_cast<uint16_t>(w[i] >> 16), kind16);
+        }
+      }
+      acc((double)q0.x, (double)x[0]);
+      acc((double)q0.y, (double)x[1]);
+      acc((double)q0.z, (double)x[2]);
+      acc((double)q0.w, (double)x[3]);
+      acc((double)q1.x, (double)x[4]);
+      acc((double)q1.y, (double)x[5]);
+      acc((double)q1.z, (double)x[6]);
+      acc((double)q1.w, (double)x[7]);
+    }
+  } else {
+    for (int c = lane; c < dim; c += 32)
+      acc((double)qv[c], g32 ? (double)g32[c] : (double)h16_to_f32(g16[c], kind16));
   }
   a = warp_sum_f64(a);
   if (metric == RBOD_EUCLID) return -a;
@@ -60,55 +96,6 @@ __device__ __forceinline__ float user_score(double s, int metric) {
   return metric == RBOD_EUCLID ? (float)sqrt(-s) : (float)s;
 }
 __device__ __forceinline__ float user_no_result(int metric) { return metric == RBOD_EUCLID ? INFINITY : -INFINITY; }
-
-// ---------------------------------------------------------------------------------------------
-// merge_partials: one CTA per query, bitonic sort (descending) of packed keys in shared memory.
-// key = ordered(score) << 32 | ~idx   (ties: smaller row index first); 0 = padding.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-merge_partials_kernel(const float* __restrict__ part_score, const uint32_t* __restrict__ part_idx, int slices,
-                      int64_t q_pad, int kc, int m_pow2, const float* __restrict__ tau_init,
-                      uint32_t* __restrict__ cand_idx, float* __restrict__ cand_tau) {
-  extern __shared__ unsigned long long keys[];
-  const int64_t q = blockIdx.x;
-  const int m = slices * kc;
-  for (int i = threadIdx.x; i < m_pow2; i += blockDim.x) {
-    unsigned long long key = 0ull;
-    if (i < m) {
-      const int s = i / kc, j = i - s * kc;
-      const size_t off = ((size_t)s * q_pad + q) * kc + j;
-      const uint32_t idx = part_idx[off];
-      if (idx != 0xffffffffu)
-        key = (static_cast<unsigned long long>(f32_to_ordered(part_score[off])) << 32) |
-              static_cast<unsigned long long>(~idx);
-    }
-    keys[i] = key;
-  }
-  __syncthreads();
-  for (int size = 2; size <= m_pow2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < (m_pow2 >> 1); i += blockDim.x) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const unsigned long long a = keys[lo], b = keys[hi];
-        if (desc ? (a < b) : (a > b)) { keys[lo] = b; keys[hi] = a; }
-      }
-      __syncthreads();
-    }
-  }
-  for (int j = threadIdx.x; j < kc; j += blockDim.x) {
-    const unsigned long long key = j < m_pow2 ? keys[j] : 0ull;
-    cand_idx[q * kc + j] = key ? ~static_cast<uint32_t>(key & 0xffffffffull) : 0xffffffffu;
-  }
-  if (threadIdx.x == 0) {
-    const unsigned long long key = (kc - 1) < m_pow2 ? keys[kc - 1] : 0ull;
-    float tau = key ? ordered_to_f32(static_cast<uint32_t>(key >> 32)) : -INFINITY;
-    // rows below the pre-sampled starting threshold were dropped without ever entering a list
-    if (tau_init != nullptr) tau = fmaxf(tau, tau_init[q]);
-    cand_tau[q] = tau;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // tau_init: starting threshold of a query = the smallest of its `groups` sample-group maxima.  Every
@@ -135,75 +122,16 @@ tau_init_kernel(const float* __restrict__ groupmax, int groups, int splits, int6
 }
 
 // ---------------------------------------------------------------------------------------------
-// rescore: one warp per (query, candidate)
+// finish: one CTA per query (see the file header)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-rescore_kernel(const float* __restrict__ q, const double* __restrict__ q_qq, const float* __restrict__ master32,
-               const uint16_t* __restrict__ rows16, int kind16, int dim, int64_t ld32, int64_t ld16, int metric,
-               const uint32_t* __restrict__ cand_idx, int64_t n_pairs, int kc, double* __restrict__ cand_score) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int64_t nw = (int64_t)gridDim.x * 8;
-  for (int64_t p = w0; p < n_pairs; p += nw) {
-    const uint32_t idx = cand_idx[p];
-    if (idx == 0xffffffffu) {
-      if (lane == 0) cand_score[p] = -INFINITY;
-      continue;
-    }
-    const int64_t qi = p / kc;
-    const double sc = exact_pair_score(q + qi * dim, q_qq[qi], master32 ? master32 + (int64_t)idx * ld32 : nullptr,
-                                       master32 ? nullptr : rows16 + (int64_t)idx * ld16, kind16, dim, metric, lane);
-    if (lane == 0) cand_score[p] = sc;
-  }
-}
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_WARPS = FIN_THREADS / 32;
+constexpr int FIN_MAX_SLICES = 2 * FIN_THREADS;
+constexpr int FIN_MAX_KEYS = 8192;
 
-// ---------------------------------------------------------------------------------------------
-// select: one warp per query, rank by counting over kc <= 128 candidates
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict__ cand_idx,
-              const float* __restrict__ cand_tau, const float* __restrict__ q_dq, const float* __restrict__ stats,
-              const double* __restrict__ q_qq, int metric, int master16, int shadow, int dp, int64_t Q, int kc, int k, float* __restrict__ out_scores,
-              int64_t* __restrict__ out_rows,
-              double* __restrict__ out_scores64, int* __restrict__ n_flag, int* __restrict__ flag_q,
-              double* __restrict__ flag_thr, float* __restrict__ flag_lo, float* __restrict__ max_eps) {
-  __shared__ double s_sc[4][K3_MAX_KC];
-  __shared__ uint32_t s_ix[4][K3_MAX_KC];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t q = (int64_t)blockIdx.x * 4 + w;
-  if (q >= Q) return;
-  for (int j = lane; j < kc; j += 32) {
-    s_sc[w][j] = cand_score[q * kc + j];
-    s_ix[w][j] = cand_idx[q * kc + j];
-  }
-  for (int j = lane; j < k; j += 32) {
-    out_scores[q * k + j] = user_no_result(metric);
-    out_rows[q * k + j] = -1;
-    if (out_scores64) out_scores64[q * k + j] = -INFINITY;
-  }
-  __syncwarp();
-  double kth = -INFINITY;  // exact score of rank k-1, if it exists
-  int have_kth = 0;
-  for (int j = lane; j < kc; j += 32) {
-    const double s = s_sc[w][j];
-    const uint32_t ix = s_ix[w][j];
-    if (ix == 0xffffffffu) continue;
-    int rank = 0;
-    for (int i = 0; i < kc; ++i) {
-      const uint32_t oi = s_ix[w][i];
-      if (oi != 0xffffffffu && beats(s_sc[w][i], oi, s, ix)) ++rank;
-    }
-    if (rank < k) {
-      out_scores[q * k + rank] = user_score(s, metric);
-      out_rows[q * k + rank] = (int64_t)ix;
-      if (out_scores64) out_scores64[q * k + rank] = s;
-      if (rank == k - 1) { kth = s; have_kth = 1; }
-    }
-  }
-  // broadcast the k-th score
-  const uint32_t who = __ballot_sync(FULL_MASK, have_kth);
-  const float tau = cand_tau[q];
-  if (tau == -INFINITY) return;  // nothing was dropped for this query: exact by construction
+// Certification of one query's answer (one thread).  tau bounds the approximate score of every row that was dropped
+// anywhere; kth is the k-th exact score (if k candidates exist).
+__device__ void certify_query(const FinishArgs& P, int64_t q, float tau, bool have_kth, double kth) {
   // Certification margin: every row the tensor-core pass dropped has approximate score <= tau, and
   //   |approx - exact cosine| <= ||q16 - unit(q)|| * max||g16||      (query rounding, Cauchy-Schwarz)
   //                            + dp * 2^-23 * max||g16||              (fp32 accumulation in the tensor core)
@@ -213,6 +141,9 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
   // scales the score instead of adding to it: (|tau| + e) * d / (1 - d).
   // With an fp16 shadow as the search operand, the operand norm is stats[2] and its distance to the stored
   // row, stats[3], adds to the query term.
+  const float* stats = P.stats;
+  const int metric = P.metric;
+  const bool master16 = P.master16 != 0, shadow = P.shadow != 0;
   const float gmax = (shadow ? stats[2] : stats[0]) * 1.000001f, gdev = stats[1] * 1.000001f;
   // DOT collections: nothing is normalised, so every term scales with the query norm |q| and the row term is
   // |q| * ||g16 - g|| (zero for 16-bit masters, whose operand is the stored row).
@@ -220,41 +151,203 @@ select_kernel(const double* __restrict__ cand_score, const uint32_t* __restrict_
   // approximation of (key + |q|^2) / 2 for the exact key = -|q - g|^2.  Nothing is normalised, so the dot-product
   // terms are those of DOT, plus the rounding of the bias and of its addition: 2^-23 (|q| G + G^2), G = max |g|.
   const bool unnorm = metric != RBOD_COSINE;
-  const float qn = unnorm ? (float)sqrt(q_qq[q]) * 1.000001f + q_dq[q] : 1.0f;
-  const float e = q_dq[q] * gmax + (float)dp * 1.2e-7f * gmax * qn + (shadow ? stats[3] * 1.000001f * qn : 0.0f);
+  const float qn = unnorm ? (float)sqrt(P.q_qq[q]) * 1.000001f + P.q_dq[q] : 1.0f;
+  const float e = P.q_dq[q] * gmax + (float)P.dp * 1.2e-7f * gmax * qn + (shadow ? stats[3] * 1.000001f * qn : 0.0f);
   const float row_term = unnorm ? (master16 ? 0.0f : qn * gdev)
                                 : (master16 ? (fabsf(tau) + e) * gdev / (1.0f - gdev) : gdev);
   const float gbig = gmax + (master16 ? 0.0f : gdev);
   const float bias_term = metric == RBOD_EUCLID ? 1.2e-7f * (qn * gbig + gbig * gbig) : 0.0f;
   const float eps = e + row_term + bias_term + fabsf(tau) * 1e-6f + 1e-7f;
-  const double qq_half = metric == RBOD_EUCLID ? 0.5 * q_qq[q] : 0.0;
+  const double qq_half = metric == RBOD_EUCLID ? 0.5 * P.q_qq[q] : 0.0;
   bool flagged = true;
-  if (who) {
-    const int src = __ffs(who) - 1;
-    const double kth_b = __shfl_sync(FULL_MASK, kth, src);
+  if (have_kth) {
     // the k-th exact score in the domain the tensor-core pass works in
-    const double kth_a = metric == RBOD_EUCLID ? 0.5 * kth_b + qq_half : kth_b;
+    const double kth_a = metric == RBOD_EUCLID ? 0.5 * kth + qq_half : kth;
     flagged = !((double)tau + (double)eps < kth_a);
-    kth = kth_b;
   } else {
     // Fewer than k candidates although rows were dropped: the pre-sampled starting threshold sat above this
     // query's k-th best score (possible only when the sample misrepresents the gallery).  The host reruns the
     // search without the pre-pass.
     kth = -INFINITY;
-    if (lane == 0) atomicAdd(n_flag + 4, 1);
+    atomicAdd(P.n_flag + 4, 1);
   }
-  if (lane == 0) {
-    atomic_max_nonneg(max_eps, eps);
-    if (flagged) {
-      const int slot = atomicAdd(n_flag, 1);
-      flag_q[slot] = (int)q;
-      flag_thr[slot] = kth;
-      // Threshold for the collecting second pass: every row whose exact score reaches kth has an
-      // approximate score above lo (same error model, applied from the exact side).
-      const float kf = (float)(metric == RBOD_EUCLID ? 0.5 * kth + qq_half : kth);
-      const float lo = unnorm ? kf - e - row_term - bias_term
-                              : (master16 ? kf - fabsf(kf) * gdev - e : kf - e - gdev);
-      flag_lo[slot] = kth == -INFINITY ? -INFINITY : lo - fabsf(kf) * 2e-6f - 2e-7f;
+  atomic_max_nonneg(P.max_eps, eps);
+  if (flagged) {
+    const int slot = atomicAdd(P.n_flag, 1);
+    P.flag_q[slot] = (int)q;
+    P.flag_thr[slot] = kth;
+    // Threshold for the collecting second pass: every row whose exact score reaches kth has an
+    // approximate score above lo (same error model, applied from the exact side).
+    const float kf = (float)(metric == RBOD_EUCLID ? 0.5 * kth + qq_half : kth);
+    const float lo = unnorm ? kf - e - row_term - bias_term
+                            : (master16 ? kf - fabsf(kf) * gdev - e : kf - e - gdev);
+    P.flag_lo[slot] = kth == -INFINITY ? -INFINITY : lo - fabsf(kf) * 2e-6f - 2e-7f;
+  }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P) {
+  extern __shared__ unsigned long long keys[];   // [n_cap]: ordered(score) << 32 | ~row; distinct, larger = better
+  __shared__ int s_off[FIN_MAX_SLICES + 1];
+  __shared__ int s_wsum[FIN_WARPS];
+  __shared__ unsigned int s_cnt[3];
+  __shared__ uint32_t s_hmax[FIN_WARPS], s_hmin[FIN_WARPS];
+  __shared__ unsigned long long s_sel[K3_MAX_KC];
+  __shared__ double s_sc[K3_MAX_KC];
+  __shared__ int s_nsel, s_have_kth;
+  __shared__ double s_kth;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t q = blockIdx.x;
+  const int kc = P.kc, k = P.k;
+
+  // (1) list lengths -> exclusive offsets (two slices per thread)
+  int c0 = 0, c1 = 0;
+  if (2 * tid < P.slices) c0 = min(max(P.list_cnt[(size_t)(2 * tid) * P.q_pad + q], 0), P.list_stride);
+  if (2 * tid + 1 < P.slices) c1 = min(max(P.list_cnt[(size_t)(2 * tid + 1) * P.q_pad + q], 0), P.list_stride);
+  int incl = c0 + c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  if (tid == 0) {
+    s_cnt[0] = s_cnt[1] = s_cnt[2] = 0u;
+    s_nsel = 0;
+    s_have_kth = 0;
+    s_kth = -INFINITY;
+  }
+  __syncthreads();
+  int wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < FIN_WARPS; ++w) {
+    if (w < warp) wbase += s_wsum[w];
+    total += s_wsum[w];
+  }
+  const int excl = wbase + incl - c0 - c1;
+  if (2 * tid < P.slices) s_off[2 * tid] = excl;
+  if (2 * tid + 1 < P.slices) s_off[2 * tid + 1] = excl + c0;
+  if (tid == 0) s_off[P.slices] = total;
+  const int n_tot = min(total, P.n_cap);
+  __syncthreads();
+
+  // gather the lists as packed keys
+  for (int s = warp; s < P.slices; s += FIN_WARPS) {
+    const int off = s_off[s], cs = s_off[s + 1] - off;
+    const uint2* lst = P.lists + ((size_t)s * P.q_pad + q) * P.list_stride;
+    for (int j = lane; j < cs; j += 32)
+      if (off + j < n_tot) {
+        const uint2 e = lst[j];
+        keys[off + j] = (static_cast<unsigned long long>(f32_to_ordered(__uint_as_float(e.x))) << 32) |
+                        static_cast<unsigned long long>(~e.y);
+      }
+  }
+  __syncthreads();
+
+  // (2) the kc-th largest key by a most-significant-bit-first radix descent, one block-wide count per bit, starting
+  // at the first bit in which the scores differ at all.  Keys are distinct (a row appears once), so the descent ends
+  // with exactly kc keys at or above the decided prefix -- usually long before the last bit.
+  unsigned long long T = 0ull;
+  if (n_tot > kc) {
+    uint32_t hmax = 0u, hmin = 0xffffffffu;
+    for (int j = tid; j < n_tot; j += FIN_THREADS) {
+      const uint32_t h = static_cast<uint32_t>(keys[j] >> 32);
+      hmax = max(hmax, h);
+      hmin = min(hmin, h);
+    }
+    hmax = __reduce_max_sync(FULL_MASK, hmax);
+    hmin = __reduce_min_sync(FULL_MASK, hmin);
+    if (lane == 0) {
+      s_hmax[warp] = hmax;
+      s_hmin[warp] = hmin;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < FIN_WARPS; ++w) {
+      hmax = max(hmax, s_hmax[w]);
+      hmin = min(hmin, s_hmin[w]);
+    }
+    const uint32_t diff = hmax ^ hmin;
+    int b = diff ? 32 + (31 - __clz(diff)) : 31;
+    unsigned long long prefix = static_cast<unsigned long long>(diff ? (hmax & ~((2u << (b - 32)) - 1u)) : hmax) << 32;
+    int remaining = kc, share = n_tot, it = 0;
+    while (b >= 0 && share != remaining) {
+      const unsigned long long want = (prefix >> b) | 1ull;
+      int cc = 0;
+      for (int j = tid; j < n_tot; j += FIN_THREADS) cc += ((keys[j] >> b) == want) ? 1 : 0;
+      cc = __reduce_add_sync(FULL_MASK, cc);
+      if (lane == 0 && cc) atomicAdd(&s_cnt[it % 3], (unsigned int)cc);
+      if (tid == 0) s_cnt[(it + 1) % 3] = 0u;   // last read two iterations ago, next used after this barrier
+      __syncthreads();
+      const int ctot = (int)s_cnt[it % 3];
+      if (ctot >= remaining) {
+        prefix |= 1ull << b;
+        share = ctot;
+      } else {
+        remaining -= ctot;
+        share -= ctot;
+      }
+      --b;
+      ++it;
+    }
+    T = prefix;
+  }
+  for (int j = tid; j < n_tot; j += FIN_THREADS) {
+    const unsigned long long key = keys[j];
+    if (key >= T) {
+      const int pos = atomicAdd(&s_nsel, 1);
+      if (pos < K3_MAX_KC) s_sel[pos] = key;
+    }
+  }
+  for (int j = tid; j < k; j += FIN_THREADS) {
+    P.out_scores[q * k + j] = user_no_result(P.metric);
+    P.out_rows[q * k + j] = -1;
+    if (P.out_scores64) P.out_scores64[q * k + j] = -INFINITY;
+  }
+  __syncthreads();
+  const int nsel = min(min(s_nsel, kc), K3_MAX_KC);
+
+  // (3) exact scores, one warp per candidate
+  const float* qv = P.q + q * P.dim;
+  const double qq = P.q_qq[q];
+  for (int cnd = warp; cnd < nsel; cnd += FIN_WARPS) {
+    const uint32_t idx = ~static_cast<uint32_t>(s_sel[cnd]);
+    const double sc = exact_pair_score(qv, qq, P.master32 ? P.master32 + (int64_t)idx * P.ld32 : nullptr,
+                                       P.master32 ? nullptr : P.rows16 + (int64_t)idx * P.ld16, P.kind16, P.dim,
+                                       P.metric, lane);
+    if (lane == 0) s_sc[cnd] = sc;
+  }
+  __syncthreads();
+
+  // (4) rank by counting over the nsel <= 128 candidates
+  if (tid < nsel) {
+    const double s = s_sc[tid];
+    const uint32_t ix = ~static_cast<uint32_t>(s_sel[tid]);
+    int rank = 0;
+    for (int i = 0; i < nsel; ++i)
+      if (beats(s_sc[i], ~static_cast<uint32_t>(s_sel[i]), s, ix)) ++rank;
+    if (rank < k) {
+      P.out_scores[q * k + rank] = user_score(s, P.metric);
+      P.out_rows[q * k + rank] = (int64_t)ix;
+      if (P.out_scores64) P.out_scores64[q * k + rank] = s;
+      if (rank == k - 1) {
+        s_kth = s;
+        s_have_kth = 1;
+      }
+    }
+  }
+  __syncthreads();
+
+  // (5) certification
+  if (warp == 0) {
+    uint32_t hmin = 0xffffffffu;
+    for (int i = lane; i < nsel; i += 32) hmin = min(hmin, static_cast<uint32_t>(s_sel[i] >> 32));
+    hmin = __reduce_min_sync(FULL_MASK, hmin);
+    if (lane == 0) {
+      // kc or more candidates: everything dropped (by a prune of K3 or by the selection above) scores at most the
+      // kc-th best approximate score.  Fewer: no list was ever pruned, only the pre-sampled threshold dropped rows.
+      float tau = total >= kc ? ordered_to_f32(hmin) : -INFINITY;
+      if (P.tau_init != nullptr) tau = fmaxf(tau, P.tau_init[q]);
+      if (tau != -INFINITY) certify_query(P, q, tau, s_have_kth != 0, s_kth);   // else exact by construction
     }
   }
 }
@@ -442,21 +535,6 @@ merge_topk_kernel(const double* __restrict__ scores64, const int64_t* __restrict
 
 }  // namespace
 
-int launch_merge_partials(const float* part_score, const uint32_t* part_idx, int slices, int64_t q_pad,
-                          int64_t Q, int kc, const float* tau_init, uint32_t* cand_idx, float* cand_tau,
-                          cudaStream_t st) {
-  if (Q <= 0) return RBOD_OK;
-  int m = slices * kc, p2 = 32;
-  while (p2 < m) p2 <<= 1;
-  if (p2 > 8192) return set_error(RBOD_E_INVAL, "merge_partials: %d candidates per query exceed 8192", m);
-  const size_t smem = (size_t)p2 * 8;
-  RBOD_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  merge_partials_kernel<<<(unsigned)Q, 256, smem, st>>>(part_score, part_idx, slices, q_pad, kc, p2, tau_init,
-                                                        cand_idx, cand_tau);
-  RBOD_CUDA(cudaGetLastError());
-  return RBOD_OK;
-}
-
 int launch_tau_init(const float* groupmax, int groups, int splits, int64_t q_pad, uint32_t* tau_shared,
                     float* tau_init, cudaStream_t st) {
   if (q_pad <= 0) return RBOD_OK;
@@ -466,28 +544,22 @@ int launch_tau_init(const float* groupmax, int groups, int splits, int64_t q_pad
   return RBOD_OK;
 }
 
-int launch_rescore(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16, int kind16,
-                   int dim, int64_t ld32, int64_t ld16, int metric, const uint32_t* cand_idx, int64_t Q, int kc,
-                   double* cand_score, cudaStream_t st) {
-  const int64_t n_pairs = Q * kc;
-  if (n_pairs <= 0) return RBOD_OK;
-  const int64_t want = (n_pairs + 7) / 8;
-  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
-  rescore_kernel<<<grid, 256, 0, st>>>(q, q_qq, master32, rows16, kind16, dim, ld32, ld16, metric, cand_idx, n_pairs,
-                                       kc, cand_score);
-  RBOD_CUDA(cudaGetLastError());
-  return RBOD_OK;
-}
-
-int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
-                  const float* stats, const double* q_qq, int metric, int master16, int shadow, int dp, int64_t Q, int kc,
-                  int k, float* out_scores, int64_t* out_rows, double* out_scores64, int* n_flag, int* flag_q,
-                  double* flag_thr, float* flag_lo, float* max_eps, cudaStream_t st) {
+int launch_finish(const FinishArgs& A, int64_t Q, cudaStream_t st) {
   if (Q <= 0) return RBOD_OK;
-  if (kc > K3_MAX_KC) return set_error(RBOD_E_INVAL, "select: kc %d > %d", kc, K3_MAX_KC);
-  select_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, st>>>(cand_score, cand_idx, cand_tau, q_dq, stats, q_qq, metric, master16, shadow, dp, Q, kc, k,
-                                                         out_scores, out_rows, out_scores64, n_flag, flag_q,
-                                                         flag_thr, flag_lo, max_eps);
+  if (A.kc < 1 || A.kc > K3_MAX_KC || A.k < 1 || A.k > A.kc)
+    return set_error(RBOD_E_INVAL, "finish: k %d / kc %d outside [1, %d]", A.k, A.kc, K3_MAX_KC);
+  if (A.slices < 1 || A.slices > FIN_MAX_SLICES)
+    return set_error(RBOD_E_INVAL, "finish: %d slices outside [1, %d]", A.slices, FIN_MAX_SLICES);
+  if (A.n_cap < 1 || A.n_cap > FIN_MAX_KEYS)
+    return set_error(RBOD_E_INVAL, "finish: %d candidates per query exceed %d", A.n_cap, FIN_MAX_KEYS);
+  static bool configured[64] = {false};   // raising the dynamic shared-memory limit: once per device and process
+  int dev = 0;
+  RBOD_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    RBOD_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIN_MAX_KEYS * 8));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  finish_kernel<<<(unsigned)Q, FIN_THREADS, (size_t)A.n_cap * 8, st>>>(A);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

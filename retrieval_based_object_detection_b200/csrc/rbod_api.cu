@@ -159,6 +159,7 @@ static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct SearchPlan {
   int kc, slices, grid, num_qt, tiles_total, num_stages, a_tmem_kb, kbs;
+  int list_cap, list_stride, final_cap, n_cap;   // candidate-list geometry (see K3Launch / FinishArgs)
   int64_t q_pad;
   size_t smem;
 };
@@ -183,7 +184,7 @@ static int plan_search(const rbod_gallery* g, int64_t Q, int k, int variant, int
   P->num_qt = (int)(P->q_pad / q_per_unit);
   P->tiles_total = (int)((g->rows + K3_TILE_N - 1) / K3_TILE_N);
   // slices: balance (units per CTA) x (tiles per unit); fewer slices on ties (less merge work)
-  const int max_slices = std::max(1, std::min({P->tiles_total, 8192 / kc, 2 * workers}));
+  const int max_slices = std::max(1, std::min({P->tiles_total, 8192 / kc, 2 * workers, 512}));
   double best = 1e300;
   int best_s = 1;
   for (int s = 1; s <= max_slices; ++s) {
@@ -201,8 +202,15 @@ static int plan_search(const rbod_gallery* g, int64_t Q, int k, int variant, int
   // box: 78.3 -> 81.8), Q=2048 79.3 -> 80.7; 1M x 512 fp32 (520 tiles per unit) 884 -> 849 k, Q <= 512 5-10 % slower.
   const int want_kbs = g->k3_kbs ? g->k3_kbs
                                  : ((P->num_qt >= 16 && P->tiles_total / std::max(1, P->slices) >= 2048) ? 4 : 2);
-  RBOD_TRY(k3_plan(variant, want_kbs, kc, g->dp, smem_optin, g->hybrid, &P->num_stages, &P->a_tmem_kb, &P->kbs,
+  RBOD_TRY(k3_plan(variant, want_kbs, g->dp, smem_optin, g->hybrid, &P->num_stages, &P->a_tmem_kb, &P->kbs,
                    &P->smem));
+  // Candidate lists: a list is pruned back to ~kc entries whenever it reaches list_cap (>= 2 kc, so at least kc
+  // appends pay for one prune); a tile may append 128 entries before the check, hence the stride.  Lists are left
+  // unpruned at the end of a unit unless the query's slices together could exceed what the finish kernel sorts.
+  P->list_cap = kc <= 32 ? 64 : (kc <= 64 ? 128 : 256);
+  P->list_stride = P->list_cap + K3_TILE_N;
+  P->final_cap = std::max(kc, std::min(P->list_stride - 1, 8192 / P->slices));
+  P->n_cap = std::min(8192, P->slices * P->final_cap);
   return RBOD_OK;
 }
 
@@ -277,7 +285,7 @@ int rbod_destroy(rbod_gallery* g) {
   if (g->row_bias) cudaFree(g->row_bias);
   if (g->stats) cudaFree(g->stats);
   DevBuf* bufs[] = {&g->stage_rows, &g->stage_slots, &g->stage_norms, &g->q32, &g->q16, &g->q_dq, &g->q_qq, &g->tau_shared,
-                    &g->part_score, &g->part_idx, &g->cand_idx, &g->cand_tau, &g->cand_score, &g->out_scores,
+                    &g->lists, &g->list_cnt, &g->out_scores,
                     &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->flag_lo, &g->fq16, &g->groupmax, &g->tau_init, &g->coll_score,
                     &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->sync_counters, &g->seg_idx, &g->seg_off, &g->seg_out,
                     &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->seg_scratch, &g->seg_member, &g->gather_idx,
@@ -304,8 +312,7 @@ int rbod_info(const rbod_gallery* g, rbod_gallery_info* out) {
   out->rows = g->rows;
   out->capacity = g->capacity;
   size_t ws = 0;
-  const DevBuf* bufs[] = {&g->stage_rows, &g->q32, &g->q16, &g->part_score, &g->part_idx, &g->cand_idx,
-                          &g->cand_score, &g->out_scores, &g->out_rows, &g->out_scores64, &g->coll_score,
+  const DevBuf* bufs[] = {&g->stage_rows, &g->q32, &g->q16, &g->lists, &g->list_cnt, &g->out_scores, &g->out_rows, &g->out_scores64, &g->coll_score,
                           &g->coll_idx, &g->mask_dev, &g->dump, &g->seg_idx, &g->seg_out, &g->seg_partials,
                           &g->gather_out};
   for (const DevBuf* b : bufs) ws += b->cap;
@@ -696,8 +703,11 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.debug_epi = g->debug_epi;
   L.a_fmt = query_kind(g) == 1 ? 1 : 0;
   L.b_fmt = query_kind(g) == 1 ? 1 : 0;
-  L.part_score = g->part_score.as<float>();
-  L.part_idx = g->part_idx.as<uint32_t>();
+  L.lists = g->lists.as<uint2>();
+  L.list_cnt = g->list_cnt.as<int>();
+  L.list_cap = P.list_cap;
+  L.list_stride = P.list_stride;
+  L.final_cap = P.final_cap;
   L.row_mask = mask_dev;
   L.row_bias = g->metric == RBOD_EUCLID ? g->row_bias : nullptr;
   L.tau_shared = (g->tau_share && dump == nullptr && collect == nullptr && sample == nullptr)
@@ -725,6 +735,12 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
     L.sync_counters = g->sync_counters.as<int>();
   }
   return launch_k3(L, st);
+}
+
+static int ensure_lists(rbod_gallery* g, const SearchPlan& P) {
+  RBOD_TRY(g->lists.ensure((size_t)P.slices * P.q_pad * P.list_stride * sizeof(uint2)));
+  RBOD_TRY(g->list_cnt.ensure((size_t)P.slices * P.q_pad * sizeof(int)));
+  return RBOD_OK;
 }
 
 static int prepare_queries(rbod_gallery* g, const float* queries, int64_t Q, const SearchPlan& P, cudaStream_t st,
@@ -884,7 +900,6 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   }
 
   RBOD_TRY(g->flags.ensure(64));
-  RBOD_CUDA(cudaMemsetAsync(g->flags.p, 0, 64, st));
   int* d_flags = g->flags.as<int>();
   int64_t launches = 0;
 
@@ -903,78 +918,104 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   const void* mask_dev = nullptr;
   if (row_mask) RBOD_TRY(to_device(row_mask, (size_t)((g->rows + 31) / 32) * 4, g->mask_dev, st, &mask_dev));
 
-  const float* q_dev = nullptr;
-  RBOD_TRY(prepare_queries(g, queries, Q, P, st, &q_dev));
-  ++launches;
-
-  const size_t part_elems = (size_t)P.slices * P.q_pad * P.kc;
-  RBOD_TRY(g->part_score.ensure(part_elems * 4));
-  RBOD_TRY(g->part_idx.ensure(part_elems * 4));
-  RBOD_TRY(g->cand_idx.ensure((size_t)Q * P.kc * 4));
-  RBOD_TRY(g->cand_tau.ensure((size_t)Q * 4));
-  RBOD_TRY(g->cand_score.ensure((size_t)Q * P.kc * 8));
+  RBOD_TRY(ensure_lists(g, P));
   RBOD_TRY(g->flag_q.ensure((size_t)Q * 4));
   RBOD_TRY(g->flag_thr.ensure((size_t)Q * 8));
   RBOD_TRY(g->flag_lo.ensure((size_t)P.q_pad * 4 + 1024));   // read as [q_pad of the second pass]
 
-  if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev0, st));
   // Threshold pre-pass: row maxima over K3_SAMPLE_GROUPS strided samples of the gallery give every query a
-  // starting threshold, so the candidate heaps of the main pass skip their cold start (see tau_init_kernel).
+  // starting threshold, so the candidate lists of the main pass skip their cold start (see tau_init_kernel).
   // Each group's comb is split over enough units to fill the chip, so a small batch does not stream the sample on
   // eight SMs (Q <= 128 on 12.5M x 768: 0.48 ms before the split, next to a 2.9 ms main pass).  Batches of at most
   // 8 queries skip it: their epilogue has almost nothing to insert (measured: Q = 1 is 0.47 ms faster without,
   // Q = 16 already 0.17 ms slower).  presample = 2 forces it.
-  const float* tau_init = nullptr;
   const int sample_tiles = std::max(1, P.tiles_total / (K3_SAMPLE_RATIO * P.kc));
   const bool sample_pays = g->presample >= 2 || Q > 8;
-  if (g->tau_share && g->presample && sample_pays && P.tiles_total >= 10 * P.kc &&
-      P.tiles_total / sample_tiles >= K3_SAMPLE_GROUPS) {
-    SearchPlan PA = P;
-    const int workers = g->k3_variant == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
-    const int splits = std::max(1, std::min({16, sample_tiles, workers / (K3_SAMPLE_GROUPS * std::max(1, PA.num_qt))}));
-    PA.slices = K3_SAMPLE_GROUPS * splits;
-    PA.grid = (int)std::min<int64_t>((int64_t)PA.slices * PA.num_qt, workers) * (g->k3_variant == 2 ? 2 : 1);
-    RBOD_TRY(g->groupmax.ensure((size_t)PA.slices * P.q_pad * 4));
-    RBOD_TRY(g->tau_init.ensure((size_t)P.q_pad * 4));
-    K3Sample S;
-    S.groupmax = g->groupmax.as<float>();
-    S.tiles = sample_tiles;
-    S.stride = P.tiles_total / sample_tiles;
-    S.splits = splits;
-    RBOD_TRY(run_k3(g, PA, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st,
-                    &S));
-    RBOD_TRY(launch_tau_init(g->groupmax.as<float>(), K3_SAMPLE_GROUPS, splits, P.q_pad,
-                             g->tau_shared.as<uint32_t>(), g->tau_init.as<float>(), st));
-    tau_init = g->tau_init.as<float>();
-    launches += 2;
-  }
-  RBOD_TRY(run_k3(g, P, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st));
-  if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev1, st));
-  ++launches;
-
-  RBOD_TRY(launch_merge_partials(g->part_score.as<float>(), g->part_idx.as<uint32_t>(), P.slices, P.q_pad, Q, P.kc,
-                                 tau_init, g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(), st));
-  RBOD_TRY(launch_rescore(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp,
-                          g->metric, g->cand_idx.as<uint32_t>(), Q, P.kc, g->cand_score.as<double>(), st));
-  RBOD_TRY(launch_select(g->cand_score.as<double>(), g->cand_idx.as<uint32_t>(), g->cand_tau.as<float>(),
-                         g->q_dq.as<float>(), g->stats, g->q_qq.as<double>(), g->metric, g->dtype != RBOD_F32,
-                         g->use_shadow, g->dp, Q, P.kc, k, d_scores,
-                         d_rows, d_scores64, d_flags,
-                         g->flag_q.as<int>(), g->flag_thr.as<double>(), g->flag_lo.as<float>(),
-                         reinterpret_cast<float*>(d_flags + 3), st));
-  launches += 3;
-
+  bool use_sample = g->tau_share && g->presample && sample_pays && P.tiles_total >= 10 * P.kc &&
+                    P.tiles_total / sample_tiles >= K3_SAMPLE_GROUPS;
   int hflags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  RBOD_CUDA(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
-  RBOD_CUDA(cudaStreamSynchronize(st));
-  if (hflags[4] > 0 && tau_init != nullptr) {
-    // a starting threshold cut below k candidates for some query: redo the call without the pre-pass
-    const int saved = g->presample;
-    g->presample = 0;
-    const int rc = rbod_search(g, queries, Q, k, row_mask, out_scores, out_rows, out_scores64, stats, stream);
-    g->presample = saved;
-    if (rc == RBOD_OK && stats) stats->presample_retries = hflags[4];
-    return rc;
+  const float* q_dev = nullptr;
+  int64_t retries = 0;
+  for (int attempt = 0;; ++attempt) {
+    RBOD_CUDA(cudaMemsetAsync(g->flags.p, 0, 64, st));
+    RBOD_TRY(prepare_queries(g, queries, Q, P, st, &q_dev));
+    ++launches;
+    if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev0, st));
+    const float* tau_init = nullptr;
+    if (use_sample) {
+      SearchPlan PA = P;
+      const int workers = g->k3_variant == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
+      const int splits = std::max(1, std::min({16, sample_tiles, workers / (K3_SAMPLE_GROUPS * std::max(1, PA.num_qt))}));
+      PA.slices = K3_SAMPLE_GROUPS * splits;
+      PA.grid = (int)std::min<int64_t>((int64_t)PA.slices * PA.num_qt, workers) * (g->k3_variant == 2 ? 2 : 1);
+      RBOD_TRY(g->groupmax.ensure((size_t)PA.slices * P.q_pad * 4));
+      RBOD_TRY(g->tau_init.ensure((size_t)P.q_pad * 4));
+      K3Sample S;
+      S.groupmax = g->groupmax.as<float>();
+      S.tiles = sample_tiles;
+      S.stride = P.tiles_total / sample_tiles;
+      S.splits = splits;
+      RBOD_TRY(run_k3(g, PA, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st,
+                      &S));
+      RBOD_TRY(launch_tau_init(g->groupmax.as<float>(), K3_SAMPLE_GROUPS, splits, P.q_pad,
+                               g->tau_shared.as<uint32_t>(), g->tau_init.as<float>(), st));
+      tau_init = g->tau_init.as<float>();
+      launches += 2;
+    }
+    RBOD_TRY(run_k3(g, P, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st));
+    if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev1, st));
+    ++launches;
+
+    FinishArgs F;
+    memset(&F, 0, sizeof(F));
+    F.lists = g->lists.as<uint2>();
+    F.list_cnt = g->list_cnt.as<int>();
+    F.slices = P.slices;
+    F.list_stride = P.list_stride;
+    F.n_cap = P.n_cap;
+    F.kc = P.kc;
+    F.k = k;
+    F.q_pad = P.q_pad;
+    F.tau_init = tau_init;
+    F.q = q_dev;
+    F.q_qq = g->q_qq.as<double>();
+    F.q_dq = g->q_dq.as<float>();
+    F.stats = g->stats;
+    F.master32 = g->master32;
+    F.rows16 = g->rows16;
+    F.kind16 = g->kind16;
+    F.dim = g->dim;
+    F.metric = g->metric;
+    F.master16 = g->dtype != RBOD_F32;
+    F.shadow = g->use_shadow;
+    F.dp = g->dp;
+    F.ld32 = g->dim;
+    F.ld16 = g->dp;
+    F.out_scores = d_scores;
+    F.out_rows = d_rows;
+    F.out_scores64 = d_scores64;
+    F.n_flag = d_flags;
+    F.flag_q = g->flag_q.as<int>();
+    F.flag_thr = g->flag_thr.as<double>();
+    F.flag_lo = g->flag_lo.as<float>();
+    F.max_eps = reinterpret_cast<float*>(d_flags + 3);
+    RBOD_TRY(launch_finish(F, Q, st));
+    ++launches;
+
+    // The answer and the certification flags travel together: in the common case (every query certified) this is
+    // the only synchronisation of the call.
+    RBOD_TRY(copy_out(out_scores, d_scores, nout * 4, st));
+    RBOD_TRY(copy_out(out_rows, d_rows, nout * 8, st));
+    if (out_scores64) RBOD_TRY(copy_out(out_scores64, d_scores64, nout * 8, st));
+    RBOD_CUDA(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+    RBOD_CUDA(cudaStreamSynchronize(st));
+    if (hflags[4] > 0 && tau_init != nullptr && attempt == 0) {
+      // a starting threshold cut below k candidates for some query: once more without the pre-pass
+      retries = hflags[4];
+      use_sample = false;
+      continue;
+    }
+    break;
   }
   const int n_flag = hflags[0];
   float max_eps;
@@ -1048,11 +1089,13 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     }
     RBOD_CUDA(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
   }
-
-  RBOD_TRY(copy_out(out_scores, d_scores, nout * 4, st));
-  RBOD_TRY(copy_out(out_rows, d_rows, nout * 8, st));
-  if (out_scores64) RBOD_TRY(copy_out(out_scores64, d_scores64, nout * 8, st));
-  RBOD_CUDA(cudaStreamSynchronize(st));
+  if (n_flag > 0) {
+    // the second pass rewrote the flagged queries' rows of the answer
+    RBOD_TRY(copy_out(out_scores, d_scores, nout * 4, st));
+    RBOD_TRY(copy_out(out_rows, d_rows, nout * 8, st));
+    if (out_scores64) RBOD_TRY(copy_out(out_scores64, d_scores64, nout * 8, st));
+    RBOD_CUDA(cudaStreamSynchronize(st));
+  }
   if (hflags[1])
     return set_error(RBOD_E_OVERFLOW, "rbod_search: more than 4096 rows tie around the k-th score of a query");
 
@@ -1062,6 +1105,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     stats->sweep_queries = n_sweep;
     stats->total_launches = launches;
     stats->max_eps = max_eps;
+    stats->presample_retries = retries;
     if (g->time_k3) {
       float ms = 0.f;
       RBOD_CUDA(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
@@ -1085,9 +1129,7 @@ int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* o
   RBOD_TRY(plan_search(g, Q, 1, g->k3_variant, smem_optin, &P));
   const float* q_dev = nullptr;
   RBOD_TRY(prepare_queries(g, queries, Q, P, st, &q_dev));
-  const size_t part_elems = (size_t)P.slices * P.q_pad * P.kc;
-  RBOD_TRY(g->part_score.ensure(part_elems * 4));
-  RBOD_TRY(g->part_idx.ensure(part_elems * 4));
+  RBOD_TRY(ensure_lists(g, P));
   const int64_t ld = g->rows;
   const bool out_dev = is_device_ptr(out);
   float* dst = out;
@@ -1125,6 +1167,10 @@ int rbod_debug_plan(int32_t dim, int64_t rows, int64_t Q, int32_t k, int32_t var
   out[6] = P.kbs;
   out[7] = P.a_tmem_kb;
   out[8] = (int64_t)P.smem;
+  out[9] = P.list_cap;
+  out[10] = P.list_stride;
+  out[11] = P.final_cap;
+  out[12] = P.n_cap;
   return RBOD_OK;
 }
 

@@ -61,14 +61,17 @@ struct K3Launch {
   int slices;
   int64_t q_valid;
   int64_t q_pad;
-  int kc;                 // candidates per (query, slice); multiple of 32
+  int kc;                 // candidates a prune keeps per (query, slice) list, <= K3_MAX_KC
   int num_stages;
   int a_tmem_kb;          // k-blocks of the query tile kept in TMEM (rest resident in smem)
   int variant;            // 0 = A in TMEM, 1 = A streamed through smem, 2 = A in TMEM + CTA pairs (cta_group::2)
   int kbs;                // k-blocks per pipeline stage of the variant-0 kernel (2 or 4)
   int a_fmt, b_fmt;       // 0 = f16, 1 = bf16
-  float* part_score;      // [slices][q_pad][kc]
-  uint32_t* part_idx;     // [slices][q_pad][kc]
+  uint2* lists;           // [slices][q_pad][list_stride] candidate lists {score bits, row index} (select mode)
+  int* list_cnt;          // [slices][q_pad] entries per list when its unit is done
+  int list_cap;           // prune trigger: 64 (kc <= 32), 128 (kc <= 64) or 256
+  int list_stride;        // list_cap + K3_TILE_N
+  int final_cap;          // lists longer than this get a last exact prune to kc entries
   const uint32_t* row_mask;
   const float* row_bias;  // EUCLID collections: [capacity rounded up to whole tiles] -|g|^2 / 2 per stored row
   uint32_t* tau_shared;   // [q_pad] ordered-key thresholds shared across slices, preset to key(-inf); or nullptr
@@ -111,7 +114,7 @@ int launch_segment_delegates(const float* master32, const uint16_t* rows16, int 
                              int64_t* out_member, int* err_flag, cudaStream_t st);
 // K3
 int k3_configure(int device);
-int k3_plan(int variant, int want_kbs, int kc, int dp, int smem_optin, int allow_hybrid, int* num_stages,
+int k3_plan(int variant, int want_kbs, int dp, int smem_optin, int allow_hybrid, int* num_stages,
             int* a_tmem_kb, int* kbs_out, size_t* smem_bytes);
 int k3_box_rows(int variant);   // gallery rows per TMA box (64 for the CTA-pair kernel)
 int launch_k3(const K3Launch& L, cudaStream_t st);
@@ -119,18 +122,33 @@ int launch_k3(const K3Launch& L, cudaStream_t st);
 int launch_prep_queries(const float* q, int64_t Q, int64_t q_pad, int dim, int dp, int kind16, int normalize,
                         uint16_t* q16, float* q_dq, double* q_qq, uint32_t* tau_shared, cudaStream_t st);
 // K4 family
-int launch_merge_partials(const float* part_score, const uint32_t* part_idx, int slices, int64_t q_pad,
-                          int64_t Q, int kc, const float* tau_init, uint32_t* cand_idx, float* cand_tau,
-                          cudaStream_t st);
 int launch_tau_init(const float* groupmax, int groups, int splits, int64_t q_pad, uint32_t* tau_shared,
                     float* tau_init, cudaStream_t st);
-int launch_rescore(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16, int kind16,
-                   int dim, int64_t ld32, int64_t ld16, int metric, const uint32_t* cand_idx, int64_t Q, int kc,
-                   double* cand_score, cudaStream_t st);
-int launch_select(const double* cand_score, const uint32_t* cand_idx, const float* cand_tau, const float* q_dq,
-                  const float* stats, const double* q_qq, int metric, int master16, int shadow, int dp, int64_t Q, int kc,
-                  int k, float* out_scores, int64_t* out_rows, double* out_scores64, int* n_flag, int* flag_q,
-                  double* flag_thr, float* flag_lo, float* max_eps, cudaStream_t st);
+// finish: merge of a query's per-slice lists, exact rescoring, top-k, certification (one CTA per query)
+struct FinishArgs {
+  const uint2* lists;      // [slices][q_pad][list_stride] {score bits, row index}
+  const int* list_cnt;     // [slices][q_pad]
+  int slices, list_stride, n_cap, kc, k;
+  int64_t q_pad;
+  const float* tau_init;   // [q_pad] pre-sampled starting thresholds, or nullptr
+  const float* q;          // [Q, dim] queries as given
+  const double* q_qq;      // [q_pad] |q|^2
+  const float* q_dq;       // [q_pad] rounding radius of the 16-bit query
+  const float* stats;      // gallery maxima (K1)
+  const float* master32;
+  const uint16_t* rows16;
+  int kind16, dim, metric, master16, shadow, dp;
+  int64_t ld32, ld16;
+  float* out_scores;
+  int64_t* out_rows;
+  double* out_scores64;
+  int* n_flag;
+  int* flag_q;
+  double* flag_thr;
+  float* flag_lo;
+  float* max_eps;
+};
+int launch_finish(const FinishArgs& A, int64_t Q, cudaStream_t st);
 int launch_gather_flagged(const uint16_t* q16, int dp, const int* flag_q, int f0, int nf, int64_t nf_pad,
                           uint16_t* fq16, int* coll_cnt, cudaStream_t st);
 int launch_rescore_collected(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
@@ -187,7 +205,7 @@ struct rbod_gallery {
   // workspaces
   rbod::DevBuf stage_rows, stage_slots, stage_norms;          // upsert staging
   rbod::DevBuf q32, q16, q_dq, q_qq, tau_shared;              // query prep
-  rbod::DevBuf part_score, part_idx, cand_idx, cand_tau, cand_score;
+  rbod::DevBuf lists, list_cnt;                                // K3 candidate lists
   rbod::DevBuf out_scores, out_rows, out_scores64;
   rbod::DevBuf flags;      // ints: [0]=n_flag [1]=overflow [2]=err; float max_eps at [3]
   rbod::DevBuf flag_q, flag_thr, flag_lo, fq16, groupmax, tau_init;

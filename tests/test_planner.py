@@ -13,9 +13,10 @@ SMS, SMEM_OPTIN = 148, 232448          # B200
 
 def _plan(dim, rows, Q, k, variant=0):
     lib = _native.load()
-    out = (ctypes.c_int64 * 9)()
+    out = (ctypes.c_int64 * 13)()
     rc = lib.rbod_debug_plan(dim, rows, Q, k, variant, SMS, SMEM_OPTIN, out)
-    return rc, dict(zip(("kc", "slices", "grid", "num_qt", "tiles", "stages", "kbs", "a_tmem_kb", "smem"), list(out)))
+    return rc, dict(zip(("kc", "slices", "grid", "num_qt", "tiles", "stages", "kbs", "a_tmem_kb", "smem", "list_cap",
+                         "list_stride", "final_cap", "n_cap"), list(out)))
 
 
 DIMS = (3, 64, 100, 128, 320, 512, 640, 768)
@@ -33,7 +34,12 @@ def test_every_accepted_shape_gets_a_plan_within_the_kernel_limits(variant):
         per_unit = 256 if variant == 2 else 128
         assert p["kc"] >= k and p["kc"] <= 128 and p["kc"] % 8 == 0
         assert p["tiles"] == (rows + 127) // 128 and p["num_qt"] == (Q + per_unit - 1) // per_unit
-        assert 1 <= p["slices"] <= p["tiles"] and p["slices"] * p["kc"] <= 8192         # merge_partials sorts <= 8192 keys
+        assert 1 <= p["slices"] <= min(p["tiles"], 512) and p["slices"] * p["kc"] <= 8192   # the finish kernel holds <= 8192 keys
+        # candidate lists: pruned at list_cap >= 2 kc back to ~kc, a tile may append 128 entries before the check;
+        # what reaches the finish kernel fits its key buffer
+        assert p["list_cap"] in (64, 128, 256) and p["list_cap"] >= 2 * p["kc"] and p["list_stride"] == p["list_cap"] + 128
+        assert p["kc"] <= p["final_cap"] < p["list_stride"] and p["n_cap"] == min(8192, p["slices"] * p["final_cap"])
+        assert p["slices"] * p["final_cap"] <= 8192 or p["final_cap"] == p["kc"]
         assert 1 <= p["grid"] <= SMS and (variant != 2 or p["grid"] % 2 == 0)            # cooperative launch: <= 1 CTA / SM
         assert p["grid"] <= p["slices"] * p["num_qt"] * (2 if variant == 2 else 1)
         assert p["smem"] <= SMEM_OPTIN
@@ -59,8 +65,11 @@ def test_planner_policies():
     assert head["kbs"] == 4 and head["stages"] == 2 and head["a_tmem_kb"] == 8 and head["slices"] == 11
     assert _plan(768, 10_000_000, 256, 10)[1]["kbs"] == 2            # small batch
     assert _plan(512, 1_000_000, 10_000, 10)[1]["kbs"] == 2          # short units
+    # candidate lists live in global memory: k = 100 gets the same pipeline as k = 10 (round 1: 128 KB of heaps in
+    # shared memory cost it the hybrid layout and the second accumulator buffer)
     k100 = _plan(768, 10_000_000, 10_000, 100)[1]
-    assert k100["kbs"] == 2 and k100["stages"] >= 2
+    assert {x: k100[x] for x in ("kbs", "stages", "a_tmem_kb", "smem")} == {x: head[x] for x in ("kbs", "stages", "a_tmem_kb", "smem")}
+    assert (head["list_cap"], k100["list_cap"], k100["list_stride"]) == (64, 256, 384)
     # small batches spread one query tile over (almost) every SM
     assert _plan(768, 12_500_000, 1, 10)[1]["slices"] >= 140
     # what the tensor-core pass does not take is refused here (rbod_search routes it to the fp64 sweep)
