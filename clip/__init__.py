@@ -6,12 +6,19 @@ here.
 (same architecture and output width, 512) and the standard 224x224 preprocessing, so
 31_clip_embedding_and_save_vector.py runs unchanged end to end.  The embeddings are
 shape/dtype-faithful but semantically meaningless; the encoder stays in PyTorch exactly as the
-north star says -- it is not part of the accelerated hot path.  If the real ``clip`` package is
-installed ahead of this directory on sys.path, it is used instead.
+north star says -- it is not part of the accelerated hot path.
+
+This directory usually sits FIRST on sys.path (the repo root), so it would shadow a real ``clip``
+installation.  ``load`` therefore looks for a real one on the rest of sys.path first and hands the
+call over to it; only when there is none does it build the random tower, and it says so loudly
+(``UserWarning`` + a line on stderr) unless ``RBOD_FAKE_CLIP=1`` acknowledges the stand-in.
 """
 from __future__ import annotations
 
-import math
+import importlib.util
+import os
+import sys
+import warnings
 from typing import List, Tuple
 
 import torch
@@ -106,7 +113,48 @@ class _Preprocess:
         return (x - mean) / std
 
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_real = None
+
+
+def _find_real_clip():
+    """The ``clip`` package of a real installation (OpenAI's: a ``clip/clip.py`` next to its ``__init__``), looked up
+    on every sys.path entry except the one this stand-in lives in; None if there is none."""
+    global _real
+    if _real is not None:
+        return _real or None
+    _real = False
+    for entry in sys.path:
+        base = os.path.abspath(entry or os.getcwd())
+        cand = os.path.join(base, "clip")
+        if os.path.abspath(cand) == _HERE or not os.path.isfile(os.path.join(cand, "__init__.py")):
+            continue
+        if not os.path.isfile(os.path.join(cand, "clip.py")):
+            continue
+        spec = importlib.util.spec_from_file_location("_rbod_real_clip", os.path.join(cand, "__init__.py"),
+                                                      submodule_search_locations=[cand])
+        try:
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules["_rbod_real_clip"] = mod
+            spec.loader.exec_module(mod)
+            _real = mod
+            break
+        except Exception as exc:  # noqa: BLE001 -- a broken installation must not take the scripts down
+            sys.modules.pop("_rbod_real_clip", None)
+            warnings.warn(f"found a clip installation at {cand} but could not import it ({exc!r}); using the stand-in")
+    return _real or None
+
+
 def load(name: str = "ViT-B/32", device="cpu", jit: bool = False, download_root=None) -> Tuple[CLIP, _Preprocess]:
+    real = _find_real_clip()
+    if real is not None:
+        return real.load(name, device=device, jit=jit, download_root=download_root)
+    if os.environ.get("RBOD_FAKE_CLIP", "0") != "1":
+        msg = (f"clip.load({name!r}): no real `clip` installation found -- returning a RANDOM-INIT stand-in image tower "
+               f"({__file__}). Embeddings have the right shape and dtype but carry NO meaning. "
+               "Set RBOD_FAKE_CLIP=1 to acknowledge this and silence the warning.")
+        warnings.warn(msg, UserWarning, stacklevel=2)
+        print("WARNING: " + msg, file=sys.stderr)
     if name not in _MODELS:
         raise RuntimeError(f"Model {name} not found; available models = {available_models()}")
     gen_state = torch.random.get_rng_state()

@@ -209,6 +209,13 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
 int rbod_merge_topk(const double* scores64, const int64_t* ids, int32_t G, int64_t Q, int32_t k,
                     float* out_scores, int64_t* out_ids, double* out_scores64, void* stream);
 
+/* The same merge over ONE gathered buffer: every rank contributes [2][Q][k] 8-byte words -- its fp64 scores
+ * (rbod_search's out_scores64) followed by its LOCAL row slots (out_rows) -- so a sharded search needs a single
+ * all-gather; gathered = [G][2][Q][k] (device).  shard_row0: host array of G global row offsets added to the
+ * non-negative slots of shard g (NULL = slots are already global ids).                                     */
+int rbod_merge_topk_packed(const void* gathered, const int64_t* shard_row0, int32_t G, int64_t Q, int32_t k,
+                           float* out_scores, int64_t* out_ids, double* out_scores64, void* stream);
+
 /* --- test hook --------------------------------------------------------------------------
  * Raw scores of the tcgen05 pass (before top-k and rescoring): out[q, r] for r < rows,
  * fp32, device or host.  Small problems only (Q * rows <= 2^28).                          */

@@ -10,8 +10,8 @@ The arithmetic lives in librbod.so (hand-written sm_100a CUDA behind the C ABI o
 Importing this package does not load the library; the first Gallery does, and fails loudly if the
 extension has not been built or no B200 is present.
 """
-from .gallery import Gallery, SearchResult, merge_topk, l2norm_pack, segment_finish  # noqa: F401
+from .gallery import Gallery, SearchResult, merge_topk, merge_topk_packed, l2norm_pack, segment_finish  # noqa: F401
 from .sharded import ShardedGallery, shard_range  # noqa: F401
 
-__all__ = ["Gallery", "SearchResult", "merge_topk", "l2norm_pack", "segment_finish", "ShardedGallery", "shard_range"]
+__all__ = ["Gallery", "SearchResult", "merge_topk", "merge_topk_packed", "l2norm_pack", "segment_finish", "ShardedGallery", "shard_range"]
 __version__ = "0.1.0"

@@ -75,6 +75,7 @@ SIGNATURES = {
     "rbod_segment_delegates": (ctypes.c_int, [_P, _I32, _P, _P, _I64, ctypes.c_double, _P, _P, _P]),
     "rbod_search": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, ctypes.POINTER(SearchStats), _P]),
     "rbod_merge_topk": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
+    "rbod_merge_topk_packed": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
     "rbod_debug_scores": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "rbod_debug_plan": (ctypes.c_int, [_I32, _I64, _I64, _I32, _I32, _I32, _I32, ctypes.POINTER(_I64)]),
 }

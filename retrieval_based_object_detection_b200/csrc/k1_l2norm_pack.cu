@@ -228,6 +228,51 @@ l2norm_pack_generic_kernel(const float* __restrict__ in, int64_t n, int dim, con
   }
 }
 
+// fp16 shadow of a bf16 collection built after the fact (a search with k > 40 asks for it, see rbod_api.cu): one warp
+// per stored row, 16-byte loads and stores over the padded row, each bf16 value rounded to fp16 exactly as K1 does
+// when the shadow exists from the start; stats[2] / stats[3] = max ||shadow row|| / max ||shadow row - stored row||.
+// HBM-bound: 4 bytes per element.
+__global__ void __launch_bounds__(256)
+build_shadow_kernel(const uint16_t* __restrict__ rows16, int64_t n, int dp, uint16_t* __restrict__ shadow16,
+                    float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t nw = static_cast<int64_t>(gridDim.x) * 8;
+  float wmax_n = 0.f, wmax_d = 0.f;
+  for (int64_t r = w0; r < n; r += nw) {
+    const uint4* src = reinterpret_cast<const uint4*>(rows16 + r * dp);
+    uint4* dst = reinterpret_cast<uint4*>(shadow16 + r * dp);
+    float ssn = 0.f, ssd = 0.f;
+    for (int c = lane; c < dp / 8; c += 32) {
+      const uint4 h = __ldcs(src + c);
+      const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float f0 = h16_to_f32(static_cast<uint16_t>(w[i] & 0xffffu), 1);
+        const float f1 = h16_to_f32(static_cast<uint16_t>(w[i] >> 16), 1);
+        const uint16_t t0 = f32_to_h16(f0, 2), t1 = f32_to_h16(f1, 2);
+        const float g0 = h16_to_f32(t0, 2), g1 = h16_to_f32(t1, 2);
+        ssn += g0 * g0 + g1 * g1;
+        ssd += (g0 - f0) * (g0 - f0) + (g1 - f1) * (g1 - f1);
+        o[i] = static_cast<uint32_t>(t0) | (static_cast<uint32_t>(t1) << 16);
+      }
+      dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ssn += __shfl_xor_sync(FULL_MASK, ssn, o);
+      ssd += __shfl_xor_sync(FULL_MASK, ssd, o);
+    }
+    wmax_n = fmaxf(wmax_n, sqrtf(ssn));
+    wmax_d = fmaxf(wmax_d, sqrtf(ssd));
+  }
+  if (lane == 0) {
+    atomic_max_nonneg(stats + 2, wmax_n);
+    atomic_max_nonneg(stats + 3, wmax_d);
+  }
+}
+
 // EUCLID collections: row_bias[slot] = fp32(-|stored row|^2 / 2), the per-row term the K3 epilogue adds so that the
 // tensor-core score q . g - |g|^2 / 2 orders rows by Euclidean distance.  Sum in fp64 over the row AS STORED (after
 // K1), one warp per row; slots = slots_dev[i] or slot0 + i.
@@ -320,6 +365,15 @@ int launch_l2norm_pack(const float* in, int64_t n, int dim, const int64_t* slots
   }
 #undef RBOD_K1_CASE
 #undef RBOD_K1_ARGS
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
+int launch_build_shadow(const uint16_t* rows16, int64_t n, int dp, uint16_t* shadow16, float* stats, cudaStream_t st) {
+  if (n <= 0) return RBOD_OK;
+  const int64_t want = (n + 7) / 8;
+  const int grid = (int)(want < 148 * 32 ? want : 148 * 32);
+  build_shadow_kernel<<<grid, 256, 0, st>>>(rows16, n, dp, shadow16, stats);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

@@ -400,7 +400,11 @@ exact_collect_kernel(const float* __restrict__ q, const double* __restrict__ q_q
       if (lane == 0) {
         const double den = sqrt(q_qq[qi]) * gn;
         const double s = metric == RBOD_EUCLID ? -acc : (metric == RBOD_DOT ? acc : (den > 0.0 ? acc / den : 0.0));
-        if (s >= flag_thr[f0 + f]) {
+        // the threshold is the provisional k-th exact score as the finish kernel summed it; this sweep adds the same
+        // products in another order, so the very row that set the threshold may come out an ulp lower here: collect
+        // with a margin far above fp64 summation noise (select_collected ranks by this sweep's own scores)
+        const double thr = flag_thr[f0 + f];
+        if (s >= thr - 1e-12 * fmax(1.0, fabs(thr))) {
           const int slot = atomicAdd(coll_cnt + f, 1);
           if (slot < cap) {
             coll_score[(size_t)f * cap + slot] = s;
@@ -491,20 +495,28 @@ rescore_collected_kernel(const float* __restrict__ q, const double* __restrict__
 
 // ---------------------------------------------------------------------------------------------
 // merge_topk: one warp per query, lane g walks the (sorted) list of shard g.  G <= 32.
+// Shard g's scores start at scores64 + g * shard_stride, its ids at ids + g * shard_stride (8-byte words), so the
+// same kernel reads two separately gathered arrays (stride Q * k) or ONE gathered buffer in which every rank sent
+// its scores and its local row slots back to back (stride 2 * Q * k); row0[g] >= 0 turns local slots into global ids.
 // ---------------------------------------------------------------------------------------------
+struct MergeRow0 { long long v[32]; };
+
 __global__ void __launch_bounds__(256)
-merge_topk_kernel(const double* __restrict__ scores64, const int64_t* __restrict__ ids, int G, int64_t Q, int k,
-                  float* __restrict__ out_scores, int64_t* __restrict__ out_ids, double* __restrict__ out_scores64) {
+merge_topk_kernel(const double* __restrict__ scores64, const int64_t* __restrict__ ids, int64_t shard_stride, int G,
+                  int64_t Q, int k, const MergeRow0 row0, float* __restrict__ out_scores,
+                  int64_t* __restrict__ out_ids, double* __restrict__ out_scores64) {
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (q >= Q) return;
   int pos = 0;
-  const double* sc = scores64 + ((size_t)lane * Q + q) * k;
-  const int64_t* id = ids + ((size_t)lane * Q + q) * k;
+  const int src = lane < G ? lane : 0;
+  const double* sc = scores64 + (size_t)src * shard_stride + q * k;
+  const int64_t* id = ids + (size_t)src * shard_stride + q * k;
+  const long long off = row0.v[src];
   const long long kEmpty = 0x7fffffffffffffffll;
   double hs = -INFINITY;
   long long hi = kEmpty;
-  if (lane < G && k > 0 && id[0] >= 0) { hs = sc[0]; hi = id[0]; }
+  if (lane < G && k > 0 && id[0] >= 0) { hs = sc[0]; hi = id[0] + off; }
   for (int j = 0; j < k; ++j) {
     // warp arg-best over (score desc, id asc); empty heads lose
     double bs = hs;
@@ -527,7 +539,7 @@ merge_topk_kernel(const double* __restrict__ scores64, const int64_t* __restrict
     if (bi == kEmpty) continue;  // uniform: all lanes agree on the winner
     if (lane == bl) {
       ++pos;
-      if (pos < k && id[pos] >= 0) { hs = sc[pos]; hi = id[pos]; }
+      if (pos < k && id[pos] >= 0) { hs = sc[pos]; hi = id[pos] + off; }
       else { hs = -INFINITY; hi = kEmpty; }
     }
   }
@@ -614,12 +626,15 @@ int launch_rescore_collected(const float* q, const double* q_qq, const float* ma
   return RBOD_OK;
 }
 
-int launch_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t Q, int k, float* out_scores,
-                      int64_t* out_ids, double* out_scores64, cudaStream_t st) {
+int launch_merge_topk(const double* scores64, const int64_t* ids, int64_t shard_stride, const int64_t* row0_host,
+                      int G, int64_t Q, int k, float* out_scores, int64_t* out_ids, double* out_scores64,
+                      cudaStream_t st) {
   if (Q <= 0 || k <= 0) return RBOD_OK;
   if (G < 1 || G > 32) return set_error(RBOD_E_UNSUPPORTED, "merge_topk: G=%d outside [1, 32]", G);
-  merge_topk_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(scores64, ids, G, Q, k, out_scores, out_ids,
-                                                            out_scores64);
+  MergeRow0 r0;
+  for (int g = 0; g < 32; ++g) r0.v[g] = (row0_host != nullptr && g < G) ? (long long)row0_host[g] : 0ll;
+  merge_topk_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(scores64, ids, shard_stride, G, Q, k, r0, out_scores,
+                                                            out_ids, out_scores64);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

@@ -364,6 +364,8 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
         RBOD_CUDA(cudaMemset(g->shadow16, 0, (size_t)g->capacity * g->dp * 2));
       }
     }
+  } else if (!strcmp(key, "auto_shadow")) {
+    g->auto_shadow = value != 0;
   } else if (!strcmp(key, "presample")) {
     if (value < 0 || value > 2) return set_error(RBOD_E_INVAL, "presample must be 0 (off), 1 (when it pays) or 2 (always)");
     g->presample = (int)value;
@@ -883,6 +885,25 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   const int smem_optin = k3_configure(g->device);
   if (smem_optin < 0) return smem_optin;
 
+  // bf16 COSINE collections: a bf16 query sits up to 2e-3 from the exact unit query, more than the gap between the
+  // k-th and the (k + slack)-th score once k reaches the high tens (10M rows, k = 100: 17-37 % of the queries were
+  // not certified and took the collecting second pass).  An fp16 copy of the stored rows as the search operand brings
+  // the margin to 4e-4 -- bf16 -> fp16 is exact for values of magnitude >= 2^-14 -- at the price of 2 more bytes per
+  // element, so it is built the first time such a search arrives (one HBM-bound pass) and kept up to date by K1.
+  if (g->dtype == RBOD_BF16 && g->metric == RBOD_COSINE && !g->use_shadow && g->auto_shadow && k > 40 && g->rows > 0) {
+    uint16_t* nsh = nullptr;
+    if (cudaMalloc(&nsh, (size_t)g->capacity * g->dp * 2) == cudaSuccess) {
+      RBOD_CUDA(cudaMemsetAsync(nsh, 0, (size_t)g->capacity * g->dp * 2, st));
+      RBOD_CUDA(cudaMemsetAsync(g->stats + 2, 0, 2 * sizeof(float), st));
+      RBOD_TRY(launch_build_shadow(g->rows16, g->rows, g->dp, nsh, g->stats, st));
+      g->shadow16 = nsh;
+      g->use_shadow = 1;
+    } else {
+      cudaGetLastError();
+      g->auto_shadow = 0;   // no room for it: searches stay on the bf16 operand (still exact, more second passes)
+    }
+  }
+
   const size_t nout = (size_t)Q * k;
   RBOD_TRY(g->out_scores.ensure(nout * 4));
   RBOD_TRY(g->out_rows.ensure(nout * 8));
@@ -1181,7 +1202,22 @@ int rbod_merge_topk(const double* scores64, const int64_t* ids, int32_t G, int64
   if (!is_device_ptr(scores64) || !is_device_ptr(ids) || !is_device_ptr(out_scores) || !is_device_ptr(out_ids) ||
       (out_scores64 && !is_device_ptr(out_scores64)))
     return set_error(RBOD_E_INVAL, "rbod_merge_topk: device pointers only");
-  return launch_merge_topk(scores64, ids, G, Q, k, out_scores, out_ids, out_scores64,
+  return launch_merge_topk(scores64, ids, Q * k, nullptr, G, Q, k, out_scores, out_ids, out_scores64,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int rbod_merge_topk_packed(const void* gathered, const int64_t* shard_row0, int32_t G, int64_t Q, int32_t k,
+                           float* out_scores, int64_t* out_ids, double* out_scores64, void* stream) {
+  if (!gathered || !out_scores || !out_ids || Q < 0 || k < 1)
+    return set_error(RBOD_E_INVAL, "rbod_merge_topk_packed: bad arguments");
+  if (!is_device_ptr(gathered) || !is_device_ptr(out_scores) || !is_device_ptr(out_ids) ||
+      (out_scores64 && !is_device_ptr(out_scores64)))
+    return set_error(RBOD_E_INVAL, "rbod_merge_topk_packed: device pointers only (shard_row0 is a host array)");
+  if (shard_row0 && is_device_ptr(shard_row0))
+    return set_error(RBOD_E_INVAL, "rbod_merge_topk_packed: shard_row0 must be a host pointer (or NULL)");
+  const double* sc = static_cast<const double*>(gathered);
+  const int64_t* id = static_cast<const int64_t*>(gathered) + Q * k;
+  return launch_merge_topk(sc, id, 2 * Q * k, shard_row0, G, Q, k, out_scores, out_ids, out_scores64,
                            static_cast<cudaStream_t>(stream));
 }
 

@@ -173,8 +173,11 @@ int launch_dist_collect(int metric, const double* q64, const float* master32, co
 int launch_dist_select(const double* coll_key, const uint32_t* coll_idx, int* coll_cnt, const int* qsel, int nf,
                        int cap, int k, int sample, int metric, double* thr, int* active, int* n_active,
                        float* out_scores, int64_t* out_rows, double* out_keys, cudaStream_t st);
-int launch_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t Q, int k, float* out_scores,
-                      int64_t* out_ids, double* out_scores64, cudaStream_t st);
+int launch_merge_topk(const double* scores64, const int64_t* ids, int64_t shard_stride, const int64_t* row0_host,
+                      int G, int64_t Q, int k, float* out_scores, int64_t* out_ids, double* out_scores64,
+                      cudaStream_t st);
+// bf16 collection -> fp16 search operand built after the fact (rbod_api.cu: auto_shadow)
+int launch_build_shadow(const uint16_t* rows16, int64_t n, int dp, uint16_t* shadow16, float* stats, cudaStream_t st);
 
 }  // namespace rbod
 
@@ -187,6 +190,7 @@ struct rbod_gallery {
   uint16_t* shadow16 = nullptr; // [capacity, dp] fp16 copy of a bf16 gallery used as the search operand (option)
   float* row_bias = nullptr;    // [capacity + 128] EUCLID collections: -|stored row|^2 / 2 (the K3 epilogue adds it)
   int use_shadow = 0;
+  int auto_shadow = 1;          // bf16 COSINE collections: build the fp16 shadow when a search with k > 40 arrives
   float* stats = nullptr;       // device [4]: max ||row16||, max ||row16 - unit(master)||, max ||shadow||,
                                 // max ||shadow - row16||
   int num_sms = 148;

@@ -231,6 +231,28 @@ def merge_topk(scores64, ids, k: int, stream=None):
     return out_s, out_i, out_d
 
 
+def merge_topk_packed(gathered, shard_row0, k: int, stream=None):
+    """K4 over ONE gathered buffer: ``gathered`` [G, 2, Q, k] int64 words on the device, where [:, 0] holds each
+    shard's float64 scores (bit pattern) and [:, 1] its LOCAL row slots; ``shard_row0`` = the G global row offsets.
+    -> (scores f32, global ids i64, scores f64), each [Q, k]."""
+    torch = sys.modules["torch"]
+    lib = N.load()
+    G, two, Q, kk = gathered.shape
+    if two != 2 or kk != k:
+        raise ValueError("merge_topk_packed: expected a [G, 2, Q, k] buffer")
+    gathered = gathered.contiguous()
+    row0 = np.ascontiguousarray(shard_row0, dtype=np.int64)
+    if row0.shape != (G,):
+        raise ValueError("merge_topk_packed: one row offset per shard")
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=gathered.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=gathered.device)
+    out_d = torch.empty((Q, k), dtype=torch.float64, device=gathered.device)
+    N.check(lib.rbod_merge_topk_packed(gathered.data_ptr(), row0.ctypes.data, G, Q, k, out_s.data_ptr(),
+                                       out_i.data_ptr(), out_d.data_ptr(),
+                                       stream if stream is not None else _current_stream()))
+    return out_s, out_i, out_d
+
+
 def segment_finish(sums, counts, normalize: bool = True, stream=None):
     """sums [C, dim] float64 and counts [C] int64 (torch CUDA tensors, already reduced over the shards) ->
     delegate vectors [C, dim] float32: fp32(sum / count), L2-normalised for COSINE collections."""

@@ -1,9 +1,11 @@
 """Row-sharded multi-GPU search: one process per GPU, gallery rows block-partitioned over ranks.
 
-Each rank searches its own rows (K3 + exact rescoring -> local top-k with float64 scores), the
-(Q, k) lists are exchanged with ONE all-gather over NCCL/NVLink, and every rank merges the G lists
-with K4 (``rbod_merge_topk``).  Scores travel as float64 so the merged order is exactly the
-(score desc, id asc) order a single GPU would produce.  No other collective is on the data path.
+Each rank searches its own rows (K3 + exact rescoring -> local top-k with float64 scores) straight
+into one packed [2, Q, k] buffer (scores, then local row slots), the buffers are exchanged with ONE
+all-gather over NCCL/NVLink, and every rank merges the G lists with K4 (``rbod_merge_topk_packed``,
+which also turns local slots into global ids).  Scores travel as float64 so the merged order is
+exactly the (score desc, id asc) order a single GPU would produce.  No other collective is on the
+data path.
 
 The reference has no multi-GPU path at all; this implements BASELINE.json's
 "shard the gallery by rows ... merge the global top-k with an NCCL allgather".
@@ -64,6 +66,7 @@ class ShardedGallery:
         self._finish = finish
         self.metric = metric
         self.local = None
+        self._buf = None       # packed [2, Q, k] result buffer + fp32 scores, reused across searches of one shape
         if create_local:
             from .gallery import Gallery
 
@@ -78,29 +81,41 @@ class ShardedGallery:
         """Appends this rank's rows (global ids row_start + local slot)."""
         return self.local.upsert(rows)
 
-    def search(self, queries, k: int):
-        """Global top-k on every rank: (scores f32 [Q,k], global ids i64 [Q,k], scores f64 [Q,k])."""
+    def shard_offsets(self):
+        """Global row offset of every rank's shard (what K4 adds to the local row slots)."""
+        return [shard_range(self.n_rows_total, r, self.world)[0] for r in range(self.world)]
+
+    def search(self, queries, k: int, out_host=None):
+        """Global top-k on every rank: (scores f32 [Q,k], global ids i64 [Q,k], scores f64 [Q,k]).
+
+        The local search writes its float64 scores and local row slots into ONE [2, Q, k] buffer of 8-byte words;
+        a single all-gather moves it; K4 merges the gathered [G, 2, Q, k] buffer and adds each shard's row offset."""
         import torch
 
         if self._local_search is not None:
             s64, rows = self._local_search(queries, k)
+            packed = torch.stack([s64.to(torch.float64).contiguous().view(torch.int64), rows.to(torch.int64)], 0)
         else:
-            res = self.local.search(queries, k, want_scores64=True)
-            s64, rows = res.scores64, res.rows
-            if not isinstance(s64, torch.Tensor):
-                s64, rows = torch.from_numpy(s64), torch.from_numpy(rows)
-        ids = torch.where(rows >= 0, rows + self.row_start, rows)
+            Q = int(queries.shape[0]) if getattr(queries, "ndim", 2) == 2 else 1
+            dev = torch.device("cuda", self.local.device)
+            if self._buf is None or tuple(self._buf[0].shape) != (2, Q, k):
+                self._buf = (torch.empty((2, Q, k), dtype=torch.int64, device=dev),
+                             torch.empty((Q, k), dtype=torch.float32, device=dev))
+            packed, s32 = self._buf
+            self.local.search(queries, k, out=(s32, packed[1], packed[0].view(torch.float64)))
         if self.world == 1:
-            g_s, g_i = s64.unsqueeze(0), ids.unsqueeze(0)
+            gathered = packed.unsqueeze(0)
         else:
-            g_s = all_gather_stack(s64, self.group)
-            g_i = all_gather_stack(ids, self.group)
+            gathered = all_gather_stack(packed, self.group)
         if self._merge is not None:
-            out = self._merge(g_s, g_i, k)
+            off = torch.tensor(self.shard_offsets(), dtype=torch.int64).view(-1, 1, 1)
+            g_i = gathered[:, 1]
+            g_i = torch.where(g_i >= 0, g_i + off.to(g_i.device), g_i)
+            out = self._merge(gathered[:, 0].contiguous().view(torch.float64), g_i, k)
         else:
-            from .gallery import merge_topk
+            from .gallery import merge_topk_packed
 
-            out = merge_topk(g_s, g_i, k)
+            out = merge_topk_packed(gathered, self.shard_offsets(), k)
         if self.metric in ("euclid", "manhattan"):
             # the lists travel and merge as ordering keys (-d^2 / -d, larger = closer); hand back distances
             s32, ids, keys = out

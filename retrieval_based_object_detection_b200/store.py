@@ -11,7 +11,8 @@ arithmetic: everything here is bookkeeping in Python; every vector operation goe
 * ``Filter(must=[FieldCondition(key, match=MatchValue(value))])`` = AND of payload equalities;
   a ``None`` payload value never matches                 32_…py:125-129; 33_…py:98-103,117-137
 * state survives the process (the scripts are separate processes talking to one server):
-  ``meta.json`` + snapshot (``points.json``, ``vectors.npy``) + an append-only ``wal.jsonl``.
+  ``meta.json`` + a versioned snapshot (``snap-<N>/points.json`` + ``snap-<N>/vectors.npy``, made current by
+  an atomic rename of the ``CURRENT`` pointer file) + an append-only ``wal.jsonl`` replayed in log order.
 
 Single-point upserts (31_…py:179 sends one RPC per image) are appended to the WAL and kept in a
 host staging dict; they reach the GPU in one batched K1 launch on the first read that needs
@@ -89,8 +90,11 @@ class Collection:
         self.slot_of: Dict[Any, int] = {}
         self.payloads: List[dict] = []
         self.index: Dict[str, Dict[Any, Set[int]]] = {}
+        self.list_keys: Set[str] = set()    # payload keys that ever held a list: matched per element, never by column
         self.pending: Dict[int, np.ndarray] = {}
         self.snapshot_vectors: Optional[np.ndarray] = None  # stored rows loaded from disk, not yet on device
+        self.snap_src: Optional[np.ndarray] = None          # slot -> row of snapshot_vectors (-1: vector is staged)
+        self._snap_no = 0                                   # number of the current snapshot directory
         self.gallery = None
         self._order: Optional[List[int]] = None
         self._columns: Dict[str, Any] = {}     # key -> (int32 codes per slot, {value key -> code}); rebuilt lazily
@@ -112,38 +116,78 @@ class Collection:
             open(os.path.join(directory, "wal.jsonl"), "w").close()
         return col
 
+    @staticmethod
+    def _snapshot_dir(directory: str):
+        """-> (snapshot number, directory holding points.json + vectors.npy) of the current snapshot, or (0, None).
+        ``CURRENT`` names the snapshot; a collection written by an older build has the two files next to meta.json."""
+        cur = os.path.join(directory, "CURRENT")
+        if os.path.exists(cur):
+            with open(cur, encoding="utf-8") as f:
+                no = int(f.read().strip() or 0)
+            d = os.path.join(directory, f"snap-{no}")
+            if no > 0 and os.path.isdir(d):
+                return no, d
+            raise RuntimeError(f"collection at {directory!r}: CURRENT names snapshot {no}, which does not exist")
+        if os.path.exists(os.path.join(directory, "points.json")) and os.path.exists(os.path.join(directory, "vectors.npy")):
+            return 0, directory
+        return 0, None
+
     @classmethod
     def open(cls, directory: str, device: int):
         with open(cls.meta_path(directory), encoding="utf-8") as f:
             meta = json.load(f)
         col = cls(directory, meta["name"], meta["dim"], meta["distance"], meta.get("dtype", "f32"), device)
-        ppath, vpath = os.path.join(directory, "points.json"), os.path.join(directory, "vectors.npy")
-        if os.path.exists(ppath) and os.path.exists(vpath):
-            with open(ppath, encoding="utf-8") as f:
+        col._snap_no, sdir = cls._snapshot_dir(directory)
+        if sdir is not None:
+            with open(os.path.join(sdir, "points.json"), encoding="utf-8") as f:
                 pts = json.load(f)
-            vec = np.load(vpath, mmap_mode="r")      # paged in chunk by chunk when the gallery is materialised
+            vec = np.load(os.path.join(sdir, "vectors.npy"), mmap_mode="r")   # paged in when the gallery is materialised
             if vec.shape != (len(pts), col.dim):
                 raise RuntimeError(f"collection {col.name!r}: snapshot shape {vec.shape} != ({len(pts)}, {col.dim})")
             for pid, payload in pts:
                 col._add_point(pid if isinstance(pid, int) else str(pid), payload)
             col.snapshot_vectors = vec
-        wal = os.path.join(directory, "wal.jsonl")
-        if os.path.exists(wal):
-            with open(wal, encoding="utf-8") as f:
-                for line in f:
-                    line = line.strip()
-                    if not line:
-                        continue
-                    try:
-                        rec = json.loads(line)
-                    except json.JSONDecodeError:
-                        break  # torn tail of an interrupted append
+            col.snap_src = np.arange(len(pts), dtype=np.int64)
+        col._replay_wal()
+        return col
+
+    def _replay_wal(self) -> None:
+        """Applies wal.jsonl strictly in log order on the host (no device needed): upserts are staged, deletes take
+        effect at once -- a later upsert of the same id is a new point.  A torn tail (interrupted append) is cut off
+        the file, so the next append starts on a fresh line and later records are never glued to garbage."""
+        wal = os.path.join(self.directory, "wal.jsonl")
+        if not os.path.exists(wal):
+            return
+        good_end = 0
+        needs_newline = False
+        with open(wal, "rb") as f:
+            data = f.read()
+        pos = 0
+        while pos < len(data):
+            nl = data.find(b"\n", pos)
+            end = len(data) if nl < 0 else nl + 1
+            line = data[pos:end].strip()
+            if line:
+                try:
+                    rec = json.loads(line.decode("utf-8"))
                     if rec.get("op") == "upsert":
                         vec = np.frombuffer(base64.b64decode(rec["vec"]), dtype=np.float32)
-                        col._stage(rec["id"], vec, rec["payload"])
+                        if vec.shape[0] != self.dim:
+                            raise ValueError("vector length")
+                        self._stage(rec["id"], vec, rec["payload"])
                     elif rec.get("op") == "delete":
-                        col._wal_deletes = getattr(col, "_wal_deletes", []) + [rec["id"]]
-        return col
+                        self._delete_host(rec["id"])
+                except (ValueError, KeyError, UnicodeDecodeError):
+                    break      # torn or corrupt record: everything from here on is dropped
+                needs_newline = nl < 0
+            good_end = end
+            pos = end
+        if good_end < len(data) or needs_newline:
+            with open(wal, "r+b") as f:
+                f.truncate(good_end)
+                if needs_newline:
+                    f.seek(good_end)
+                    f.write(b"\n")
 
     def _write_meta(self) -> None:
         meta = {"name": self.name, "dim": self.dim, "distance": self.distance, "dtype": self.dtype,
@@ -162,22 +206,47 @@ class Collection:
         self._wal.flush()
 
     def save(self) -> None:
-        """Snapshot stored vectors + points and truncate the WAL (needs the device copy)."""
+        """Snapshot stored vectors + points and truncate the WAL (needs the device copy).  The snapshot is one unit:
+        both files are written into a fresh ``snap-<N>`` directory, which becomes current by an atomic rename of the
+        ``CURRENT`` pointer; a crash at any point leaves either the old snapshot with the whole WAL or the new one
+        (whose WAL records, if still there, replay to the same state)."""
         if self.directory is None or not self._dirty:
             return
         if self.gallery is None:
             return  # nothing materialised in this process: the WAL already holds every change
         vec = self.stored_vectors(range(len(self.ids))) if self.ids else np.zeros((0, self.dim), np.float32)
-        tmp_v, tmp_p = os.path.join(self.directory, "vectors.tmp.npy"), os.path.join(self.directory, "points.tmp.json")
-        np.save(tmp_v, vec)
-        with open(tmp_p, "w", encoding="utf-8") as f:
+        no = self._snap_no + 1
+        sdir = os.path.join(self.directory, f"snap-{no}")
+        if os.path.isdir(sdir):
+            shutil.rmtree(sdir)           # left behind by a crash before its CURRENT switch
+        os.makedirs(sdir)
+        with open(os.path.join(sdir, "vectors.npy"), "wb") as f:
+            np.save(f, vec)
+            f.flush()
+            os.fsync(f.fileno())
+        with open(os.path.join(sdir, "points.json"), "w", encoding="utf-8") as f:
             json.dump([[pid, pl] for pid, pl in zip(self.ids, self.payloads)], f)
-        os.replace(tmp_v, os.path.join(self.directory, "vectors.npy"))
-        os.replace(tmp_p, os.path.join(self.directory, "points.json"))
+            f.flush()
+            os.fsync(f.fileno())
+        tmp = os.path.join(self.directory, "CURRENT.tmp")
+        with open(tmp, "w", encoding="utf-8") as f:
+            f.write(str(no))
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, os.path.join(self.directory, "CURRENT"))
         if self._wal is not None:
             self._wal.close()
             self._wal = None
         open(os.path.join(self.directory, "wal.jsonl"), "w").close()
+        old = os.path.join(self.directory, f"snap-{self._snap_no}")
+        self._snap_no = no
+        if os.path.isdir(old):
+            shutil.rmtree(old, ignore_errors=True)
+        for legacy in ("vectors.npy", "points.json"):
+            try:
+                os.unlink(os.path.join(self.directory, legacy))
+            except FileNotFoundError:
+                pass
         self._dirty = False
 
     def close(self) -> None:
@@ -197,6 +266,8 @@ class Collection:
 
     def _index_add(self, slot: int, payload: dict) -> None:
         for key, value in payload.items():
+            if isinstance(value, (list, tuple)):
+                self.list_keys.add(key)
             values = value if isinstance(value, (list, tuple)) else [value]
             for v in values:
                 if _indexable(v):
@@ -279,13 +350,22 @@ class Collection:
                                    device=self.device)
             if self.dtype in ("bf16", "bfloat16") and os.environ.get("RBOD_BF16_SHADOW", "0") == "1":
                 self.gallery.set_option("shadow16", 1)    # fp16 search operand: tighter certification, 2x memory
-            if self.snapshot_vectors is not None and len(self.snapshot_vectors):
+            if self.snapshot_vectors is not None and self.snap_src is not None and len(self.snap_src):
                 # the snapshot file is memory-mapped: stream it to the device in 256 MB pieces (stored form, no K1
-                # normalisation), so reopening a large collection never holds a second copy in host memory
+                # normalisation), so reopening a large collection never holds a second copy in host memory.  Slots
+                # whose vector was re-upserted since (snap_src < 0) get a placeholder row here and their staged
+                # vector in the flush that follows; deletes replayed from the WAL have already permuted snap_src.
+                src = self.snap_src
+                identity = len(src) <= len(self.snapshot_vectors) and bool((src == np.arange(len(src))).all())
                 step = max(1, (256 << 20) // (4 * self.dim))
-                for a in range(0, len(self.snapshot_vectors), step):
-                    self.gallery.upsert(np.ascontiguousarray(self.snapshot_vectors[a:a + step], dtype=np.float32), raw=True)
+                for a in range(0, len(src), step):
+                    if identity:
+                        rows = self.snapshot_vectors[a:a + step]
+                    else:
+                        rows = self.snapshot_vectors[np.maximum(src[a:a + step], 0)]
+                    self.gallery.upsert(np.ascontiguousarray(rows, dtype=np.float32), raw=True)
             self.snapshot_vectors = None
+            self.snap_src = None
         return self.gallery
 
     def flush(self) -> None:
@@ -296,9 +376,6 @@ class Collection:
             rows = np.stack([self.pending[int(s)] for s in slots])
             g.upsert(rows, slots=slots)
             self.pending.clear()
-        for pid in getattr(self, "_wal_deletes", []):
-            self._delete_now(pid)
-        self._wal_deletes = []
 
     def stored_vectors(self, slots: Iterable[int]) -> np.ndarray:
         """Stored (normalised) float32 vectors of the given slots, from the device."""
@@ -307,6 +384,39 @@ class Collection:
             return np.zeros((0, self.dim), dtype=np.float32)
         self.flush()
         return self.gallery.get_rows(slots)
+
+    def _delete_host(self, pid) -> bool:
+        """Delete before the gallery exists (WAL replay): the same swap-with-last as ``_delete_now``, applied to the
+        host-side vector sources -- staged vectors and the slot -> snapshot-row map -- instead of device rows."""
+        assert self.gallery is None
+        slot = self.slot_of.get(pid)
+        if slot is None:
+            return False
+        last = len(self.ids) - 1
+        n_snap = 0 if self.snap_src is None else len(self.snap_src)
+        self._index_remove(slot, self.payloads[slot])
+        self.pending.pop(slot, None)
+        if slot != last:
+            moved = self.ids[last]
+            self._index_remove(last, self.payloads[last])
+            self.ids[slot], self.payloads[slot] = moved, self.payloads[last]
+            self.slot_of[moved] = slot
+            self._index_add(slot, self.payloads[slot])
+            if last in self.pending:
+                self.pending[slot] = self.pending.pop(last)
+                if slot < n_snap:
+                    self.snap_src[slot] = -1
+            elif slot < n_snap and last < n_snap:
+                self.snap_src[slot] = self.snap_src[last]
+        if last < n_snap:
+            self.snap_src = self.snap_src[:last].copy()
+        self.ids.pop()
+        self.payloads.pop()
+        del self.slot_of[pid]
+        self._order = None
+        self._columns_n = -1
+        self._dirty = True
+        return True
 
     def _delete_now(self, pid) -> bool:
         slot = self.slot_of.get(pid)
@@ -518,9 +628,11 @@ class Collection:
         if flt is None:
             return None
         must = getattr(flt, "must", None) or []
+        # a key that ever held a list matches per element (as Qdrant's MatchValue does on arrays): the dictionary-encoded
+        # column holds one code per row and cannot express that, so such filters take the general evaluator
         simple = (not (getattr(flt, "should", None) or []) and not (getattr(flt, "must_not", None) or []) and
                   all(getattr(c, "key", None) is not None and hasattr(getattr(c, "match", None), "value")
-                      and getattr(c, "range", None) is None for c in must))
+                      and getattr(c, "range", None) is None and c.key not in self.list_keys for c in must))
         if not simple:
             return self.row_mask(self.filter_slots(flt))
         n = len(self.ids)

@@ -148,6 +148,38 @@ def test_bf16_gallery_with_fp16_shadow_operand(G):
     g.close()
 
 
+def test_bf16_gallery_builds_its_fp16_shadow_when_k_is_large(G):
+    """A bf16 COSINE collection searched with k > 40 gets the fp16 search operand on the fly (one pass over the stored
+    rows): the first k = 100 search is already certified with the small margin, rows upserted afterwards land in both
+    copies, and the stored rows / ids / scores stay those of the bf16 gallery."""
+    n, dim, Q, k = 120000, 768, 200, 100
+    x = O.synthetic_unit_rows(n, dim, seed=21)
+    x[5, :40] *= 1e-6                                    # elements far below fp16's normal range
+    g = G(dim, dtype="bf16", capacity=n // 2)
+    g.upsert(x[: n // 2])
+    q = O.synthetic_unit_rows(Q, dim, seed=77)
+    q[0] = x[5]
+    r10 = g.search(q, 10)                                # k <= 40: plain bf16 operand
+    assert r10.stats["max_eps"] > 1e-3
+    stored_half = g.get_rows(np.arange(n // 2))
+    res = g.search(q, k, want_scores64=True)             # builds the shadow
+    ws, wi = O.cosine_topk(q, stored_half, k)
+    assert np.array_equal(res.rows, wi) and np.allclose(res.scores64, ws, rtol=1e-5, atol=1e-9)
+    assert res.stats["max_eps"] < 6e-4 and res.stats["fallback_queries"] <= 2
+    g.upsert(x[n // 2:])                                 # grows the gallery: both copies follow
+    stored = g.get_rows(np.arange(n))
+    assert np.array_equal(stored[: n // 2], stored_half)
+    for kk in (100, 10):
+        res = g.search(q, kk, want_scores64=True)
+        ws, wi = O.cosine_topk(q, stored, kk)
+        assert np.array_equal(res.rows, wi) and np.allclose(res.scores64, ws, rtol=1e-5, atol=1e-9)
+        assert res.stats["max_eps"] < 6e-4
+    got = g.debug_scores(q[:4])                           # raw tensor-core scores now come from the fp16 operand
+    qn = O.l2_normalize_store(q[:4], "f16")[0].astype(np.float64)
+    assert np.abs(got - qn @ O.round_store(stored, "f16").astype(np.float64).T).max() < 2e-5
+    g.close()
+
+
 @pytest.mark.parametrize("tau_share", [0, 1])
 def test_k100_bf16_uncertified_queries_take_the_collect_pass(G, tau_share):
     """bf16 rounding leaves little slack at k=100 (kc=128): a good share of the queries is not certified by
@@ -155,8 +187,10 @@ def test_k100_bf16_uncertified_queries_take_the_collect_pass(G, tau_share):
     n, dim, Q, k = 120000, 768, 200, 100
     g, stored, x = _mk(G, n, dim, "bf16", seed=21)
     g.set_option("tau_share", tau_share)
+    g.set_option("auto_shadow", 0)                       # stay on the bf16 operand: this test is about the second pass
     q = O.synthetic_unit_rows(Q, dim, seed=77)
     res = g.search(q, k, want_scores64=True)
+    assert res.stats["fallback_queries"] > 0 and res.stats["k3_launches"] == 2
     ws, wi = O.cosine_topk(q, stored, k)
     assert np.array_equal(res.rows, wi), f"ids differ in {(res.rows != wi).any(axis=1).sum()} of {Q} queries"
     assert np.allclose(res.scores64, ws, rtol=1e-5, atol=1e-9)
@@ -185,7 +219,7 @@ def test_threshold_prepass_keeps_the_answer_exact(G, dtype, ordered):
         res = g.search(q, k, want_scores64=True)
         assert np.array_equal(res.rows, wi), (presample, (res.rows != wi).any(axis=1).sum())
         assert np.allclose(res.scores64, ws, rtol=1e-5, atol=1e-9)
-        assert res.stats["total_launches"] >= (7 if presample else 5)      # pre-pass = K3 sample launch + tau_init
+        assert res.stats["total_launches"] >= (5 if presample else 3)      # pre-pass = K3 sample launch + tau_init
         resm = g.search(q, k, row_mask=O.pack_row_mask(mask), want_scores64=True)
         assert np.array_equal(resm.rows, wmi)
     g.close()

@@ -378,7 +378,8 @@ def test_distance_of_a_collection_survives_reopening(client, store_dir):
     client.upsert("eu", points=[m.PointStruct(id=100 + i, vector=vecs[i].tolist(), payload={"i": i}) for i in range(n)])
     assert client.search("eu", vecs[4].tolist(), limit=1)[0].id == 104            # materialises the device copy
     qc._close_all()                                                               # snapshot: vectors.npy + points.json
-    assert os.path.exists(os.path.join(store_dir, "localhost_6333", "eu", "vectors.npy"))
+    assert os.path.exists(os.path.join(store_dir, "localhost_6333", "eu", "snap-1", "vectors.npy"))
+    assert open(os.path.join(store_dir, "localhost_6333", "eu", "CURRENT")).read() == "1"
     c2 = qc.QdrantClient(host="localhost", port=6333)
     assert c2.get_collection("eu").config.params.vectors.distance == m.Distance.EUCLID
     hits = c2.search("eu", vecs[4].tolist(), limit=4, with_vectors=True)
@@ -390,3 +391,167 @@ def test_distance_of_a_collection_survives_reopening(client, store_dir):
     page2, nxt2 = c2.scroll("eu", limit=7, offset=nxt)
     assert [r.id for r in page1] == list(range(100, 107)) and nxt == 107
     assert [r.id for r in page2] == list(range(107, 114)) and nxt2 == 114
+
+
+def test_wal_replays_in_log_order_without_a_snapshot(client, store_dir):
+    """upsert X, delete X, upsert X(v2) in processes that never save(): the reopened collection holds X(v2) -- the WAL
+    is replayed strictly in order (deletes used to be queued behind every upsert, which lost X) -- and the host
+    metadata is right before any vector is read."""
+    import qdrant_client as qc
+
+    m = _models()
+    client.recreate_collection(collection_name="w", vectors_config=m.VectorParams(size=8, distance=m.Distance.COSINE))
+    v1, v2, v3 = (np.arange(8) + 1.0), (np.arange(8)[::-1] + 1.0), np.ones(8)
+    client.upsert("w", points=[m.PointStruct(id=1, vector=v1.tolist(), payload={"v": 1}),
+                               m.PointStruct(id=2, vector=v3.tolist(), payload={"v": 3})])
+    qc._ROOTS.clear()                                                      # crash-like: no save(), the WAL holds it all
+    c2 = qc.QdrantClient(host="localhost", port=6333)
+    c2.delete("w", points_selector=[1])
+    c2.upsert("w", points=[m.PointStruct(id=1, vector=v2.tolist(), payload={"v": 2})])
+    qc._ROOTS.clear()
+    c3 = qc.QdrantClient(host="localhost", port=6333)
+    col = c3._root.get("w")
+    assert col.gallery is None                                             # nothing below needs the device yet
+    assert c3.count("w").count == 2 and c3.get_collection("w").points_count == 2
+    assert [(r.id, r.payload) for r in c3.scroll("w", limit=10)[0]] == [(1, {"v": 2}), (2, {"v": 3})]
+    recs, _ = c3.scroll("w", limit=10, with_vectors=True)
+    want = {1: O.l2_normalize_store(v2[None, :].astype(np.float32), "f32")[0][0], 2: O.l2_normalize_store(v3[None, :].astype(np.float32), "f32")[0][0]}
+    for r in recs:
+        assert np.array_equal(np.asarray(r.vector, dtype=np.float32), want[r.id])
+    # ... and a plain delete survives a reopen without save() too
+    c3.delete("w", points_selector=[2])
+    qc._ROOTS.clear()
+    c4 = qc.QdrantClient(host="localhost", port=6333)
+    assert [r.id for r in c4.scroll("w", limit=10)[0]] == [1]
+
+
+def test_wal_deletes_of_snapshot_rows_replay_on_the_host(client, store_dir):
+    """Deletes and re-upserts journalled AFTER a snapshot: the replay permutes the slot -> snapshot-row map on the
+    host, and the rows that reach the device are the right ones in the right slots."""
+    import qdrant_client as qc
+
+    m = _models()
+    vecs, ids = _fill(client, n=10)
+    before = {r.id: r.vector for r in client.scroll("thesis", limit=100, with_vectors=True)[0]}
+    qc._close_all()                                                        # snapshot of 10 rows
+    c2 = qc.QdrantClient(host="localhost", port=6333)
+    c2.delete("thesis", points_selector=[ids[2], ids[9]])                  # journalled: a middle row and the last row
+    newv = (np.arange(512) % 7 + 1.0).astype(np.float32)
+    c2.upsert("thesis", points=[m.PointStruct(id=ids[5], vector=newv.tolist(), payload={"class_name": "re"})])   # overwrite
+    c2.upsert("thesis", points=[m.PointStruct(id=77, vector=(newv * 2 + 1).tolist(), payload={"class_name": "new"})])
+    c2.delete("thesis", points_selector=[ids[0]])
+    qc._ROOTS.clear()                                                      # crash-like
+    c3 = qc.QdrantClient(host="localhost", port=6333)
+    col = c3._root.get("thesis")
+    assert col.gallery is None and c3.count("thesis").count == 8
+    got = {r.id: (r.vector, r.payload) for r in c3.scroll("thesis", limit=100, with_vectors=True)[0]}
+    gone = {str(uuid.UUID(ids[i])) for i in (0, 2, 9)}
+    assert set(got) == (set(before) - gone) | {77}
+    for pid, (vec, payload) in got.items():
+        if pid == str(uuid.UUID(ids[5])):
+            assert payload == {"class_name": "re"}
+            assert np.array_equal(np.asarray(vec, np.float32), O.l2_normalize_store(newv[None, :], "f32")[0][0])
+        elif pid == 77:
+            assert np.array_equal(np.asarray(vec, np.float32), O.l2_normalize_store((newv * 2 + 1)[None, :], "f32")[0][0])
+        else:
+            assert vec == before[pid]
+
+
+def test_torn_wal_tail_is_truncated_and_later_records_survive(client, store_dir):
+    """A process dies in the middle of a WAL append.  The next open drops the torn record AND truncates the file, so
+    what the next process appends starts on a fresh line and is still there after yet another reopen."""
+    import os
+
+    import qdrant_client as qc
+
+    m = _models()
+    client.recreate_collection(collection_name="t", vectors_config=m.VectorParams(size=4, distance=m.Distance.COSINE))
+    client.upsert("t", points=[m.PointStruct(id=1, vector=[1, 0, 0, 0], payload={})])
+    qc._ROOTS.clear()
+    wal = os.path.join(store_dir, "localhost_6333", "t", "wal.jsonl")
+    good = os.path.getsize(wal)
+    with open(wal, "ab") as f:
+        f.write(b'{"op":"upsert","id":2,"payload":{},"vec":"AAAA')          # torn: no closing quote, no newline
+    c2 = qc.QdrantClient(host="localhost", port=6333)
+    assert c2.count("t").count == 1 and os.path.getsize(wal) == good
+    c2.upsert("t", points=[m.PointStruct(id=3, vector=[0, 1, 0, 0], payload={})])
+    qc._ROOTS.clear()
+    c3 = qc.QdrantClient(host="localhost", port=6333)
+    assert [r.id for r in c3.scroll("t", limit=10)[0]] == [1, 3]
+
+
+def test_snapshot_is_one_atomic_unit(client, store_dir):
+    """save() writes a fresh snap-<N> directory and switches CURRENT with one rename: a crash before the switch
+    leaves the previous snapshot in force (a half-written snap directory is ignored and later overwritten)."""
+    import os
+
+    import qdrant_client as qc
+
+    m = _models()
+    _fill(client, n=6)
+    client.scroll("thesis", with_vectors=True, limit=1)                     # materialise, so close() snapshots
+    qc._close_all()
+    base = os.path.join(store_dir, "localhost_6333", "thesis")
+    assert open(os.path.join(base, "CURRENT")).read() == "1" and os.path.isdir(os.path.join(base, "snap-1"))
+    # a crashed second save: snap-2 exists with a vectors file of the wrong shape, CURRENT still says 1
+    os.makedirs(os.path.join(base, "snap-2"))
+    np.save(os.path.join(base, "snap-2", "vectors.npy"), np.zeros((99, 512), np.float32))
+    c2 = qc.QdrantClient(host="localhost", port=6333)
+    assert c2.count("thesis").count == 6
+    c2.upsert("thesis", points=[m.PointStruct(id=5, vector=np.ones(512).tolist(), payload={})])
+    c2.scroll("thesis", with_vectors=True, limit=1)                         # materialise, so close() snapshots
+    qc._close_all()
+    assert open(os.path.join(base, "CURRENT")).read() == "2" and not os.path.isdir(os.path.join(base, "snap-1"))
+    assert np.load(os.path.join(base, "snap-2", "vectors.npy")).shape == (7, 512)
+    assert qc.QdrantClient(host="localhost", port=6333).count("thesis").count == 7
+
+
+def test_list_valued_payloads_match_per_element_in_search_too(client):
+    """MatchValue on a list-valued payload field matches any element (Qdrant semantics).  scroll / count / delete
+    always did; the bitmask fast path of search / query_points / build_delegates must agree with them."""
+    m = _models()
+    client.recreate_collection(collection_name="tags", vectors_config=m.VectorParams(size=8, distance=m.Distance.COSINE))
+    rng = np.random.default_rng(3)
+    vecs = rng.standard_normal((6, 8)).astype(np.float32)
+    tags = [["red", "round"], ["blue"], "red", ["green", "red"], None, ["blue", "round"]]
+    client.upsert("tags", points=[m.PointStruct(id=i, vector=vecs[i].tolist(), payload={"tag": tags[i], "n": i})
+                                  for i in range(6)])
+    flt = m.Filter(must=[m.FieldCondition(key="tag", match=m.MatchValue(value="red"))])
+    by_scroll = sorted(r.id for r in client.scroll("tags", scroll_filter=flt, limit=10)[0])
+    assert by_scroll == [0, 2, 3] and client.count("tags", count_filter=flt).count == 3
+    hits = client.search("tags", query_vector=vecs[3].tolist(), query_filter=flt, limit=10)
+    assert sorted(h.id for h in hits) == by_scroll and hits[0].id == 3
+    col = client._root.get("tags")
+    assert np.array_equal(col.filter_mask(flt), col.row_mask(col.filter_slots(flt)))
+    # a key without lists still takes the vectorised column path and agrees with the general evaluator
+    flt_n = m.Filter(must=[m.FieldCondition(key="n", match=m.MatchValue(value=4))])
+    assert np.array_equal(col.filter_mask(flt_n), col.row_mask(col.filter_slots(flt_n)))
+
+
+def test_clip_stand_in_is_loud_and_defers_to_a_real_installation(tmp_path, monkeypatch):
+    """The top-level ``clip`` directory is a random-init stand-in that sits first on sys.path.  It must say so
+    (UserWarning) unless RBOD_FAKE_CLIP=1 acknowledges it, and hand ``load`` over to a real clip package found
+    anywhere else on sys.path."""
+    import sys
+    import warnings
+
+    import clip
+
+    monkeypatch.setattr(clip, "_real", None)
+    monkeypatch.delenv("RBOD_FAKE_CLIP", raising=False)
+    with pytest.warns(UserWarning, match="RANDOM-INIT stand-in"):
+        model, _ = clip.load("ViT-B/32", device="cpu")
+    assert model.visual.proj.shape == (768, 512)
+    monkeypatch.setenv("RBOD_FAKE_CLIP", "1")
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        clip.load("ViT-B/32", device="cpu")
+    # a "real" installation elsewhere on sys.path (OpenAI's layout: clip/__init__.py + clip/clip.py) wins
+    real = tmp_path / "site" / "clip"
+    real.mkdir(parents=True)
+    (real / "clip.py").write_text("def load(name, device='cpu', jit=False, download_root=None):\n    return ('REAL', name, device)\n")
+    (real / "__init__.py").write_text("from .clip import *\nfrom .clip import load\n")
+    monkeypatch.setattr(clip, "_real", None)
+    monkeypatch.syspath_prepend(str(tmp_path / "site"))
+    assert clip.load("ViT-B/32", device="cpu") == ("REAL", "ViT-B/32", "cpu")
+    sys.modules.pop("_rbod_real_clip", None)
