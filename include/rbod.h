@@ -221,6 +221,13 @@ int rbod_merge_topk_packed(const void* gathered, const int64_t* shard_row0, int3
  * fp32, device or host.  Small problems only (Q * rows <= 2^28).                          */
 int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* out, void* stream);
 
+/* With option "k3_prof" = 1 the main tensor-core launches of this collection's searches accumulate SM cycles spent
+ * waiting, summed over CTAs (warp role: what it waited for): out16[0] producer: a free pipeline stage, [1] producer:
+ * the L2-sharing throttle, [2] MMA issuer: the query tile, [3] MMA issuer: a free accumulator (epilogue behind),
+ * [4] MMA issuer: gallery data (TMA behind), [5] epilogue warps: a finished accumulator, [6] epilogue warps: list
+ * prunes, [7] total cycles of the CTAs, [8] CTAs, [9] epilogue warps, [10] prunes.  Reads and clears the counters. */
+int rbod_debug_profile(rbod_gallery* g, int64_t* out16);
+
 /* Host-only: the work decomposition rbod_search would choose for a tensor-core search of Q queries, top k, over a
  * gallery of `rows` vectors of `dim` columns on a device with `num_sms` SMs and `smem_optin` bytes of opt-in shared
  * memory per CTA (B200: 148, 232448).  Needs no GPU.  out[0..12] = candidates per query, slices, grid, query tiles,

@@ -77,6 +77,7 @@ SIGNATURES = {
     "rbod_merge_topk": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
     "rbod_merge_topk_packed": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
     "rbod_debug_scores": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
+    "rbod_debug_profile": (ctypes.c_int, [_P, ctypes.POINTER(_I64)]),
     "rbod_debug_plan": (ctypes.c_int, [_I32, _I64, _I64, _I32, _I32, _I32, _I32, ctypes.POINTER(_I64)]),
 }
 

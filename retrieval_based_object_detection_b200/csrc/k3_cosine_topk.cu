@@ -91,6 +91,7 @@ struct alignas(64) K3Params {
   int num_acc;     // accumulator buffers (1 or 2)
   int acc_col0;    // first accumulator column in TMEM
   int debug_epi;   // bring-up only: 1 = epilogue loads the tile but selects nothing, 2 = does not even load it
+  unsigned long long* prof;   // optional [16] cycle counters (option "k3_prof"): where each warp role waits
   uint32_t idesc;
 };
 
@@ -103,6 +104,19 @@ struct K3Barriers {
   uint32_t tmem_base;
   uint32_t pad;
 };
+
+// Blocking wait that, when profiling is on, adds the cycles it took to `acc` (a register of the calling role).
+__device__ __forceinline__ void k3_wait(uint64_t* bar, uint32_t parity, int tag, bool prof, unsigned long long& acc) {
+  if (prof) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity, tag);
+    acc += (unsigned long long)(clock64() - t0);
+  } else {
+    mbar_wait(bar, parity, tag);
+  }
+}
+enum { K3P_PROD_EMPTY = 0, K3P_PROD_THROTTLE, K3P_MMA_AREADY, K3P_MMA_TEMPTY, K3P_MMA_FULL, K3P_EPI_TFULL, K3P_EPI_PRUNE,
+       K3P_CTA_CYCLES, K3P_CTAS, K3P_EPI_WARPS, K3P_PRUNES };
 
 // Per-row candidate list = an append-only array of {score bits, row index} in global memory, owned by the row's
 // epilogue thread for the life of a work unit.  Appending costs one 8-byte store; nothing is ordered.  When a list
@@ -320,6 +334,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
     // The whole warp walks the schedule (warp-uniform control flow); one elected lane issues.
     int stage = 0;
     uint32_t phase = 0;
+    const bool prof = P.prof != nullptr;
+    unsigned long long w_empty = 0ull, w_throttle = 0ull;
+    const long long t_start = prof ? clock64() : 0ll;
     for (int u = worker; u < num_units; u += num_workers) {
       const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
       const K3TileRange tr = k3_unit_tiles(P, slice);
@@ -349,6 +366,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
             if (w >= P.sync_lead) {
               const volatile int* flag = cnt + (w - P.sync_lead);
               if (*flag < gsize) {
+                const long long c0 = prof ? clock64() : 0ll;
                 const uint64_t w0 = global_timer_ns();
                 while (*flag < gsize) {
                   __nanosleep(128);
@@ -358,6 +376,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
                     __trap();
                   }
                 }
+                if (prof) w_throttle += (unsigned long long)(clock64() - c0);
               }
             }
           }
@@ -366,7 +385,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         for (int ch = 0; ch < num_chunks; ++ch) {
           const int kb0 = ch * G::KBS;
           const int nkb = min(G::KBS, P.num_kb - kb0);
-          mbar_wait(&bars->empty[stage], phase ^ 1u, 1);
+          k3_wait(&bars->empty[stage], phase ^ 1u, 1, prof, w_empty);
           if (elect_one()) {
             uint8_t* sb = stage_base + (size_t)stage * G::STAGE_BYTES;
             if (PAIR) {
@@ -395,6 +414,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         }
       }
     }
+    if (prof && lane == 0) {
+      atomicAdd(P.prof + K3P_PROD_EMPTY, w_empty);
+      atomicAdd(P.prof + K3P_PROD_THROTTLE, w_throttle);
+      atomicAdd(P.prof + K3P_CTA_CYCLES, (unsigned long long)(clock64() - t_start));
+      atomicAdd(P.prof + K3P_CTAS, 1ull);
+    }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     // Warp-converged loop; elect.sync picks the issuing lane so descriptors stay in uniform registers.
@@ -404,6 +429,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0, unit_par = 0;
+      const bool prof = P.prof != nullptr;
+      unsigned long long w_aready = 0ull, w_tempty = 0ull, w_full = 0ull;
       const uint32_t tmem_b = __shfl_sync(FULL_MASK, tmem_base, 0);
       const uint32_t smem_stage0 = __shfl_sync(FULL_MASK, smem_u32(stage_base), 0);
       const uint32_t smem_tail0 = __shfl_sync(FULL_MASK, smem_u32(a_tail), 0);
@@ -412,18 +439,18 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         const int slice = u / P.num_qt;
         const K3TileRange tr = k3_unit_tiles(P, slice);
         if (VARIANT == 0) {
-          mbar_wait(&bars->a_ready, unit_par, 2);
+          k3_wait(&bars->a_ready, unit_par, 2, prof, w_aready);
           unit_par ^= 1u;
           tc_fence_after();
         }
         for (int ti = 0; ti < tr.n; ++ti) {
-          mbar_wait(&bars->tempty[acc], acc_phase ^ 1u, 3);
+          k3_wait(&bars->tempty[acc], acc_phase ^ 1u, 3, prof, w_tempty);
           tc_fence_after();
           const uint32_t d_tmem = tmem_b + (uint32_t)(P.acc_col0 + acc * K3_TILE_N);
           for (int ch = 0; ch < num_chunks; ++ch) {
             const int kb0 = ch * G::KBS;
             const int nkb = min(G::KBS, P.num_kb - kb0);
-            mbar_wait(&bars->full[stage], phase, 4);
+            k3_wait(&bars->full[stage], phase, 4, prof, w_full);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t sb = smem_stage0 + (uint32_t)stage * (uint32_t)G::STAGE_BYTES;
@@ -470,6 +497,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
           if (++acc == P.num_acc) { acc = 0; acc_phase ^= 1u; }
         }
       }
+      if (prof && lane == 0) {
+        atomicAdd(P.prof + K3P_MMA_AREADY, w_aready);
+        atomicAdd(P.prof + K3P_MMA_TEMPTY, w_tempty);
+        atomicAdd(P.prof + K3P_MMA_FULL, w_full);
+      }
     }
   } else {
     // ================================ epilogue ====================================
@@ -480,6 +512,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
     const int kc = P.kc;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool prof = P.prof != nullptr;
+    unsigned long long w_tfull = 0ull, w_prune = 0ull, n_prune = 0ull;
     // barriers the MMA issuer waits on live in the leader CTA
     const uint32_t a_ready_leader = PAIR ? mapa_u32(smem_u32(&bars->a_ready), 0) : 0u;
     const uint32_t tempty_leader0 = PAIR ? mapa_u32(smem_u32(&bars->tempty[0]), 0) : 0u;
@@ -540,7 +574,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         const int t = tr.t0 + ti * tr.step;
         if (tau_cell != nullptr && (ti & (K3_TAU_REFRESH - 1)) == K3_TAU_REFRESH - 1)
           tau = fmaxf(tau, ordered_to_f32(ld_relaxed_u32(tau_cell)));
-        mbar_wait(&bars->tfull[acc], acc_phase, 5);
+        k3_wait(&bars->tfull[acc], acc_phase, 5, prof, w_tfull);
         tc_fence_after();
         if (P.debug_epi == 2) {
           tc_fence_before();
@@ -671,6 +705,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
           }
           const int cnt = (int)(wp - my_list);
           unsigned need = __ballot_sync(FULL_MASK, cnt >= P.list_cap);
+          const long long p0 = (prof && need) ? clock64() : 0ll;
+          if (prof) n_prune += __popc(need);
           while (need) {
             const int L = __ffs(need) - 1;
             need &= need - 1;
@@ -686,6 +722,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
               }
             }
           }
+          if (prof && p0) w_prune += (unsigned long long)(clock64() - p0);
         }
       }
 
@@ -705,6 +742,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         }
         if (qg < P.q_valid) P.list_cnt[(size_t)slice * P.q_pad + qg] = cnt;
       }
+    }
+    if (prof && lane == 0) {
+      atomicAdd(P.prof + K3P_EPI_TFULL, w_tfull);
+      atomicAdd(P.prof + K3P_EPI_PRUNE, w_prune);
+      atomicAdd(P.prof + K3P_EPI_WARPS, 1ull);
+      atomicAdd(P.prof + K3P_PRUNES, n_prune);
     }
   }
 
@@ -916,6 +959,7 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   P.sync_windows = L.sync_windows;
   P.a_tmem_kb = L.a_tmem_kb;
   P.debug_epi = L.debug_epi;
+  P.prof = L.prof;
   P.num_acc = (L.variant == 1 || L.a_tmem_kb * 32 + 2 * K3_TILE_N <= TMEM_COLS) ? 2 : 1;
   P.acc_col0 = TMEM_COLS - P.num_acc * K3_TILE_N;
   P.idesc = make_idesc_f16(L.a_fmt, L.b_fmt, L.variant == 2 ? 2 * K3_TILE_M : K3_TILE_M, K3_TILE_N);

@@ -287,7 +287,7 @@ int rbod_destroy(rbod_gallery* g) {
   DevBuf* bufs[] = {&g->stage_rows, &g->stage_slots, &g->stage_norms, &g->q32, &g->q16, &g->q_dq, &g->q_qq, &g->tau_shared,
                     &g->lists, &g->list_cnt, &g->out_scores,
                     &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->flag_lo, &g->fq16, &g->groupmax, &g->tau_init, &g->coll_score,
-                    &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->sync_counters, &g->seg_idx, &g->seg_off, &g->seg_out,
+                    &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->sync_counters, &g->prof, &g->seg_idx, &g->seg_off, &g->seg_out,
                     &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->seg_scratch, &g->seg_member, &g->gather_idx,
                     &g->gather_out, &g->dist_q64, &g->dist_thr, &g->dist_ctl};
   for (DevBuf* b : bufs) b->release();
@@ -375,6 +375,8 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
     g->tau_share = value != 0;
   } else if (!strcmp(key, "debug_epi")) {
     g->debug_epi = (int)value;   // bring-up only: results are wrong when non-zero
+  } else if (!strcmp(key, "k3_prof")) {
+    g->k3_prof = value != 0;
   } else if (!strcmp(key, "hybrid")) {
     g->hybrid = value != 0;
   } else if (!strcmp(key, "l2_sync")) {
@@ -703,6 +705,13 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.variant = g->k3_variant;
   L.kbs = P.kbs;
   L.debug_epi = g->debug_epi;
+  if (g->k3_prof && collect == nullptr && sample == nullptr && dump == nullptr) {
+    if (g->prof.p == nullptr) {
+      RBOD_TRY(g->prof.ensure(16 * sizeof(unsigned long long)));
+      RBOD_CUDA(cudaMemsetAsync(g->prof.p, 0, 16 * sizeof(unsigned long long), st));
+    }
+    L.prof = g->prof.as<unsigned long long>();
+  }
   L.a_fmt = query_kind(g) == 1 ? 1 : 0;
   L.b_fmt = query_kind(g) == 1 ? 1 : 0;
   L.lists = g->lists.as<uint2>();
@@ -1162,6 +1171,17 @@ int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* o
   RBOD_TRY(run_k3(g, P, Q, g->q16.as<uint16_t>(), nullptr, nullptr, dst, ld, st));
   if (!out_dev) RBOD_CUDA(cudaMemcpyAsync(out, dst, (size_t)Q * ld * 4, cudaMemcpyDeviceToHost, st));
   RBOD_CUDA(cudaStreamSynchronize(st));
+  return RBOD_OK;
+}
+
+int rbod_debug_profile(rbod_gallery* g, int64_t* out16) {
+  if (!g || !out16) return set_error(RBOD_E_INVAL, "rbod_debug_profile: NULL argument");
+  memset(out16, 0, 16 * sizeof(int64_t));
+  if (g->prof.p == nullptr) return RBOD_OK;
+  RBOD_CUDA(cudaSetDevice(g->device));
+  RBOD_CUDA(cudaDeviceSynchronize());
+  RBOD_CUDA(cudaMemcpy(out16, g->prof.p, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  RBOD_CUDA(cudaMemset(g->prof.p, 0, 16 * sizeof(int64_t)));
   return RBOD_OK;
 }
 

@@ -86,6 +86,7 @@ struct K3Launch {
   int* sync_counters;     // zeroed [slices * sync_span * sync_windows] ints, or nullptr
   int sync_window, sync_lead, sync_span, sync_windows;
   int debug_epi;          // bring-up: 1 = epilogue selects nothing, 2 = epilogue does not read the tile
+  unsigned long long* prof;   // optional [16] wait-cycle counters (option k3_prof), see k3_cosine_topk.cu
   int grid;
   size_t smem_bytes;
 };
@@ -200,6 +201,7 @@ struct rbod_gallery {
   int slack = -1;  // -1 = automatic
   int time_k3 = 0;
   int debug_epi = 0;
+  int k3_prof = 0;        // accumulate where the K3 warp roles wait (rbod_debug_profile reads and clears)
   int presample = 1;      // threshold pre-pass over a strided sample of the gallery (needs tau_share)
   int collect_pass = 1;   // uncertified queries get a collecting tensor-core pass before the fp64 sweep
   int tau_share = 1;      // slices of one query share their candidate threshold through global memory
@@ -214,7 +216,7 @@ struct rbod_gallery {
   rbod::DevBuf flags;      // ints: [0]=n_flag [1]=overflow [2]=err; float max_eps at [3]
   rbod::DevBuf flag_q, flag_thr, flag_lo, fq16, groupmax, tau_init;
   rbod::DevBuf coll_score, coll_idx, coll_cnt;
-  rbod::DevBuf mask_dev, dump, sync_counters;
+  rbod::DevBuf mask_dev, dump, sync_counters, prof;
   rbod::DevBuf seg_idx, seg_off, seg_out, seg_partials, seg_prefix, seg_arrive, seg_scratch, seg_member;
   rbod::DevBuf gather_idx, gather_out;
   rbod::DevBuf dist_q64, dist_thr, dist_ctl;   // K5: widened query batch, thresholds, {qsel, active, n_active}

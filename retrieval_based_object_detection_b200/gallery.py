@@ -205,6 +205,14 @@ class Gallery:
         stats = {f: getattr(st, f) for f, _ in st._fields_}
         return SearchResult(scores, rows, s64, stats)
 
+    def debug_profile(self) -> dict:
+        """Wait-cycle counters of the K3 launches since the last call (needs set_option("k3_prof", 1)); clears them."""
+        out = (ctypes.c_int64 * 16)()
+        N.check(self._lib.rbod_debug_profile(self._h, out))
+        names = ("prod_wait_empty", "prod_wait_throttle", "mma_wait_query_tile", "mma_wait_accumulator", "mma_wait_data",
+                 "epi_wait_accumulator", "epi_prune", "cta_cycles", "ctas", "epi_warps", "prunes")
+        return dict(zip(names, list(out)))
+
     def debug_scores(self, queries):
         """Raw scores of the tcgen05 pass (test hook): [Q, rows] float32."""
         keep, p_q = self._in(queries, np.float32, "float32")
