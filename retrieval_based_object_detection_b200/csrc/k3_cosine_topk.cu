@@ -842,7 +842,7 @@ int make_tmap_2d_sw128(CUtensorMap* out, const void* base, int64_t rows, int dp,
 
 static size_t k3_stage_bytes(int variant, int kbs) {
   if (variant == 1) return (size_t)K3Geom<1, 0, 2>::STAGE_BYTES;
-  if (variant == 2) return (size_t)K3Geom<0, 1, 4>::STAGE_BYTES;
+  if (variant == 2) return kbs == 4 ? (size_t)K3Geom<0, 1, 4>::STAGE_BYTES : (size_t)K3Geom<0, 1, 2>::STAGE_BYTES;
   return kbs == 4 ? (size_t)K3Geom<0, 0, 4>::STAGE_BYTES : (size_t)K3Geom<0, 0, 2>::STAGE_BYTES;
 }
 
@@ -880,7 +880,11 @@ int k3_plan(int variant, int want_kbs, int dp, int smem_optin, int allow_hybrid,
   };
   int st = 0, tmem_kb = 0, tail = 0, kbs = variant == 2 ? 4 : 2;
   bool ok = false;
-  if (variant == 0 && want_kbs == 4) {
+  if (variant == 2 && want_kbs == 2) {
+    ok = attempt(2, 2, &st, &tmem_kb, &tail);
+    if (ok) kbs = 2;
+  }
+  if (!ok && variant == 0 && want_kbs == 4) {
     ok = attempt(4, 2, &st, &tmem_kb, &tail);
     // two accumulator buffers matter more than coarse stages: never trade the hybrid layout for them
     if (ok && num_kb > 8 && allow_hybrid && tail == 0) ok = false;
@@ -913,6 +917,7 @@ int k3_configure(int device) {
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<1, 0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   if (device >= 0 && device < 64) cached_optin[device] = optin;
   return optin;
 }
@@ -998,7 +1003,8 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   cfg.numAttrs = na;
   if (L.row_bias != nullptr && L.variant != 0)
     return set_error(RBOD_E_UNSUPPORTED, "k3: the row-bias (EUCLID) epilogue exists for variant 0 only");
-  if (L.variant == 2) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 4, 0>, P));
+  if (L.variant == 2 && L.kbs == 2) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 2, 0>, P));
+  else if (L.variant == 2) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 4, 0>, P));
   else if (L.variant == 0 && L.row_bias != nullptr && L.kbs == 4)
     RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 4, 1>, P));
   else if (L.variant == 0 && L.row_bias != nullptr)

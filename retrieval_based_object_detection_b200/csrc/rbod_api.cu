@@ -197,11 +197,13 @@ static int plan_search(const rbod_gallery* g, int64_t Q, int k, int variant, int
   P->slices = best_s;
   const int64_t units = (int64_t)P->slices * P->num_qt;
   P->grid = (int)std::min<int64_t>(units, workers) * (variant == 2 ? 2 : 1);
-  // Coarse 4-k-block stages for long tensor-bound units (>= 16 query tiles, >= 2048 gallery tiles per unit), fine ones
-  // otherwise.  Same-box A/B, three alternating runs each: 10M x 768 bf16 Q=10^4 78.2 -> 78.8 k queries/s (another
-  // box: 78.3 -> 81.8), Q=2048 79.3 -> 80.7; 1M x 512 fp32 (520 tiles per unit) 884 -> 849 k, Q <= 512 5-10 % slower.
-  const int want_kbs = g->k3_kbs ? g->k3_kbs
-                                 : ((P->num_qt >= 16 && P->tiles_total / std::max(1, P->slices) >= 2048) ? 4 : 2);
+  // Coarse 4-k-block stages (fewer barrier round trips per tile) whenever a CTA pair of query tiles or more is in
+  // flight; fine 2-k-block stages for a single query tile, where the launch is HBM-bound and a later first MMA costs
+  // more than the round trips.  With the candidate lists out of shared memory both layouts keep the hybrid query tile
+  // and two accumulators at any k.  Same-box A/B (tools/k3_where.py, kbs 2 -> 4): 10M x 768 bf16 Q=10^4 1107 -> 1166
+  // TF/s; its 8-GPU shard (1.25M rows) 1099 -> 1274 (k = 100: 1074 -> 1211); 1M x 512 fp32 Q=10^4 1105 -> 1178;
+  // 12.5M x 768 fp16 Q=1024 1042 -> 1127, Q=256 1039 -> 1062, Q=128 854 -> 762 (worse), Q <= 16 equal.
+  const int want_kbs = g->k3_kbs ? g->k3_kbs : ((variant == 2 || P->num_qt >= 2) ? 4 : 2);
   RBOD_TRY(k3_plan(variant, want_kbs, g->dp, smem_optin, g->hybrid, &P->num_stages, &P->a_tmem_kb, &P->kbs,
                    &P->smem));
   // Candidate lists: a list is pruned back to ~kc entries whenever it reaches list_cap (>= 2 kc, so at least kc

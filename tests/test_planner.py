@@ -60,11 +60,14 @@ def test_planner_policies():
     assert _plan(768, 10_000, 10_000, 128)[1]["kc"] == 128
     assert _plan(768, 10_000_000, 10_000, 10)[1]["kc"] == 32
     assert _plan(768, 10_000_000, 10_000, 100)[1]["kc"] == 128
-    # coarse stages only for long tensor-bound units, and never at the price of the hybrid layout
+    # coarse stages from two query tiles up (never at the price of the hybrid layout), fine stages for a single tile
     head = _plan(768, 10_000_000, 10_000, 10)[1]
     assert head["kbs"] == 4 and head["stages"] == 2 and head["a_tmem_kb"] == 8 and head["slices"] == 11
-    assert _plan(768, 10_000_000, 256, 10)[1]["kbs"] == 2            # small batch
-    assert _plan(512, 1_000_000, 10_000, 10)[1]["kbs"] == 2          # short units
+    assert _plan(768, 10_000_000, 256, 10)[1]["kbs"] == 4
+    assert _plan(768, 10_000_000, 128, 10)[1]["kbs"] == 2            # one query tile: HBM-bound
+    shard = _plan(768, 1_250_000, 10_000, 10)[1]                     # the headline gallery's 8-GPU shard
+    assert shard["kbs"] == 4 and shard["a_tmem_kb"] == 8
+    assert _plan(512, 1_000_000, 10_000, 10)[1]["kbs"] == 4
     # candidate lists live in global memory: k = 100 gets the same pipeline as k = 10 (round 1: 128 KB of heaps in
     # shared memory cost it the hybrid layout and the second accumulator buffer)
     k100 = _plan(768, 10_000_000, 10_000, 100)[1]

@@ -47,7 +47,7 @@ def main():
     ref_rows = None
     for spec in a.sets.split(";"):
         opts = dict(defaults)
-        for kv in [x for x in spec.split(",") if x]:
+        for kv in [x for x in spec.replace("+", ",").split(",") if x]:
             key, _, val = kv.partition("=")
             opts[key] = int(val)
         for key, val in opts.items():
