@@ -7,6 +7,7 @@
 #   smoke            __graft_entry__.smoke()
 #   bench[:args]     python bench.py --no-cpu-baseline <args>   (args: comma separated, e.g. bench:--k,100,--steps,3)
 #   fullbench[:args] python bench.py <args>                     (the driver's command line)
+#   mbench:<N>[:args] torchrun --nproc-per-node N bench.py --gpus N <args>   (run under gpurun --gpus N)
 #   sweep:<rows>:<dtype>:<Qlist>   bench.py --sweep on one shard (Qlist with '+' for ',')
 #   probe:<args>     python tools/probe.py <args>  (comma separated)
 #   copy             this box's copy bandwidth (tools/probe.py copy)
@@ -44,6 +45,13 @@ for step in "$@"; do
       timeout 900 python bench.py $args > $O/${tag}_full$n.json 2> $O/${tag}_full$n.err
       echo "rc=$?"; tail -3 $O/${tag}_full$n.err | cut -c1-300
       python tools/bench_brief.py $O/${tag}_full$n.json ;;
+    mbench)
+      IFS=: read -r ngpu margs <<< "$rest"
+      n=$(ls $O/${tag}_mbench*.json 2>/dev/null | wc -l)
+      timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $ngpu --master-addr 127.0.0.1 --master-port 29517 \
+        bench.py --gpus $ngpu ${margs//,/ } > $O/${tag}_mbench$n.json 2> $O/${tag}_mbench$n.err
+      echo "rc=$?"; grep -v "^W\|^\*\*\*\|OMP_NUM_THREADS" $O/${tag}_mbench$n.err | tail -5 | cut -c1-300
+      python tools/bench_brief.py $O/${tag}_mbench$n.json ;;
     sweep)
       IFS=: read -r rows dtype qs <<< "$rest"
       timeout 600 python bench.py --rows $rows --dtype $dtype --sweep ${qs//+/,} > $O/${tag}_sweep_${rows}_${dtype}.json 2> $O/${tag}_sweep.err
