@@ -86,7 +86,8 @@ typedef struct rbod_gallery_info {
   int32_t dtype;          /* RBOD_F32 / RBOD_BF16 / RBOD_F16                       */
   int32_t metric;         /* RBOD_COSINE / RBOD_DOT / RBOD_EUCLID / RBOD_MANHATTAN */
   int32_t device;         /* CUDA device ordinal                                   */
-  int32_t reserved;
+  int32_t coop_refusals;    /* tensor-core launches that ran without the L2-sharing throttle because the runtime */
+                            /* refused a cooperative launch (grid not co-resident); 0 on a whole B200           */
   int64_t rows;           /* number of row slots in use (max slot + 1)             */
   int64_t capacity;       /* allocated row slots                                   */
   int64_t bytes_device;   /* device bytes held by the handle (gallery + workspace) */
@@ -129,12 +130,16 @@ int rbod_truncate(rbod_gallery* g, int64_t rows);
  * "time_k3" (1 = fill stats.k3_ms), "tau_share" (slices of a query share their threshold),
  * "collect_pass" (tensor-core second pass for uncertified queries), "presample" (sampled
  * starting thresholds: 0 = never, 1 = for batches of more than 8 queries, 2 = always), "l2_sync" / "sync_window" /
- * "sync_lead" (L2-sharing producer throttle), "hybrid" (query tile split TMEM / smem). */
+ * "sync_lead" (L2-sharing producer throttle), "hybrid" (query tile split TMEM / smem), "auto_shadow" (bf16 COSINE
+ * collections build an fp16 search operand on the first search with k > 40; default 1), "k3_prof" (wait-cycle
+ * counters, see rbod_debug_profile), "debug_grid_scale" (test hook: over-sized grid, exercises the fallback taken
+ * when a cooperative launch is refused). */
 int rbod_set_option(rbod_gallery* g, const char* key, int64_t value);
 
 /* --- K1: normalise + pack on upsert ----------------------------------------------------
  * rows:      [n, dim] fp32, host or device.
- * row_slots: [n] int64 destination slots (host or device), or NULL to append.
+ * row_slots: [n] int64 destination slots (host or device; a device array is read back for validation), or NULL to
+ *            append.
  *            A slot equal to the current count appends; smaller overwrites (upsert-by-id
  *            is resolved to a slot by the caller).
  * out_norms: optional [n] fp32 L2 norms of the incoming rows (host or device), or NULL.   */

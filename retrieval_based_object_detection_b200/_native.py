@@ -34,7 +34,7 @@ DISTANCE_METRICS = ("euclid", "manhattan")
 
 class GalleryInfo(ctypes.Structure):
     _fields_ = [("dim", ctypes.c_int32), ("dim_padded", ctypes.c_int32), ("dtype", ctypes.c_int32),
-                ("metric", ctypes.c_int32), ("device", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("metric", ctypes.c_int32), ("device", ctypes.c_int32), ("coop_refusals", ctypes.c_int32),
                 ("rows", ctypes.c_int64), ("capacity", ctypes.c_int64), ("bytes_device", ctypes.c_int64),
                 ("max_row_norm", ctypes.c_float), ("max_row_dev", ctypes.c_float)]
 

@@ -916,6 +916,7 @@ int k3_configure(int device) {
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 0, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<1, 0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<1, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   if (device >= 0 && device < 64) cached_optin[device] = optin;
@@ -1001,17 +1002,30 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (L.row_bias != nullptr && L.variant != 0)
-    return set_error(RBOD_E_UNSUPPORTED, "k3: the row-bias (EUCLID) epilogue exists for variant 0 only");
-  if (L.variant == 2 && L.kbs == 2) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 2, 0>, P));
-  else if (L.variant == 2) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 4, 0>, P));
-  else if (L.variant == 0 && L.row_bias != nullptr && L.kbs == 4)
-    RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 4, 1>, P));
-  else if (L.variant == 0 && L.row_bias != nullptr)
-    RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 2, 1>, P));
-  else if (L.variant == 0 && L.kbs == 4) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 4, 0>, P));
-  else if (L.variant == 0) RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 2, 0>, P));
-  else RBOD_CUDA(cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<1, 0, 2, 0>, P));
+  if (L.row_bias != nullptr && L.variant == 2)
+    return set_error(RBOD_E_UNSUPPORTED, "k3: the row-bias (EUCLID) epilogue is not built for the CTA-pair kernel");
+  auto launch = [&]() -> cudaError_t {
+    if (L.variant == 2 && L.kbs == 2) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 2, 0>, P);
+    if (L.variant == 2) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 4, 0>, P);
+    if (L.variant == 0 && L.row_bias != nullptr && L.kbs == 4) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 4, 1>, P);
+    if (L.variant == 0 && L.row_bias != nullptr) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 2, 1>, P);
+    if (L.variant == 0 && L.kbs == 4) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 4, 0>, P);
+    if (L.variant == 0) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 2, 0>, P);
+    if (L.row_bias != nullptr) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<1, 0, 2, 1>, P);
+    return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<1, 0, 2, 0>, P);
+  };
+  cudaError_t e = launch();
+  if (e == cudaErrorCooperativeLaunchTooLarge && L.sync_counters != nullptr) {
+    // The runtime cannot keep the whole grid resident (fewer SMs than the planner assumed: another tenant, MPS, a green
+    // context).  CTAs that wait for each other are then not allowed: drop the L2-sharing throttle -- the only thing
+    // that needs co-residency -- and launch again as an ordinary grid.  Same result, more DRAM traffic.
+    cudaGetLastError();
+    P.sync_counters = nullptr;
+    cfg.numAttrs = na - 1;          // the cooperative attribute was added last
+    if (L.coop_refused) ++*L.coop_refused;
+    e = launch();
+  }
+  if (e != cudaSuccess) return set_error(RBOD_E_IO, "k3 launch failed: %s", cudaGetErrorString(e));
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
 // ---------------------------------------------------------------------------------------------
 // exact fallback
 // ---------------------------------------------------------------------------------------------
-constexpr int EX_NMAX = 32;  // dim <= 1024
+constexpr int EX_NMAX = 64;  // dim <= 2048 (K3_MAX_DP_WIDE)
 
 __global__ void __launch_bounds__(256)
 exact_collect_kernel(const float* __restrict__ q, const double* __restrict__ q_qq,

@@ -313,6 +313,7 @@ int rbod_info(const rbod_gallery* g, rbod_gallery_info* out) {
   out->device = g->device;
   out->rows = g->rows;
   out->capacity = g->capacity;
+  out->coop_refusals = g->coop_refusals;
   size_t ws = 0;
   const DevBuf* bufs[] = {&g->stage_rows, &g->q32, &g->q16, &g->lists, &g->list_cnt, &g->out_scores, &g->out_rows, &g->out_scores64, &g->coll_score,
                           &g->coll_idx, &g->mask_dev, &g->dump, &g->seg_idx, &g->seg_out, &g->seg_partials,
@@ -342,8 +343,8 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
   if (!g || !key) return set_error(RBOD_E_INVAL, "rbod_set_option: NULL argument");
   if (!strcmp(key, "k3_variant")) {
     if (value < 0 || value > 2) return set_error(RBOD_E_INVAL, "k3_variant must be 0, 1 or 2");
-    if (value != 0 && g->metric == RBOD_EUCLID)
-      return set_error(RBOD_E_UNSUPPORTED, "k3_variant: EUCLID collections use variant 0 (the row-bias epilogue)");
+    if (value == 2 && g->metric == RBOD_EUCLID)
+      return set_error(RBOD_E_UNSUPPORTED, "k3_variant: the row-bias (EUCLID) epilogue is not built for the CTA-pair kernel");
     g->k3_variant = (int)value;
   } else if (!strcmp(key, "k3_kbs")) {
     if (value != 0 && value != 2 && value != 4) return set_error(RBOD_E_INVAL, "k3_kbs must be 0 (auto), 2 or 4");
@@ -377,6 +378,9 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
     g->tau_share = value != 0;
   } else if (!strcmp(key, "debug_epi")) {
     g->debug_epi = (int)value;   // bring-up only: results are wrong when non-zero
+  } else if (!strcmp(key, "debug_grid_scale")) {
+    if (value < 1 || value > 8) return set_error(RBOD_E_INVAL, "debug_grid_scale must be in [1, 8]");
+    g->debug_grid_scale = (int)value;
   } else if (!strcmp(key, "k3_prof")) {
     g->k3_prof = value != 0;
   } else if (!strcmp(key, "hybrid")) {
@@ -403,8 +407,14 @@ int rbod_upsert(rbod_gallery* g, const float* rows, int64_t n, const int64_t* ro
   if (n == 0) return RBOD_OK;
   RBOD_CUDA(cudaSetDevice(g->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (row_slots && is_device_ptr(row_slots))
-    return set_error(RBOD_E_INVAL, "rbod_upsert: row_slots must be a host pointer (or NULL to append)");
+  std::vector<int64_t> slots_host;
+  if (row_slots && is_device_ptr(row_slots)) {
+    // slots living on the device are read back: they are validated (range, no holes) on the host
+    slots_host.resize((size_t)n);
+    RBOD_CUDA(cudaMemcpyAsync(slots_host.data(), row_slots, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    RBOD_CUDA(cudaStreamSynchronize(st));
+    row_slots = slots_host.data();
+  }
 
   int64_t new_rows = g->rows + n;
   if (row_slots) {
@@ -665,6 +675,11 @@ int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx
 // 16-bit type the (unit-norm) queries are rounded to for the tensor-core pass: the gallery's own.
 // (Measured on B200: a kind::f16 MMA whose instruction descriptor mixes an fp16 A with a bf16 B
 // raises "illegal instruction", so both operands must share one format.)
+// The kernel flavour a collection's searches run on: rows wider than the TMEM-resident query tile allows (768 columns)
+// stream the query tile through shared memory next to the gallery tile (variant 1: twice the L2 -> SM traffic per
+// flop, still two orders of magnitude faster than the fp64 sweep such collections took before).
+static int search_variant(const rbod_gallery* g) { return g->dp > K3_MAX_DP ? 1 : g->k3_variant; }
+
 static int query_kind(const rbod_gallery* g) { return g->use_shadow ? 2 : g->kind16; }
 static const uint16_t* search_operand(const rbod_gallery* g) { return g->use_shadow ? g->shadow16 : g->rows16; }
 
@@ -685,7 +700,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
                   const K3Sample* sample = nullptr) {
   K3Launch L;
   memset(&L, 0, sizeof(L));
-  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, search_operand(g), g->rows, g->dp, k3_box_rows(g->k3_variant)));
+  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, search_operand(g), g->rows, g->dp, k3_box_rows(search_variant(g))));
   RBOD_TRY(make_tmap_2d_sw128(&L.tmap_a, q16, P.q_pad, g->dp, K3_TILE_M));
   L.q16 = q16;
   if (collect) {
@@ -704,7 +719,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.kc = P.kc;
   L.num_stages = P.num_stages;
   L.a_tmem_kb = P.a_tmem_kb;
-  L.variant = g->k3_variant;
+  L.variant = search_variant(g);
   L.kbs = P.kbs;
   L.debug_epi = g->debug_epi;
   if (g->k3_prof && collect == nullptr && sample == nullptr && dump == nullptr) {
@@ -733,10 +748,11 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   }
   L.dump = dump;
   L.dump_ld = dump_ld;
-  L.grid = P.grid;
+  L.grid = P.grid * std::max(1, g->debug_grid_scale);   // > 1 only under the test hook: the extra CTAs find no unit
   L.smem_bytes = P.smem;
+  L.coop_refused = &g->coop_refusals;
   if (g->l2_sync && dump == nullptr && sample == nullptr) {
-    const int workers = g->k3_variant == 2 ? P.grid / 2 : P.grid;
+    const int workers = search_variant(g) == 2 ? P.grid / 2 : P.grid;
     const int max_tiles = (P.tiles_total + P.slices - 1) / P.slices + 1;
     L.sync_window = std::max(1, g->sync_window);
     L.sync_lead = std::max(1, g->sync_lead);
@@ -850,9 +866,9 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   if (stats) memset(stats, 0, sizeof(*stats));
   if (Q == 0) return RBOD_OK;
   // What the tensor-core pass does not cover takes the exact fp64 sweep (K5): MANHATTAN (not a contraction), vectors
-  // wider than K3_MAX_DP columns, and k beyond the K3 candidate lists.  Everything else -- COSINE, DOT and EUCLID
-  // (row-bias epilogue) up to 768 columns, k <= 128 -- runs on the tensor cores.
-  const bool distance_metric = g->metric == RBOD_MANHATTAN || g->dp > K3_MAX_DP || k > K3_MAX_KC;
+  // wider than K3_MAX_DP_WIDE columns, and k beyond the K3 candidate lists.  Everything else -- COSINE, DOT and EUCLID
+  // (row-bias epilogue) up to 2048 columns, k <= 128 -- runs on the tensor cores.
+  const bool distance_metric = g->metric == RBOD_MANHATTAN || g->dp > K3_MAX_DP_WIDE || k > K3_MAX_KC;
   if (Q > (1ll << 24)) return set_error(RBOD_E_INVAL, "rbod_search: Q too large");
   if (g->rows >= 0xffffffffll) return set_error(RBOD_E_UNSUPPORTED, "rbod_search: more than 2^32-2 rows per shard");
   RBOD_CUDA(cudaSetDevice(g->device));
@@ -924,7 +940,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   double* d_scores64 = (out_scores64 && is_device_ptr(out_scores64)) ? out_scores64 : g->out_scores64.as<double>();
 
   SearchPlan P;
-  RBOD_TRY(plan_search(g, Q, k, g->k3_variant, smem_optin, &P));
+  RBOD_TRY(plan_search(g, Q, k, search_variant(g), smem_optin, &P));
   if (stats) {
     stats->queries = Q;
     stats->candidates = P.kc;
@@ -976,10 +992,10 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     const float* tau_init = nullptr;
     if (use_sample) {
       SearchPlan PA = P;
-      const int workers = g->k3_variant == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
+      const int workers = search_variant(g) == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
       const int splits = std::max(1, std::min({16, sample_tiles, workers / (K3_SAMPLE_GROUPS * std::max(1, PA.num_qt))}));
       PA.slices = K3_SAMPLE_GROUPS * splits;
-      PA.grid = (int)std::min<int64_t>((int64_t)PA.slices * PA.num_qt, workers) * (g->k3_variant == 2 ? 2 : 1);
+      PA.grid = (int)std::min<int64_t>((int64_t)PA.slices * PA.num_qt, workers) * (search_variant(g) == 2 ? 2 : 1);
       RBOD_TRY(g->groupmax.ensure((size_t)PA.slices * P.q_pad * 4));
       RBOD_TRY(g->tau_init.ensure((size_t)P.q_pad * 4));
       K3Sample S;
@@ -1060,7 +1076,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     // score can still reach the query's provisional k-th exact score, rescore those exactly, select.
     const int cap = K3_COLLECT_CAP;
     SearchPlan P2;
-    RBOD_TRY(plan_search(g, n_flag, k, g->k3_variant, smem_optin, &P2));
+    RBOD_TRY(plan_search(g, n_flag, k, search_variant(g), smem_optin, &P2));
     RBOD_TRY(g->fq16.ensure((size_t)P2.q_pad * g->dp * 2));
     RBOD_TRY(g->coll_cnt.ensure((size_t)P2.q_pad * 4));
     RBOD_TRY(g->coll_idx.ensure((size_t)P2.q_pad * cap * 4));
@@ -1150,7 +1166,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
 int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* out, void* stream) {
   if (!g || !queries || !out || Q < 1) return set_error(RBOD_E_INVAL, "rbod_debug_scores: bad arguments");
   if (g->rows < 1) return set_error(RBOD_E_INVAL, "rbod_debug_scores: empty gallery");
-  if (g->dp > K3_MAX_DP) return set_error(RBOD_E_UNSUPPORTED, "rbod_debug_scores: dim too large");
+  if (g->dp > K3_MAX_DP_WIDE) return set_error(RBOD_E_UNSUPPORTED, "rbod_debug_scores: dim too large");
   if ((double)Q * (double)g->rows > (double)(1ll << 28))
     return set_error(RBOD_E_INVAL, "rbod_debug_scores: Q * rows > 2^28");
   RBOD_CUDA(cudaSetDevice(g->device));
@@ -1158,7 +1174,7 @@ int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* o
   const int smem_optin = k3_configure(g->device);
   if (smem_optin < 0) return smem_optin;
   SearchPlan P;
-  RBOD_TRY(plan_search(g, Q, 1, g->k3_variant, smem_optin, &P));
+  RBOD_TRY(plan_search(g, Q, 1, search_variant(g), smem_optin, &P));
   const float* q_dev = nullptr;
   RBOD_TRY(prepare_queries(g, queries, Q, P, st, &q_dev));
   RBOD_TRY(ensure_lists(g, P));
@@ -1196,11 +1212,12 @@ int rbod_debug_plan(int32_t dim, int64_t rows, int64_t Q, int32_t k, int32_t var
   g.dp = round_up(dim, K3_KBLOCK);
   g.rows = rows;
   g.num_sms = num_sms;
-  if (g.dp > K3_MAX_DP || k > K3_MAX_KC)
+  if (g.dp > K3_MAX_DP_WIDE || k > K3_MAX_KC)
     return set_error(RBOD_E_UNSUPPORTED, "rbod_debug_plan: dim %d / k %d take the fp64 sweep, not the tensor-core pass",
                      dim, k);
+  g.k3_variant = variant;
   SearchPlan P;
-  RBOD_TRY(plan_search(&g, Q, k, variant, smem_optin, &P));
+  RBOD_TRY(plan_search(&g, Q, k, search_variant(&g), smem_optin, &P));
   out[0] = P.kc;
   out[1] = P.slices;
   out[2] = P.grid;

@@ -42,7 +42,8 @@ constexpr int K2_SEG_CHUNK = 256;    // rows per K2 work item (one warp)
 constexpr int K3_TILE_M = 128;       // queries per CTA (TMEM lanes)
 constexpr int K3_TILE_N = 128;       // gallery rows per accumulator buffer (one tcgen05.mma N)
 constexpr int K3_KBLOCK = 64;        // 16-bit elements per 128-byte swizzle row
-constexpr int K3_MAX_DP = 768;       // A operand must fit 384 TMEM columns
+constexpr int K3_MAX_DP = 768;       // query tile resident in TMEM (+ smem tail): A operand must fit 384 TMEM columns
+constexpr int K3_MAX_DP_WIDE = 2048; // wider rows (up to this) stream the query tile through shared memory (variant 1)
 constexpr int K3_THREADS = 192;      // warp0 TMA, warp1 MMA, warps 2-5 epilogue
 constexpr int K3_MAX_KC = 128;
 constexpr int K3_COLLECT_CAP = 1024; // rows a collecting pass records per query before it reports overflow
@@ -89,6 +90,7 @@ struct K3Launch {
   unsigned long long* prof;   // optional [16] wait-cycle counters (option k3_prof), see k3_cosine_topk.cu
   int grid;
   size_t smem_bytes;
+  int* coop_refused;      // optional host counter: ++ when the cooperative launch was refused and the throttle dropped
 };
 
 // kernels (each returns RBOD_OK or sets the error) -----------------------------------------
@@ -201,6 +203,8 @@ struct rbod_gallery {
   int slack = -1;  // -1 = automatic
   int time_k3 = 0;
   int debug_epi = 0;
+  int debug_grid_scale = 1;  // test hook: launch this many times the planned CTAs (forces a cooperative-launch refusal)
+  int coop_refusals = 0;     // K3 launches that fell back to an ordinary grid (rbod_info reports it)
   int k3_prof = 0;        // accumulate where the K3 warp roles wait (rbod_debug_profile reads and clears)
   int presample = 1;      // threshold pre-pass over a strided sample of the gallery (needs tau_share)
   int collect_pass = 1;   // uncertified queries get a collecting tensor-core pass before the fp64 sweep

@@ -78,7 +78,7 @@ class Gallery:
     def info(self) -> dict:
         gi = N.GalleryInfo()
         N.check(self._lib.rbod_info(self._h, ctypes.byref(gi)))
-        return {f: getattr(gi, f) for f, _ in gi._fields_ if f != "reserved"}
+        return {f: getattr(gi, f) for f, _ in gi._fields_}
 
     def truncate(self, rows: int) -> None:
         N.check(self._lib.rbod_truncate(self._h, int(rows)))

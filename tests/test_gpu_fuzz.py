@@ -32,8 +32,8 @@ for metric, dtype in itertools.product(("cosine", "dot", "euclid", "manhattan"),
                       int(_rng.choice([1, 5, 33])), bool(_rng.integers(0, 2)), int(_rng.integers(0, 1 << 30))))
 
 
-# beyond the tensor-core pass: vectors wider than 768 columns and k above its candidate lists take the exact fp64
-# sweep (K5) for every distance
+# vectors wider than 768 columns stream the query tile through shared memory (K3 variant 1; MANHATTAN still takes the
+# fp64 sweep), and k above the tensor-core candidate lists takes the exact fp64 sweep (K5) for every distance
 for metric in ("cosine", "dot", "euclid", "manhattan"):
     CASES.append((metric, "f32", 3000, 1024, 9, 5, False, 77))
     CASES.append((metric, "bf16", 2500, 1280, 40, 10, True, 78))

@@ -43,6 +43,26 @@ def test_raw_tensor_core_scores(G, variant, dtype, n, dim, Q):
     g.close()
 
 
+@pytest.mark.parametrize("dtype,dim", [("bf16", 1024), ("f16", 1280), ("f32", 2048)])
+def test_wide_vectors_stay_on_the_tensor_cores(G, dtype, dim):
+    """Rows wider than the TMEM-resident query tile allows (768 columns; e.g. 1024- and 1280-wide CLIP towers) run on
+    the kernel flavour that streams the query tile through shared memory -- not on the fp64 sweep: raw tensor-core
+    scores cell by cell, then ids identical to the brute force with no query left to the sweep."""
+    n, Q, k = 40_000, 260, 10
+    g, stored, x = _mk(G, n, dim, dtype, seed=dim)
+    q = O.synthetic_unit_rows(Q, dim, seed=5)
+    q[:100] = x[500:600] + 0.2 * O.synthetic_unit_rows(100, dim, seed=6)
+    got = g.debug_scores(q[:9])
+    kind = "bf16" if dtype == "bf16" else "f16"
+    want = O.l2_normalize_store(q[:9], kind)[0].astype(np.float64) @ O.round_store(stored, kind).astype(np.float64).T
+    assert np.abs(got - want).max() < 3e-5
+    res = g.search(q, k, want_scores64=True)
+    ws, wi = O.cosine_topk(q, stored, k)
+    assert np.array_equal(res.rows, wi) and np.allclose(res.scores64, ws, rtol=1e-5, atol=1e-9)
+    assert res.stats["k3_launches"] >= 1 and res.stats["sweep_queries"] == 0 and res.stats["candidates"] == 32
+    g.close()
+
+
 CASES = [
     # dtype, n, dim, Q, k, clustered
     ("f32", 1000, 512, 1000, 5, True),        # config C1 shape: 1k gallery, top-5
@@ -587,4 +607,46 @@ def test_euclid_collection_on_the_tensor_core_path(G, dtype):
     g.upsert(q[7:8], slots=np.array([123], dtype=np.int64))
     r2 = g.search(q[7:8], 3)
     assert int(r2.rows[0, 0]) == 123 and float(r2.scores[0, 0]) <= (0.0 if dtype == "f32" else 1e-1)
+    g.close()
+
+
+def test_refused_cooperative_launch_falls_back_to_a_plain_grid(G):
+    """The L2-sharing throttle makes CTAs of one launch wait for each other, so it asks for a cooperative launch; when
+    the runtime refuses (the grid cannot be co-resident: fewer SMs than planned) the search must drop the throttle and
+    run as an ordinary grid -- same exact answer, no error, no poisoned context.  The test hook over-sizes the grid
+    (2 CTAs per SM with one resident), which makes the runtime refuse."""
+    n, dim, Q, k = 150_000, 768, 129, 10                 # several slices x 2 query tiles: the throttle is in play
+    g, stored, x = _mk(G, n, dim, "bf16", seed=9)
+    q = O.synthetic_unit_rows(Q, dim, seed=10)
+    ws, wi = O.cosine_topk(q, stored, k)
+    res = g.search(q, k, want_scores64=True)
+    assert np.array_equal(res.rows, wi) and g.info()["coop_refusals"] == 0
+    g.set_option("debug_grid_scale", 2)
+    res = g.search(q, k, want_scores64=True)
+    assert np.array_equal(res.rows, wi) and np.allclose(res.scores64, ws, rtol=1e-5, atol=1e-9)
+    assert g.info()["coop_refusals"] >= 1
+    g.set_option("debug_grid_scale", 1)
+    res = g.search(q, k)
+    assert np.array_equal(res.rows, wi)                  # and the collection keeps working
+    g.close()
+
+
+def test_upsert_accepts_device_resident_slots(G):
+    """include/rbod.h: row_slots may live on the host or on the device."""
+    import torch
+
+    g = G(64, dtype="f32", capacity=16)
+    x = torch.randn(8, 64, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    g.upsert(x)
+    y = torch.randn(2, 64, device="cuda", generator=torch.Generator("cuda").manual_seed(4))
+    slots = torch.tensor([5, 8], dtype=torch.int64, device="cuda")      # overwrite row 5, append row 8
+    import ctypes
+
+    from retrieval_based_object_detection_b200 import _native as N
+
+    N.check(g._lib.rbod_upsert(g._h, y.data_ptr(), 2, slots.data_ptr(), None, 0, None))
+    torch.cuda.synchronize()
+    assert len(g) == 9
+    rows = g.get_rows(torch.tensor([5, 8], device="cuda"))
+    assert torch.allclose(rows, y / y.norm(dim=1, keepdim=True), atol=1e-6)
     g.close()

@@ -76,5 +76,9 @@ def test_planner_policies():
     # small batches spread one query tile over (almost) every SM
     assert _plan(768, 12_500_000, 1, 10)[1]["slices"] >= 140
     # what the tensor-core pass does not take is refused here (rbod_search routes it to the fp64 sweep)
-    assert _plan(1024, 1000, 1, 1)[0] == _native.RBOD_E_UNSUPPORTED
+    # rows wider than 768 columns stream the query tile through shared memory (variant 1) whatever variant was asked for
+    for dim in (1024, 1280, 2048):
+        wide = _plan(dim, 1_000_000, 10_000, 10, variant=0)[1]
+        assert wide["a_tmem_kb"] == 0 and wide["kbs"] == 2 and wide["stages"] >= 2 and wide["smem"] <= SMEM_OPTIN
+    assert _plan(2049, 1000, 1, 1)[0] == _native.RBOD_E_UNSUPPORTED
     assert _plan(512, 1000, 1, 129)[0] == _native.RBOD_E_UNSUPPORTED
