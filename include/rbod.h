@@ -124,8 +124,9 @@ int64_t rbod_count(const rbod_gallery* g);
 int rbod_info(const rbod_gallery* g, rbod_gallery_info* out);
 /* Shrinks the number of used row slots (rows beyond `rows` are forgotten). */
 int rbod_truncate(rbod_gallery* g, int64_t rows);
-/* Tunables: "k3_variant" (0 = query tile resident in TMEM, 1 = query tile streamed through smem,
- * 2 = TMEM-resident + CTA pairs / cta_group::2), "k3_kbs" (64-element k-blocks per pipeline stage of variant 0:
+/* Tunables: "k3_variant" (-1 = chosen per search: CTA pairs above 128 queries, single CTA below; 0 = query tile
+ * resident in TMEM, 1 = query tile streamed through smem, 2 = TMEM-resident + CTA pairs / cta_group::2; rows wider
+ * than 768 columns always use 1), "k3_kbs" (64-element k-blocks per pipeline stage of variant 0:
  * 0 = chosen by batch size, 2, 4), "slack" (extra candidates kept per query),
  * "time_k3" (1 = fill stats.k3_ms), "tau_share" (slices of a query share their threshold),
  * "collect_pass" (tensor-core second pass for uncertified queries), "presample" (sampled
@@ -230,11 +231,12 @@ int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* o
  * waiting, summed over CTAs (warp role: what it waited for): out16[0] producer: a free pipeline stage, [1] producer:
  * the L2-sharing throttle, [2] MMA issuer: the query tile, [3] MMA issuer: a free accumulator (epilogue behind),
  * [4] MMA issuer: gallery data (TMA behind), [5] epilogue warps: a finished accumulator, [6] epilogue warps: list
- * prunes, [7] total cycles of the CTAs, [8] CTAs, [9] epilogue warps, [10] prunes.  Reads and clears the counters. */
+ * prunes, [7] total cycles of the CTAs, [8] CTAs, [9] epilogue warps, [10] prunes, [11] as [0] for the second CTA of a pair,
+ * [12] producer: issuing TMA loads, [13] MMA issuer: issuing MMAs and commits.  Reads and clears the counters. */
 int rbod_debug_profile(rbod_gallery* g, int64_t* out16);
 
 /* Host-only: the work decomposition rbod_search would choose for a tensor-core search of Q queries, top k, over a
- * gallery of `rows` vectors of `dim` columns on a device with `num_sms` SMs and `smem_optin` bytes of opt-in shared
+ * gallery of `rows` vectors of `dim` columns (`variant` as the "k3_variant" option, -1 = automatic) on a device with `num_sms` SMs and `smem_optin` bytes of opt-in shared
  * memory per CTA (B200: 148, 232448).  Needs no GPU.  out[0..12] = candidates per query, slices, grid, query tiles,
  * gallery tiles, pipeline stages, k-blocks per stage, query-tile k-blocks kept in TMEM, dynamic shared memory bytes,
  * candidate-list prune trigger, list stride, longest list handed to the merge, keys the merge holds per query.

@@ -116,7 +116,7 @@ __device__ __forceinline__ void k3_wait(uint64_t* bar, uint32_t parity, int tag,
   }
 }
 enum { K3P_PROD_EMPTY = 0, K3P_PROD_THROTTLE, K3P_MMA_AREADY, K3P_MMA_TEMPTY, K3P_MMA_FULL, K3P_EPI_TFULL, K3P_EPI_PRUNE,
-       K3P_CTA_CYCLES, K3P_CTAS, K3P_EPI_WARPS, K3P_PRUNES };
+       K3P_CTA_CYCLES, K3P_CTAS, K3P_EPI_WARPS, K3P_PRUNES, K3P_PROD_EMPTY_FOLLOWER, K3P_PROD_ISSUE, K3P_MMA_ISSUE };
 
 // Per-row candidate list = an append-only array of {score bits, row index} in global memory, owned by the row's
 // epilogue thread for the life of a work unit.  Appending costs one 8-byte store; nothing is ordered.  When a list
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
     tma_prefetch_desc(&P.tmap_b);
     if (VARIANT == 1) tma_prefetch_desc(&P.tmap_a);
     for (int s = 0; s < P.num_stages; ++s) {
-      mbar_init(&bars->full[s], PAIR ? 2 : 1);
+      mbar_init(&bars->full[s], 1);   // CTA pair: the leader's expect_tx covers both halves, the follower only sends bytes
       mbar_init(&bars->empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
     int stage = 0;
     uint32_t phase = 0;
     const bool prof = P.prof != nullptr;
-    unsigned long long w_empty = 0ull, w_throttle = 0ull;
+    unsigned long long w_empty = 0ull, w_throttle = 0ull, w_issue = 0ull;
     const long long t_start = prof ? clock64() : 0ll;
     for (int u = worker; u < num_units; u += num_workers) {
       const int slice = u / P.num_qt, qt = u - slice * P.num_qt;
@@ -386,13 +386,17 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
           const int kb0 = ch * G::KBS;
           const int nkb = min(G::KBS, P.num_kb - kb0);
           k3_wait(&bars->empty[stage], phase ^ 1u, 1, prof, w_empty);
+          const long long i0 = prof ? clock64() : 0ll;
           if (elect_one()) {
             uint8_t* sb = stage_base + (size_t)stage * G::STAGE_BYTES;
             if (PAIR) {
-              // both halves report to the leader's barrier, which expects the bytes of the whole tile
+              // Both halves report their bytes to the leader's barrier, which expects the whole tile; the leader's
+              // arrive.expect_tx is the barrier's only arrival.  (Bytes of the follower may land before the leader has
+              // armed the phase: the transaction count goes negative for a moment, the phase cannot complete before
+              // the leader's arrival.  A second, remote arrival from the follower -- release semantics at cluster
+              // scope -- kept the follower's producer busy 95 % of the time and starved the MMA issuer for half of it.)
               const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[stage]), 0);
               if (rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * nkb * G::B_KB_BYTES);
-              else mbar_arrive_cluster(full_leader);
               for (int j = 0; j < nkb; ++j)
                 tma_load_2d_pair(sb + j * G::B_KB_BYTES, &P.tmap_b, full_leader, (kb0 + j) * K3_KBLOCK,
                                  t * K3_TILE_N + (int)rank * G::BOX_N);
@@ -410,12 +414,14 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
             }
           }
           __syncwarp();
+          if (prof) w_issue += (unsigned long long)(clock64() - i0);
           if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
     if (prof && lane == 0) {
-      atomicAdd(P.prof + K3P_PROD_EMPTY, w_empty);
+      atomicAdd(P.prof + (rank == 0 ? K3P_PROD_EMPTY : K3P_PROD_EMPTY_FOLLOWER), w_empty);
+      atomicAdd(P.prof + K3P_PROD_ISSUE, w_issue);
       atomicAdd(P.prof + K3P_PROD_THROTTLE, w_throttle);
       atomicAdd(P.prof + K3P_CTA_CYCLES, (unsigned long long)(clock64() - t_start));
       atomicAdd(P.prof + K3P_CTAS, 1ull);
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
       int acc = 0;
       uint32_t acc_phase = 0, unit_par = 0;
       const bool prof = P.prof != nullptr;
-      unsigned long long w_aready = 0ull, w_tempty = 0ull, w_full = 0ull;
+      unsigned long long w_aready = 0ull, w_tempty = 0ull, w_full = 0ull, w_mma = 0ull;
       const uint32_t tmem_b = __shfl_sync(FULL_MASK, tmem_base, 0);
       const uint32_t smem_stage0 = __shfl_sync(FULL_MASK, smem_u32(stage_base), 0);
       const uint32_t smem_tail0 = __shfl_sync(FULL_MASK, smem_u32(a_tail), 0);
@@ -451,6 +457,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
             const int kb0 = ch * G::KBS;
             const int nkb = min(G::KBS, P.num_kb - kb0);
             k3_wait(&bars->full[stage], phase, 4, prof, w_full);
+            const long long m0 = prof ? clock64() : 0ll;
             tc_fence_after();
             if (elect_one()) {
               const uint32_t sb = smem_stage0 + (uint32_t)stage * (uint32_t)G::STAGE_BYTES;
@@ -492,6 +499,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
               }
             }
             __syncwarp();
+            if (prof) w_mma += (unsigned long long)(clock64() - m0);
             if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
           }
           if (++acc == P.num_acc) { acc = 0; acc_phase ^= 1u; }
@@ -501,6 +509,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
         atomicAdd(P.prof + K3P_MMA_AREADY, w_aready);
         atomicAdd(P.prof + K3P_MMA_TEMPTY, w_tempty);
         atomicAdd(P.prof + K3P_MMA_FULL, w_full);
+        atomicAdd(P.prof + K3P_MMA_ISSUE, w_mma);
       }
     }
   } else {
@@ -580,7 +589,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+            if (PAIR) mbar_arrive_cluster_relaxed(acc == 0 ? tempty_leader0 : tempty_leader1);
             else mbar_arrive(&bars->tempty[acc]);
           }
           if (++acc == P.num_acc) { acc = 0; acc_phase ^= 1u; }
@@ -597,7 +606,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_cosine_topk_kernel(const __g
           __syncwarp();
           // TMEM tile is in registers: hand it back to the MMA issuer (one arrival per warp)
           if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+            if (PAIR) mbar_arrive_cluster_relaxed(acc == 0 ? tempty_leader0 : tempty_leader1);
             else mbar_arrive(&bars->tempty[acc]);
           }
 #pragma unroll
@@ -919,6 +928,7 @@ int k3_configure(int device) {
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<1, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  RBOD_CUDA(cudaFuncSetAttribute(k3_cosine_topk_kernel<0, 1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   if (device >= 0 && device < 64) cached_optin[device] = optin;
   return optin;
 }
@@ -1002,9 +1012,10 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (L.row_bias != nullptr && L.variant == 2)
-    return set_error(RBOD_E_UNSUPPORTED, "k3: the row-bias (EUCLID) epilogue is not built for the CTA-pair kernel");
+  if (L.variant == 2 && L.row_bias != nullptr && L.kbs != 4)
+    return set_error(RBOD_E_UNSUPPORTED, "k3: the row-bias (EUCLID) CTA-pair kernel is built with 4-k-block stages only");
   auto launch = [&]() -> cudaError_t {
+    if (L.variant == 2 && L.row_bias != nullptr) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 4, 1>, P);
     if (L.variant == 2 && L.kbs == 2) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 2, 0>, P);
     if (L.variant == 2) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 1, 4, 0>, P);
     if (L.variant == 0 && L.row_bias != nullptr && L.kbs == 4) return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<0, 0, 4, 1>, P);

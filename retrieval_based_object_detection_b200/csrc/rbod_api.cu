@@ -158,6 +158,7 @@ static int grow(rbod_gallery* g, int64_t need, cudaStream_t st) {
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct SearchPlan {
+  int variant;   // kernel flavour this plan is for (0 single CTA, 1 streamed query tile, 2 CTA pairs)
   int kc, slices, grid, num_qt, tiles_total, num_stages, a_tmem_kb, kbs;
   int list_cap, list_stride, final_cap, n_cap;   // candidate-list geometry (see K3Launch / FinishArgs)
   int64_t q_pad;
@@ -178,6 +179,7 @@ static int plan_search(const rbod_gallery* g, int64_t Q, int k, int variant, int
     return set_error(RBOD_E_UNSUPPORTED, "search: k=%d (+slack) needs %d candidates per query, max is %d", k, kc,
                      K3_MAX_KC);
   P->kc = kc;
+  P->variant = variant;
   const int q_per_unit = variant == 2 ? 2 * K3_TILE_M : K3_TILE_M;   // a CTA pair owns 256 queries
   const int workers = variant == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
   P->q_pad = (Q + q_per_unit - 1) / q_per_unit * q_per_unit;
@@ -342,9 +344,7 @@ int rbod_truncate(rbod_gallery* g, int64_t rows) {
 int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
   if (!g || !key) return set_error(RBOD_E_INVAL, "rbod_set_option: NULL argument");
   if (!strcmp(key, "k3_variant")) {
-    if (value < 0 || value > 2) return set_error(RBOD_E_INVAL, "k3_variant must be 0, 1 or 2");
-    if (value == 2 && g->metric == RBOD_EUCLID)
-      return set_error(RBOD_E_UNSUPPORTED, "k3_variant: the row-bias (EUCLID) epilogue is not built for the CTA-pair kernel");
+    if (value < -1 || value > 2) return set_error(RBOD_E_INVAL, "k3_variant must be -1 (by batch size), 0, 1 or 2");
     g->k3_variant = (int)value;
   } else if (!strcmp(key, "k3_kbs")) {
     if (value != 0 && value != 2 && value != 4) return set_error(RBOD_E_INVAL, "k3_kbs must be 0 (auto), 2 or 4");
@@ -678,7 +678,14 @@ int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx
 // The kernel flavour a collection's searches run on: rows wider than the TMEM-resident query tile allows (768 columns)
 // stream the query tile through shared memory next to the gallery tile (variant 1: twice the L2 -> SM traffic per
 // flop, still two orders of magnitude faster than the fp64 sweep such collections took before).
-static int search_variant(const rbod_gallery* g) { return g->dp > K3_MAX_DP ? 1 : g->k3_variant; }
+// Otherwise (option k3_variant = -1, the default): CTA pairs (cta_group::2, M = 256 per pair, each CTA streaming half
+// of every gallery tile) as soon as a second query tile exists -- 1555 vs 1166 TFLOP/s on the headline shape, same box
+// -- and the single-CTA kernel for batches of at most 128 queries, where a pair would idle one of its two SMs.
+static int search_variant(const rbod_gallery* g, int64_t Q) {
+  if (g->dp > K3_MAX_DP) return 1;
+  if (g->k3_variant >= 0) return g->k3_variant;
+  return Q > K3_TILE_M ? 2 : 0;
+}
 
 static int query_kind(const rbod_gallery* g) { return g->use_shadow ? 2 : g->kind16; }
 static const uint16_t* search_operand(const rbod_gallery* g) { return g->use_shadow ? g->shadow16 : g->rows16; }
@@ -700,7 +707,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
                   const K3Sample* sample = nullptr) {
   K3Launch L;
   memset(&L, 0, sizeof(L));
-  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, search_operand(g), g->rows, g->dp, k3_box_rows(search_variant(g))));
+  RBOD_TRY(make_tmap_2d_sw128(&L.tmap_b, search_operand(g), g->rows, g->dp, k3_box_rows(P.variant)));
   RBOD_TRY(make_tmap_2d_sw128(&L.tmap_a, q16, P.q_pad, g->dp, K3_TILE_M));
   L.q16 = q16;
   if (collect) {
@@ -719,7 +726,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.kc = P.kc;
   L.num_stages = P.num_stages;
   L.a_tmem_kb = P.a_tmem_kb;
-  L.variant = search_variant(g);
+  L.variant = P.variant;
   L.kbs = P.kbs;
   L.debug_epi = g->debug_epi;
   if (g->k3_prof && collect == nullptr && sample == nullptr && dump == nullptr) {
@@ -752,7 +759,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.smem_bytes = P.smem;
   L.coop_refused = &g->coop_refusals;
   if (g->l2_sync && dump == nullptr && sample == nullptr) {
-    const int workers = search_variant(g) == 2 ? P.grid / 2 : P.grid;
+    const int workers = P.variant == 2 ? P.grid / 2 : P.grid;
     const int max_tiles = (P.tiles_total + P.slices - 1) / P.slices + 1;
     L.sync_window = std::max(1, g->sync_window);
     L.sync_lead = std::max(1, g->sync_lead);
@@ -940,7 +947,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   double* d_scores64 = (out_scores64 && is_device_ptr(out_scores64)) ? out_scores64 : g->out_scores64.as<double>();
 
   SearchPlan P;
-  RBOD_TRY(plan_search(g, Q, k, search_variant(g), smem_optin, &P));
+  RBOD_TRY(plan_search(g, Q, k, search_variant(g, Q), smem_optin, &P));
   if (stats) {
     stats->queries = Q;
     stats->candidates = P.kc;
@@ -992,10 +999,10 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     const float* tau_init = nullptr;
     if (use_sample) {
       SearchPlan PA = P;
-      const int workers = search_variant(g) == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
+      const int workers = P.variant == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
       const int splits = std::max(1, std::min({16, sample_tiles, workers / (K3_SAMPLE_GROUPS * std::max(1, PA.num_qt))}));
       PA.slices = K3_SAMPLE_GROUPS * splits;
-      PA.grid = (int)std::min<int64_t>((int64_t)PA.slices * PA.num_qt, workers) * (search_variant(g) == 2 ? 2 : 1);
+      PA.grid = (int)std::min<int64_t>((int64_t)PA.slices * PA.num_qt, workers) * (P.variant == 2 ? 2 : 1);
       RBOD_TRY(g->groupmax.ensure((size_t)PA.slices * P.q_pad * 4));
       RBOD_TRY(g->tau_init.ensure((size_t)P.q_pad * 4));
       K3Sample S;
@@ -1076,7 +1083,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     // score can still reach the query's provisional k-th exact score, rescore those exactly, select.
     const int cap = K3_COLLECT_CAP;
     SearchPlan P2;
-    RBOD_TRY(plan_search(g, n_flag, k, search_variant(g), smem_optin, &P2));
+    RBOD_TRY(plan_search(g, n_flag, k, search_variant(g, n_flag), smem_optin, &P2));
     RBOD_TRY(g->fq16.ensure((size_t)P2.q_pad * g->dp * 2));
     RBOD_TRY(g->coll_cnt.ensure((size_t)P2.q_pad * 4));
     RBOD_TRY(g->coll_idx.ensure((size_t)P2.q_pad * cap * 4));
@@ -1174,7 +1181,7 @@ int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* o
   const int smem_optin = k3_configure(g->device);
   if (smem_optin < 0) return smem_optin;
   SearchPlan P;
-  RBOD_TRY(plan_search(g, Q, 1, search_variant(g), smem_optin, &P));
+  RBOD_TRY(plan_search(g, Q, 1, search_variant(g, Q), smem_optin, &P));
   const float* q_dev = nullptr;
   RBOD_TRY(prepare_queries(g, queries, Q, P, st, &q_dev));
   RBOD_TRY(ensure_lists(g, P));
@@ -1205,7 +1212,7 @@ int rbod_debug_profile(rbod_gallery* g, int64_t* out16) {
 
 int rbod_debug_plan(int32_t dim, int64_t rows, int64_t Q, int32_t k, int32_t variant, int32_t num_sms,
                     int32_t smem_optin, int64_t* out) {
-  if (!out || dim < 1 || rows < 1 || Q < 1 || k < 1 || variant < 0 || variant > 2 || num_sms < 2)
+  if (!out || dim < 1 || rows < 1 || Q < 1 || k < 1 || variant < -1 || variant > 2 || num_sms < 2)
     return set_error(RBOD_E_INVAL, "rbod_debug_plan: bad arguments");
   rbod_gallery g;                 // host fields only: nothing is allocated, nothing touches a device
   g.dim = dim;
@@ -1217,7 +1224,7 @@ int rbod_debug_plan(int32_t dim, int64_t rows, int64_t Q, int32_t k, int32_t var
                      dim, k);
   g.k3_variant = variant;
   SearchPlan P;
-  RBOD_TRY(plan_search(&g, Q, k, search_variant(&g), smem_optin, &P));
+  RBOD_TRY(plan_search(&g, Q, k, search_variant(&g, Q), smem_optin, &P));
   out[0] = P.kc;
   out[1] = P.slices;
   out[2] = P.grid;

@@ -103,14 +103,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) runs out, whichever is
+// first; an arrival wakes it at once.  A generous hint keeps waiting warps off the issue ports (a bare try_wait
+// returns after a short, implementation-defined time, and the software loop around it burns issue slots and power).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(done)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
       : "memory");
   return done != 0;
 }
@@ -164,6 +167,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
 // arrive on an mbarrier anywhere in the cluster (address from mapa_u32)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// The same without release semantics: for barriers that only hand over tensor-memory buffers, whose reads are already
+// complete (tcgen05.wait::ld) when the arrival is issued.  A release at cluster scope would first wait for this
+// thread's outstanding global stores (the candidate-list appends).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-CTA TMA load: data lands in this CTA's smem, completion bytes are signalled on `bar_cluster_addr`
 // (the leader CTA's barrier).

@@ -198,7 +198,7 @@ struct rbod_gallery {
                                 // max ||shadow - row16||
   int num_sms = 148;
   // options
-  int k3_variant = 0;
+  int k3_variant = -1;    // -1 = by batch size (CTA pairs above 128 queries), 0 / 1 / 2 force a kernel flavour
   int k3_kbs = 0;         // k-blocks per stage of the single-CTA kernel: 0 = by batch size, 2, 4
   int slack = -1;  // -1 = automatic
   int time_k3 = 0;

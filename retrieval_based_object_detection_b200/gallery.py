@@ -210,7 +210,8 @@ class Gallery:
         out = (ctypes.c_int64 * 16)()
         N.check(self._lib.rbod_debug_profile(self._h, out))
         names = ("prod_wait_empty", "prod_wait_throttle", "mma_wait_query_tile", "mma_wait_accumulator", "mma_wait_data",
-                 "epi_wait_accumulator", "epi_prune", "cta_cycles", "ctas", "epi_warps", "prunes")
+                 "epi_wait_accumulator", "epi_prune", "cta_cycles", "ctas", "epi_warps", "prunes", "prod_wait_empty_follower",
+                 "prod_issue", "mma_issue")
         return dict(zip(names, list(out)))
 
     def debug_scores(self, queries):

@@ -73,6 +73,11 @@ def test_planner_policies():
     k100 = _plan(768, 10_000_000, 10_000, 100)[1]
     assert {x: k100[x] for x in ("kbs", "stages", "a_tmem_kb", "smem")} == {x: head[x] for x in ("kbs", "stages", "a_tmem_kb", "smem")}
     assert (head["list_cap"], k100["list_cap"], k100["list_stride"]) == (64, 256, 384)
+    # left to itself (variant -1) the planner pairs CTAs (256 queries per unit, even grid) above 128 queries
+    auto = _plan(768, 10_000_000, 10_000, 10, variant=-1)[1]
+    assert auto["num_qt"] == 40 and auto["grid"] == 148 and auto["kbs"] == 4 and auto["a_tmem_kb"] == 8 and auto["stages"] >= 4
+    assert _plan(768, 10_000_000, 128, 10, variant=-1)[1]["num_qt"] == 1 and _plan(768, 10_000_000, 129, 10, variant=-1)[1]["num_qt"] == 1
+    assert _plan(768, 10_000_000, 128, 10, variant=-1)[1]["kbs"] == 2 and _plan(768, 10_000_000, 129, 10, variant=-1)[1]["kbs"] == 4
     # small batches spread one query tile over (almost) every SM
     assert _plan(768, 12_500_000, 1, 10)[1]["slices"] >= 140
     # what the tensor-core pass does not take is refused here (rbod_search routes it to the fp64 sweep)

@@ -79,7 +79,8 @@ def main():
                "kc": st["candidates"], "same_ids_as_first": same,
                "mma_wait_data": round(p["mma_wait_data"] / cyc, 4), "mma_wait_accumulator": round(p["mma_wait_accumulator"] / cyc, 4),
                "mma_wait_query_tile": round(p["mma_wait_query_tile"] / cyc, 4),
-               "prod_wait_empty": round(p["prod_wait_empty"] / cyc, 4), "prod_wait_throttle": round(p["prod_wait_throttle"] / cyc, 4),
+               "prod_wait_empty": round(p["prod_wait_empty"] / cyc, 4), "prod_wait_empty_follower": round(p["prod_wait_empty_follower"] / cyc, 4),
+               "prod_issue": round(p["prod_issue"] / cyc, 4), "mma_issue": round(p["mma_issue"] / cyc, 4), "prod_wait_throttle": round(p["prod_wait_throttle"] / cyc, 4),
                "epi_wait_accumulator": round(p["epi_wait_accumulator"] / (cyc * epi / ctas), 4),
                "epi_prune": round(p["epi_prune"] / (cyc * epi / ctas), 4), "prunes": p["prunes"], "ctas": p["ctas"],
                "mcycles_per_cta": round(cyc / ctas / 1e6 / max(a.iters, 1), 3)}
