@@ -1003,7 +1003,7 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (L.sync_counters != nullptr) {
+  if (L.sync_counters != nullptr && !L.no_coop) {
     // The L2-sharing throttle makes CTAs of one launch wait for each other: ask for a cooperative launch so
     // the runtime guarantees (or refuses) co-residency of the whole grid (grid <= number of SMs, 1 CTA per SM).
     attr[na].id = cudaLaunchAttributeCooperative;
@@ -1026,7 +1026,7 @@ int launch_k3(const K3Launch& L, cudaStream_t st) {
     return cudaLaunchKernelEx(&cfg, k3_cosine_topk_kernel<1, 0, 2, 0>, P);
   };
   cudaError_t e = launch();
-  if (e == cudaErrorCooperativeLaunchTooLarge && L.sync_counters != nullptr) {
+  if (e == cudaErrorCooperativeLaunchTooLarge && L.sync_counters != nullptr && !L.no_coop) {
     // The runtime cannot keep the whole grid resident (fewer SMs than the planner assumed: another tenant, MPS, a green
     // context).  CTAs that wait for each other are then not allowed: drop the L2-sharing throttle -- the only thing
     // that needs co-residency -- and launch again as an ordinary grid.  Same result, more DRAM traffic.

@@ -378,6 +378,9 @@ int rbod_set_option(rbod_gallery* g, const char* key, int64_t value) {
     g->tau_share = value != 0;
   } else if (!strcmp(key, "debug_epi")) {
     g->debug_epi = (int)value;   // bring-up only: results are wrong when non-zero
+  } else if (!strcmp(key, "coop_launch")) {
+    g->coop_launch = value != 0;   // 0 is for profilers that cannot replay cooperative cluster launches (ncu): nothing
+                                   // then guarantees that the CTAs the throttle makes wait for each other are co-resident
   } else if (!strcmp(key, "debug_grid_scale")) {
     if (value < 1 || value > 8) return set_error(RBOD_E_INVAL, "debug_grid_scale must be in [1, 8]");
     g->debug_grid_scale = (int)value;
@@ -758,6 +761,7 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   L.grid = P.grid * std::max(1, g->debug_grid_scale);   // > 1 only under the test hook: the extra CTAs find no unit
   L.smem_bytes = P.smem;
   L.coop_refused = &g->coop_refusals;
+  L.no_coop = !g->coop_launch;
   if (g->l2_sync && dump == nullptr && sample == nullptr) {
     const int workers = P.variant == 2 ? P.grid / 2 : P.grid;
     const int max_tiles = (P.tiles_total + P.slices - 1) / P.slices + 1;

@@ -90,6 +90,7 @@ struct K3Launch {
   unsigned long long* prof;   // optional [16] wait-cycle counters (option k3_prof), see k3_cosine_topk.cu
   int grid;
   size_t smem_bytes;
+  int no_coop;            // profiling only: keep the throttle but skip the cooperative-launch attribute
   int* coop_refused;      // optional host counter: ++ when the cooperative launch was refused and the throttle dropped
 };
 
@@ -203,6 +204,7 @@ struct rbod_gallery {
   int slack = -1;  // -1 = automatic
   int time_k3 = 0;
   int debug_epi = 0;
+  int coop_launch = 1;       // 0 (profiling only): throttled launches do not ask for a cooperative launch
   int debug_grid_scale = 1;  // test hook: launch this many times the planned CTAs (forces a cooperative-launch refusal)
   int coop_refusals = 0;     // K3 launches that fell back to an ordinary grid (rbod_info reports it)
   int k3_prof = 0;        // accumulate where the K3 warp roles wait (rbod_debug_profile reads and clears)
