@@ -22,6 +22,8 @@
 #include "rbod_common.cuh"
 #include "rbod_internal.h"
 
+#include <algorithm>
+
 namespace rbod {
 
 namespace {
@@ -129,41 +131,53 @@ constexpr int FIN_WARPS = FIN_THREADS / 32;
 constexpr int FIN_MAX_SLICES = 2 * FIN_THREADS;
 constexpr int FIN_MAX_KEYS = 8192;
 
-// Certification of one query's answer (one thread).  tau bounds the approximate score of every row that was dropped
-// anywhere; kth is the k-th exact score (if k candidates exist).
-__device__ void certify_query(const FinishArgs& P, int64_t q, float tau, bool have_kth, double kth) {
-  // Certification margin: every row the tensor-core pass dropped has approximate score <= tau, and
-  //   |approx - exact cosine| <= ||q16 - unit(q)|| * max||g16||      (query rounding, Cauchy-Schwarz)
-  //                            + dp * 2^-23 * max||g16||              (fp32 accumulation in the tensor core)
-  //                            + row term
-  // The row term is ||g16 - unit(G)|| for fp32 masters (their 16-bit shadow is rounded independently);
-  // for 16-bit masters g16 IS the stored row and only its norm deviates from 1 by d = stats[1], which
-  // scales the score instead of adding to it: (|tau| + e) * d / (1 - d).
-  // With an fp16 shadow as the search operand, the operand norm is stats[2] and its distance to the stored
-  // row, stats[3], adds to the query term.
+// The error model of the tensor-core pass for one query (one thread): eps bounds |approximate score - exact score in
+// the approximate domain| for EVERY row of the collection, given that tau bounds the approximate scores in play.
+//   |approx - exact cosine| <= ||q16 - unit(q)|| * max||g16||      (query rounding, Cauchy-Schwarz)
+//                            + dp * 2^-23 * max||g16||              (fp32 accumulation in the tensor core)
+//                            + row term
+// The row term is ||g16 - unit(G)|| for fp32 masters (their 16-bit shadow is rounded independently);
+// for 16-bit masters g16 IS the stored row and only its norm deviates from 1 by d = stats[1], which
+// scales the score instead of adding to it: (|tau| + e) * d / (1 - d).
+// With an fp16 shadow as the search operand, the operand norm is stats[2] and its distance to the stored
+// row, stats[3], adds to the query term.
+// DOT collections: nothing is normalised, so every term scales with the query norm |q| and the row term is
+// |q| * ||g16 - g|| (zero for 16-bit masters, whose operand is the stored row).
+// EUCLID collections: the tensor-core pass scores a = q16 . g16 + bias32 with bias32 = fp32(-|g|^2 / 2), an
+// approximation of (key + |q|^2) / 2 for the exact key = -|q - g|^2.  Nothing is normalised, so the dot-product
+// terms are those of DOT, plus the rounding of the bias and of its addition: 2^-23 (|q| G + G^2), G = max |g|.
+struct QueryMargin { float e, row_term, bias_term, eps, gdev; bool unnorm, master16; double qq_half; };
+
+__device__ QueryMargin query_margin(const FinishArgs& P, int64_t q, float tau) {
+  QueryMargin M;
   const float* stats = P.stats;
   const int metric = P.metric;
-  const bool master16 = P.master16 != 0, shadow = P.shadow != 0;
-  const float gmax = (shadow ? stats[2] : stats[0]) * 1.000001f, gdev = stats[1] * 1.000001f;
-  // DOT collections: nothing is normalised, so every term scales with the query norm |q| and the row term is
-  // |q| * ||g16 - g|| (zero for 16-bit masters, whose operand is the stored row).
-  // EUCLID collections: the tensor-core pass scores a = q16 . g16 + bias32 with bias32 = fp32(-|g|^2 / 2), an
-  // approximation of (key + |q|^2) / 2 for the exact key = -|q - g|^2.  Nothing is normalised, so the dot-product
-  // terms are those of DOT, plus the rounding of the bias and of its addition: 2^-23 (|q| G + G^2), G = max |g|.
-  const bool unnorm = metric != RBOD_COSINE;
-  const float qn = unnorm ? (float)sqrt(P.q_qq[q]) * 1.000001f + P.q_dq[q] : 1.0f;
-  const float e = P.q_dq[q] * gmax + (float)P.dp * 1.2e-7f * gmax * qn + (shadow ? stats[3] * 1.000001f * qn : 0.0f);
-  const float row_term = unnorm ? (master16 ? 0.0f : qn * gdev)
-                                : (master16 ? (fabsf(tau) + e) * gdev / (1.0f - gdev) : gdev);
-  const float gbig = gmax + (master16 ? 0.0f : gdev);
-  const float bias_term = metric == RBOD_EUCLID ? 1.2e-7f * (qn * gbig + gbig * gbig) : 0.0f;
-  const float eps = e + row_term + bias_term + fabsf(tau) * 1e-6f + 1e-7f;
-  const double qq_half = metric == RBOD_EUCLID ? 0.5 * P.q_qq[q] : 0.0;
+  M.master16 = P.master16 != 0;
+  const bool shadow = P.shadow != 0;
+  const float gmax = (shadow ? stats[2] : stats[0]) * 1.000001f;
+  M.gdev = stats[1] * 1.000001f;
+  M.unnorm = metric != RBOD_COSINE;
+  const float qn = M.unnorm ? (float)sqrt(P.q_qq[q]) * 1.000001f + P.q_dq[q] : 1.0f;
+  M.e = P.q_dq[q] * gmax + (float)P.dp * 1.2e-7f * gmax * qn + (shadow ? stats[3] * 1.000001f * qn : 0.0f);
+  M.row_term = M.unnorm ? (M.master16 ? 0.0f : qn * M.gdev)
+                        : (M.master16 ? (fabsf(tau) + M.e) * M.gdev / (1.0f - M.gdev) : M.gdev);
+  const float gbig = gmax + (M.master16 ? 0.0f : M.gdev);
+  M.bias_term = metric == RBOD_EUCLID ? 1.2e-7f * (qn * gbig + gbig * gbig) : 0.0f;
+  M.eps = M.e + M.row_term + M.bias_term + fabsf(tau) * 1e-6f + 1e-7f;
+  M.qq_half = metric == RBOD_EUCLID ? 0.5 * P.q_qq[q] : 0.0;
+  return M;
+}
+
+// Certification of one query's answer (one thread).  tau bounds the approximate score of every row that was dropped
+// anywhere; kth is the k-th exact score (if k candidates exist): if tau + eps < kth no dropped row can belong to the
+// top k.  Otherwise the query joins the flag list of the collecting second pass.
+__device__ void certify_query(const FinishArgs& P, int64_t q, float tau, const QueryMargin& M, bool have_kth, double kth) {
+  const int metric = P.metric;
   bool flagged = true;
   if (have_kth) {
     // the k-th exact score in the domain the tensor-core pass works in
-    const double kth_a = metric == RBOD_EUCLID ? 0.5 * kth + qq_half : kth;
-    flagged = !((double)tau + (double)eps < kth_a);
+    const double kth_a = metric == RBOD_EUCLID ? 0.5 * kth + M.qq_half : kth;
+    flagged = !((double)tau + (double)M.eps < kth_a);
   } else {
     // Fewer than k candidates although rows were dropped: the pre-sampled starting threshold sat above this
     // query's k-th best score (possible only when the sample misrepresents the gallery).  The host reruns the
@@ -171,18 +185,101 @@ __device__ void certify_query(const FinishArgs& P, int64_t q, float tau, bool ha
     kth = -INFINITY;
     atomicAdd(P.n_flag + 4, 1);
   }
-  atomic_max_nonneg(P.max_eps, eps);
+  atomic_max_nonneg(P.max_eps, M.eps);
   if (flagged) {
     const int slot = atomicAdd(P.n_flag, 1);
     P.flag_q[slot] = (int)q;
     P.flag_thr[slot] = kth;
     // Threshold for the collecting second pass: every row whose exact score reaches kth has an
     // approximate score above lo (same error model, applied from the exact side).
-    const float kf = (float)(metric == RBOD_EUCLID ? 0.5 * kth + qq_half : kth);
-    const float lo = unnorm ? kf - e - row_term - bias_term
-                            : (master16 ? kf - fabsf(kf) * gdev - e : kf - e - gdev);
+    const float kf = (float)(metric == RBOD_EUCLID ? 0.5 * kth + M.qq_half : kth);
+    const float lo = M.unnorm ? kf - M.e - M.row_term - M.bias_term
+                              : (M.master16 ? kf - fabsf(kf) * M.gdev - M.e : kf - M.e - M.gdev);
     P.flag_lo[slot] = kth == -INFINITY ? -INFINITY : lo - fabsf(kf) * 2e-6f - 2e-7f;
   }
+}
+
+// Exact score of (query, stored row) with the query already widened to fp64 in shared memory: one warp per pair,
+// every lane returns it.  Vector path (dim % 8 == 0, rows 16-byte aligned): the whole row is in flight before the
+// first multiply (up to 4 x 16 bytes per lane for 16-bit rows up to 1024 columns), 8 elements per lane and step.
+template <int METRIC>
+__device__ __forceinline__ void score_step8(const double* __restrict__ q8, const float (&x)[8], double& a, double& b) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double xd = (double)x[i];
+    if (METRIC == RBOD_EUCLID) {
+      const double d = q8[i] - xd;
+      a = fma(d, d, a);
+    } else {
+      a = fma(q8[i], xd, a);
+      if (METRIC == RBOD_COSINE) b = fma(xd, xd, b);
+    }
+  }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& h, int kind16, float (&x)[8]) {
+  const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[2 * i] = h16_to_f32(static_cast<uint16_t>(w[i] & 0xffffu), kind16);
+    x[2 * i + 1] = h16_to_f32(static_cast<uint16_t>(w[i] >> 16), kind16);
+  }
+}
+
+template <int METRIC>
+__device__ __forceinline__ double exact_score_q64(const double* __restrict__ q64, double qq,
+                                                  const float* __restrict__ g32, const uint16_t* __restrict__ g16,
+                                                  int kind16, int dim, int lane) {
+  double a = 0.0, b = 0.0;
+  const bool vec = (dim & 7) == 0 &&
+                   (g32 ? (reinterpret_cast<uintptr_t>(g32) & 15) == 0 : (reinterpret_cast<uintptr_t>(g16) & 15) == 0);
+  if (vec && g32 == nullptr && dim <= 1024) {
+    uint4 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c0 = lane * 8 + 256 * i;
+      h[i] = c0 < dim ? __ldg(reinterpret_cast<const uint4*>(g16 + c0)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c0 = lane * 8 + 256 * i;
+      if (c0 < dim) {
+        float x[8];
+        unpack8(h[i], kind16, x);
+        score_step8<METRIC>(q64 + c0, x, a, b);
+      }
+    }
+  } else if (vec) {
+    for (int c0 = lane * 8; c0 < dim; c0 += 256) {
+      float x[8];
+      if (g32) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g32 + c0));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(g32 + c0 + 4));
+        x[0] = g0.x; x[1] = g0.y; x[2] = g0.z; x[3] = g0.w;
+        x[4] = g1.x; x[5] = g1.y; x[6] = g1.z; x[7] = g1.w;
+      } else {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(g16 + c0)), kind16, x);
+      }
+      score_step8<METRIC>(q64 + c0, x, a, b);
+    }
+  } else {
+    for (int c = lane; c < dim; c += 32) {
+      const double xd = g32 ? (double)g32[c] : (double)h16_to_f32(g16[c], kind16);
+      if (METRIC == RBOD_EUCLID) {
+        const double d = q64[c] - xd;
+        a = fma(d, d, a);
+      } else {
+        a = fma(q64[c], xd, a);
+        if (METRIC == RBOD_COSINE) b = fma(xd, xd, b);
+      }
+    }
+  }
+  a = warp_sum_f64(a);
+  if (METRIC == RBOD_EUCLID) return -a;
+  if (METRIC == RBOD_DOT) return a;
+  b = warp_sum_f64(b);
+  const double den = sqrt(qq) * sqrt(b);
+  return den > 0.0 ? a / den : 0.0;
 }
 
 __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P) {
@@ -191,9 +288,10 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
   __shared__ int s_wsum[FIN_WARPS];
   __shared__ unsigned int s_cnt[3];
   __shared__ uint32_t s_hmax[FIN_WARPS], s_hmin[FIN_WARPS];
-  __shared__ unsigned long long s_sel[K3_MAX_KC];
+  __shared__ unsigned long long s_sel[K3_MAX_KC], s_sel2[K3_MAX_KC];
   __shared__ double s_sc[K3_MAX_KC];
-  __shared__ int s_nsel, s_have_kth;
+  __shared__ float s_cut;
+  __shared__ int s_nsel, s_nres, s_have_kth;
   __shared__ double s_kth;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t q = blockIdx.x;
@@ -213,6 +311,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
   if (tid == 0) {
     s_cnt[0] = s_cnt[1] = s_cnt[2] = 0u;
     s_nsel = 0;
+    s_nres = 0;
     s_have_kth = 0;
     s_kth = -INFINITY;
   }
@@ -306,31 +405,79 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
   __syncthreads();
   const int nsel = min(min(s_nsel, kc), K3_MAX_KC);
 
-  // (3) exact scores, one warp per candidate
+  // kc or more candidates: everything dropped (by a prune of K3 or by the selection above) scores at most the
+  // kc-th best approximate score.  Fewer: no list was ever pruned, only the pre-sampled threshold dropped rows.
+  uint32_t hmin = 0xffffffffu, hbest = 0u;
+  for (int i = lane; i < nsel; i += 32) {
+    hmin = min(hmin, static_cast<uint32_t>(s_sel[i] >> 32));
+    hbest = max(hbest, static_cast<uint32_t>(s_sel[i] >> 32));
+  }
+  hmin = __reduce_min_sync(FULL_MASK, hmin);
+  hbest = __reduce_max_sync(FULL_MASK, hbest);
+  float tau = total >= kc ? ordered_to_f32(hmin) : -INFINITY;
+  if (P.tau_init != nullptr) tau = fmaxf(tau, P.tau_init[q]);
+  const QueryMargin M = query_margin(P, q, tau);
+  // the same bound for the CANDIDATES, whose scores reach up to the best approximate score: for unit-norm 16-bit
+  // masters the row term scales with the score it perturbs
+  const float s_best = nsel > 0 ? fabsf(ordered_to_f32(hbest)) : 0.0f;
+  const float eps_cand = (!M.unnorm && M.master16)
+                             ? M.e + (fmaxf(s_best, fabsf(tau) == INFINITY ? 0.0f : fabsf(tau)) + M.e) * M.gdev / (1.0f - M.gdev) +
+                                   s_best * 1e-6f + 1e-7f
+                             : M.eps + s_best * 1e-6f;
+
+  // (3) exact scores.  Not every candidate needs one: the error model puts every row's approximate score within eps
+  // of its exact score (in the approximate domain), so a candidate more than 2 eps below the k-th best APPROXIMATE
+  // score is beaten by k others exactly as well and cannot be in the answer.  The keys of the candidates that stay
+  // are compacted to the front; the query is widened to fp64 once, into the (now free) key buffer.
+  double* q64 = reinterpret_cast<double*>(keys);
   const float* qv = P.q + q * P.dim;
+  for (int c = tid; c < P.dim; c += FIN_THREADS) q64[c] = (double)qv[c];
+  unsigned long long mykey = 0ull;
+  bool keep = false;
+  if (tid < nsel) {
+    mykey = s_sel[tid];
+    keep = true;
+    if (nsel > k) {
+      int above = 0;
+      for (int i = 0; i < nsel; ++i) above += s_sel[i] > mykey ? 1 : 0;
+      if (above == k - 1) s_cut = ordered_to_f32(static_cast<uint32_t>(mykey >> 32));   // the k-th best approximate score
+    }
+  }
+  __syncthreads();
+  if (tid < nsel && nsel > k)
+    keep = ordered_to_f32(static_cast<uint32_t>(mykey >> 32)) >= s_cut - 2.0f * eps_cand;
+  if (keep) {
+    const int pos = atomicAdd(&s_nres, 1);
+    s_sel2[pos] = mykey;
+  }
+  __syncthreads();
+  const int nres = s_nres;
   const double qq = P.q_qq[q];
-  for (int cnd = warp; cnd < nsel; cnd += FIN_WARPS) {
-    const uint32_t idx = ~static_cast<uint32_t>(s_sel[cnd]);
-    const double sc = exact_pair_score(qv, qq, P.master32 ? P.master32 + (int64_t)idx * P.ld32 : nullptr,
-                                       P.master32 ? nullptr : P.rows16 + (int64_t)idx * P.ld16, P.kind16, P.dim,
-                                       P.metric, lane);
+  for (int cnd = warp; cnd < nres; cnd += FIN_WARPS) {
+    const uint32_t idx = ~static_cast<uint32_t>(s_sel2[cnd]);
+    const float* g32 = P.master32 ? P.master32 + (int64_t)idx * P.ld32 : nullptr;
+    const uint16_t* g16 = P.master32 ? nullptr : P.rows16 + (int64_t)idx * P.ld16;
+    double sc;
+    if (P.metric == RBOD_COSINE) sc = exact_score_q64<RBOD_COSINE>(q64, qq, g32, g16, P.kind16, P.dim, lane);
+    else if (P.metric == RBOD_DOT) sc = exact_score_q64<RBOD_DOT>(q64, qq, g32, g16, P.kind16, P.dim, lane);
+    else sc = exact_score_q64<RBOD_EUCLID>(q64, qq, g32, g16, P.kind16, P.dim, lane);
     if (lane == 0) s_sc[cnd] = sc;
   }
   __syncthreads();
 
-  // (4) rank by counting over the nsel <= 128 candidates
-  if (tid < nsel) {
-    const double s = s_sc[tid];
-    const uint32_t ix = ~static_cast<uint32_t>(s_sel[tid]);
+  // (4) rank by counting over the rescored candidates
+  if (tid < nres) {
+    const double sv = s_sc[tid];
+    const uint32_t ix = ~static_cast<uint32_t>(s_sel2[tid]);
     int rank = 0;
-    for (int i = 0; i < nsel; ++i)
-      if (beats(s_sc[i], ~static_cast<uint32_t>(s_sel[i]), s, ix)) ++rank;
+    for (int i = 0; i < nres; ++i)
+      if (beats(s_sc[i], ~static_cast<uint32_t>(s_sel2[i]), sv, ix)) ++rank;
     if (rank < k) {
-      P.out_scores[q * k + rank] = user_score(s, P.metric);
+      P.out_scores[q * k + rank] = user_score(sv, P.metric);
       P.out_rows[q * k + rank] = (int64_t)ix;
-      if (P.out_scores64) P.out_scores64[q * k + rank] = s;
+      if (P.out_scores64) P.out_scores64[q * k + rank] = sv;
       if (rank == k - 1) {
-        s_kth = s;
+        s_kth = sv;
         s_have_kth = 1;
       }
     }
@@ -338,18 +485,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
   __syncthreads();
 
   // (5) certification
-  if (warp == 0) {
-    uint32_t hmin = 0xffffffffu;
-    for (int i = lane; i < nsel; i += 32) hmin = min(hmin, static_cast<uint32_t>(s_sel[i] >> 32));
-    hmin = __reduce_min_sync(FULL_MASK, hmin);
-    if (lane == 0) {
-      // kc or more candidates: everything dropped (by a prune of K3 or by the selection above) scores at most the
-      // kc-th best approximate score.  Fewer: no list was ever pruned, only the pre-sampled threshold dropped rows.
-      float tau = total >= kc ? ordered_to_f32(hmin) : -INFINITY;
-      if (P.tau_init != nullptr) tau = fmaxf(tau, P.tau_init[q]);
-      if (tau != -INFINITY) certify_query(P, q, tau, s_have_kth != 0, s_kth);   // else exact by construction
-    }
-  }
+  if (tid == 0 && tau != -INFINITY) certify_query(P, q, tau, M, s_have_kth != 0, s_kth);   // else exact by construction
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -562,6 +698,7 @@ int launch_finish(const FinishArgs& A, int64_t Q, cudaStream_t st) {
     return set_error(RBOD_E_INVAL, "finish: k %d / kc %d outside [1, %d]", A.k, A.kc, K3_MAX_KC);
   if (A.slices < 1 || A.slices > FIN_MAX_SLICES)
     return set_error(RBOD_E_INVAL, "finish: %d slices outside [1, %d]", A.slices, FIN_MAX_SLICES);
+  if (A.dim > FIN_MAX_KEYS) return set_error(RBOD_E_UNSUPPORTED, "finish: dim %d > %d", A.dim, FIN_MAX_KEYS);
   if (A.n_cap < 1 || A.n_cap > FIN_MAX_KEYS)
     return set_error(RBOD_E_INVAL, "finish: %d candidates per query exceed %d", A.n_cap, FIN_MAX_KEYS);
   static bool configured[64] = {false};   // raising the dynamic shared-memory limit: once per device and process
@@ -571,7 +708,7 @@ int launch_finish(const FinishArgs& A, int64_t Q, cudaStream_t st) {
     RBOD_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIN_MAX_KEYS * 8));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  finish_kernel<<<(unsigned)Q, FIN_THREADS, (size_t)A.n_cap * 8, st>>>(A);
+  finish_kernel<<<(unsigned)Q, FIN_THREADS, (size_t)std::max(A.n_cap, A.dim) * 8, st>>>(A);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }
