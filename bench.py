@@ -759,6 +759,18 @@ def side_configs(a, E: Env, g, r0, n_local, q_dev):
                         "k2_sharded_max_ulp_vs_single_gpu": float(t.item()), "ok": bool(t.item() <= 1.0),
                         "collectives": "all-reduce of [C, dim] fp64 sums (61 MB) + [C] counts per build"})
             sg.local.close()
+        # the other three delegate types of 32_create_delegate_vector.py:12-26 on the same classes (K2b, one CTA per class,
+        # fp64 like the reference): centroid / weighted re-read the class 2-3 times (L2 hits), the medoid is O(n^2 d)
+        k2b = {}
+        for kind in ("centroid", "weighted", "medoid"):
+            full.segment_delegates(kind, off, row_idx=order)
+            ms_k = E.timed(lambda: full.segment_delegates(kind, off, row_idx=order), 3) / 3
+            k2b[kind] = {"ms": ms_k, "gbs": alg / ms_k / 1e6, "frac_of_hbm": alg / ms_k / 1e6 / hbm}
+        n_c = n // C
+        k2b["medoid"]["fp64_tflops"] = 3.0 * C * n_c * n_c * dim / (k2b["medoid"]["ms"] / 1e3) / 1e12
+        k2b["medoid"]["bound"] = ("fp64 CUDA cores: 3 flop per (member pair, column); no measured fp64 peak on this pool "
+                                  "(nominal B200 fp64: ~37 TFLOP/s)")
+        rec["k2b_other_delegates"] = k2b
         # query-vs-centroid top-5: 10^4 queries against the 10^4 delegates
         cent = Gallery(dim, dtype="f32", capacity=C, device=dev.index)
         cent.upsert(want)
@@ -806,6 +818,43 @@ def side_configs(a, E: Env, g, r0, n_local, q_dev):
                 "search_operand": "fp16 shadow of the fp32 rows; exact rescoring reads the fp32 master"}
 
     guarded("C2", c2)
+
+    # ---- distance menu of util/qdrant_manager.py:61-66 beyond COSINE, 1M x 512 fp32, top-10: EUCLID runs on the
+    # tensor cores (row-bias epilogue), MANHATTAN on the exact fp64 sweep K5
+    def f4():
+        if world != 1:
+            return None
+        n, dim, k = 1_000_000, 512, 10
+        rec = {"config": "f4: 1M x 512 fp32, other distances, top-10, 1 GPU"}
+        gen = torch.Generator(dev).manual_seed(3333)
+        for metric, Q in (("euclid", 10_000), ("manhattan", 256)):
+            gal = Gallery(dim, dtype="f32", metric=metric, capacity=n, device=dev.index)
+            g2 = torch.Generator(dev).manual_seed(3334)
+            for s in range(0, n, 250_000):
+                gal.upsert(torch.randn(250_000, dim, device=dev, generator=g2))
+            q = torch.randn(Q, dim, device=dev, generator=gen)
+            o = (torch.empty((Q, k), dtype=torch.float32, device=dev), torch.empty((Q, k), dtype=torch.int64, device=dev),
+                 torch.empty((Q, k), dtype=torch.float64, device=dev))
+            gal.search(q, k, out=o)
+            ms = E.timed(lambda: gal.search(q, k, out=o), 2) / 2
+            rows = gal.get_rows(torch.arange(n, device=dev))
+            d = torch.cdist(q[:32].double(), rows.double(), p=2.0 if metric == "euclid" else 1.0)
+            same = bool((torch.topk(d, k, dim=1, largest=False).indices == o[1][:32]).all().item())
+            r = {"queries": Q, "ms": ms, "qps": Q / ms * 1e3, "ids_identical_to_fp64_cdist": same}
+            if metric == "manhattan":
+                r["fp64_tflops"] = 2.0 * Q * n * dim / (ms / 1e3) / 1e12
+                r["bound"] = ("fp64 CUDA cores (K5): DADD + |.| per (query, row, column); no measured fp64 peak on this "
+                              "pool (nominal B200 fp64: ~37 TFLOP/s)")
+            else:
+                r["tflops"] = 2.0 * Q * n * dim / (ms / 1e3) / 1e12
+                r["bound"] = "tensor (K3 with the -|g|^2/2 row bias), of the measured bf16 burst peak"
+                r["frac"] = r["tflops"] / burst
+            rec[metric] = r
+            gal.close()
+            del rows, d
+        return rec
+
+    guarded("f4", f4)
 
     # ---- C5: 100M x 768 fp16 over 8 GPUs (12.5M rows = 19.2 GB per GPU), batch sweep 1..65536, top-10
     def c5():
