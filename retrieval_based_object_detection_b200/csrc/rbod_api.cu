@@ -290,7 +290,7 @@ int rbod_destroy(rbod_gallery* g) {
   if (g->stats) cudaFree(g->stats);
   DevBuf* bufs[] = {&g->stage_rows, &g->stage_slots, &g->stage_norms, &g->q32, &g->q16, &g->q_dq, &g->q_qq, &g->tau_shared,
                     &g->lists, &g->list_cnt, &g->out_scores,
-                    &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->flag_lo, &g->fq16, &g->groupmax, &g->tau_init, &g->coll_score,
+                    &g->out_rows, &g->out_scores64, &g->flags, &g->flag_q, &g->flag_thr, &g->flag_lo, &g->flag_row, &g->sweep_ctl, &g->fq16, &g->groupmax, &g->tau_init, &g->coll_score,
                     &g->coll_idx, &g->coll_cnt, &g->mask_dev, &g->dump, &g->sync_counters, &g->prof, &g->seg_idx, &g->seg_off, &g->seg_out,
                     &g->seg_partials, &g->seg_prefix, &g->seg_arrive, &g->seg_scratch, &g->seg_member, &g->gather_idx,
                     &g->gather_out, &g->dist_q64, &g->dist_thr, &g->dist_ctl};
@@ -1129,22 +1129,44 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     }
   }
   if (n_sweep > 0) {
-    const int cap = 4096, batch = 32;
+    const int cap = 4096, batch = 32, max_tighten = 12;
     RBOD_TRY(g->coll_score.ensure((size_t)batch * cap * 8));
     RBOD_TRY(g->coll_idx.ensure((size_t)batch * cap * 4));
     RBOD_TRY(g->coll_cnt.ensure((size_t)batch * 4));
+    RBOD_TRY(g->flag_row.ensure((size_t)n_sweep * 4));
+    RBOD_TRY(g->sweep_ctl.ensure((size_t)(batch + 1) * 4));
+    RBOD_CUDA(cudaMemsetAsync(g->flag_row.p, 0xff, (size_t)n_sweep * 4, st));   // no row bound yet
+    int* d_active = g->sweep_ctl.as<int>();
+    int* d_nactive = d_active + batch;
     for (int f0 = 0; f0 < n_sweep; f0 += batch) {
       const int nf = std::min(batch, n_sweep - f0);
       RBOD_CUDA(cudaMemsetAsync(g->coll_cnt.p, 0, (size_t)batch * 4, st));
-      RBOD_TRY(launch_exact_collect(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim,
-                                    g->dp, g->metric, g->rows, static_cast<const uint32_t*>(mask_dev),
-                                    g->flag_q.as<int>(), g->flag_thr.as<double>(), f0, nf, cap,
-                                    g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
-                                    g->num_sms, st));
+      const int* active = nullptr;   // first sweep: every query of the batch
+      for (int it = 0;; ++it) {
+        RBOD_TRY(launch_exact_collect(q_dev, g->q_qq.as<double>(), g->master32, g->rows16, g->kind16, g->dim, g->dim,
+                                      g->dp, g->metric, g->rows, static_cast<const uint32_t*>(mask_dev),
+                                      g->flag_q.as<int>(), g->flag_thr.as<double>(), g->flag_row.as<uint32_t>(), active, f0,
+                                      nf, cap, g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(),
+                                      g->coll_cnt.as<int>(), g->num_sms, st));
+        // lists that overflowed (a wide cluster of ties around the k-th score) are tightened to the k-th best
+        // (score, row) pair they did record and swept again, the others are left as they are
+        RBOD_CUDA(cudaMemsetAsync(d_nactive, 0, 4, st));
+        RBOD_TRY(launch_tighten(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(), f0, nf,
+                                cap, k, g->flag_thr.as<double>(), g->flag_row.as<uint32_t>(), d_active, d_nactive, st));
+        launches += 2;
+        int n_active = 0;
+        RBOD_CUDA(cudaMemcpyAsync(&n_active, d_nactive, 4, cudaMemcpyDeviceToHost, st));
+        RBOD_CUDA(cudaStreamSynchronize(st));
+        if (n_active == 0) break;
+        if (it >= max_tighten)
+          return set_error(RBOD_E_OVERFLOW, "rbod_search: a tie cluster around the k-th score did not resolve in %d sweeps",
+                           max_tighten);
+        active = d_active;
+      }
       RBOD_TRY(launch_select_collected(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(),
                                        g->coll_cnt.as<int>(), g->flag_q.as<int>(), f0, nf, cap, k, g->metric, d_scores,
                                        d_rows, d_scores64, d_flags + 1, st));
-      launches += 2;
+      ++launches;
     }
     RBOD_CUDA(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
   }

@@ -650,3 +650,30 @@ def test_upsert_accepts_device_resident_slots(G):
     rows = g.get_rows(torch.tensor([5, 8], device="cuda"))
     assert torch.allclose(rows, y / y.norm(dim=1, keepdim=True), atol=1e-6)
     g.close()
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_tie_cluster_wider_than_the_sweep_list_still_answers(G, dtype):
+    """More identical rows than even the exact sweep records per query (4096) -- the same image upserted under many
+    ids, or a block of all-equal vectors: the search used to fail with RBOD_E_OVERFLOW.  The sweep now tightens an
+    overflowing list to the k-th best (score, row) pair it did record and sweeps again, so the answer is the k
+    smallest row slots of the tie, exactly as the (score desc, id asc) order says."""
+    n, dim = 14_000, 256
+    x = O.synthetic_unit_rows(n, dim, seed=77)
+    x[3000:9500] = x[17]                                   # 6501 copies of row 17
+    g = G(dim, dtype=dtype, capacity=n)
+    g.upsert(x)
+    stored = g.get_rows(np.arange(n))
+    q = np.stack([x[17], x[12000], x[17] + 0.01 * x[12000]]).astype(np.float32)
+    for k in (10, 100):
+        res = g.search(q, k, want_scores64=True)
+        ws, wi = OC.cosine_topk(q, stored, k)              # sequential C oracle: identical rows -> identical scores
+        assert np.array_equal(res.rows, wi), (k, int((res.rows != wi).any(axis=1).sum()))
+        assert list(res.rows[0][:4]) == [17, 3000, 3001, 3002]
+        assert np.allclose(res.scores64, ws, rtol=1e-5, atol=1e-9)
+        assert res.stats["sweep_queries"] >= 1
+    mask = np.ones(n, dtype=bool)
+    mask[3000:3050] = False                                # with a row mask the tie starts later
+    res = g.search(q[:1], 10, row_mask=O.pack_row_mask(mask))
+    assert list(res.rows[0]) == [17] + list(range(3050, 3059))
+    g.close()
