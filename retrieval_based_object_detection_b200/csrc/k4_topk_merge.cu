@@ -226,6 +226,42 @@ __device__ __forceinline__ void unpack8(const uint4& h, int kind16, float (&x)[8
   }
 }
 
+// A stored 16-bit row of up to 1024 columns as this lane's share of it: 8 consecutive elements per 256-column step.
+struct RowRegs { uint4 h[4]; };
+__device__ __forceinline__ void load_row16(RowRegs& R, const uint16_t* __restrict__ g16, int dim, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c0 = lane * 8 + 256 * i;
+    R.h[i] = c0 < dim ? __ldg(reinterpret_cast<const uint4*>(g16 + c0)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+template <int METRIC>
+__device__ __forceinline__ double finish_score(double a, double b, double qq) {
+  a = warp_sum_f64(a);
+  if (METRIC == RBOD_EUCLID) return -a;
+  if (METRIC == RBOD_DOT) return a;
+  b = warp_sum_f64(b);
+  const double den = sqrt(qq) * sqrt(b);
+  return den > 0.0 ? a / den : 0.0;
+}
+
+template <int METRIC>
+__device__ __forceinline__ double exact_score_regs(const double* __restrict__ q64, double qq, const RowRegs& R, int kind16,
+                                                   int dim, int lane) {
+  double a = 0.0, b = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c0 = lane * 8 + 256 * i;
+    if (c0 < dim) {
+      float x[8];
+      unpack8(R.h[i], kind16, x);
+      score_step8<METRIC>(q64 + c0, x, a, b);
+    }
+  }
+  return finish_score<METRIC>(a, b, qq);
+}
+
 template <int METRIC>
 __device__ __forceinline__ double exact_score_q64(const double* __restrict__ q64, double qq,
                                                   const float* __restrict__ g32, const uint16_t* __restrict__ g16,
@@ -233,23 +269,7 @@ __device__ __forceinline__ double exact_score_q64(const double* __restrict__ q64
   double a = 0.0, b = 0.0;
   const bool vec = (dim & 7) == 0 &&
                    (g32 ? (reinterpret_cast<uintptr_t>(g32) & 15) == 0 : (reinterpret_cast<uintptr_t>(g16) & 15) == 0);
-  if (vec && g32 == nullptr && dim <= 1024) {
-    uint4 h[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c0 = lane * 8 + 256 * i;
-      h[i] = c0 < dim ? __ldg(reinterpret_cast<const uint4*>(g16 + c0)) : make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c0 = lane * 8 + 256 * i;
-      if (c0 < dim) {
-        float x[8];
-        unpack8(h[i], kind16, x);
-        score_step8<METRIC>(q64 + c0, x, a, b);
-      }
-    }
-  } else if (vec) {
+  if (vec) {
     for (int c0 = lane * 8; c0 < dim; c0 += 256) {
       float x[8];
       if (g32) {
@@ -274,12 +294,38 @@ __device__ __forceinline__ double exact_score_q64(const double* __restrict__ q64
       }
     }
   }
-  a = warp_sum_f64(a);
-  if (METRIC == RBOD_EUCLID) return -a;
-  if (METRIC == RBOD_DOT) return a;
-  b = warp_sum_f64(b);
-  const double den = sqrt(qq) * sqrt(b);
-  return den > 0.0 ? a / den : 0.0;
+  return finish_score<METRIC>(a, b, qq);
+}
+
+// Exact scores of the candidates s_sel2[0..nres): warp w takes candidates w, w + 8, ...  For 16-bit masters up to 1024
+// columns the NEXT candidate's row is already in flight while the current one is scored (software pipelining: the
+// rescoring is a gather of 1.5 KB rows from all over HBM, and its latency, not its arithmetic, is what costs).
+template <int METRIC>
+__device__ __forceinline__ void rescore_candidates(const FinishArgs& P, const double* __restrict__ q64, double qq,
+                                                   const unsigned long long* __restrict__ sel, int nres,
+                                                   double* __restrict__ out_sc, int warp, int lane) {
+  const bool pipelined = P.master32 == nullptr && (P.dim & 7) == 0 && P.dim <= 1024 &&
+                         (reinterpret_cast<uintptr_t>(P.rows16) & 15) == 0 && (P.ld16 & 7) == 0;
+  if (pipelined) {
+    RowRegs cur, nxt;
+    int cnd = warp;
+    if (cnd < nres) load_row16(cur, P.rows16 + (int64_t)(~static_cast<uint32_t>(sel[cnd])) * P.ld16, P.dim, lane);
+    for (; cnd < nres; cnd += FIN_WARPS) {
+      const int nx = cnd + FIN_WARPS;
+      if (nx < nres) load_row16(nxt, P.rows16 + (int64_t)(~static_cast<uint32_t>(sel[nx])) * P.ld16, P.dim, lane);
+      const double sc = exact_score_regs<METRIC>(q64, qq, cur, P.kind16, P.dim, lane);
+      if (lane == 0) out_sc[cnd] = sc;
+      cur = nxt;
+    }
+    return;
+  }
+  for (int cnd = warp; cnd < nres; cnd += FIN_WARPS) {
+    const uint32_t idx = ~static_cast<uint32_t>(sel[cnd]);
+    const float* g32 = P.master32 ? P.master32 + (int64_t)idx * P.ld32 : nullptr;
+    const uint16_t* g16 = P.master32 ? nullptr : P.rows16 + (int64_t)idx * P.ld16;
+    const double sc = exact_score_q64<METRIC>(q64, qq, g32, g16, P.kind16, P.dim, lane);
+    if (lane == 0) out_sc[cnd] = sc;
+  }
 }
 
 __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P) {
@@ -453,16 +499,9 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
   __syncthreads();
   const int nres = s_nres;
   const double qq = P.q_qq[q];
-  for (int cnd = warp; cnd < nres; cnd += FIN_WARPS) {
-    const uint32_t idx = ~static_cast<uint32_t>(s_sel2[cnd]);
-    const float* g32 = P.master32 ? P.master32 + (int64_t)idx * P.ld32 : nullptr;
-    const uint16_t* g16 = P.master32 ? nullptr : P.rows16 + (int64_t)idx * P.ld16;
-    double sc;
-    if (P.metric == RBOD_COSINE) sc = exact_score_q64<RBOD_COSINE>(q64, qq, g32, g16, P.kind16, P.dim, lane);
-    else if (P.metric == RBOD_DOT) sc = exact_score_q64<RBOD_DOT>(q64, qq, g32, g16, P.kind16, P.dim, lane);
-    else sc = exact_score_q64<RBOD_EUCLID>(q64, qq, g32, g16, P.kind16, P.dim, lane);
-    if (lane == 0) s_sc[cnd] = sc;
-  }
+  if (P.metric == RBOD_COSINE) rescore_candidates<RBOD_COSINE>(P, q64, qq, s_sel2, nres, s_sc, warp, lane);
+  else if (P.metric == RBOD_DOT) rescore_candidates<RBOD_DOT>(P, q64, qq, s_sel2, nres, s_sc, warp, lane);
+  else rescore_candidates<RBOD_EUCLID>(P, q64, qq, s_sel2, nres, s_sc, warp, lane);
   __syncthreads();
 
   // (4) rank by counting over the rescored candidates
