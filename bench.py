@@ -613,7 +613,7 @@ def run_b200(a):
     flops_per_launch = 2.0 * a.queries * n_local * a.dim
     achieved = flops_per_launch / (k3_avg_ms / 1e3) / 1e12 if k3_avg_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "k3_cosine_topk_kernel", "achieved": achieved, "peak": sus,
-                "unit": "TFLOP/s", "frac": achieved / sus, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / sus, "frac_of_burst": achieved / burst, "traffic": None,
                 "peak_source": f"{E.peak_src} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
                 "algorithmic": f"2*Q*N_local*D = {flops_per_launch:.3e} flop per launch", "kernel_ms": k3_avg_ms,
                 "kernel_share_of_step": k3_avg_ms * a.steps / ms_dev if ms_dev > 0 else None}
