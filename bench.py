@@ -767,9 +767,11 @@ def side_configs(a, E: Env, g, r0, n_local, q_dev):
             ms_k = E.timed(lambda: full.segment_delegates(kind, off, row_idx=order), 3) / 3
             k2b[kind] = {"ms": ms_k, "gbs": alg / ms_k / 1e6, "frac_of_hbm": alg / ms_k / 1e6 / hbm}
         n_c = n // C
-        k2b["medoid"]["fp64_tflops"] = 3.0 * C * n_c * n_c * dim / (k2b["medoid"]["ms"] / 1e3) / 1e12
-        k2b["medoid"]["bound"] = ("fp64 CUDA cores: 3 flop per (member pair, column); no measured fp64 peak on this pool "
-                                  "(nominal B200 fp64: ~37 TFLOP/s)")
+        nb = (n_c + 3) // 4
+        pairs = nb * (nb + 1) // 2 * 16                  # the tiled kernel computes 4x4 blocks of the upper triangle only
+        k2b["medoid"]["fp64_tflops"] = 3.0 * C * pairs * dim / (k2b["medoid"]["ms"] / 1e3) / 1e12
+        k2b["medoid"]["bound"] = ("fp64 CUDA cores: 3 flop (DADD, DFMA) per (member pair of the upper triangle, column); no "
+                                  "measured fp64 peak on this pool (nominal B200 fp64: ~37 TFLOP/s)")
         rec["k2b_other_delegates"] = k2b
         # query-vs-centroid top-5: 10^4 queries against the 10^4 delegates
         cent = Gallery(dim, dtype="f32", capacity=C, device=dev.index)

@@ -625,16 +625,23 @@ int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx
   if (n_classes > 0x7fffffffll) return set_error(RBOD_E_INVAL, "rbod_segment_delegates: too many classes");
   RBOD_CUDA(cudaSetDevice(g->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int64_t first = 0, total = 0;
-  if (is_device_ptr(offsets)) {
-    RBOD_CUDA(cudaMemcpyAsync(&first, offsets, 8, cudaMemcpyDeviceToHost, st));
-    RBOD_CUDA(cudaMemcpyAsync(&total, offsets + n_classes, 8, cudaMemcpyDeviceToHost, st));
-    RBOD_CUDA(cudaStreamSynchronize(st));
-  } else {
-    first = offsets[0];
-    total = offsets[n_classes];
-    for (int64_t c = 0; c < n_classes; ++c)
-      if (offsets[c + 1] < offsets[c]) return set_error(RBOD_E_INVAL, "rbod_segment_delegates: offsets not monotone");
+  int64_t first = 0, total = 0, max_class = 0;
+  {
+    // the class sizes decide which medoid kernel a class takes: a device-resident offsets array is read back once
+    std::vector<int64_t> off_host;
+    const int64_t* oh = offsets;
+    if (is_device_ptr(offsets)) {
+      off_host.resize((size_t)n_classes + 1);
+      RBOD_CUDA(cudaMemcpyAsync(off_host.data(), offsets, (size_t)(n_classes + 1) * 8, cudaMemcpyDeviceToHost, st));
+      RBOD_CUDA(cudaStreamSynchronize(st));
+      oh = off_host.data();
+    }
+    first = oh[0];
+    total = oh[n_classes];
+    for (int64_t c = 0; c < n_classes; ++c) {
+      if (oh[c + 1] < oh[c]) return set_error(RBOD_E_INVAL, "rbod_segment_delegates: offsets not monotone");
+      max_class = std::max(max_class, oh[c + 1] - oh[c]);
+    }
   }
   if (first < 0 || total < first) return set_error(RBOD_E_INVAL, "rbod_segment_delegates: bad offsets");
   if (!row_idx && total > g->rows) return set_error(RBOD_E_RANGE, "rbod_segment_delegates: offsets exceed row count");
@@ -662,7 +669,7 @@ int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx
   RBOD_TRY(launch_segment_delegates(g->master32, g->rows16, g->kind16, g->dim, g->dim, g->dp, g->rows,
                                     static_cast<const int64_t*>(idx_dev), static_cast<const int64_t*>(off_dev),
                                     n_classes, kind, alpha, g->metric == RBOD_COSINE, g->seg_scratch.as<double>(), dst,
-                                    mem_dst, g->flags.as<int>() + 2, st));
+                                    mem_dst, g->flags.as<int>() + 2, max_class, st));
   if (!out_dev)
     RBOD_CUDA(cudaMemcpyAsync(out_vectors, dst, (size_t)n_classes * g->dim * 4, cudaMemcpyDeviceToHost, st));
   if (out_member_rows && !mem_dev)

@@ -115,7 +115,7 @@ int launch_segment_finish(const double* sums, const int64_t* counts, int64_t n_c
 int launch_segment_delegates(const float* master32, const uint16_t* rows16, int kind16, int dim, int64_t ld32,
                              int64_t ld16, int64_t n_valid, const int64_t* row_idx, const int64_t* offsets,
                              int64_t n_classes, int kind, double alpha, int cosine, double* scratch, float* out,
-                             int64_t* out_member, int* err_flag, cudaStream_t st);
+                             int64_t* out_member, int* err_flag, int64_t max_class_rows, cudaStream_t st);
 // K3
 int k3_configure(int device);
 int k3_plan(int variant, int want_kbs, int dp, int smem_optin, int allow_hybrid, int* num_stages,
