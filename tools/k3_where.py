@@ -42,7 +42,7 @@ def main():
     out = (torch.empty((a.queries, a.k), dtype=torch.float32, device=dev), torch.empty((a.queries, a.k), dtype=torch.int64, device=dev),
            torch.empty((a.queries, a.k), dtype=torch.float64, device=dev))
     g.set_option("time_k3", 1)
-    defaults = {"k3_kbs": 0, "k3_variant": 0, "hybrid": 1, "l2_sync": 1, "presample": 1, "tau_share": 1, "debug_epi": 0,
+    defaults = {"k3_kbs": 0, "k3_variant": -1, "hybrid": 1, "l2_sync": 1, "presample": 1, "tau_share": 1, "debug_epi": 0,
                 "sync_window": 16, "sync_lead": 4}
     ref_rows = None
     for spec in a.sets.split(";"):
@@ -74,7 +74,7 @@ def main():
             same = bool((ref_rows == out[1]).all().item())
         cyc, epi = max(p["cta_cycles"], 1), max(p["epi_warps"], 1)
         ctas = max(p["ctas"], 1)
-        rec = {"opts": spec or "defaults", "ms": round(min(ms), 3), "k3_ms": round(min(k3), 3),
+        rec = {"opts": spec or "defaults", "ms_p50": round(sorted(ms)[len(ms) // 2], 3), "ms": round(min(ms), 3), "k3_ms": round(min(k3), 3),
                "tflops": round(2.0 * a.queries * a.rows * a.dim / (min(k3) / 1e3) / 1e12, 1), "slices": st["slices"],
                "kc": st["candidates"], "same_ids_as_first": same,
                "mma_wait_data": round(p["mma_wait_data"] / cyc, 4), "mma_wait_accumulator": round(p["mma_wait_accumulator"] / cyc, 4),
