@@ -68,9 +68,9 @@ __global__ void __launch_bounds__(256, 1)
 dist_collect_kernel(const double* __restrict__ q64, const float* __restrict__ master32,
                     const uint16_t* __restrict__ rows16, int kind16, int dim, int64_t ld32, int64_t ld16,
                     int64_t n_rows, int64_t row0, int64_t stride, const uint32_t* __restrict__ row_mask,
-                    const double* __restrict__ thr, const int* __restrict__ active, const double* __restrict__ qnorm,
-                    int nf, int cap, double* __restrict__ coll_key, uint32_t* __restrict__ coll_idx,
-                    int* __restrict__ coll_cnt) {
+                    const double* __restrict__ thr, const uint32_t* __restrict__ thr_row, const int* __restrict__ active,
+                    const double* __restrict__ qnorm, int nf, int cap, double* __restrict__ coll_key,
+                    uint32_t* __restrict__ coll_idx, int* __restrict__ coll_cnt) {
   extern __shared__ __align__(16) uint8_t k5_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool f32rows = master32 != nullptr;
@@ -78,8 +78,10 @@ dist_collect_kernel(const double* __restrict__ q64, const float* __restrict__ ma
   double* qs = reinterpret_cast<double*>(k5_smem);                                   // [2][NQ][K5_CH]
   uint32_t* xs = reinterpret_cast<uint32_t*>(k5_smem + (size_t)2 * NQ * K5_CH * 8);  // [2][8][32][pitch]
   __shared__ double thr_s[32], qn_s[32];
+  __shared__ uint32_t thr_row_s[32];   // with thr_s a (key, row) pair bound: rows tying with the key count up to this row
   if (threadIdx.x < 32) {
     thr_s[threadIdx.x] = (threadIdx.x < nf && active[threadIdx.x]) ? thr[threadIdx.x] : INFINITY;
+    thr_row_s[threadIdx.x] = (threadIdx.x < nf && thr_row != nullptr) ? thr_row[threadIdx.x] : 0xffffffffu;
     qn_s[threadIdx.x] = threadIdx.x < nf ? qnorm[threadIdx.x] : 0.0;
   }
   __syncthreads();
@@ -191,7 +193,10 @@ dist_collect_kernel(const double* __restrict__ q64, const float* __restrict__ ma
           } else {
             key = -acc[f];
           }
-          if (key >= thr_s[f]) {             // thr_s is +inf for slots beyond the batch and for finished queries
+          // thr_s is +inf for slots beyond the batch and for finished queries; a list that overflowed was tightened to
+          // the k-th best (key, row) pair it had recorded, so a cluster of duplicates wider than the list resolves to
+          // its smallest row slots instead of overflowing for ever
+          if (key > thr_s[f] || (key == thr_s[f] && (uint32_t)r <= thr_row_s[f])) {
             const int slot = atomicAdd(coll_cnt + f, 1);
             if (slot < cap) {
               coll_key[(size_t)f * cap + slot] = key;
@@ -220,8 +225,8 @@ __device__ __forceinline__ unsigned long long f64_to_ordered(double d) {
 __global__ void __launch_bounds__(256)
 dist_select_kernel(const double* __restrict__ coll_key, const uint32_t* __restrict__ coll_idx,
                    int* __restrict__ coll_cnt, const int* __restrict__ qsel, int cap, int p2_max, int k, int sample,
-                   int metric, double* __restrict__ thr, int* __restrict__ active, int* __restrict__ n_active,
-                   float* __restrict__ out_scores, int64_t* __restrict__ out_rows, double* __restrict__ out_keys) {
+                   int metric, double* __restrict__ thr, uint32_t* __restrict__ thr_row, int* __restrict__ active,
+                   int* __restrict__ n_active, float* __restrict__ out_scores, int64_t* __restrict__ out_rows, double* __restrict__ out_keys) {
   extern __shared__ __align__(16) uint8_t k5_sel_smem[];
   unsigned long long* sk = reinterpret_cast<unsigned long long*>(k5_sel_smem);       // [p2_max] ordered keys
   uint32_t* si = reinterpret_cast<uint32_t*>(k5_sel_smem + (size_t)p2_max * 8);      // [p2_max] rows
@@ -275,6 +280,8 @@ dist_select_kernel(const double* __restrict__ coll_key, const uint32_t* __restri
     const unsigned long long o = sk[k - 1];
     const unsigned long long bits = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
     thr[f] = __longlong_as_double((long long)bits);
+    // a sampled threshold must admit every tie (the sample saw only some rows); an overflowed list's bound is the pair
+    if (thr_row != nullptr) thr_row[f] = sample ? 0xffffffffu : si[k - 1];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -296,8 +303,9 @@ int launch_dist_widen_queries(const float* q, const int* qsel, int nf, int dim, 
 
 int launch_dist_collect(int metric, const double* q64, const float* master32, const uint16_t* rows16, int kind16,
                         int dim, int64_t ld32, int64_t ld16, int64_t n_rows, int64_t row0, int64_t stride,
-                        const uint32_t* row_mask, const double* thr, const int* active, const double* qnorm, int nf,
-                        int cap, double* coll_key, uint32_t* coll_idx, int* coll_cnt, int num_sms, cudaStream_t st) {
+                        const uint32_t* row_mask, const double* thr, const uint32_t* thr_row, const int* active,
+                        const double* qnorm, int nf, int cap, double* coll_key, uint32_t* coll_idx, int* coll_cnt,
+                        int num_sms, cudaStream_t st) {
   if (nf <= 0 || n_rows <= 0) return RBOD_OK;
   if (nf > 32) return set_error(RBOD_E_INVAL, "dist_collect: at most 32 queries per pass");
   const int64_t rows_visited = (n_rows - row0 + stride - 1) / stride;
@@ -310,7 +318,7 @@ int launch_dist_collect(int metric, const double* q64, const float* master32, co
     RBOD_CUDA(cudaFuncSetAttribute(dist_collect_kernel<METRIC, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)smem));                                                                \
     dist_collect_kernel<METRIC, NQ><<<grid, 256, smem, st>>>(q64, master32, rows16, kind16, dim, ld32, ld16,    \
-                                                             n_rows, row0, stride, row_mask, thr, active,      \
+                                                             n_rows, row0, stride, row_mask, thr, thr_row, active, \
                                                              qnorm, nf, cap, coll_key, coll_idx, coll_cnt);    \
   } while (0)
   // 8 accumulators per lane for batches of up to 8 queries (single-query searches of the scripts), 32 otherwise
@@ -329,16 +337,16 @@ int launch_dist_collect(int metric, const double* q64, const float* master32, co
 }
 
 int launch_dist_select(const double* coll_key, const uint32_t* coll_idx, int* coll_cnt, const int* qsel, int nf,
-                       int cap, int k, int sample, int metric, double* thr, int* active, int* n_active,
-                       float* out_scores, int64_t* out_rows, double* out_keys, cudaStream_t st) {
+                       int cap, int k, int sample, int metric, double* thr, uint32_t* thr_row, int* active,
+                       int* n_active, float* out_scores, int64_t* out_rows, double* out_keys, cudaStream_t st) {
   if (nf <= 0) return RBOD_OK;
   int p2 = 1;
   while (p2 < cap) p2 <<= 1;
   const size_t smem = (size_t)p2 * 12;
   if (smem > 200 * 1024) return set_error(RBOD_E_INVAL, "dist_select: list capacity %d too large", cap);
   RBOD_CUDA(cudaFuncSetAttribute(dist_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dist_select_kernel<<<nf, 256, smem, st>>>(coll_key, coll_idx, coll_cnt, qsel, cap, p2, k, sample, metric, thr, active,
-                                            n_active, out_scores, out_rows, out_keys);
+  dist_select_kernel<<<nf, 256, smem, st>>>(coll_key, coll_idx, coll_cnt, qsel, cap, p2, k, sample, metric, thr, thr_row,
+                                            active, n_active, out_scores, out_rows, out_keys);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

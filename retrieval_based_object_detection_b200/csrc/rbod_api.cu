@@ -818,7 +818,7 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
   RBOD_TRY(to_device(queries, (size_t)Q * g->dim * 4, g->q32, st, &qd));
   const float* q_dev = static_cast<const float*>(qd);
   RBOD_TRY(g->dist_q64.ensure((size_t)batch * g->dim * 8));
-  RBOD_TRY(g->dist_thr.ensure((size_t)2 * batch * 8));       // thresholds, then the batch's query norms
+  RBOD_TRY(g->dist_thr.ensure((size_t)2 * batch * 8 + (size_t)batch * 4));   // thresholds, query norms, row bounds
   RBOD_TRY(g->dist_ctl.ensure((size_t)(2 * batch + 1) * 4));
   RBOD_TRY(g->coll_score.ensure((size_t)batch * cap * 8));
   RBOD_TRY(g->coll_idx.ensure((size_t)batch * cap * 4));
@@ -828,6 +828,7 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
   int* d_nactive = d_qsel + 2 * batch;
   double* d_thr = g->dist_thr.as<double>();
   double* d_qnorm = d_thr + batch;
+  uint32_t* d_thr_row = reinterpret_cast<uint32_t*>(d_qnorm + batch);
   std::vector<double> h_thr(batch, -INFINITY);
   std::vector<int> h_ctl(2 * batch + 1);
   const int64_t sample_stride = (g->rows + sample_cap - 1) / sample_cap;   // > 1 iff more than `sample_cap` rows
@@ -840,17 +841,18 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
     h_ctl[2 * batch] = 0;
     RBOD_CUDA(cudaMemcpyAsync(d_qsel, h_ctl.data(), h_ctl.size() * 4, cudaMemcpyHostToDevice, st));
     RBOD_CUDA(cudaMemcpyAsync(d_thr, h_thr.data(), (size_t)batch * 8, cudaMemcpyHostToDevice, st));
+    RBOD_CUDA(cudaMemsetAsync(d_thr_row, 0xff, (size_t)batch * 4, st));   // no row bound: every tie with the threshold counts
     RBOD_CUDA(cudaMemsetAsync(g->coll_cnt.p, 0, (size_t)batch * 4, st));
     if (nf < batch) RBOD_CUDA(cudaMemsetAsync(g->dist_q64.p, 0, (size_t)batch * g->dim * 8, st));   // zero rows pad the batch
     RBOD_TRY(launch_dist_widen_queries(q_dev, d_qsel, nf, g->dim, g->dist_q64.as<double>(), d_qnorm, st));
     ++*launches;
     if (sample_stride > 1) {
       RBOD_TRY(launch_dist_collect(g->metric, g->dist_q64.as<double>(), g->master32, g->rows16, g->kind16, g->dim,
-                                   g->dim, g->dp, g->rows, 0, sample_stride, mask_dev, d_thr, d_active, d_qnorm, nf, cap,
+                                   g->dim, g->dp, g->rows, 0, sample_stride, mask_dev, d_thr, d_thr_row, d_active, d_qnorm, nf, cap,
                                    g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
                                    g->num_sms, st));
       RBOD_TRY(launch_dist_select(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
-                                  d_qsel, nf, cap, k, 1, g->metric, d_thr, d_active, d_nactive, d_scores, d_rows,
+                                  d_qsel, nf, cap, k, 1, g->metric, d_thr, d_thr_row, d_active, d_nactive, d_scores, d_rows,
                                   d_keys, st));
       *launches += 2;
     }
@@ -858,11 +860,11 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
     for (; iter < max_iter && left > 0; ++iter) {
       RBOD_CUDA(cudaMemsetAsync(d_nactive, 0, 4, st));
       RBOD_TRY(launch_dist_collect(g->metric, g->dist_q64.as<double>(), g->master32, g->rows16, g->kind16, g->dim,
-                                   g->dim, g->dp, g->rows, 0, 1, mask_dev, d_thr, d_active, d_qnorm, nf, cap,
+                                   g->dim, g->dp, g->rows, 0, 1, mask_dev, d_thr, d_thr_row, d_active, d_qnorm, nf, cap,
                                    g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
                                    g->num_sms, st));
       RBOD_TRY(launch_dist_select(g->coll_score.as<double>(), g->coll_idx.as<uint32_t>(), g->coll_cnt.as<int>(),
-                                  d_qsel, nf, cap, k, 0, g->metric, d_thr, d_active, d_nactive, d_scores, d_rows,
+                                  d_qsel, nf, cap, k, 0, g->metric, d_thr, d_thr_row, d_active, d_nactive, d_scores, d_rows,
                                   d_keys, st));
       *launches += 2;
       RBOD_CUDA(cudaMemcpyAsync(&left, d_nactive, 4, cudaMemcpyDeviceToHost, st));

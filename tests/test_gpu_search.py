@@ -677,3 +677,27 @@ def test_tie_cluster_wider_than_the_sweep_list_still_answers(G, dtype):
     res = g.search(q[:1], 10, row_mask=O.pack_row_mask(mask))
     assert list(res.rows[0]) == [17] + list(range(3050, 3059))
     g.close()
+
+
+@pytest.mark.parametrize("metric,k", [("manhattan", 10), ("cosine", 200)])
+def test_k5_tie_cluster_wider_than_its_lists(G, metric, k):
+    """The fp64 sweep (MANHATTAN, or k beyond the tensor-core lists) with more identical rows than its 8192-entry
+    lists hold: overflowing lists are tightened to the k-th best (key, row) pair, so the k smallest row slots of the
+    tie come back instead of RBOD_E_OVERFLOW."""
+    n, dim = 13_000, 64
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    x[1000:11500] = x[7]                                   # 10501 copies of row 7
+    g = G(dim, dtype="f32", metric=metric, capacity=n)
+    g.upsert(x)
+    stored = g.get_rows(np.arange(n))
+    q = np.stack([x[7], x[12000]]).astype(np.float32)
+    res = g.search(q, k, want_scores64=True)
+    if metric == "cosine":
+        ws, wi = OC.cosine_topk(q, stored, k)
+    else:
+        ws, wi, _ = O.distance_topk(q, stored, k, metric)
+    assert np.array_equal(res.rows, wi), int((res.rows != wi).any(axis=1).sum())
+    assert list(res.rows[0][:3]) == [7, 1000, 1001]
+    assert res.stats["sweep_queries"] == 2
+    g.close()
