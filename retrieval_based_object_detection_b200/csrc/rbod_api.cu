@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <vector>
 
@@ -784,6 +785,35 @@ static int run_k3(rbod_gallery* g, const SearchPlan& P, int64_t Q, const uint16_
   return launch_k3(L, st);
 }
 
+// RBOD_TRACE=1: rbod_search prints the host wall-clock time between its phases (microseconds) to stderr -- where the
+// part of a call that is not kernel time goes.
+struct Trace {
+  bool on;
+  double t0, last;
+  char buf[512];
+  int len;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+  }
+  Trace() : len(0) {
+    static const bool enabled = getenv("RBOD_TRACE") != nullptr && getenv("RBOD_TRACE")[0] == '1';
+    on = enabled;
+    t0 = last = on ? now() : 0.0;
+    buf[0] = 0;
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    const double t = now();
+    len += snprintf(buf + len, sizeof(buf) - len, " %s=%.0f", what, t - last);
+    last = t;
+  }
+  ~Trace() {
+    if (on) fprintf(stderr, "rbod_search trace (us): total=%.0f%s\n", now() - t0, buf);
+  }
+};
+
 static int ensure_lists(rbod_gallery* g, const SearchPlan& P) {
   RBOD_TRY(g->lists.ensure((size_t)P.slices * P.q_pad * P.list_stride * sizeof(uint2)));
   RBOD_TRY(g->list_cnt.ensure((size_t)P.slices * P.q_pad * sizeof(int)));
@@ -959,8 +989,10 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   int64_t* d_rows = is_device_ptr(out_rows) ? out_rows : g->out_rows.as<int64_t>();
   double* d_scores64 = (out_scores64 && is_device_ptr(out_scores64)) ? out_scores64 : g->out_scores64.as<double>();
 
+  Trace tr;
   SearchPlan P;
   RBOD_TRY(plan_search(g, Q, k, search_variant(g, Q), smem_optin, &P));
+  tr.mark("plan");
   if (stats) {
     stats->queries = Q;
     stats->candidates = P.kc;
@@ -1006,8 +1038,10 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   int64_t retries = 0;
   for (int attempt = 0;; ++attempt) {
     RBOD_CUDA(cudaMemsetAsync(g->flags.p, 0, 64, st));
+    tr.mark("setup");
     RBOD_TRY(prepare_queries(g, queries, Q, P, st, &q_dev));
     ++launches;
+    tr.mark("prep");
     if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev0, st));
     const float* tau_init = nullptr;
     if (use_sample) {
@@ -1033,6 +1067,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     RBOD_TRY(run_k3(g, P, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st));
     if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev1, st));
     ++launches;
+    tr.mark("k3_launches");
 
     FinishArgs F;
     memset(&F, 0, sizeof(F));
@@ -1069,6 +1104,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     F.max_eps = reinterpret_cast<float*>(d_flags + 3);
     RBOD_TRY(launch_finish(F, Q, st));
     ++launches;
+    tr.mark("finish_launch");
 
     // The answer and the certification flags travel together: in the common case (every query certified) this is
     // the only synchronisation of the call.
@@ -1076,7 +1112,9 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     RBOD_TRY(copy_out(out_rows, d_rows, nout * 8, st));
     if (out_scores64) RBOD_TRY(copy_out(out_scores64, d_scores64, nout * 8, st));
     RBOD_CUDA(cudaMemcpyAsync(hflags, d_flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+    tr.mark("copies");
     RBOD_CUDA(cudaStreamSynchronize(st));
+    tr.mark("sync");
     if (hflags[4] > 0 && tau_init != nullptr && attempt == 0) {
       // a starting threshold cut below k candidates for some query: once more without the pre-pass
       retries = hflags[4];
