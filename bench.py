@@ -367,51 +367,61 @@ def build_gallery(E: Env, n_total, dim, dtype, seed, opts=()):
 
 
 class Searcher:
-    """Search of a row-sharded gallery: local rbod_search into ONE packed buffer, one all-gather, K4 merge."""
+    """One search step: Gallery.search on one GPU, ShardedGallery.search (the public multi-GPU call) on several."""
 
     def __init__(self, E: Env, gal, Q, k, offs):
         torch = E.torch
         self.E, self.g, self.Q, self.k, self.offs = E, gal, Q, k, offs
         self.packed = torch.empty((2, Q, k), dtype=torch.int64, device=E.dev)          # [0] fp64 scores, [1] local rows
         self.s32 = torch.empty((Q, k), dtype=torch.float32, device=E.dev)
-        self.gathered = torch.empty((E.world, 2, Q, k), dtype=torch.int64, device=E.dev) if E.world > 1 else None
         self.host = (torch.empty((Q, k), dtype=torch.float32).pin_memory(), torch.empty((Q, k), dtype=torch.int64).pin_memory(),
                      torch.empty((Q, k), dtype=torch.float64).pin_memory())
         self.host_np = tuple(t.numpy() for t in self.host)
         self.launches = 0
         self.stats = None
+        self.sg = None
+        if E.world > 1:                                  # total rows from the shard offsets + the last shard's own count
+            cnt = E.torch.tensor([gal.count], dtype=E.torch.int64, device=E.dev)
+            E.dist.all_reduce(cnt)
+            self.n_total = int(cnt.item())
 
     def local_out(self):
         return (self.s32, self.packed[1], self.packed[0].view(self.E.torch.float64))
 
+    def shard_view(self):
+        if self.sg is None:
+            from retrieval_based_object_detection_b200 import ShardedGallery
+
+            self.sg = ShardedGallery.wrap(self.g, self.n_total)
+            assert self.sg.shard_offsets() == list(self.offs)
+        return self.sg
+
     def device_step(self, q):
         """queries and results stay on the device -> (scores f32, global ids, scores f64)"""
-        from retrieval_based_object_detection_b200 import merge_topk_packed
-
-        res = self.g.search(q, self.k, out=self.local_out())
-        self.stats = res.stats
-        self.launches += res.stats["total_launches"]
         if self.E.world == 1:
+            res = self.g.search(q, self.k, out=self.local_out())
+            self.stats = res.stats
+            self.launches += res.stats["total_launches"]
             return self.local_out()
-        self.E.dist.all_gather_into_tensor(self.gathered, self.packed)
-        self.launches += 1                               # K4 merge (NCCL's own kernels not counted)
-        return merge_topk_packed(self.gathered, self.offs, self.k)
+        # the public multi-GPU call (ShardedGallery.search): local search, ONE packed all-gather, K4 merge -- or, from
+        # k = 32 on, the split form with the global cut exchanged before the exact rescoring
+        sg = self.shard_view()
+        out = sg.search(q, self.k)
+        self.stats = sg.last_stats
+        self.launches += sg.last_stats["total_launches"]        # ours: local search kernels + K4 (NCCL's not counted)
+        return out
 
     def host_step(self, q_np):
         """queries from pinned host memory, (merged) results back into pinned host memory"""
-        from retrieval_based_object_detection_b200 import merge_topk_packed
-
         if self.E.world == 1:
             res = self.g.search(q_np, self.k, out=self.host_np)
             self.launches += res.stats["total_launches"]
             return self.host_np
-        res = self.g.search(q_np, self.k, out=self.local_out())            # H2D of the queries inside rbod_search
-        self.launches += res.stats["total_launches"] + 1
-        self.E.dist.all_gather_into_tensor(self.gathered, self.packed)
-        merged = merge_topk_packed(self.gathered, self.offs, self.k)
-        for h, m in zip(self.host, merged):
-            h.copy_(m, non_blocking=True)
-        self.E.torch.cuda.synchronize()
+        # each rank uploads 1/G of the batch over its own PCIe link + an all-gather over NVLink, then as device_step,
+        # results into the pinned host buffers, one synchronisation
+        sg = self.shard_view()
+        sg.search(q_np, self.k, out_host=self.host)
+        self.launches += sg.last_stats["total_launches"]        # ours: local search kernels + K4 (NCCL's not counted)
         return self.host_np
 
 
@@ -703,11 +713,23 @@ def side_configs(a, E: Env, g, r0, n_local, q_dev):
             S.host_step(q_np)
         ms_h = E.timed(lambda: S.host_step(q_np), steps)
         k3m = statistics.mean(k3)
+        unc = statistics.mean(fb) / a.queries
         tf = 2.0 * a.queries * n_local * a.dim / (k3m / 1e3) / 1e12
-        return {"config": "C4: 10M x 768 bf16, top-100, row shards + allgather merge", "k": k, "n_gpus": world,
+        extra = {}
+        if world > 1:
+            # the same steps with every rank rescoring its own k candidates (no global cut exchanged first)
+            sgv = S.shard_view()
+            extra["split_search"] = dict(sgv.last_split or {})
+            keep_min = sgv.split_min_k
+            sgv.split_min_k = 1 << 30
+            for _ in range(2):
+                step()
+            extra["value_without_global_cut"] = a.queries * steps / (E.timed(step, steps) / 1e3)
+            sgv.split_min_k = keep_min
+        return {"config": "C4: 10M x 768 bf16, top-100, row shards + allgather merge", "k": k, "n_gpus": world, **extra,
                 "queries_per_step": a.queries, "value": a.queries * steps / (ms / 1e3), "unit": UNIT,
                 "ms_per_step": ms / steps, "e2e_value": a.queries * steps / (ms_h / 1e3), "k3_ms": k3m, "k3_tflops": tf,
-                "k3_frac_of_sustained": tf / sus, "uncertified_fraction": statistics.mean(fb) / a.queries,
+                "k3_frac_of_sustained": tf / sus, "uncertified_fraction": unc,
                 "candidates": S.stats["candidates"],
                 "search_operand": "fp16 shadow of the bf16 rows (built on the first k > 40 search)", "parity": par}
 

@@ -198,12 +198,12 @@ int rbod_segment_delegates(rbod_gallery* g, int32_t kind, const int64_t* row_idx
  * out_rows:     [Q, k] int64 row slots; -1 (score -inf) where fewer than k rows qualify.
  * out_scores64: optional [Q, k] fp64 scores (what the multi-GPU merge consumes), or NULL.
  * stats:        optional.
- * COSINE, DOT and EUCLID collections up to 768 columns with k <= 128 run on the tensor-core pass; MANHATTAN, wider
+ * COSINE, DOT and EUCLID collections up to 2048 columns with k <= 128 run on the tensor-core pass; MANHATTAN, wider
  * vectors and larger k (up to 1024) take the exact fp64 sweep on the CUDA cores (kernel K5) -- same results.
  * EUCLID / MANHATTAN collections: out_scores holds the DISTANCE (sqrt of the squared sum / sum of absolute
  * differences), ascending, +inf where fewer than k rows qualify; ties broken by smaller row slot;
  * out_scores64 holds the ordering key (-squared distance / -L1 distance, larger = closer), which is what
- * rbod_merge_topk orders by.  MANHATTAN (and EUCLID wider than 768 columns): k <= 1024.   */
+ * rbod_merge_topk orders by.  MANHATTAN (and EUCLID wider than 2048 columns): k <= 1024.   */
 int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, const uint32_t* row_mask,
                 float* out_scores, int64_t* out_rows, double* out_scores64, rbod_search_stats* stats,
                 void* stream);
@@ -221,6 +221,43 @@ int rbod_merge_topk(const double* scores64, const int64_t* ids, int32_t G, int64
  * non-negative slots of shard g (NULL = slots are already global ids).                                     */
 int rbod_merge_topk_packed(const void* gathered, const int64_t* shard_row0, int32_t G, int64_t Q, int32_t k,
                            float* out_scores, int64_t* out_ids, double* out_scores64, void* stream);
+
+/* --- Split search for row-sharded collections (multi-GPU) --------------------------------------
+ * rbod_search makes every shard compute exact scores for its own k best candidates although the merge keeps k of the
+ * G*k.  The split form puts one small exchange in the middle so that a shard rescoring only what can still be in the
+ * GLOBAL answer:
+ *   1. rbod_search_begin   query prep, threshold pre-pass, K3, selection.  Writes out_approx [Q][approx_m + 1] (device,
+ *                          fp32): the shard's approx_m best APPROXIMATE scores, descending, -inf padded, then the
+ *                          bound on |approximate - exact| for this query on this shard.  1 <= approx_m <= k; the
+ *                          global cut below is exact when no shard holds more than approx_m of the global top k and
+ *                          a valid (lower) bound otherwise, G * approx_m >= k is required.  No synchronisation.
+ *   2. (caller)            all-gather of out_approx -> [G][Q][approx_m + 1]
+ *   3. rbod_global_cut     out_cut [Q][2] (device, fp32): {k-th largest gathered score, largest gathered bound}
+ *   4. rbod_search_end     exact fp64 scores for the candidates within 2 bounds of the cut, ranked; writes the
+ *                          shard's list in the packed layout rbod_merge_topk_packed takes -- out_scores64 [Q][k],
+ *                          out_rows [Q][k] (local slots, -1 padded) -- and out_ubound [Q] (fp64): an upper bound, in
+ *                          the domain of out_scores64, on every row of the shard that was never a candidate (-inf if
+ *                          none was dropped).  Device pointers only; the three are normally slices of ONE buffer of
+ *                          2*Q*k + Q 8-byte words.  Must follow rbod_search_begin on the same handle with the same
+ *                          Q and k, nothing else searched in between; device `queries` must stay valid until then.
+ *   5. (caller)            all-gather of that buffer -> [G][2*Q*k + Q]
+ *   6. rbod_merge_topk_certified   K4 over the gathered buffer, plus the certification: query q is exact when the
+ *                          merged k-th score beats every shard's bound; the others are listed in out_flag_q
+ *                          [up to Q] (device int32, unordered), their number in out_n_flag (device int32).  The caller
+ *                          answers those with rbod_search (+ rbod_merge_topk_packed) and overwrites their rows.
+ * Collections / k that rbod_search answers with the exact sweep (MANHATTAN, > 2048 columns, k > 128) and empty
+ * shards are refused by rbod_search_begin with RBOD_E_UNSUPPORTED: use rbod_search there.                        */
+int rbod_search_begin(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, int32_t approx_m,
+                      const uint32_t* row_mask, float* out_approx, rbod_search_stats* stats, void* stream);
+int rbod_global_cut(const float* gathered_approx, int32_t G, int64_t Q, int32_t approx_m, int32_t k, float* out_cut,
+                    void* stream);
+int rbod_search_end(rbod_gallery* g, const float* cut, int64_t Q, int32_t k, double* out_scores64, int64_t* out_rows,
+                    double* out_ubound, rbod_search_stats* stats, void* stream);
+int rbod_merge_topk_certified(const void* gathered, const int64_t* shard_row0, int32_t G, int64_t Q, int32_t k,
+                              float* out_scores, int64_t* out_ids, double* out_scores64, int32_t* out_flag_q,
+                              int32_t* out_n_flag, void* stream);
+/* K3 time (threshold pre-pass + main pass) of the handle's last search, option time_k3 = 1; waits for that search. */
+int rbod_last_k3_ms(rbod_gallery* g, float* out_ms);
 
 /* --- test hook --------------------------------------------------------------------------
  * Raw scores of the tcgen05 pass (before top-k and rescoring): out[q, r] for r < rows,

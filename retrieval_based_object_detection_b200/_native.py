@@ -76,6 +76,11 @@ SIGNATURES = {
     "rbod_search": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, ctypes.POINTER(SearchStats), _P]),
     "rbod_merge_topk": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
     "rbod_merge_topk_packed": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
+    "rbod_search_begin": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, ctypes.POINTER(SearchStats), _P]),
+    "rbod_global_cut": (ctypes.c_int, [_P, _I32, _I64, _I32, _I32, _P, _P]),
+    "rbod_search_end": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, ctypes.POINTER(SearchStats), _P]),
+    "rbod_merge_topk_certified": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P, _P, _P]),
+    "rbod_last_k3_ms": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),
     "rbod_debug_scores": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "rbod_debug_profile": (ctypes.c_int, [_P, ctypes.POINTER(_I64)]),
     "rbod_debug_plan": (ctypes.c_int, [_I32, _I64, _I64, _I32, _I32, _I32, _I32, ctypes.POINTER(_I64)]),

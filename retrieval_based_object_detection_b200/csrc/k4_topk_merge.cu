@@ -342,114 +342,128 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t q = blockIdx.x;
   const int kc = P.kc, k = P.k;
+  int total = 0, nsel = 0;
 
-  // (1) list lengths -> exclusive offsets (two slices per thread)
-  int c0 = 0, c1 = 0;
-  if (2 * tid < P.slices) c0 = min(max(P.list_cnt[(size_t)(2 * tid) * P.q_pad + q], 0), P.list_stride);
-  if (2 * tid + 1 < P.slices) c1 = min(max(P.list_cnt[(size_t)(2 * tid + 1) * P.q_pad + q], 0), P.list_stride);
-  int incl = c0 + c1;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(FULL_MASK, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_wsum[warp] = incl;
-  if (tid == 0) {
-    s_cnt[0] = s_cnt[1] = s_cnt[2] = 0u;
-    s_nsel = 0;
-    s_nres = 0;
-    s_have_kth = 0;
-    s_kth = -INFINITY;
-  }
-  __syncthreads();
-  int wbase = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < FIN_WARPS; ++w) {
-    if (w < warp) wbase += s_wsum[w];
-    total += s_wsum[w];
-  }
-  const int excl = wbase + incl - c0 - c1;
-  if (2 * tid < P.slices) s_off[2 * tid] = excl;
-  if (2 * tid + 1 < P.slices) s_off[2 * tid + 1] = excl + c0;
-  if (tid == 0) s_off[P.slices] = total;
-  const int n_tot = min(total, P.n_cap);
-  __syncthreads();
-
-  // gather the lists as packed keys
-  for (int s = warp; s < P.slices; s += FIN_WARPS) {
-    const int off = s_off[s], cs = s_off[s + 1] - off;
-    const uint2* lst = P.lists + ((size_t)s * P.q_pad + q) * P.list_stride;
-    for (int j = lane; j < cs; j += 32)
-      if (off + j < n_tot) {
-        const uint2 e = lst[j];
-        keys[off + j] = (static_cast<unsigned long long>(f32_to_ordered(__uint_as_float(e.x))) << 32) |
-                        static_cast<unsigned long long>(~e.y);
-      }
-  }
-  __syncthreads();
-
-  // (2) the kc-th largest key by a most-significant-bit-first radix descent, one block-wide count per bit, starting
-  // at the first bit in which the scores differ at all.  Keys are distinct (a row appears once), so the descent ends
-  // with exactly kc keys at or above the decided prefix -- usually long before the last bit.
-  unsigned long long T = 0ull;
-  if (n_tot > kc) {
-    uint32_t hmax = 0u, hmin = 0xffffffffu;
-    for (int j = tid; j < n_tot; j += FIN_THREADS) {
-      const uint32_t h = static_cast<uint32_t>(keys[j] >> 32);
-      hmax = max(hmax, h);
-      hmin = min(hmin, h);
+  if (P.mode == FIN_RESUME) {
+    // second half of a split search (rbod_search_end): the selection of the first half comes back from global memory
+    if (tid == 0) {
+      s_nres = 0;
+      s_have_kth = 0;
+      s_kth = -INFINITY;
     }
-    hmax = __reduce_max_sync(FULL_MASK, hmax);
-    hmin = __reduce_min_sync(FULL_MASK, hmin);
-    if (lane == 0) {
-      s_hmax[warp] = hmax;
-      s_hmin[warp] = hmin;
+    nsel = min(max(P.sel_n[q], 0), min(kc, K3_MAX_KC));
+    if (tid < nsel) s_sel[tid] = P.sel_keys[q * kc + tid];
+  } else {
+    // (1) list lengths -> exclusive offsets (two slices per thread)
+    int c0 = 0, c1 = 0;
+    if (2 * tid < P.slices) c0 = min(max(P.list_cnt[(size_t)(2 * tid) * P.q_pad + q], 0), P.list_stride);
+    if (2 * tid + 1 < P.slices) c1 = min(max(P.list_cnt[(size_t)(2 * tid + 1) * P.q_pad + q], 0), P.list_stride);
+    int incl = c0 + c1;
+  #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    if (tid == 0) {
+      s_cnt[0] = s_cnt[1] = s_cnt[2] = 0u;
+      s_nsel = 0;
+      s_nres = 0;
+      s_have_kth = 0;
+      s_kth = -INFINITY;
     }
     __syncthreads();
-#pragma unroll
+    int wbase = 0;
+    total = 0;
+  #pragma unroll
     for (int w = 0; w < FIN_WARPS; ++w) {
-      hmax = max(hmax, s_hmax[w]);
-      hmin = min(hmin, s_hmin[w]);
+      if (w < warp) wbase += s_wsum[w];
+      total += s_wsum[w];
     }
-    const uint32_t diff = hmax ^ hmin;
-    int b = diff ? 32 + (31 - __clz(diff)) : 31;
-    unsigned long long prefix = static_cast<unsigned long long>(diff ? (hmax & ~((2u << (b - 32)) - 1u)) : hmax) << 32;
-    int remaining = kc, share = n_tot, it = 0;
-    while (b >= 0 && share != remaining) {
-      const unsigned long long want = (prefix >> b) | 1ull;
-      int cc = 0;
-      for (int j = tid; j < n_tot; j += FIN_THREADS) cc += ((keys[j] >> b) == want) ? 1 : 0;
-      cc = __reduce_add_sync(FULL_MASK, cc);
-      if (lane == 0 && cc) atomicAdd(&s_cnt[it % 3], (unsigned int)cc);
-      if (tid == 0) s_cnt[(it + 1) % 3] = 0u;   // last read two iterations ago, next used after this barrier
-      __syncthreads();
-      const int ctot = (int)s_cnt[it % 3];
-      if (ctot >= remaining) {
-        prefix |= 1ull << b;
-        share = ctot;
-      } else {
-        remaining -= ctot;
-        share -= ctot;
+    const int excl = wbase + incl - c0 - c1;
+    if (2 * tid < P.slices) s_off[2 * tid] = excl;
+    if (2 * tid + 1 < P.slices) s_off[2 * tid + 1] = excl + c0;
+    if (tid == 0) s_off[P.slices] = total;
+    const int n_tot = min(total, P.n_cap);
+    __syncthreads();
+
+    // gather the lists as packed keys
+    for (int s = warp; s < P.slices; s += FIN_WARPS) {
+      const int off = s_off[s], cs = s_off[s + 1] - off;
+      const uint2* lst = P.lists + ((size_t)s * P.q_pad + q) * P.list_stride;
+      for (int j = lane; j < cs; j += 32)
+        if (off + j < n_tot) {
+          const uint2 e = lst[j];
+          keys[off + j] = (static_cast<unsigned long long>(f32_to_ordered(__uint_as_float(e.x))) << 32) |
+                          static_cast<unsigned long long>(~e.y);
+        }
+    }
+    __syncthreads();
+
+    // (2) the kc-th largest key by a most-significant-bit-first radix descent, one block-wide count per bit, starting
+    // at the first bit in which the scores differ at all.  Keys are distinct (a row appears once), so the descent ends
+    // with exactly kc keys at or above the decided prefix -- usually long before the last bit.
+    unsigned long long T = 0ull;
+    if (n_tot > kc) {
+      uint32_t hmax = 0u, hmin = 0xffffffffu;
+      for (int j = tid; j < n_tot; j += FIN_THREADS) {
+        const uint32_t h = static_cast<uint32_t>(keys[j] >> 32);
+        hmax = max(hmax, h);
+        hmin = min(hmin, h);
       }
-      --b;
-      ++it;
+      hmax = __reduce_max_sync(FULL_MASK, hmax);
+      hmin = __reduce_min_sync(FULL_MASK, hmin);
+      if (lane == 0) {
+        s_hmax[warp] = hmax;
+        s_hmin[warp] = hmin;
+      }
+      __syncthreads();
+  #pragma unroll
+      for (int w = 0; w < FIN_WARPS; ++w) {
+        hmax = max(hmax, s_hmax[w]);
+        hmin = min(hmin, s_hmin[w]);
+      }
+      const uint32_t diff = hmax ^ hmin;
+      int b = diff ? 32 + (31 - __clz(diff)) : 31;
+      unsigned long long prefix = static_cast<unsigned long long>(diff ? (hmax & ~((2u << (b - 32)) - 1u)) : hmax) << 32;
+      int remaining = kc, share = n_tot, it = 0;
+      while (b >= 0 && share != remaining) {
+        const unsigned long long want = (prefix >> b) | 1ull;
+        int cc = 0;
+        for (int j = tid; j < n_tot; j += FIN_THREADS) cc += ((keys[j] >> b) == want) ? 1 : 0;
+        cc = __reduce_add_sync(FULL_MASK, cc);
+        if (lane == 0 && cc) atomicAdd(&s_cnt[it % 3], (unsigned int)cc);
+        if (tid == 0) s_cnt[(it + 1) % 3] = 0u;   // last read two iterations ago, next used after this barrier
+        __syncthreads();
+        const int ctot = (int)s_cnt[it % 3];
+        if (ctot >= remaining) {
+          prefix |= 1ull << b;
+          share = ctot;
+        } else {
+          remaining -= ctot;
+          share -= ctot;
+        }
+        --b;
+        ++it;
+      }
+      T = prefix;
     }
-    T = prefix;
-  }
-  for (int j = tid; j < n_tot; j += FIN_THREADS) {
-    const unsigned long long key = keys[j];
-    if (key >= T) {
-      const int pos = atomicAdd(&s_nsel, 1);
-      if (pos < K3_MAX_KC) s_sel[pos] = key;
+    for (int j = tid; j < n_tot; j += FIN_THREADS) {
+      const unsigned long long key = keys[j];
+      if (key >= T) {
+        const int pos = atomicAdd(&s_nsel, 1);
+        if (pos < K3_MAX_KC) s_sel[pos] = key;
+      }
     }
   }
-  for (int j = tid; j < k; j += FIN_THREADS) {
-    P.out_scores[q * k + j] = user_no_result(P.metric);
-    P.out_rows[q * k + j] = -1;
-    if (P.out_scores64) P.out_scores64[q * k + j] = -INFINITY;
-  }
+  if (P.mode != FIN_SELECT)
+    for (int j = tid; j < k; j += FIN_THREADS) {
+      P.out_scores[q * k + j] = user_no_result(P.metric);
+      P.out_rows[q * k + j] = -1;
+      if (P.out_scores64) P.out_scores64[q * k + j] = -INFINITY;
+    }
   __syncthreads();
-  const int nsel = min(min(s_nsel, kc), K3_MAX_KC);
+  if (P.mode != FIN_RESUME) nsel = min(min(s_nsel, kc), K3_MAX_KC);
 
   // kc or more candidates: everything dropped (by a prune of K3 or by the selection above) scores at most the
   // kc-th best approximate score.  Fewer: no list was ever pruned, only the pre-sampled threshold dropped rows.
@@ -460,8 +474,13 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
   }
   hmin = __reduce_min_sync(FULL_MASK, hmin);
   hbest = __reduce_max_sync(FULL_MASK, hbest);
-  float tau = total >= kc ? ordered_to_f32(hmin) : -INFINITY;
-  if (P.tau_init != nullptr) tau = fmaxf(tau, P.tau_init[q]);
+  float tau;
+  if (P.mode == FIN_RESUME) {
+    tau = P.sel_tau[q];
+  } else {
+    tau = total >= kc ? ordered_to_f32(hmin) : -INFINITY;
+    if (P.tau_init != nullptr) tau = fmaxf(tau, P.tau_init[q]);
+  }
   const QueryMargin M = query_margin(P, q, tau);
   // the same bound for the CANDIDATES, whose scores reach up to the best approximate score: for unit-norm 16-bit
   // masters the row term scales with the score it perturbs
@@ -470,6 +489,26 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
                              ? M.e + (fmaxf(s_best, fabsf(tau) == INFINITY ? 0.0f : fabsf(tau)) + M.e) * M.gdev / (1.0f - M.gdev) +
                                    s_best * 1e-6f + 1e-7f
                              : M.eps + s_best * 1e-6f;
+
+  if (P.mode == FIN_SELECT) {
+    // first half of a split search (rbod_search_begin): keep the selection and the threshold, and publish the
+    // approx_m best approximate scores plus this shard's error bound for them -- what the other shards need to
+    // place the GLOBAL k-th best approximate score
+    if (tid < nsel) {
+      const unsigned long long mykey = s_sel[tid];
+      P.sel_keys[q * kc + tid] = mykey;
+      int above = 0;
+      for (int i = 0; i < nsel; ++i) above += s_sel[i] > mykey ? 1 : 0;
+      if (above < P.approx_m) P.out_approx[q * (P.approx_m + 1) + above] = ordered_to_f32(static_cast<uint32_t>(mykey >> 32));
+    }
+    for (int j = nsel + tid; j < P.approx_m; j += FIN_THREADS) P.out_approx[q * (P.approx_m + 1) + j] = -INFINITY;
+    if (tid == 0) {
+      P.sel_n[q] = nsel;
+      P.sel_tau[q] = tau;
+      P.out_approx[q * (P.approx_m + 1) + P.approx_m] = eps_cand;
+    }
+    return;
+  }
 
   // (3) exact scores.  Not every candidate needs one: the error model puts every row's approximate score within eps
   // of its exact score (in the approximate domain), so a candidate more than 2 eps below the k-th best APPROXIMATE
@@ -490,8 +529,14 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
     }
   }
   __syncthreads();
-  if (tid < nsel && nsel > k)
+  if (P.mode == FIN_RESUME) {
+    // the cut is the k-th best approximate score over ALL shards and the bound the largest any shard reported: a
+    // candidate more than 2 eps below it is beaten exactly by k rows somewhere and cannot be in the global answer
+    const float2 ext = P.ext_cut[q];
+    if (tid < nsel) keep = ordered_to_f32(static_cast<uint32_t>(mykey >> 32)) >= ext.x - 2.0f * fmaxf(eps_cand, ext.y);
+  } else if (tid < nsel && nsel > k) {
     keep = ordered_to_f32(static_cast<uint32_t>(mykey >> 32)) >= s_cut - 2.0f * eps_cand;
+  }
   if (keep) {
     const int pos = atomicAdd(&s_nres, 1);
     s_sel2[pos] = mykey;
@@ -524,7 +569,51 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_kernel(const FinishArgs P)
   __syncthreads();
 
   // (5) certification
+  if (P.mode == FIN_RESUME) {
+    // The local list is complete only down to the global cut, so the k-th local score certifies nothing; what the
+    // merge needs is an upper bound, in the domain of the exact keys, on every row this shard never listed
+    if (tid == 0) {
+      double ub = -INFINITY;
+      if (tau != -INFINITY) {
+        ub = (double)tau + (double)M.eps;
+        if (P.metric == RBOD_EUCLID) ub = 2.0 * (ub - M.qq_half);
+        atomic_max_nonneg(P.max_eps, M.eps);
+      }
+      P.ubound[q] = ub;
+    }
+    return;
+  }
   if (tid == 0 && tau != -INFINITY) certify_query(P, q, tau, M, s_have_kth != 0, s_kth);   // else exact by construction
+}
+
+// k-th largest approximate score of a query over the lists the shards published (rbod_search_begin), and the largest
+// error bound among them: one warp per query, MSB-first descent over the order-preserving integer image.
+__global__ void __launch_bounds__(128) global_cut_kernel(const float* __restrict__ gathered, int G, int64_t Q, int m, int k,
+                                                         float2* __restrict__ out) {
+  extern __shared__ uint32_t gc_vals[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= Q) return;
+  uint32_t* v = gc_vals + (size_t)warp * G * m;
+  const int n = G * m;
+  float eps = 0.0f;
+  for (int g = 0; g < G; ++g) {
+    const float* src = gathered + ((size_t)g * Q + q) * (m + 1);
+    for (int j = lane; j < m; j += 32) v[g * m + j] = f32_to_ordered(src[j]);
+    eps = fmaxf(eps, src[m]);
+  }
+  __syncwarp();
+  uint32_t prefix = 0u;
+  int remaining = k;   // the answer is the remaining-th largest among the values that share the decided prefix
+  for (int b = 31; b >= 0; --b) {
+    const uint32_t want = (prefix >> b) | 1u;
+    int c = 0;
+    for (int j = lane; j < n; j += 32) c += ((v[j] >> b) == want) ? 1 : 0;
+    c = __reduce_add_sync(FULL_MASK, c);
+    if (c >= remaining) prefix |= 1u << b;
+    else remaining -= c;
+  }
+  if (lane == 0) out[q] = make_float2(n >= k ? ordered_to_f32(prefix) : -INFINITY, eps);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -720,10 +809,12 @@ struct MergeRow0 { long long v[32]; };
 __global__ void __launch_bounds__(256)
 merge_topk_kernel(const double* __restrict__ scores64, const int64_t* __restrict__ ids, int64_t shard_stride, int G,
                   int64_t Q, int k, const MergeRow0 row0, float* __restrict__ out_scores,
-                  int64_t* __restrict__ out_ids, double* __restrict__ out_scores64) {
+                  int64_t* __restrict__ out_ids, double* __restrict__ out_scores64,
+                  const double* __restrict__ ubound, int* __restrict__ flag_q, int* __restrict__ n_flag) {
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (q >= Q) return;
+  double kth = -INFINITY;   // the k-th merged score, if there are k
   int pos = 0;
   const int src = lane < G ? lane : 0;
   const double* sc = scores64 + (size_t)src * shard_stride + q * k;
@@ -752,12 +843,21 @@ merge_topk_kernel(const double* __restrict__ scores64, const int64_t* __restrict
       out_ids[q * k + j] = valid ? (int64_t)bi : -1;
       if (out_scores64) out_scores64[q * k + j] = valid ? bs : -INFINITY;
     }
+    if (j == k - 1 && bi != kEmpty) kth = bs;
     if (bi == kEmpty) continue;  // uniform: all lanes agree on the winner
     if (lane == bl) {
       ++pos;
       if (pos < k && id[pos] >= 0) { hs = sc[pos]; hi = id[pos] + off; }
       else { hs = -INFINITY; hi = kEmpty; }
     }
+  }
+  if (ubound != nullptr) {
+    // split searches (rbod_search_end): shard g vouches that no row it left unlisted scores above ubound[g][q]; the
+    // merged answer is exact when its k-th score beats every shard's bound
+    double ub = lane < G ? ubound[(size_t)lane * shard_stride + q] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ub = fmax(ub, __shfl_xor_sync(FULL_MASK, ub, o));
+    if (lane == 0 && ub != -INFINITY && !(ub < kth)) flag_q[atomicAdd(n_flag, 1)] = (int)q;
   }
 }
 
@@ -852,15 +952,27 @@ int launch_rescore_collected(const float* q, const double* q_qq, const float* ma
   return RBOD_OK;
 }
 
+int launch_global_cut(const float* gathered, int G, int64_t Q, int m, int k, float* out_cut2, cudaStream_t st) {
+  if (Q <= 0) return RBOD_OK;
+  if (G < 1 || G > 32 || m < 1 || m > K3_MAX_KC || k < 1 || (int64_t)G * m < k)
+    return set_error(RBOD_E_INVAL, "global_cut: G=%d lists of %d scores for k=%d", G, m, k);
+  const size_t per_warp = (size_t)G * m * 4;
+  const int warps = (int)std::max<size_t>(1, std::min<size_t>(4, (48 * 1024) / per_warp));
+  global_cut_kernel<<<(unsigned)((Q + warps - 1) / warps), warps * 32, per_warp * warps, st>>>(
+      gathered, G, Q, m, k, reinterpret_cast<float2*>(out_cut2));
+  RBOD_CUDA(cudaGetLastError());
+  return RBOD_OK;
+}
+
 int launch_merge_topk(const double* scores64, const int64_t* ids, int64_t shard_stride, const int64_t* row0_host,
                       int G, int64_t Q, int k, float* out_scores, int64_t* out_ids, double* out_scores64,
-                      cudaStream_t st) {
+                      cudaStream_t st, const double* ubound, int* flag_q, int* n_flag) {
   if (Q <= 0 || k <= 0) return RBOD_OK;
   if (G < 1 || G > 32) return set_error(RBOD_E_UNSUPPORTED, "merge_topk: G=%d outside [1, 32]", G);
   MergeRow0 r0;
   for (int g = 0; g < 32; ++g) r0.v[g] = (row0_host != nullptr && g < G) ? (long long)row0_host[g] : 0ll;
   merge_topk_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(scores64, ids, shard_stride, G, Q, k, r0, out_scores,
-                                                            out_ids, out_scores64);
+                                                            out_ids, out_scores64, ubound, flag_q, n_flag);
   RBOD_CUDA(cudaGetLastError());
   return RBOD_OK;
 }

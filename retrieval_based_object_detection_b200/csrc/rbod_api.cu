@@ -907,6 +907,123 @@ static int search_distance(rbod_gallery* g, const float* queries, int64_t Q, int
   return RBOD_OK;
 }
 
+// bf16 COSINE collections: a bf16 query sits up to 2e-3 from the exact unit query, more than the gap between the
+// k-th and the (k + slack)-th score once k reaches the high tens (10M rows, k = 100: 17-37 % of the queries were
+// not certified and took the collecting second pass).  An fp16 copy of the stored rows as the search operand brings
+// the margin to 4e-4 -- bf16 -> fp16 is exact for values of magnitude >= 2^-14 -- at the price of 2 more bytes per
+// element, so it is built the first time such a search arrives (one HBM-bound pass) and kept up to date by K1.
+static int maybe_build_shadow(rbod_gallery* g, int k, cudaStream_t st) {
+  if (g->dtype == RBOD_BF16 && g->metric == RBOD_COSINE && !g->use_shadow && g->auto_shadow && k > 40 && g->rows > 0) {
+    uint16_t* nsh = nullptr;
+    if (cudaMalloc(&nsh, (size_t)g->capacity * g->dp * 2) == cudaSuccess) {
+      RBOD_CUDA(cudaMemsetAsync(nsh, 0, (size_t)g->capacity * g->dp * 2, st));
+      RBOD_CUDA(cudaMemsetAsync(g->stats + 2, 0, 2 * sizeof(float), st));
+      RBOD_TRY(launch_build_shadow(g->rows16, g->rows, g->dp, nsh, g->stats, st));
+      g->shadow16 = nsh;
+      g->use_shadow = 1;
+    } else {
+      cudaGetLastError();
+      g->auto_shadow = 0;   // no room for it: searches stay on the bf16 operand (still exact, more second passes)
+    }
+  }
+  return RBOD_OK;
+}
+
+// Threshold pre-pass: row maxima over K3_SAMPLE_GROUPS strided samples of the gallery give every query a
+// starting threshold, so the candidate lists of the main pass skip their cold start (see tau_init_kernel).
+// Each group's comb is split over enough units to fill the chip, so a small batch does not stream the sample on
+// eight SMs (Q <= 128 on 12.5M x 768: 0.48 ms before the split, next to a 2.9 ms main pass).  Batches of at most
+// 8 queries skip it: their epilogue has almost nothing to insert (measured: Q = 1 is 0.47 ms faster without,
+// Q = 16 already 0.17 ms slower).  presample = 2 forces it.
+static bool presample_pays(const rbod_gallery* g, const SearchPlan& P, int64_t Q, int* sample_tiles) {
+  *sample_tiles = std::max(1, P.tiles_total / (K3_SAMPLE_RATIO * P.kc));
+  const bool sample_pays = g->presample >= 2 || Q > 8;
+  return g->tau_share && g->presample && sample_pays && P.tiles_total >= 10 * P.kc &&
+         P.tiles_total / *sample_tiles >= K3_SAMPLE_GROUPS;
+}
+
+// Everything of a search up to and including the main K3 launch: flags cleared, queries prepared, the optional
+// threshold pre-pass, the candidate lists filled.
+static int launch_front(rbod_gallery* g, const float* queries, int64_t Q, const SearchPlan& P, const uint32_t* mask_dev,
+                        bool use_sample, int sample_tiles, cudaStream_t st, const float** q_dev_out,
+                        const float** tau_init_out, int64_t* launches_io, Trace& tr) {
+  int64_t launches = *launches_io;
+  const float* q_dev = nullptr;
+  RBOD_CUDA(cudaMemsetAsync(g->flags.p, 0, 64, st));
+  tr.mark("setup");
+  RBOD_TRY(prepare_queries(g, queries, Q, P, st, &q_dev));
+  ++launches;
+  tr.mark("prep");
+  if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev0, st));
+  const float* tau_init = nullptr;
+  if (use_sample) {
+    SearchPlan PA = P;
+    const int workers = P.variant == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
+    const int splits = std::max(1, std::min({16, sample_tiles, workers / (K3_SAMPLE_GROUPS * std::max(1, PA.num_qt))}));
+    PA.slices = K3_SAMPLE_GROUPS * splits;
+    PA.grid = (int)std::min<int64_t>((int64_t)PA.slices * PA.num_qt, workers) * (P.variant == 2 ? 2 : 1);
+    RBOD_TRY(g->groupmax.ensure((size_t)PA.slices * P.q_pad * 4));
+    RBOD_TRY(g->tau_init.ensure((size_t)P.q_pad * 4));
+    K3Sample S;
+    S.groupmax = g->groupmax.as<float>();
+    S.tiles = sample_tiles;
+    S.stride = P.tiles_total / sample_tiles;
+    S.splits = splits;
+    RBOD_TRY(run_k3(g, PA, Q, g->q16.as<uint16_t>(), mask_dev, nullptr, nullptr, 0, st,
+                    &S));
+    RBOD_TRY(launch_tau_init(g->groupmax.as<float>(), K3_SAMPLE_GROUPS, splits, P.q_pad,
+                             g->tau_shared.as<uint32_t>(), g->tau_init.as<float>(), st));
+    tau_init = g->tau_init.as<float>();
+    launches += 2;
+  }
+  RBOD_TRY(run_k3(g, P, Q, g->q16.as<uint16_t>(), mask_dev, nullptr, nullptr, 0, st));
+  if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev1, st));
+  ++launches;
+  tr.mark("k3_launches");
+  *q_dev_out = q_dev;
+  *tau_init_out = tau_init;
+  *launches_io = launches;
+  return RBOD_OK;
+}
+
+static void fill_finish(rbod_gallery* g, const SearchPlan& P, int k, const float* tau_init, const float* q_dev,
+                        float* d_scores, int64_t* d_rows, double* d_scores64, FinishArgs* Fp) {
+  FinishArgs& F = *Fp;
+  int* d_flags = g->flags.as<int>();
+  memset(&F, 0, sizeof(F));
+  F.lists = g->lists.as<uint2>();
+  F.list_cnt = g->list_cnt.as<int>();
+  F.slices = P.slices;
+  F.list_stride = P.list_stride;
+  F.n_cap = P.n_cap;
+  F.kc = P.kc;
+  F.k = k;
+  F.q_pad = P.q_pad;
+  F.tau_init = tau_init;
+  F.q = q_dev;
+  F.q_qq = g->q_qq.as<double>();
+  F.q_dq = g->q_dq.as<float>();
+  F.stats = g->stats;
+  F.master32 = g->master32;
+  F.rows16 = g->rows16;
+  F.kind16 = g->kind16;
+  F.dim = g->dim;
+  F.metric = g->metric;
+  F.master16 = g->dtype != RBOD_F32;
+  F.shadow = g->use_shadow;
+  F.dp = g->dp;
+  F.ld32 = g->dim;
+  F.ld16 = g->dp;
+  F.out_scores = d_scores;
+  F.out_rows = d_rows;
+  F.out_scores64 = d_scores64;
+  F.n_flag = d_flags;
+  F.flag_q = g->flag_q.as<int>();
+  F.flag_thr = g->flag_thr.as<double>();
+  F.flag_lo = g->flag_lo.as<float>();
+  F.max_eps = reinterpret_cast<float*>(d_flags + 3);
+}
+
 int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, const uint32_t* row_mask,
                 float* out_scores, int64_t* out_rows, double* out_scores64, rbod_search_stats* stats,
                 void* stream) {
@@ -914,6 +1031,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   if (Q < 0 || k < 1 || (Q > 0 && (!queries || !out_scores || !out_rows)))
     return set_error(RBOD_E_INVAL, "rbod_search: bad arguments");
   if (stats) memset(stats, 0, sizeof(*stats));
+  g->pending.valid = 0;   // a full search reuses the query buffers a pending rbod_search_begin left behind
   if (Q == 0) return RBOD_OK;
   // What the tensor-core pass does not cover takes the exact fp64 sweep (K5): MANHATTAN (not a contraction), vectors
   // wider than K3_MAX_DP_WIDE columns, and k beyond the K3 candidate lists.  Everything else -- COSINE, DOT and EUCLID
@@ -962,24 +1080,7 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   const int smem_optin = k3_configure(g->device);
   if (smem_optin < 0) return smem_optin;
 
-  // bf16 COSINE collections: a bf16 query sits up to 2e-3 from the exact unit query, more than the gap between the
-  // k-th and the (k + slack)-th score once k reaches the high tens (10M rows, k = 100: 17-37 % of the queries were
-  // not certified and took the collecting second pass).  An fp16 copy of the stored rows as the search operand brings
-  // the margin to 4e-4 -- bf16 -> fp16 is exact for values of magnitude >= 2^-14 -- at the price of 2 more bytes per
-  // element, so it is built the first time such a search arrives (one HBM-bound pass) and kept up to date by K1.
-  if (g->dtype == RBOD_BF16 && g->metric == RBOD_COSINE && !g->use_shadow && g->auto_shadow && k > 40 && g->rows > 0) {
-    uint16_t* nsh = nullptr;
-    if (cudaMalloc(&nsh, (size_t)g->capacity * g->dp * 2) == cudaSuccess) {
-      RBOD_CUDA(cudaMemsetAsync(nsh, 0, (size_t)g->capacity * g->dp * 2, st));
-      RBOD_CUDA(cudaMemsetAsync(g->stats + 2, 0, 2 * sizeof(float), st));
-      RBOD_TRY(launch_build_shadow(g->rows16, g->rows, g->dp, nsh, g->stats, st));
-      g->shadow16 = nsh;
-      g->use_shadow = 1;
-    } else {
-      cudaGetLastError();
-      g->auto_shadow = 0;   // no room for it: searches stay on the bf16 operand (still exact, more second passes)
-    }
-  }
+  RBOD_TRY(maybe_build_shadow(g, k, st));
 
   const size_t nout = (size_t)Q * k;
   RBOD_TRY(g->out_scores.ensure(nout * 4));
@@ -1023,85 +1124,17 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
   RBOD_TRY(g->flag_thr.ensure((size_t)Q * 8));
   RBOD_TRY(g->flag_lo.ensure((size_t)P.q_pad * 4 + 1024));   // read as [q_pad of the second pass]
 
-  // Threshold pre-pass: row maxima over K3_SAMPLE_GROUPS strided samples of the gallery give every query a
-  // starting threshold, so the candidate lists of the main pass skip their cold start (see tau_init_kernel).
-  // Each group's comb is split over enough units to fill the chip, so a small batch does not stream the sample on
-  // eight SMs (Q <= 128 on 12.5M x 768: 0.48 ms before the split, next to a 2.9 ms main pass).  Batches of at most
-  // 8 queries skip it: their epilogue has almost nothing to insert (measured: Q = 1 is 0.47 ms faster without,
-  // Q = 16 already 0.17 ms slower).  presample = 2 forces it.
-  const int sample_tiles = std::max(1, P.tiles_total / (K3_SAMPLE_RATIO * P.kc));
-  const bool sample_pays = g->presample >= 2 || Q > 8;
-  bool use_sample = g->tau_share && g->presample && sample_pays && P.tiles_total >= 10 * P.kc &&
-                    P.tiles_total / sample_tiles >= K3_SAMPLE_GROUPS;
+  int sample_tiles = 1;
+  bool use_sample = presample_pays(g, P, Q, &sample_tiles);
   int hflags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const float* q_dev = nullptr;
   int64_t retries = 0;
   for (int attempt = 0;; ++attempt) {
-    RBOD_CUDA(cudaMemsetAsync(g->flags.p, 0, 64, st));
-    tr.mark("setup");
-    RBOD_TRY(prepare_queries(g, queries, Q, P, st, &q_dev));
-    ++launches;
-    tr.mark("prep");
-    if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev0, st));
     const float* tau_init = nullptr;
-    if (use_sample) {
-      SearchPlan PA = P;
-      const int workers = P.variant == 2 ? std::max(1, g->num_sms / 2) : g->num_sms;
-      const int splits = std::max(1, std::min({16, sample_tiles, workers / (K3_SAMPLE_GROUPS * std::max(1, PA.num_qt))}));
-      PA.slices = K3_SAMPLE_GROUPS * splits;
-      PA.grid = (int)std::min<int64_t>((int64_t)PA.slices * PA.num_qt, workers) * (P.variant == 2 ? 2 : 1);
-      RBOD_TRY(g->groupmax.ensure((size_t)PA.slices * P.q_pad * 4));
-      RBOD_TRY(g->tau_init.ensure((size_t)P.q_pad * 4));
-      K3Sample S;
-      S.groupmax = g->groupmax.as<float>();
-      S.tiles = sample_tiles;
-      S.stride = P.tiles_total / sample_tiles;
-      S.splits = splits;
-      RBOD_TRY(run_k3(g, PA, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st,
-                      &S));
-      RBOD_TRY(launch_tau_init(g->groupmax.as<float>(), K3_SAMPLE_GROUPS, splits, P.q_pad,
-                               g->tau_shared.as<uint32_t>(), g->tau_init.as<float>(), st));
-      tau_init = g->tau_init.as<float>();
-      launches += 2;
-    }
-    RBOD_TRY(run_k3(g, P, Q, g->q16.as<uint16_t>(), static_cast<const uint32_t*>(mask_dev), nullptr, nullptr, 0, st));
-    if (g->time_k3) RBOD_CUDA(cudaEventRecord(g->ev1, st));
-    ++launches;
-    tr.mark("k3_launches");
-
+    RBOD_TRY(launch_front(g, queries, Q, P, static_cast<const uint32_t*>(mask_dev), use_sample, sample_tiles, st, &q_dev,
+                          &tau_init, &launches, tr));
     FinishArgs F;
-    memset(&F, 0, sizeof(F));
-    F.lists = g->lists.as<uint2>();
-    F.list_cnt = g->list_cnt.as<int>();
-    F.slices = P.slices;
-    F.list_stride = P.list_stride;
-    F.n_cap = P.n_cap;
-    F.kc = P.kc;
-    F.k = k;
-    F.q_pad = P.q_pad;
-    F.tau_init = tau_init;
-    F.q = q_dev;
-    F.q_qq = g->q_qq.as<double>();
-    F.q_dq = g->q_dq.as<float>();
-    F.stats = g->stats;
-    F.master32 = g->master32;
-    F.rows16 = g->rows16;
-    F.kind16 = g->kind16;
-    F.dim = g->dim;
-    F.metric = g->metric;
-    F.master16 = g->dtype != RBOD_F32;
-    F.shadow = g->use_shadow;
-    F.dp = g->dp;
-    F.ld32 = g->dim;
-    F.ld16 = g->dp;
-    F.out_scores = d_scores;
-    F.out_rows = d_rows;
-    F.out_scores64 = d_scores64;
-    F.n_flag = d_flags;
-    F.flag_q = g->flag_q.as<int>();
-    F.flag_thr = g->flag_thr.as<double>();
-    F.flag_lo = g->flag_lo.as<float>();
-    F.max_eps = reinterpret_cast<float*>(d_flags + 3);
+    fill_finish(g, P, k, tau_init, q_dev, d_scores, d_rows, d_scores64, &F);
     RBOD_TRY(launch_finish(F, Q, st));
     ++launches;
     tr.mark("finish_launch");
@@ -1241,6 +1274,147 @@ int rbod_search(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, con
     }
   }
   return RBOD_OK;
+}
+
+// ---- split search: the two halves of rbod_search around an exchange between shards ---------------------------
+// begin: query prep, threshold pre-pass, K3, selection of the kc best approximate candidates per query; publishes
+// the approx_m best approximate scores and the error bound.  end: exact scores for the candidates that can still
+// reach the GLOBAL top k (cut = the k-th best approximate score over all shards), local ranking, and an upper bound
+// on everything the shard never listed, which rbod_merge_topk_certified checks against the merged k-th score.
+int rbod_search_begin(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, int32_t approx_m,
+                      const uint32_t* row_mask, float* out_approx, rbod_search_stats* stats, void* stream) {
+  if (!g) return set_error(RBOD_E_INVAL, "rbod_search_begin: NULL handle");
+  g->pending.valid = 0;
+  if (Q < 1 || k < 1 || !queries || !out_approx || approx_m < 1 || approx_m > k)
+    return set_error(RBOD_E_INVAL, "rbod_search_begin: bad arguments");
+  if (!is_device_ptr(out_approx)) return set_error(RBOD_E_INVAL, "rbod_search_begin: out_approx must be device memory");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (g->metric == RBOD_MANHATTAN || g->dp > K3_MAX_DP_WIDE || k > K3_MAX_KC)
+    return set_error(RBOD_E_UNSUPPORTED, "rbod_search_begin: this collection / k is answered by the exact sweep; use rbod_search");
+  if (g->rows < 1) return set_error(RBOD_E_UNSUPPORTED, "rbod_search_begin: empty shard; use rbod_search");
+  if (Q > (1ll << 24)) return set_error(RBOD_E_INVAL, "rbod_search_begin: Q too large");
+  if (g->rows >= 0xffffffffll) return set_error(RBOD_E_UNSUPPORTED, "rbod_search_begin: more than 2^32-2 rows per shard");
+  RBOD_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int smem_optin = k3_configure(g->device);
+  if (smem_optin < 0) return smem_optin;
+  RBOD_TRY(maybe_build_shadow(g, k, st));
+  Trace tr;
+  SearchPlan P;
+  RBOD_TRY(plan_search(g, Q, k, search_variant(g, Q), smem_optin, &P));
+  RBOD_TRY(g->flags.ensure(64));
+  const void* mask_dev = nullptr;
+  if (row_mask) RBOD_TRY(to_device(row_mask, (size_t)((g->rows + 31) / 32) * 4, g->mask_dev, st, &mask_dev));
+  RBOD_TRY(ensure_lists(g, P));
+  RBOD_TRY(g->sel_keys.ensure((size_t)Q * P.kc * 8));
+  RBOD_TRY(g->sel_n.ensure((size_t)Q * 4));
+  RBOD_TRY(g->sel_tau.ensure((size_t)Q * 4));
+  int sample_tiles = 1;
+  const bool use_sample = presample_pays(g, P, Q, &sample_tiles);
+  const float* q_dev = nullptr;
+  const float* tau_init = nullptr;
+  int64_t launches = 0;
+  RBOD_TRY(launch_front(g, queries, Q, P, static_cast<const uint32_t*>(mask_dev), use_sample, sample_tiles, st, &q_dev,
+                        &tau_init, &launches, tr));
+  FinishArgs F;
+  fill_finish(g, P, k, tau_init, q_dev, nullptr, nullptr, nullptr, &F);
+  F.mode = FIN_SELECT;
+  F.approx_m = approx_m;
+  F.sel_keys = g->sel_keys.as<unsigned long long>();
+  F.sel_n = g->sel_n.as<int>();
+  F.sel_tau = g->sel_tau.as<float>();
+  F.out_approx = out_approx;
+  RBOD_TRY(launch_finish(F, Q, st));
+  ++launches;
+  g->pending.Q = Q;
+  g->pending.k = k;
+  g->pending.kc = P.kc;
+  g->pending.approx_m = approx_m;
+  g->pending.q_pad = P.q_pad;
+  g->pending.q_dev = q_dev;
+  g->pending.launches = launches;
+  g->pending.valid = 1;
+  if (stats) {
+    stats->queries = Q;
+    stats->candidates = P.kc;
+    stats->slices = P.slices;
+    stats->k3_launches = 1;
+    stats->total_launches = launches;
+  }
+  return RBOD_OK;
+}
+
+int rbod_global_cut(const float* gathered_approx, int32_t G, int64_t Q, int32_t approx_m, int32_t k, float* out_cut,
+                    void* stream) {
+  if (!gathered_approx || !out_cut || Q < 0) return set_error(RBOD_E_INVAL, "rbod_global_cut: bad arguments");
+  if (!is_device_ptr(gathered_approx) || !is_device_ptr(out_cut))
+    return set_error(RBOD_E_INVAL, "rbod_global_cut: device pointers only");
+  return launch_global_cut(gathered_approx, G, Q, approx_m, k, out_cut, static_cast<cudaStream_t>(stream));
+}
+
+int rbod_search_end(rbod_gallery* g, const float* cut, int64_t Q, int32_t k, double* out_scores64, int64_t* out_rows,
+                    double* out_ubound, rbod_search_stats* stats, void* stream) {
+  if (!g) return set_error(RBOD_E_INVAL, "rbod_search_end: NULL handle");
+  if (!g->pending.valid || g->pending.Q != Q || g->pending.k != k)
+    return set_error(RBOD_E_INVAL, "rbod_search_end: no matching rbod_search_begin is pending on this handle");
+  g->pending.valid = 0;
+  if (!cut || !out_scores64 || !out_rows || !out_ubound)
+    return set_error(RBOD_E_INVAL, "rbod_search_end: bad arguments");
+  if (!is_device_ptr(cut) || !is_device_ptr(out_scores64) || !is_device_ptr(out_rows) || !is_device_ptr(out_ubound))
+    return set_error(RBOD_E_INVAL, "rbod_search_end: device pointers only");
+  RBOD_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RBOD_TRY(g->out_scores.ensure((size_t)Q * k * 4));
+  SearchPlan P;
+  memset(&P, 0, sizeof(P));
+  P.kc = g->pending.kc;
+  P.q_pad = g->pending.q_pad;
+  P.slices = 1;
+  P.n_cap = 1;
+  FinishArgs F;
+  fill_finish(g, P, k, nullptr, g->pending.q_dev, g->out_scores.as<float>(), out_rows, out_scores64, &F);
+  F.mode = FIN_RESUME;
+  F.sel_keys = g->sel_keys.as<unsigned long long>();
+  F.sel_n = g->sel_n.as<int>();
+  F.sel_tau = g->sel_tau.as<float>();
+  F.ext_cut = reinterpret_cast<const float2*>(cut);
+  F.ubound = out_ubound;
+  RBOD_TRY(launch_finish(F, Q, st));
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->queries = Q;
+    stats->candidates = P.kc;
+    stats->k3_launches = 1;
+    stats->total_launches = g->pending.launches + 1;   // k3_ms: rbod_last_k3_ms, after the caller's own synchronisation
+  }
+  return RBOD_OK;
+}
+
+int rbod_last_k3_ms(rbod_gallery* g, float* out_ms) {
+  if (!g || !out_ms) return set_error(RBOD_E_INVAL, "rbod_last_k3_ms: bad arguments");
+  if (!g->time_k3) return set_error(RBOD_E_INVAL, "rbod_last_k3_ms: option time_k3 is off");
+  RBOD_CUDA(cudaSetDevice(g->device));
+  RBOD_CUDA(cudaEventSynchronize(g->ev1));
+  RBOD_CUDA(cudaEventElapsedTime(out_ms, g->ev0, g->ev1));
+  return RBOD_OK;
+}
+
+int rbod_merge_topk_certified(const void* gathered, const int64_t* shard_row0, int32_t G, int64_t Q, int32_t k,
+                              float* out_scores, int64_t* out_ids, double* out_scores64, int32_t* out_flag_q,
+                              int32_t* out_n_flag, void* stream) {
+  if (!gathered || !out_scores || !out_ids || !out_flag_q || !out_n_flag || Q < 0 || k < 1)
+    return set_error(RBOD_E_INVAL, "rbod_merge_topk_certified: bad arguments");
+  if (!is_device_ptr(gathered) || !is_device_ptr(out_scores) || !is_device_ptr(out_ids) || !is_device_ptr(out_flag_q) ||
+      !is_device_ptr(out_n_flag) || (out_scores64 && !is_device_ptr(out_scores64)))
+    return set_error(RBOD_E_INVAL, "rbod_merge_topk_certified: device pointers only (shard_row0 is a host array)");
+  if (shard_row0 && is_device_ptr(shard_row0))
+    return set_error(RBOD_E_INVAL, "rbod_merge_topk_certified: shard_row0 must be a host pointer (or NULL)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RBOD_CUDA(cudaMemsetAsync(out_n_flag, 0, 4, st));
+  const double* sc = static_cast<const double*>(gathered);
+  const int64_t* id = static_cast<const int64_t*>(gathered) + Q * k;
+  return launch_merge_topk(sc, id, 2 * Q * k + Q, shard_row0, G, Q, k, out_scores, out_ids, out_scores64, st,
+                           sc + 2 * Q * k, out_flag_q, out_n_flag);
 }
 
 int rbod_debug_scores(rbod_gallery* g, const float* queries, int64_t Q, float* out, void* stream) {

@@ -151,8 +151,19 @@ struct FinishArgs {
   double* flag_thr;
   float* flag_lo;
   float* max_eps;
+  // split search (rbod_search_begin / rbod_search_end): FIN_SELECT stops after the selection and publishes it,
+  // FIN_RESUME picks it up, rescoring only what can still reach the global answer
+  int mode, approx_m;
+  unsigned long long* sel_keys;   // [Q][kc] selected candidates
+  int* sel_n;                     // [Q]
+  float* sel_tau;                 // [Q] threshold below which rows were dropped
+  float* out_approx;              // [Q][approx_m + 1]: best approximate scores (descending), then the error bound
+  const float2* ext_cut;          // [Q] {global k-th best approximate score, largest error bound of any shard}
+  double* ubound;                 // [Q] upper bound (exact-key domain) on the rows this shard never listed
 };
+enum { FIN_FULL = 0, FIN_SELECT = 1, FIN_RESUME = 2 };
 int launch_finish(const FinishArgs& A, int64_t Q, cudaStream_t st);
+int launch_global_cut(const float* gathered, int G, int64_t Q, int m, int k, float* out_cut2, cudaStream_t st);
 int launch_gather_flagged(const uint16_t* q16, int dp, const int* flag_q, int f0, int nf, int64_t nf_pad,
                           uint16_t* fq16, int* coll_cnt, cudaStream_t st);
 int launch_rescore_collected(const float* q, const double* q_qq, const float* master32, const uint16_t* rows16,
@@ -182,7 +193,7 @@ int launch_dist_select(const double* coll_key, const uint32_t* coll_idx, int* co
                        int* n_active, float* out_scores, int64_t* out_rows, double* out_keys, cudaStream_t st);
 int launch_merge_topk(const double* scores64, const int64_t* ids, int64_t shard_stride, const int64_t* row0_host,
                       int G, int64_t Q, int k, float* out_scores, int64_t* out_ids, double* out_scores64,
-                      cudaStream_t st);
+                      cudaStream_t st, const double* ubound = nullptr, int* flag_q = nullptr, int* n_flag = nullptr);
 // bf16 collection -> fp16 search operand built after the fact (rbod_api.cu: auto_shadow)
 int launch_build_shadow(const uint16_t* rows16, int64_t n, int dp, uint16_t* shadow16, float* stats, cudaStream_t st);
 
@@ -226,6 +237,14 @@ struct rbod_gallery {
   rbod::DevBuf flag_q, flag_thr, flag_lo, flag_row, sweep_ctl, fq16, groupmax, tau_init;
   rbod::DevBuf coll_score, coll_idx, coll_cnt;
   rbod::DevBuf mask_dev, dump, sync_counters, prof;
+  rbod::DevBuf sel_keys, sel_n, sel_tau;       // split search: the selection rbod_search_begin leaves for rbod_search_end
+  struct {                                     // what rbod_search_end needs to know about the pending rbod_search_begin
+    int64_t Q = 0;
+    int k = 0, kc = 0, approx_m = 0, valid = 0;
+    int64_t q_pad = 0;
+    const float* q_dev = nullptr;
+    int64_t launches = 0;
+  } pending;
   rbod::DevBuf seg_idx, seg_off, seg_out, seg_partials, seg_prefix, seg_arrive, seg_scratch, seg_member;
   rbod::DevBuf gather_idx, gather_out;
   rbod::DevBuf dist_q64, dist_thr, dist_ctl;   // K5: widened query batch, thresholds, {qsel, active, n_active}

@@ -53,6 +53,7 @@ class Gallery:
         self.dtype = dtype
         self.metric = metric
         self.device = int(device)
+        self.options = {}     # what set_option was given
         N.check(self._lib.rbod_create(self.dim, N.DTYPES[dtype], N.METRICS[metric], int(capacity), self.device,
                                       ctypes.byref(self._h)))
 
@@ -85,6 +86,7 @@ class Gallery:
 
     def set_option(self, key: str, value: int) -> None:
         N.check(self._lib.rbod_set_option(self._h, key.encode(), int(value)))
+        self.options[key] = int(value)
 
     # -- pointer plumbing -------------------------------------------------------------------
     def _in(self, x, dtype_np, dtype_name: str):
@@ -205,6 +207,41 @@ class Gallery:
         stats = {f: getattr(st, f) for f, _ in st._fields_}
         return SearchResult(scores, rows, s64, stats)
 
+    # -- split search (row-sharded collections): see include/rbod.h "Split search" ------------------------------
+    def search_begin(self, queries, k: int, approx_m: int, out_approx, row_mask=None, stream=None) -> dict:
+        """First half: K3 + selection; fills ``out_approx`` [Q, approx_m + 1] float32 (torch CUDA tensor) with this
+        shard's best approximate scores and its error bound.  Device ``queries`` must stay alive until search_end."""
+        keep, p_q = self._in(queries, np.float32, "float32")
+        if keep.ndim != 2 or keep.shape[1] != self.dim:
+            raise ValueError(f"search_begin: expected [Q, {self.dim}] queries, got {tuple(keep.shape)}")
+        Q = int(keep.shape[0])
+        if tuple(out_approx.shape) != (Q, approx_m + 1) or not out_approx.is_contiguous():
+            raise ValueError("search_begin: out_approx must be a contiguous [Q, approx_m + 1] float32 tensor")
+        k_mask, p_mask = self._in(row_mask, np.uint32, "int32")
+        st = N.SearchStats()
+        N.check(self._lib.rbod_search_begin(self._h, p_q, Q, int(k), int(approx_m), p_mask, out_approx.data_ptr(),
+                                            ctypes.byref(st), stream if stream is not None else _current_stream()))
+        self._pending_queries = keep
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def search_end(self, cut, k: int, packed, stream=None) -> dict:
+        """Second half: ``cut`` [Q, 2] float32 from global_cut; ``packed`` = ONE contiguous int64 CUDA tensor of
+        2*Q*k + Q words that receives [Q,k] float64 scores, [Q,k] local row slots and the [Q] float64 bounds."""
+        Q = int(cut.shape[0])
+        if packed.numel() != 2 * Q * k + Q or not packed.is_contiguous():
+            raise ValueError("search_end: packed must hold 2*Q*k + Q 8-byte words")
+        base = packed.data_ptr()
+        st = N.SearchStats()
+        N.check(self._lib.rbod_search_end(self._h, cut.data_ptr(), Q, int(k), base, base + 8 * Q * k, base + 16 * Q * k,
+                                          ctypes.byref(st), stream if stream is not None else _current_stream()))
+        self._pending_queries = None
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def last_k3_ms(self) -> float:
+        out = ctypes.c_float()
+        N.check(self._lib.rbod_last_k3_ms(self._h, ctypes.byref(out)))
+        return float(out.value)
+
     def debug_profile(self) -> dict:
         """Wait-cycle counters of the K3 launches since the last call (needs set_option("k3_prof", 1)); clears them."""
         out = (ctypes.c_int64 * 16)()
@@ -260,6 +297,44 @@ def merge_topk_packed(gathered, shard_row0, k: int, stream=None):
                                        out_i.data_ptr(), out_d.data_ptr(),
                                        stream if stream is not None else _current_stream()))
     return out_s, out_i, out_d
+
+
+def global_cut(gathered_approx, k: int, stream=None):
+    """[G, Q, m + 1] gathered search_begin outputs (float32, CUDA) -> [Q, 2] {global k-th best approximate score,
+    largest error bound}."""
+    torch = sys.modules["torch"]
+    lib = N.load()
+    G, Q, m1 = gathered_approx.shape
+    gathered_approx = gathered_approx.contiguous()
+    out = torch.empty((Q, 2), dtype=torch.float32, device=gathered_approx.device)
+    N.check(lib.rbod_global_cut(gathered_approx.data_ptr(), G, Q, m1 - 1, int(k), out.data_ptr(),
+                                stream if stream is not None else _current_stream()))
+    return out
+
+
+def merge_topk_certified(gathered, shard_row0, Q: int, k: int, stream=None):
+    """K4 + certification over the gathered search_end buffers: ``gathered`` [G, 2*Q*k + Q] int64 words (CUDA).
+    -> (scores f32, global ids, scores f64, flag_q int32 [Q], n_flag int32 [1]); flag_q[:n_flag] are the queries whose
+    merged answer is not certified (to be answered by a full search)."""
+    torch = sys.modules["torch"]
+    lib = N.load()
+    G, words = gathered.shape
+    if words != 2 * Q * k + Q:
+        raise ValueError("merge_topk_certified: expected [G, 2*Q*k + Q] words")
+    gathered = gathered.contiguous()
+    row0 = np.ascontiguousarray(shard_row0, dtype=np.int64)
+    if row0.shape != (G,):
+        raise ValueError("merge_topk_certified: one row offset per shard")
+    dev = gathered.device
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    out_d = torch.empty((Q, k), dtype=torch.float64, device=dev)
+    flag_q = torch.empty((Q,), dtype=torch.int32, device=dev)
+    n_flag = torch.empty((1,), dtype=torch.int32, device=dev)
+    N.check(lib.rbod_merge_topk_certified(gathered.data_ptr(), row0.ctypes.data, G, Q, k, out_s.data_ptr(),
+                                          out_i.data_ptr(), out_d.data_ptr(), flag_q.data_ptr(), n_flag.data_ptr(),
+                                          stream if stream is not None else _current_stream()))
+    return out_s, out_i, out_d, flag_q, n_flag
 
 
 def segment_finish(sums, counts, normalize: bool = True, stream=None):

@@ -67,11 +67,23 @@ class ShardedGallery:
         self.metric = metric
         self.local = None
         self._buf = None       # packed [2, Q, k] result buffer + fp32 scores, reused across searches of one shape
+        self._qbuf = None      # device staging of the query batch when it arrives in host memory
+        self._sbuf = None      # buffers of the split search, reused across searches of one shape
+        self.split_min_k = 32  # from this k on a multi-GPU search exchanges a global cut before rescoring (_search_split)
+        self.last_split = None # {"flagged": n} of the last split search
+        self.last_stats = None
         if create_local:
             from .gallery import Gallery
 
             self.local = Gallery(dim, dtype=dtype, metric=metric, capacity=self.row_end - self.row_start,
                                  device=self.rank if device is None else device)
+
+    @classmethod
+    def wrap(cls, local_gallery, n_rows_total: int, metric: str = "cosine", group=None):
+        """A sharded view over an existing per-rank ``Gallery`` that already holds rows shard_range(n, rank, G)."""
+        sg = cls(local_gallery.dim, n_rows_total, metric=metric, group=group, create_local=False)
+        sg.local = local_gallery
+        return sg
 
     @property
     def local_rows(self) -> int:
@@ -85,13 +97,110 @@ class ShardedGallery:
         """Global row offset of every rank's shard (what K4 adds to the local row slots)."""
         return [shard_range(self.n_rows_total, r, self.world)[0] for r in range(self.world)]
 
+    def _upload_split(self, queries):
+        """Host query batch -> device, each rank paying for 1/G of the PCIe traffic.
+
+        Every rank holds the same [Q, dim] float32 batch in host memory (the caller's contract for a sharded search);
+        rank r copies rows [r*per, (r+1)*per) over its own PCIe link and one all-gather over NVLink completes the batch
+        on every GPU, instead of G full copies competing for host memory bandwidth."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)) if isinstance(queries, np.ndarray) \
+            else queries.to(torch.float32).contiguous()
+        if q.ndim == 1:
+            q = q.unsqueeze(0)
+        Q, dim = int(q.shape[0]), int(q.shape[1])
+        per = -(-Q // self.world)
+        dev = torch.device("cuda", self.local.device)
+        if self._qbuf is None or tuple(self._qbuf[0].shape) != (self.world * per, dim):
+            self._qbuf = (torch.empty((self.world * per, dim), dtype=torch.float32, device=dev),
+                          torch.zeros((per, dim), dtype=torch.float32, device=dev))
+        full, mine = self._qbuf
+        lo, hi = min(Q, self.rank * per), min(Q, (self.rank + 1) * per)
+        if hi > lo:
+            mine[: hi - lo].copy_(q[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(full, mine, group=self.group)
+        return full[:Q]
+
+    def _split_applies(self, k: int) -> bool:
+        return (self._local_search is None and self._merge is None and self.world > 1 and k >= self.split_min_k
+                and k <= 128 and self.metric in ("cosine", "dot", "euclid") and self.dim <= 2048
+                and self.n_rows_total >= self.world)
+
+    def _search_split(self, queries, k: int):
+        """Global top-k with ONE small exchange before the exact rescoring (include/rbod.h "Split search").
+
+        A plain sharded search makes every rank rescore its own k best candidates per query in fp64 although the merge
+        keeps k of the G*k.  Here each rank first publishes its best APPROXIMATE scores (all-gather of [Q, m+1] floats),
+        every rank derives the global k-th best approximate score, and a rank rescoring only its candidates within two
+        error bounds of that cut does 1/G of the work.  The second all-gather carries the exact lists plus, per query,
+        a bound on what the shard never listed; K4 merges and certifies; the rare uncertified queries are answered by
+        the plain path and patched in."""
+        import torch
+        import torch.distributed as dist
+
+        from .gallery import global_cut, merge_topk_certified, merge_topk_packed
+
+        Q = int(queries.shape[0])
+        G = self.world
+        m = min(k, max(8, -(-2 * k // G) + 8))
+        dev = torch.device("cuda", self.local.device)
+        words = 2 * Q * k + Q
+        if self._sbuf is None or self._sbuf[0] != (Q, k, m):
+            self._sbuf = ((Q, k, m), torch.empty((Q, m + 1), dtype=torch.float32, device=dev),
+                          torch.empty((G, Q, m + 1), dtype=torch.float32, device=dev),
+                          torch.empty((words,), dtype=torch.int64, device=dev),
+                          torch.empty((G, words), dtype=torch.int64, device=dev))
+        _, approx, g_approx, packed, g_packed = self._sbuf
+        st0 = self.local.search_begin(queries, k, m, approx)
+        dist.all_gather_into_tensor(g_approx, approx, group=self.group)
+        cut = global_cut(g_approx, k)
+        st1 = self.local.search_end(cut, k, packed)
+        dist.all_gather_into_tensor(g_packed, packed, group=self.group)
+        s32, ids, s64, flag_q, n_flag = merge_topk_certified(g_packed, self.shard_offsets(), Q, k)
+        n = int(n_flag.item())                           # the one synchronisation of the call
+        self.last_stats = dict(st0, total_launches=st1["total_launches"] + 2)   # + global_cut, K4
+        self.last_split = {"flagged": n, "approx_m": m}
+        if self.local.options.get("time_k3"):
+            self.last_stats["k3_ms"] = self.local.last_k3_ms()
+        if n > 0:
+            # every rank sees the same gathered data, hence the same list: answer those queries the plain way
+            idx = torch.sort(flag_q[:n].to(torch.int64)).values
+            sub = queries[idx].contiguous()
+            loc = torch.empty((2, n, k), dtype=torch.int64, device=dev)
+            l32 = torch.empty((n, k), dtype=torch.float32, device=dev)
+            st2 = self.local.search(sub, k, out=(l32, loc[1], loc[0].view(torch.float64))).stats
+            g_loc = torch.empty((G, 2, n, k), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(g_loc, loc, group=self.group)
+            f32, fids, f64 = merge_topk_packed(g_loc, self.shard_offsets(), k)
+            s32[idx], ids[idx], s64[idx] = f32, fids, f64
+            self.last_stats["total_launches"] += st2["total_launches"] + 1
+            self.last_stats["fallback_queries"] = n
+        return s32, ids, s64
+
     def search(self, queries, k: int, out_host=None):
         """Global top-k on every rank: (scores f32 [Q,k], global ids i64 [Q,k], scores f64 [Q,k]).
 
         The local search writes its float64 scores and local row slots into ONE [2, Q, k] buffer of 8-byte words;
-        a single all-gather moves it; K4 merges the gathered [G, 2, Q, k] buffer and adds each shard's row offset."""
+        a single all-gather moves it; K4 merges the gathered [G, 2, Q, k] buffer and adds each shard's row offset.
+        ``queries`` in host memory must be the same batch on every rank (each rank uploads 1/G of it, see
+        ``_upload_split``); ``out_host`` = three host tensors (pinned for an asynchronous copy) that receive the
+        merged (scores f32, ids, scores f64) and are returned after one synchronisation."""
         import torch
 
+        if self._local_search is None and self.world > 1 and not getattr(queries, "is_cuda", False):
+            queries = self._upload_split(queries)
+        if self._split_applies(k):
+            if not hasattr(queries, "is_cuda"):
+                queries = torch.as_tensor(queries)
+            if not queries.is_cuda:
+                queries = queries.to(torch.device("cuda", self.local.device), torch.float32)
+            if queries.ndim == 1:
+                queries = queries.unsqueeze(0)
+            out = self._search_split(queries.to(torch.float32).contiguous(), k)
+            return self._deliver(out, out_host)
         if self._local_search is not None:
             s64, rows = self._local_search(queries, k)
             packed = torch.stack([s64.to(torch.float64).contiguous().view(torch.int64), rows.to(torch.int64)], 0)
@@ -102,7 +211,9 @@ class ShardedGallery:
                 self._buf = (torch.empty((2, Q, k), dtype=torch.int64, device=dev),
                              torch.empty((Q, k), dtype=torch.float32, device=dev))
             packed, s32 = self._buf
-            self.local.search(queries, k, out=(s32, packed[1], packed[0].view(torch.float64)))
+            self.last_stats = dict(self.local.search(queries, k, out=(s32, packed[1], packed[0].view(torch.float64))).stats)
+            self.last_stats["total_launches"] += 1       # K4 below
+            self.last_split = None
         if self.world == 1:
             gathered = packed.unsqueeze(0)
         else:
@@ -116,12 +227,23 @@ class ShardedGallery:
             from .gallery import merge_topk_packed
 
             out = merge_topk_packed(gathered, self.shard_offsets(), k)
+        return self._deliver(out, out_host)
+
+    def _deliver(self, out, out_host):
+        import torch
+
         if self.metric in ("euclid", "manhattan"):
             # the lists travel and merge as ordering keys (-d^2 / -d, larger = closer); hand back distances
             s32, ids, keys = out
             dist = torch.sqrt(-keys) if self.metric == "euclid" else -keys
             dist = torch.where(ids >= 0, dist, torch.full_like(dist, float("inf")))
-            return dist.to(torch.float32), ids, keys
+            out = (dist.to(torch.float32), ids, keys)
+        if out_host is not None:
+            for h, m in zip(out_host, out):
+                h.copy_(m, non_blocking=True)
+            if out[0].is_cuda:
+                torch.cuda.synchronize(out[0].device)
+            return tuple(out_host)
         return out
 
     def segment_mean(self, offsets, row_idx=None):

@@ -52,6 +52,25 @@ def main():
     top = torch.topk(sc, k, dim=1)
     out["cosine_ids_equal"] = bool(torch.equal(top.indices, ids))
     out["cosine_max_score_err"] = float((top.values - s64).abs().max())
+    # the same batch from HOST memory (Q = 300 is not a multiple of the world size): every rank uploads 1/G of it and an
+    # all-gather completes it; results land in caller-owned host tensors
+    host = (torch.empty(Q, k).pin_memory(), torch.empty(Q, k, dtype=torch.int64).pin_memory(),
+            torch.empty(Q, k, dtype=torch.float64).pin_memory())
+    h32, hids, h64 = sg.search(q.cpu().numpy(), k, out_host=host)
+    out["host_queries_ids_equal"] = bool(torch.equal(hids, ids.cpu()) and torch.equal(h64, s64.cpu()))
+
+    # top-100 takes the split form (global cut exchanged before the exact rescoring), device and host queries
+    s32c, idsc, s64c = sg.search(q, 100)
+    top100 = torch.topk(sc, 100, dim=1)
+    out["split_k100_ids_equal"] = bool(torch.equal(top100.indices, idsc))
+    out["split_k100_max_score_err"] = float((top100.values - s64c).abs().max())
+    out["split_k100"] = dict(sg.last_split or {})
+    _, idsh, _ = sg.search(q.cpu().numpy(), 100)
+    out["split_k100_host_ids_equal"] = bool(torch.equal(idsh, idsc))
+    sg.split_min_k = 1                                  # the same form at k = 10
+    _, idsd, s64d = sg.search(q, k)
+    out["split_k10_ids_equal"] = bool(torch.equal(idsd, ids) and torch.equal(s64d, s64))
+    sg.split_min_k = 32
 
     # ---- delegates over shards vs one gallery
     loc = labels[a:b]
@@ -68,7 +87,7 @@ def main():
     out["delegate_empty_class_zero"] = bool((cent[7] == 0).all())
     whole.close()
 
-    # ---- search, EUCLID fp32 (K5 + key merge)
+    # ---- search, EUCLID fp32 (K3 with the row-bias epilogue + key merge)
     n2, dim2 = 60_001, 256
     x2, q2 = x[:n2, :dim2].contiguous(), q[:64, :dim2].contiguous()
     a2, b2 = shard_range(n2, rank, world)
@@ -78,9 +97,14 @@ def main():
     top2 = torch.topk(torch.cdist(q2.double(), x2.double()), k, dim=1, largest=False)
     out["euclid_ids_equal"] = bool(torch.equal(top2.indices, ids2))
     out["euclid_max_rel_err"] = float(((top2.values - d32.double()).abs() / top2.values.clamp_min(1e-30)).max())
+    d40, ids40, _ = se.search(q2, 40)                   # split form on a EUCLID collection
+    top40 = torch.topk(torch.cdist(q2.double(), x2.double()), 40, dim=1, largest=False)
+    out["euclid_split_k40_ids_equal"] = bool(torch.equal(top40.indices, ids40)) and se.last_split is not None
 
-    ok = (out["cosine_ids_equal"] and out["cosine_max_score_err"] < 1e-9 and out["delegate_max_ulp"] <= 1
-          and out["delegate_empty_class_zero"] and out["euclid_ids_equal"] and out["euclid_max_rel_err"] < 1e-6)
+    ok = (out["cosine_ids_equal"] and out["host_queries_ids_equal"] and out["cosine_max_score_err"] < 1e-9 and out["delegate_max_ulp"] <= 1
+          and out["delegate_empty_class_zero"] and out["euclid_ids_equal"] and out["euclid_max_rel_err"] < 1e-6
+          and out["split_k100_ids_equal"] and out["split_k100_max_score_err"] < 1e-9 and out["split_k100_host_ids_equal"]
+          and out["split_k10_ids_equal"] and out["euclid_split_k40_ids_equal"])
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     out["ok_all_ranks"] = int(flag.item()) == 0

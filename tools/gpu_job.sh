@@ -14,6 +14,7 @@
 #   launches[:args]  ncu launch list of bench.py (after a plain run of the same command)
 #   ncu:<kernel-regex>[:args]   ncu --set full of the named kernel in bench.py
 #   py:<file>        python <file>
+#   nccl:<N>         torchrun --nproc-per-node N tools/check_sharded_nccl.py   (run under gpurun --gpus N)
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
@@ -73,6 +74,10 @@ for step in "$@"; do
       timeout 600 $cmd > $O/${tag}_plain2.log 2>&1 &&
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$kre -s 4 -c 2 -f -o $O/${tag}_prof $cmd > $O/${tag}_ncu_f.log 2>&1
       echo "rc=$?"; tail -3 $O/${tag}_ncu_f.log | cut -c1-300 ;;
+    nccl)
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $rest --master-addr 127.0.0.1 --master-port 29511 \
+        tools/check_sharded_nccl.py > $O/${tag}_nccl.json 2> $O/${tag}_nccl.err
+      echo "rc=$?"; grep -v "^W\|^\*\*\*\|OMP_NUM_THREADS" $O/${tag}_nccl.err | tail -15 | cut -c1-300; cut -c1-1500 $O/${tag}_nccl.json ;;
     py)
       timeout 900 python $args 2>&1 | tail -40 | cut -c1-400 ;;
     *) echo "unknown step $step" ;;
