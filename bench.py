@@ -307,7 +307,10 @@ class Env:
             # level, which an nccl.conf on the box can select even when the variable is unset
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
                 os.environ["NCCL_DEBUG"] = "WARN"
-            dist.init_process_group("nccl", device_id=self.dev)
+            # a rank that falls out of step must cost minutes, not the default 10-minute watchdog on every GPU
+            import datetime
+
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=240))
         self.sus, self.burst, self.hbm, self.peak_src = load_peaks()
 
     def barrier(self):
@@ -474,7 +477,12 @@ def sweep(E: Env, g, n_local, dim, k, batch_sizes, qgen, offs=None, sharded=Fals
         run = (lambda: S.device_step(qd)) if sharded else (lambda: setattr(S, "stats", g.search(qd, k, out=S.local_out()).stats))
         for _ in range(3):
             run()
-        iters = max(5, min(max_iters, int(2000 / max(1.0, S.stats["k3_ms"]))))
+        # the iteration count must be the same on every rank (each iteration holds a barrier): derive it from the
+        # slowest rank's K3 time, not from this rank's own
+        k3_ref = torch.tensor([float(S.stats["k3_ms"])], device=E.dev, dtype=torch.float64)
+        if sharded and E.world > 1:
+            dist.all_reduce(k3_ref, op=dist.ReduceOp.MAX)
+        iters = max(5, min(max_iters, int(2000 / max(1.0, float(k3_ref.item())))))
         lat, k3 = [], []
         for _ in range(iters):
             if sharded:
@@ -500,6 +508,8 @@ def sweep(E: Env, g, n_local, dim, k, batch_sizes, qgen, offs=None, sharded=Fals
                          "tflops_per_gpu": round(flops / p50 / 1e9, 1), "gbs_per_gpu": round(byts / p50 / 1e6, 1),
                          "bound": "hbm" if byts / E.hbm / 1e9 > flops / E.burst / 1e12 else "tensor",
                          "frac_of_bound": round(max(byts / E.hbm / 1e9, flops / E.burst / 1e12) / (p50 / 1e3), 3),
+                         # back-to-back iterations run at the power-capped clock: the same bound with the SUSTAINED bf16 peak
+                         "frac_of_bound_sustained": round(max(byts / E.hbm / 1e9, flops / E.sus / 1e12) / (p50 / 1e3), 3),
                          "slices": st["slices"], "fallback": st["fallback_queries"], "iters": iters})
     return rows_out
 
