@@ -529,6 +529,7 @@ def run_b200(a):
     g, r0, n_local, k1_events = build_gallery(E, a.rows, a.dim, a.dtype, 1234, a.opt)
     if a.variant >= 0:
         g.set_option("k3_variant", a.variant)
+    torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build0
 
     # ---- the two HBM-bound kernels of the path, measured on the side (not part of the timed step):
@@ -660,13 +661,16 @@ def run_b200(a):
         "dtype": a.dtype, "data": "synthetic",
         "config": {"workload": workload_name(a), "gallery_rows_total": a.rows, "rows_per_gpu": n_local, "dim": a.dim,
                    "queries_per_step": a.queries, "k": a.k,
-                   "parallelism": f"row-shard x{world} + one packed allgather + K4 merge",
+                   "parallelism": f"row-shard x{world} + one packed allgather + K4 merge (top-100: global cut exchanged first)",
                    "l2": "gallery operand per GPU is far larger than the 126 MB L2; no flush between steps",
                    "candidates_per_query": last_stats["candidates"], "slices": last_stats["slices"],
                    "fallback_queries_per_step": statistics.mean(fallback) if fallback else 0,
                    "gallery_build_s": round(t_build, 2), "options": a.opt, "per_rank": per_rank},
+        # whole job: the query batch crosses PCIe once (each rank uploads 1/N of it, an all-gather over NVLink completes
+        # it on every GPU); every rank reads the merged answer back
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": a.queries * a.dim * 4,
-                "d2h_bytes_per_step": a.queries * a.k * (4 + 8 + 8), "ms_per_step": ms_e2e / a.steps},
+                "d2h_bytes_per_step": world * a.queries * a.k * (4 + 8 + 8), "ms_per_step": ms_e2e / a.steps,
+                "call": "Gallery.search" if world == 1 else "ShardedGallery.search(host queries, out_host=pinned buffers)"},
         "gpu_launches": n_launch_timed,
         "roofline": roofline,
         "other_kernels": other_kernels,
@@ -899,6 +903,7 @@ def side_configs(a, E: Env, g, r0, n_local, q_dev):
         n_total, dim, k = 12_500_000 * world, 768, 10
         t0 = time.perf_counter()
         g5, r05, n5, _ = build_gallery(E, n_total, dim, "f16", 777)
+        torch.cuda.synchronize()
         build_s = time.perf_counter() - t0
         offs5 = [shard_range(n_total, r, world)[0] for r in range(world)]
         qgen5 = torch.Generator(dev).manual_seed(555)
