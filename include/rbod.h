@@ -245,8 +245,8 @@ int rbod_merge_topk_packed(const void* gathered, const int64_t* shard_row0, int3
  *                          merged k-th score beats every shard's bound; the others are listed in out_flag_q
  *                          [up to Q] (device int32, unordered), their number in out_n_flag (device int32).  The caller
  *                          answers those with rbod_search (+ rbod_merge_topk_packed) and overwrites their rows.
- * Collections / k that rbod_search answers with the exact sweep (MANHATTAN, > 2048 columns, k > 128) and empty
- * shards are refused by rbod_search_begin with RBOD_E_UNSUPPORTED: use rbod_search there.                        */
+ * Collections / k that rbod_search answers with the exact sweep (MANHATTAN, > 2048 columns, k > 128) are refused by
+ * rbod_search_begin with RBOD_E_UNSUPPORTED: use rbod_search there.  A shard without rows takes part with empty lists. */
 int rbod_search_begin(rbod_gallery* g, const float* queries, int64_t Q, int32_t k, int32_t approx_m,
                       const uint32_t* row_mask, float* out_approx, rbod_search_stats* stats, void* stream);
 int rbod_global_cut(const float* gathered_approx, int32_t G, int64_t Q, int32_t approx_m, int32_t k, float* out_cut,

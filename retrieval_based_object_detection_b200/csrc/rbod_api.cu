@@ -1291,11 +1291,26 @@ int rbod_search_begin(rbod_gallery* g, const float* queries, int64_t Q, int32_t 
   if (stats) memset(stats, 0, sizeof(*stats));
   if (g->metric == RBOD_MANHATTAN || g->dp > K3_MAX_DP_WIDE || k > K3_MAX_KC)
     return set_error(RBOD_E_UNSUPPORTED, "rbod_search_begin: this collection / k is answered by the exact sweep; use rbod_search");
-  if (g->rows < 1) return set_error(RBOD_E_UNSUPPORTED, "rbod_search_begin: empty shard; use rbod_search");
   if (Q > (1ll << 24)) return set_error(RBOD_E_INVAL, "rbod_search_begin: Q too large");
   if (g->rows >= 0xffffffffll) return set_error(RBOD_E_UNSUPPORTED, "rbod_search_begin: more than 2^32-2 rows per shard");
   RBOD_CUDA(cudaSetDevice(g->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g->rows < 1) {
+    // an empty shard takes part in the exchange with nothing to offer: no scores, no error bound, nothing dropped
+    std::vector<float> ha((size_t)Q * (approx_m + 1), -INFINITY);
+    for (int64_t q = 0; q < Q; ++q) ha[(size_t)q * (approx_m + 1) + approx_m] = 0.0f;
+    RBOD_CUDA(cudaMemcpyAsync(out_approx, ha.data(), ha.size() * 4, cudaMemcpyHostToDevice, st));
+    RBOD_CUDA(cudaStreamSynchronize(st));   // the host vector goes out of scope
+    g->pending.Q = Q;
+    g->pending.k = k;
+    g->pending.kc = 0;
+    g->pending.approx_m = approx_m;
+    g->pending.q_dev = nullptr;
+    g->pending.launches = 0;
+    g->pending.valid = 2;   // pending, empty shard
+    if (stats) stats->queries = Q;
+    return RBOD_OK;
+  }
   const int smem_optin = k3_configure(g->device);
   if (smem_optin < 0) return smem_optin;
   RBOD_TRY(maybe_build_shadow(g, k, st));
@@ -1364,6 +1379,21 @@ int rbod_search_end(rbod_gallery* g, const float* cut, int64_t Q, int32_t k, dou
     return set_error(RBOD_E_INVAL, "rbod_search_end: device pointers only");
   RBOD_CUDA(cudaSetDevice(g->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g->pending.kc == 0) {
+    // the empty shard of rbod_search_begin: an empty list per query, and no row it could have left unlisted
+    const size_t n = (size_t)Q * k;
+    std::vector<double> hs(n, -INFINITY), hu((size_t)Q, -INFINITY);
+    std::vector<int64_t> hr(n, -1);
+    RBOD_CUDA(cudaMemcpyAsync(out_scores64, hs.data(), n * 8, cudaMemcpyHostToDevice, st));
+    RBOD_CUDA(cudaMemcpyAsync(out_rows, hr.data(), n * 8, cudaMemcpyHostToDevice, st));
+    RBOD_CUDA(cudaMemcpyAsync(out_ubound, hu.data(), (size_t)Q * 8, cudaMemcpyHostToDevice, st));
+    RBOD_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->queries = Q;
+    }
+    return RBOD_OK;
+  }
   RBOD_TRY(g->out_scores.ensure((size_t)Q * k * 4));
   SearchPlan P;
   memset(&P, 0, sizeof(P));

@@ -135,3 +135,23 @@ def test_split_search_small_shards_masks_and_errors():
     with pytest.raises(RuntimeError, match="exact sweep"):
         gm.search_begin(torch.as_tensor(q, device=dev), 5, 5, torch.empty((Q, 6), dtype=torch.float32, device=dev))
     gm.close()
+
+
+def test_split_search_with_an_empty_shard():
+    """A rank that holds no rows yet still takes part in both exchanges: -inf scores, empty lists, no bound."""
+    from retrieval_based_object_detection_b200 import Gallery
+
+    n, dim, Q, k = 500, 64, 11, 10
+    x = O.synthetic_unit_rows(n, dim, seed=21)
+    full = Gallery(dim, dtype="f16", capacity=n)
+    full.upsert(x)
+    empty = Gallery(dim, dtype="f16", capacity=16)
+    stored = full.get_rows(np.arange(n))
+    q = O.synthetic_unit_rows(Q, dim, seed=22)
+    for shards, offs in (([empty, full], [0, 0]), ([full, empty], [0, n])):
+        s32, ids, s64, flagged, _ = _split_search(shards, offs, q, k, 10)
+        ws, wi = O.cosine_topk(q, stored, k)
+        assert np.array_equal(ids, wi) and flagged == 0
+        np.testing.assert_allclose(s64, ws, rtol=1e-9, atol=1e-12)
+    full.close()
+    empty.close()
