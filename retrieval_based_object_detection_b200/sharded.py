@@ -51,7 +51,7 @@ class ShardedGallery:
     def __init__(self, dim: int, n_rows_total: int, dtype: str = "bf16", metric: str = "cosine", group=None,
                  device: Optional[int] = None, local_search: Optional[Callable] = None,
                  merge: Optional[Callable] = None, create_local: bool = True,
-                 local_sums: Optional[Callable] = None, finish: Optional[Callable] = None):
+                 local_sums: Optional[Callable] = None, finish: Optional[Callable] = None, split_ops=None):
         import torch.distributed as dist
 
         self.group = group
@@ -64,6 +64,7 @@ class ShardedGallery:
         self._merge = merge
         self._local_sums = local_sums
         self._finish = finish
+        self._split_ops = split_ops    # test double for the split search's arithmetic (see _LibSplitOps)
         self.metric = metric
         self.local = None
         self._buf = None       # packed [2, Q, k] result buffer + fp32 scores, reused across searches of one shape
@@ -125,9 +126,23 @@ class ShardedGallery:
         return full[:Q]
 
     def _split_applies(self, k: int) -> bool:
-        return (self._local_search is None and self._merge is None and self.world > 1 and k >= self.split_min_k
-                and k <= 128 and self.metric in ("cosine", "dot", "euclid") and self.dim <= 2048
-                and self.n_rows_total >= self.world)
+        if self.world < 2 or k < self.split_min_k or k > 128:
+            return False
+        if self._split_ops is not None:
+            return True
+        return (self._local_search is None and self._merge is None and self.metric in ("cosine", "dot", "euclid")
+                and self.dim <= 2048 and self.n_rows_total >= self.world)
+
+    def _gather_into(self, out, t):
+        """out [G, ...] <- every rank's t: one all_gather_into_tensor over NCCL, a list all-gather on CPU (gloo)."""
+        import torch.distributed as dist
+
+        if t.is_cuda:
+            dist.all_gather_into_tensor(out, t, group=self.group)
+        else:
+            parts = [out[g] for g in range(self.world)]
+            dist.all_gather(parts, t.contiguous(), group=self.group)
+        return out
 
     def _search_split(self, queries, k: int):
         """Global top-k with ONE small exchange before the exact rescoring (include/rbod.h "Split search").
@@ -137,44 +152,46 @@ class ShardedGallery:
         every rank derives the global k-th best approximate score, and a rank rescoring only its candidates within two
         error bounds of that cut does 1/G of the work.  The second all-gather carries the exact lists plus, per query,
         a bound on what the shard never listed; K4 merges and certifies; the rare uncertified queries are answered by
-        the plain path and patched in."""
+        the plain path and patched in.
+
+        The six arithmetic steps are the methods of ``_LibSplitOps`` (librbod.so) or of an injected object with the
+        same methods (the gloo tests answer them with the oracle); everything else -- buffer shapes, the two
+        all-gathers, the patching of uncertified queries -- is this function."""
         import torch
-        import torch.distributed as dist
 
-        from .gallery import global_cut, merge_topk_certified, merge_topk_packed
-
+        ops = self._split_ops if self._split_ops is not None else _LibSplitOps(self.local)
         Q = int(queries.shape[0])
         G = self.world
         m = min(k, max(8, -(-2 * k // G) + 8))
-        dev = torch.device("cuda", self.local.device)
+        dev = queries.device
         words = 2 * Q * k + Q
-        if self._sbuf is None or self._sbuf[0] != (Q, k, m):
-            self._sbuf = ((Q, k, m), torch.empty((Q, m + 1), dtype=torch.float32, device=dev),
+        if self._sbuf is None or self._sbuf[0] != (Q, k, m, dev):
+            self._sbuf = ((Q, k, m, dev), torch.empty((Q, m + 1), dtype=torch.float32, device=dev),
                           torch.empty((G, Q, m + 1), dtype=torch.float32, device=dev),
                           torch.empty((words,), dtype=torch.int64, device=dev),
                           torch.empty((G, words), dtype=torch.int64, device=dev))
         _, approx, g_approx, packed, g_packed = self._sbuf
-        st0 = self.local.search_begin(queries, k, m, approx)
-        dist.all_gather_into_tensor(g_approx, approx, group=self.group)
-        cut = global_cut(g_approx, k)
-        st1 = self.local.search_end(cut, k, packed)
-        dist.all_gather_into_tensor(g_packed, packed, group=self.group)
-        s32, ids, s64, flag_q, n_flag = merge_topk_certified(g_packed, self.shard_offsets(), Q, k)
+        st0 = ops.begin(queries, k, m, approx)
+        self._gather_into(g_approx, approx)
+        cut = ops.global_cut(g_approx, k)
+        st1 = ops.end(cut, k, packed)
+        self._gather_into(g_packed, packed)
+        s32, ids, s64, flag_q, n_flag = ops.merge_certified(g_packed, self.shard_offsets(), Q, k)
         n = int(n_flag.item())                           # the one synchronisation of the call
         self.last_stats = dict(st0, total_launches=st1["total_launches"] + 2)   # + global_cut, K4
         self.last_split = {"flagged": n, "approx_m": m}
-        if self.local.options.get("time_k3"):
-            self.last_stats["k3_ms"] = self.local.last_k3_ms()
+        k3_ms = ops.k3_ms()
+        if k3_ms is not None:
+            self.last_stats["k3_ms"] = k3_ms
         if n > 0:
             # every rank sees the same gathered data, hence the same list: answer those queries the plain way
             idx = torch.sort(flag_q[:n].to(torch.int64)).values
             sub = queries[idx].contiguous()
             loc = torch.empty((2, n, k), dtype=torch.int64, device=dev)
-            l32 = torch.empty((n, k), dtype=torch.float32, device=dev)
-            st2 = self.local.search(sub, k, out=(l32, loc[1], loc[0].view(torch.float64))).stats
+            st2 = ops.plain(sub, k, loc)
             g_loc = torch.empty((G, 2, n, k), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(g_loc, loc, group=self.group)
-            f32, fids, f64 = merge_topk_packed(g_loc, self.shard_offsets(), k)
+            self._gather_into(g_loc, loc)
+            f32, fids, f64 = ops.merge_packed(g_loc, self.shard_offsets(), k)
             s32[idx], ids[idx], s64[idx] = f32, fids, f64
             self.last_stats["total_launches"] += st2["total_launches"] + 1
             self.last_stats["fallback_queries"] = n
@@ -190,12 +207,13 @@ class ShardedGallery:
         merged (scores f32, ids, scores f64) and are returned after one synchronisation."""
         import torch
 
-        if self._local_search is None and self.world > 1 and not getattr(queries, "is_cuda", False):
+        if (self._local_search is None and self._split_ops is None and self.world > 1
+                and not getattr(queries, "is_cuda", False)):
             queries = self._upload_split(queries)
         if self._split_applies(k):
             if not hasattr(queries, "is_cuda"):
                 queries = torch.as_tensor(queries)
-            if not queries.is_cuda:
+            if not queries.is_cuda and self._split_ops is None:
                 queries = queries.to(torch.device("cuda", self.local.device), torch.float32)
             if queries.ndim == 1:
                 queries = queries.unsqueeze(0)
@@ -271,3 +289,40 @@ class ShardedGallery:
         from .gallery import segment_finish
 
         return segment_finish(sums, counts, normalize=self.metric == "cosine")
+
+
+class _LibSplitOps:
+    """The arithmetic steps of ShardedGallery._search_split, answered by librbod.so on this rank's Gallery."""
+
+    def __init__(self, local):
+        self.local = local
+
+    def begin(self, queries, k, m, approx):
+        return self.local.search_begin(queries, k, m, approx)
+
+    def global_cut(self, g_approx, k):
+        from .gallery import global_cut
+
+        return global_cut(g_approx, k)
+
+    def end(self, cut, k, packed):
+        return self.local.search_end(cut, k, packed)
+
+    def merge_certified(self, g_packed, offsets, Q, k):
+        from .gallery import merge_topk_certified
+
+        return merge_topk_certified(g_packed, offsets, Q, k)
+
+    def k3_ms(self):
+        return self.local.last_k3_ms() if self.local.options.get("time_k3") else None
+
+    def plain(self, sub, k, loc):
+        import torch
+
+        l32 = torch.empty((sub.shape[0], k), dtype=torch.float32, device=sub.device)
+        return self.local.search(sub, k, out=(l32, loc[1], loc[0].view(torch.float64))).stats
+
+    def merge_packed(self, g_loc, offsets, k):
+        from .gallery import merge_topk_packed
+
+        return merge_topk_packed(g_loc, offsets, k)

@@ -155,3 +155,42 @@ def test_split_search_with_an_empty_shard():
         np.testing.assert_allclose(s64, ws, rtol=1e-9, atol=1e-12)
     full.close()
     empty.close()
+
+
+def test_sharded_gallery_split_path_on_one_rank():
+    """ShardedGallery's own orchestration of the split form and of the split query upload, on a one-rank NCCL group
+    (every line of the multi-GPU path except the peers; tools/check_sharded_nccl.py runs it on 2 GPUs)."""
+    import socket
+
+    import torch
+    import torch.distributed as dist
+
+    from retrieval_based_object_detection_b200 import ShardedGallery
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        n, dim, Q, k = 30_000, 128, 50, 40
+        x = O.synthetic_unit_rows(n, dim, seed=5)
+        sg = ShardedGallery(dim, n, dtype="f16", device=0)
+        sg.upsert_local(x)
+        sg.local.set_option("time_k3", 1)
+        stored = sg.local.get_rows(np.arange(n))
+        q = O.synthetic_unit_rows(Q, dim, seed=6)
+        ws, wi = O.cosine_topk(q, stored, k)
+        qd = sg._upload_split(q)                                  # host batch -> device through the gather
+        assert torch.equal(qd.cpu(), torch.from_numpy(q))
+        s32, ids, s64 = sg._search_split(qd, k)
+        assert np.array_equal(ids.cpu().numpy(), wi)
+        np.testing.assert_allclose(s64.cpu().numpy(), ws, rtol=1e-9, atol=1e-12)
+        assert sg.last_split == {"flagged": 0, "approx_m": k} and sg.last_stats["k3_ms"] > 0
+        host = (torch.empty(Q, k).pin_memory(), torch.empty(Q, k, dtype=torch.int64).pin_memory(),
+                torch.empty(Q, k, dtype=torch.float64).pin_memory())
+        h32, hids, h64 = sg.search(q, k, out_host=host)           # world 1: the plain path, delivered to host buffers
+        assert np.array_equal(hids.numpy(), wi)
+        sg.local.close()
+    finally:
+        dist.destroy_process_group()

@@ -179,3 +179,136 @@ def test_two_rank_euclid_search_returns_distances(tmp_path):
         assert np.array_equal(np.load(tmp_path / f"e_ids_{r}.npy"), wi)
         d = np.load(tmp_path / f"e_d_{r}.npy")
         assert np.allclose(d, wd, rtol=1e-6) and np.all(np.diff(d, axis=1) >= 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# The split form (k >= split_min_k): begin -> all-gather -> global cut -> end -> all-gather -> merge + certification ->
+# plain path for what was flagged.  The orchestration is ShardedGallery._search_split itself; the six arithmetic steps
+# librbod.so performs on a GPU are answered here by the oracle (numpy float64), with a deliberately noisy
+# "approximate" score so that the cut, the bound and the certification all have work to do.
+class _OracleSplitOps:
+    def __init__(self, stored_local, eps, slack):
+        self.g = stored_local.astype(np.float64)
+        self.gn = np.sqrt((self.g * self.g).sum(1))
+        self.eps, self.slack = float(eps), int(slack)
+        self.rescored = 0
+
+    def _exact(self, q):
+        q = np.asarray(q, dtype=np.float64)
+        return (q @ self.g.T) / (np.sqrt((q * q).sum(1))[:, None] * self.gn[None, :])
+
+    def begin(self, queries, k, m, approx):
+        q = queries.numpy()
+        ex = self._exact(q)
+        rng = np.random.default_rng(1234)                     # same noise on every call: |approx - exact| <= 0.9 eps
+        self.approx = (ex + (rng.random(ex.shape) * 1.8 - 0.9) * self.eps).astype(np.float32)
+        self.q = q
+        n = ex.shape[1]
+        kc = min(n, k + self.slack)
+        order = np.argsort(-self.approx, axis=1, kind="stable")[:, :kc]
+        self.cand = order
+        self.tau = np.where(n > kc, np.take_along_axis(self.approx, order[:, -1:], 1)[:, 0], -np.inf)
+        top = np.full((q.shape[0], m + 1), -np.inf, dtype=np.float32)
+        mm = min(m, kc)
+        top[:, :mm] = np.take_along_axis(self.approx, order[:, :mm], 1)
+        top[:, m] = self.eps
+        approx.copy_(torch.from_numpy(top))
+        return {"total_launches": 3, "candidates": kc, "fallback_queries": 0}
+
+    def global_cut(self, g_approx, k):
+        a = g_approx.numpy()
+        G, Q, m1 = a.shape
+        vals = np.sort(a[:, :, : m1 - 1].transpose(1, 0, 2).reshape(Q, -1), axis=1)[:, ::-1]
+        return torch.from_numpy(np.stack([vals[:, k - 1], a[:, :, m1 - 1].max(0)], 1).astype(np.float32))
+
+    def end(self, cut, k, packed):
+        c = cut.numpy()
+        Q = c.shape[0]
+        ex = self._exact(self.q)
+        s64 = np.full((Q, k), -np.inf)
+        rows = np.full((Q, k), -1, dtype=np.int64)
+        for i in range(Q):
+            keep = self.cand[i][self.approx[i, self.cand[i]] >= c[i, 0] - 2.0 * max(self.eps, c[i, 1])]
+            self.rescored += len(keep)
+            sc = ex[i, keep]
+            o = np.lexsort((keep, -sc))[:k]
+            s64[i, : len(o)], rows[i, : len(o)] = sc[o], keep[o]
+        ub = np.where(np.isfinite(self.tau), self.tau.astype(np.float64) + self.eps, -np.inf)
+        buf = np.concatenate([s64.reshape(-1).view(np.int64), rows.reshape(-1), ub.view(np.int64)])
+        packed.copy_(torch.from_numpy(buf))
+        return {"total_launches": 4}
+
+    def merge_certified(self, g_packed, offsets, Q, k):
+        w = g_packed.numpy()
+        G = w.shape[0]
+        s = w[:, : Q * k].copy().view(np.float64).reshape(G, Q, k)
+        r = w[:, Q * k:2 * Q * k].reshape(G, Q, k)
+        ub = w[:, 2 * Q * k:].copy().view(np.float64).reshape(G, Q).max(0)
+        ids = np.where(r >= 0, r + np.asarray(offsets, dtype=np.int64)[:, None, None], -1)
+        ms, mi = O.merge_topk(s, ids, k)
+        kth = np.where(mi[:, k - 1] >= 0, ms[:, k - 1], -np.inf)
+        flagged = np.flatnonzero(np.isfinite(ub) & ~(ub < kth)).astype(np.int32)
+        fq = np.zeros(Q, dtype=np.int32)
+        fq[: len(flagged)] = flagged[::-1]                    # unordered on the device: the host must sort
+        return (torch.from_numpy(ms.astype(np.float32)), torch.from_numpy(mi), torch.from_numpy(ms),
+                torch.from_numpy(fq), torch.tensor([len(flagged)], dtype=torch.int32))
+
+    def k3_ms(self):
+        return None
+
+    def plain(self, sub, k, loc):
+        ex = self._exact(sub.numpy())
+        s, i = O.topk_from_scores(ex, k)
+        loc[0].copy_(torch.from_numpy(s.view(np.int64)))
+        loc[1].copy_(torch.from_numpy(i))
+        return {"total_launches": 5}
+
+    def merge_packed(self, g_loc, offsets, k):
+        w = g_loc.numpy()
+        s = w[:, 0].copy().view(np.float64)
+        ids = np.where(w[:, 1] >= 0, w[:, 1] + np.asarray(offsets, dtype=np.int64)[:, None, None], -1)
+        ms, mi = O.merge_topk(s, ids, k)
+        return torch.from_numpy(ms.astype(np.float32)), torch.from_numpy(mi), torch.from_numpy(ms)
+
+
+def _split_worker(rank, world, port, n, dim, Q, k, eps, slack, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        stored = O.l2_normalize_store(O.synthetic_unit_rows(n, dim, seed=0), "bf16")[0]
+        q = O.synthetic_unit_rows(Q, dim, seed=1)
+        a, b = shard_range(n, rank, world)
+        ops = _OracleSplitOps(stored[a:b], eps, slack)
+        sg = ShardedGallery(dim, n, dtype="bf16", create_local=False, split_ops=ops)
+        sg.split_min_k = 4
+        s32, ids, s64 = sg.search(torch.from_numpy(q), k)
+        np.save(os.path.join(out_dir, f"ids_{rank}.npy"), ids.numpy())
+        np.save(os.path.join(out_dir, f"s64_{rank}.npy"), s64.numpy())
+        np.save(os.path.join(out_dir, f"info_{rank}.npy"),
+                np.array([sg.last_split["flagged"], ops.rescored, sg.last_stats["total_launches"]]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,k,eps,slack", [(400, 10, 2e-3, 22), (400, 10, 6e-2, 6), (37, 12, 2e-3, 4)])
+def test_two_rank_split_search_equals_single_brute_force(tmp_path, n, k, eps, slack):
+    """eps = 2e-3: nearly everything is certified and each rank rescoring only what clears the global cut does about
+    half the work; eps = 6e-2: the bound is useless, most queries are flagged and the plain path answers them;
+    n = 37: shards smaller than the candidate lists (nothing is ever dropped, nothing can be flagged)."""
+    dim, Q, world = 48, 13, 2
+    mp.spawn(_split_worker, args=(world, _free_port(), n, dim, Q, k, eps, slack, str(tmp_path)), nprocs=world, join=True)
+    stored = O.l2_normalize_store(O.synthetic_unit_rows(n, dim, seed=0), "bf16")[0]
+    q = O.synthetic_unit_rows(Q, dim, seed=1)
+    ws, wi = O.cosine_topk(q, stored, k)
+    infos = [np.load(tmp_path / f"info_{r}.npy") for r in range(world)]
+    for r in range(world):
+        ids, s64 = np.load(tmp_path / f"ids_{r}.npy"), np.load(tmp_path / f"s64_{r}.npy")
+        assert np.array_equal(ids, wi), (r, infos)
+        assert np.allclose(s64, ws, rtol=0, atol=1e-14)
+    assert infos[0][0] == infos[1][0]                         # every rank saw the same flag list
+    if eps > 1e-2:
+        assert infos[0][0] > 0
+    if n == 37:
+        assert infos[0][0] == 0
+    if (n, eps) == (400, 2e-3):
+        assert infos[0][1] + infos[1][1] < 0.8 * world * Q * (k + slack)   # the cut spared exact scores
