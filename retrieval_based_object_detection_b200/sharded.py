@@ -1,11 +1,13 @@
 """Row-sharded multi-GPU search: one process per GPU, gallery rows block-partitioned over ranks.
 
-Each rank searches its own rows (K3 + exact rescoring -> local top-k with float64 scores) straight
-into one packed [2, Q, k] buffer (scores, then local row slots), the buffers are exchanged with ONE
-all-gather over NCCL/NVLink, and every rank merges the G lists with K4 (``rbod_merge_topk_packed``,
-which also turns local slots into global ids).  Scores travel as float64 so the merged order is
-exactly the (score desc, id asc) order a single GPU would produce.  No other collective is on the
-data path.
+Plain form (k < 32): each rank searches its own rows (K3 + exact rescoring -> local top-k with float64 scores) straight
+into one packed [2, Q, k] buffer (scores, then local row slots), the buffers are exchanged with ONE all-gather over
+NCCL/NVLink, and every rank merges the G lists with K4 (``rbod_merge_topk_packed``, which also turns local slots into
+global ids).  Split form (k >= 32, ``_search_split``): the shards first exchange their best APPROXIMATE scores, derive
+the global k-th best, and rescore only what can still reach the global answer; a second all-gather carries the exact
+lists and a per-query bound, K4 merges and certifies.  Scores travel as float64 so the merged order is exactly the
+(score desc, id asc) order a single GPU would produce.  A query batch that arrives in host memory is uploaded 1/G per
+rank and completed by an all-gather (``_upload_split``).
 
 The reference has no multi-GPU path at all; this implements BASELINE.json's
 "shard the gallery by rows ... merge the global top-k with an NCCL allgather".
