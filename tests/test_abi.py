@@ -35,6 +35,13 @@ def test_loads_and_reports_errors_without_gpu():
     assert lib.rbod_upsert(None, None, 1, None, None, 0, None) == _native.RBOD_E_INVAL
     assert lib.rbod_search(None, None, 1, 1, None, None, None, None, None, None) == _native.RBOD_E_INVAL
     assert lib.rbod_destroy(None) == 0
+    # the split-search entry points reject missing handles / buffers before touching the device
+    assert lib.rbod_search_begin(None, None, 1, 1, 1, None, None, None, None) == _native.RBOD_E_INVAL
+    assert b"rbod_search_begin" in lib.rbod_last_error()
+    assert lib.rbod_search_end(None, None, 1, 1, None, None, None, None, None) == _native.RBOD_E_INVAL
+    assert lib.rbod_global_cut(None, 2, 1, 1, 1, None, None) == _native.RBOD_E_INVAL
+    assert lib.rbod_merge_topk_certified(None, None, 2, 1, 1, None, None, None, None, None, None) == _native.RBOD_E_INVAL
+    assert lib.rbod_last_k3_ms(None, None) == _native.RBOD_E_INVAL
 
 
 def test_product_fails_loudly_without_a_gpu():
