@@ -194,3 +194,45 @@ def test_sharded_gallery_split_path_on_one_rank():
         sg.local.close()
     finally:
         dist.destroy_process_group()
+
+
+def test_global_cut_and_certified_merge_against_numpy():
+    """The two shard-independent kernels of the split form on synthetic buffers: the k-th largest of G*m gathered
+    scores (short lists padded with -inf, duplicates, negative values) with the largest bound, and K4's certification
+    flags (k-th merged score against the largest per-shard bound; lists that dropped nothing never flag)."""
+    import torch
+
+    from retrieval_based_object_detection_b200.gallery import global_cut, merge_topk_certified
+
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    G, Q, m, k = 5, 300, 37, 50
+    a = rng.standard_normal((G, Q, m + 1)).astype(np.float32)
+    a[:, :, :m] = -np.sort(-a[:, :, :m], axis=2)
+    a[1, :, 20:m] = -np.inf                                   # a shard with a short list
+    a[:, 7, :m] = 0.25                                        # every score equal
+    a[:, :, m] = (rng.random((G, Q)) * 1e-3).astype(np.float32)
+    cut = global_cut(torch.as_tensor(a, device=dev), k).cpu().numpy()
+    vals = np.sort(a[:, :, :m].transpose(1, 0, 2).reshape(Q, -1), axis=1)[:, ::-1]
+    assert np.array_equal(cut[:, 0], vals[:, k - 1])
+    assert np.array_equal(cut[:, 1], a[:, :, m].max(0))
+
+    G, Q, k = 3, 40, 6
+    s = -np.sort(-rng.standard_normal((G, Q, k)), axis=2)
+    ids = rng.permutation(10 * G * Q * k)[: G * Q * k].reshape(G, Q, k).astype(np.int64)
+    s[0, 5, 3:], ids[0, 5, 3:] = -np.inf, -1                  # a short list
+    s[:, 9, 1:], ids[:, 9, 1:] = -np.inf, -1                  # fewer than k results in total
+    ub = rng.standard_normal((G, Q)) - 0.5
+    ub[:, :8] = -np.inf                                       # nothing was dropped anywhere: exact by construction
+    offs = [0, 1_000_000, 2_000_000]
+    packed = np.stack([np.concatenate([s[g].reshape(-1).view(np.int64), ids[g].reshape(-1), ub[g].view(np.int64)])
+                       for g in range(G)])
+    s32, mi, ms, flag_q, n_flag = merge_topk_certified(torch.as_tensor(packed, device=dev), offs, Q, k)
+    gid = np.where(ids >= 0, ids + np.asarray(offs)[:, None, None], -1)
+    ws, wi = O.merge_topk(s, gid, k)
+    assert np.array_equal(mi.cpu().numpy(), wi) and np.array_equal(ms.cpu().numpy(), ws)
+    kth = np.where(wi[:, k - 1] >= 0, ws[:, k - 1], -np.inf)
+    ubm = ub.max(0)
+    want = set(np.flatnonzero(np.isfinite(ubm) & ~(ubm < kth)).tolist())
+    n = int(n_flag.item())
+    assert set(flag_q[:n].cpu().tolist()) == want and n == len(want) and 9 in want and not (want & set(range(8)))
